@@ -1,0 +1,851 @@
+// st_model.cu — host side of the SpamTreeMV mirror: bookkeeping (spamtree_model.cpp:8-503 re-designed around ancestor
+// chains), node-major layout, device state, and the reference-named operations that launch the kernels.
+#include "st_model.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "st_kernels.cuh"
+
+namespace st {
+
+#define ST_CUDA(call, what)                                   \
+  do {                                                        \
+    cudaError_t _e = (call);                                  \
+    if (_e != cudaSuccess) return cuda_fail(_e, what);        \
+  } while (0)
+
+int Model::cuda_fail(cudaError_t e, const char* what) {
+  err = std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e);
+  return 2;  // ST_ERR_CUDA
+}
+
+// covariance_functions.cpp:34-92 (theta layout) folded with :113-135 (C_base) into per outcome-pair coefficients
+bool make_covtab(const double* theta, int n_theta, int q, CovTab& tab, std::string& err) {
+  if (q < 1 || q > kMaxQ) { err = "q outside 1..8"; return false; }
+  const int n_cbase = q > 2 ? 3 : 1, npars = 3 * q + n_cbase, kd = n_theta - npars;
+  if (kd < 0 || (q >= 2 && kd != q * (q - 1) / 2) || (q == 1 && kd != 0)) { err = "theta has the wrong length for q"; return false; }
+  const double *ai1 = theta, *ai2 = theta + q, *phi_i = theta + 2 * q, *thetamv = theta + 3 * q;
+  tab.q = q;
+  if (q == 1) {  // cexpcov(…, sigmasq = ai1(0), phi = thetamv(0)) (:220-221)
+    tab.c1[0] = ai1[0]; tab.r1[0] = thetamv[0]; tab.c2[0] = 0; tab.r2[0] = 0;
+    return true;
+  }
+  double D[kMaxQ * kMaxQ] = {0};  // vec_to_symmat: column-major fill of the strict lower triangle
+  int ix = 0;
+  for (int j = 0; j < q; j++)
+    for (int i = j + 1; i < q; i++) { D[i * q + j] = D[j * q + i] = theta[npars + ix]; ix++; }
+  for (int i = 0; i < q; i++)
+    for (int j = 0; j < q; j++) {
+      const double v = D[i * q + j];
+      const int e = i * q + j;
+      double psi_sqrt, psi2, c;
+      if (q > 2) {
+        psi_sqrt = std::exp(0.5 * thetamv[1] * std::log1p(thetamv[0] * (v == 0 ? 0.0 : v)));  // sqrt_fpsi
+        psi2 = psi_sqrt * psi_sqrt;
+        c = thetamv[2];
+      } else {
+        psi_sqrt = std::sqrt((v == 0 ? 0.0 : v) + 1);
+        psi2 = (v == 0 ? 0.0 : v) + 1.0;
+        c = thetamv[0];
+      }
+      if (v == 0) {  // "same outcome" is detected by Dmat(i,j) == 0 (:250)
+        tab.c1[e] = ai1[i] * ai1[i] / psi2; tab.r1[e] = c / psi_sqrt;
+        tab.c2[e] = ai2[i] * ai2[i];        tab.r2[e] = phi_i[i];
+      } else {
+        tab.c1[e] = ai1[i] * ai1[j] / psi2; tab.r1[e] = c / psi_sqrt;
+        tab.c2[e] = 0;                      tab.r2[e] = 0;
+      }
+    }
+  return true;
+}
+
+Model::~Model() {
+  if (device >= 0) cudaSetDevice(device);
+  for (void* p : owned) cudaFree(p);
+  if (h_scalars) cudaFreeHost(h_scalars);
+  if (h_stage) cudaFreeHost(h_stage);
+  for (auto& e : ev) if (e) cudaEventDestroy(e);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+// ------------------------------------------------------------------------------------------------------ bookkeeping
+int Model::build_bookkeeping(std::string& e) {
+  const int nb = n_blocks;
+  if ((int64_t)indexing.size() != nb || (int64_t)parents.size() != nb || (int64_t)children.size() != nb) { e = "CSR sizes do not match n_blocks"; return 1; }
+  // na_ix_all, counts (spamtree_model.cpp:80-96)
+  nobs_by_q.assign(q, 0);
+  for (int64_t i = 0; i < n_all; i++) {
+    if (mv_id[i] < 1 || mv_id[i] > q) { e = "mv_id outside 1..q"; return 1; }
+    if (std::isfinite(y[i])) { na_ix_all.push_back(i); nobs_by_q[mv_id[i] - 1]++; }
+  }
+  n_obs = (int64_t)na_ix_all.size();
+  // na_study :303-313
+  block_ct_obs.assign(nb, 0);
+  for (int b = 0; b < nb; b++)
+    for (int64_t t = indexing.ptr[b]; t < indexing.ptr[b + 1]; t++) {
+      const int64_t r = indexing.idx[t];
+      if (r < 0 || r >= n_all) { e = "indexing row out of range"; return 1; }
+      if (std::isfinite(y[r])) block_ct_obs[b]++;
+    }
+  // XtX :151-155 (over observed rows of each outcome)
+  XtX.assign(q, SmallMat(p));
+  for (int64_t i : na_ix_all) {
+    SmallMat& M = XtX[mv_id[i] - 1];
+    for (int a = 0; a < p; a++)
+      for (int b = 0; b < p; b++) M(a, b) += X[i + (size_t)a * n_all] * X[i + (size_t)b * n_all];
+  }
+  // make_gibbs_groups :194-301
+  dvec labels(block_groups);
+  std::sort(labels.begin(), labels.end());
+  labels.erase(std::unique(labels.begin(), labels.end()), labels.end());
+  n_gibbs_groups = (int)labels.size();
+  auto group_of = [&](int u) { return (int)(std::lower_bound(labels.begin(), labels.end(), block_groups[u]) - labels.begin()); };
+  for (int i = 0; i < nb; i++) {  // :201-226
+    const int u = (int)block_names[i] - 1;
+    if (u < 0 || u >= nb) { e = "block name out of range"; return 1; }
+    if (indexing.len(u) == 0) continue;
+    for (int64_t t = parents.ptr[u]; t < parents.ptr[u + 1]; t++)
+      if (block_groups[parents.idx[t]] == block_groups[u]) { e = "a block shares its group with a parent"; return 1; }
+    for (int64_t t = children.ptr[u]; t < children.ptr[u + 1]; t++)
+      if (block_groups[children.idx[t]] == block_groups[u]) { e = "a block shares its group with a child"; return 1; }
+  }
+  std::vector<ivec> temp(n_gibbs_groups);
+  for (int i = 0; i < nb; i++) {
+    const int u = (int)block_names[i] - 1;
+    if (block_ct_obs[u] > 0) temp[group_of(u)].push_back(u);
+  }
+  n_actual_groups = 0;
+  for (auto& t : temp) if (!t.empty()) n_actual_groups++;
+  u_by_block_groups.assign(n_actual_groups, ivec());
+  for (int g = 0; g < n_actual_groups; g++) u_by_block_groups[g] = temp[g];  // :257-260
+  for (int g = 0; g < n_actual_groups; g++)
+    if (u_by_block_groups[g].empty()) { e = "an empty level precedes a non-empty one (reference assumes empties are last)"; return 1; }
+  block_is_reference.assign(nb, 1);
+  std::vector<char> in_nonref(nb, 0);
+  for (size_t r = 0; r < res_is_ref.size(); r++)
+    if (res_is_ref[r] == 0 && r < u_by_block_groups.size())
+      for (int64_t u : u_by_block_groups[r]) in_nonref[u] = 1;
+  for (int i = 0; i < nb; i++) {
+    const int u = (int)block_names[i] - 1;
+    if (block_ct_obs[u] > 0) {
+      blocks_not_empty.push_back(u);
+      if (in_nonref[u]) block_is_reference[u] = 0;
+    } else {
+      blocks_predicting.push_back(u);
+      block_is_reference[u] = 0;
+    }
+  }
+  if ((int)res_is_ref.size() < n_actual_groups) { e = "res_is_ref shorter than the number of levels"; return 1; }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------ layout
+static inline long long pad2(long long v) { return (v + 1) & ~1LL; }
+
+int Model::build_layout(std::string& e) {
+  const int nb = n_blocks;
+  slot_of_block.assign(nb, -1);
+  block_of_slot.clear();
+  levels.clear();
+  auto chain_ok = [&](int u, std::string& why) {
+    // parents(u) must be parents(lp) followed by lp (tree_dep.cpp:113-119 gives exactly that), all reference blocks
+    const int64_t np = parents.len(u);
+    if (np == 0) return true;
+    const int lp = (int)parents.back(u);
+    if (slot_of_block[lp] < 0 || block_ct_obs[lp] == 0) { why = "a parent is not an observed block of a shallower level"; return false; }
+    if (!block_is_reference[lp]) { why = "a parent is not a reference block"; return false; }
+    if (parents.len(lp) != np - 1 || !std::equal(parents.row(lp), parents.row(lp) + (np - 1), parents.row(u))) {
+      why = "parent set is not the ancestor chain of its last parent";
+      return false;
+    }
+    return true;
+  };
+  auto order_level = [&](ivec us) {
+    std::sort(us.begin(), us.end(), [&](int64_t a, int64_t b) {
+      const int pa = parents.len(a) ? slot_of_block[parents.back(a)] : -1;
+      const int pb = parents.len(b) ? slot_of_block[parents.back(b)] : -1;
+      if (pa != pb) return pa < pb;
+      return a < b;
+    });
+    return us;
+  };
+  std::string why;
+  for (int g = 0; g < n_actual_groups; g++) {
+    for (int64_t u : u_by_block_groups[g])
+      if (!chain_ok((int)u, why)) { e = "unsupported DAG: " + why; return 4; }
+    ivec us = order_level(u_by_block_groups[g]);
+    LevelInfo L;
+    L.slot0 = (int)block_of_slot.size();
+    L.nslots = (int)us.size();
+    L.is_ref = res_is_ref[g] == 1 ? 1 : 0;  // indexed by group like spamtree_model.cpp:890,1037
+    for (int64_t u : us) { slot_of_block[u] = (int)block_of_slot.size(); block_of_slot.push_back((int)u); }
+    levels.push_back(L);
+  }
+  n_obs_nodes = (int)block_of_slot.size();
+  {
+    for (int64_t u : blocks_predicting) {
+      if (parents.len(u) == 0) { e = "a block without observations has no parents"; return 1; }
+      if (!chain_ok((int)u, why)) { e = "unsupported DAG (prediction block): " + why; return 4; }
+    }
+    ivec us = order_level(blocks_predicting);
+    pred_level = LevelInfo();
+    pred_level.slot0 = n_obs_nodes;
+    pred_level.nslots = (int)us.size();
+    pred_level.is_ref = 0;
+    for (int64_t u : us) { slot_of_block[u] = (int)block_of_slot.size(); block_of_slot.push_back((int)u); }
+  }
+  n_nodes = (int)block_of_slot.size();
+  // every observed block must list its parents' children consistently (used by this_is_jth_child, :411-417)
+  for (int s = 0; s < n_obs_nodes; s++) {
+    const int u = block_of_slot[s];
+    for (int64_t t = parents.ptr[u]; t < parents.ptr[u + 1]; t++) {
+      const int64_t pa = parents.idx[t];
+      const int64_t* b = children.row(pa);
+      const int64_t* en = b + children.len(pa);
+      // make_edges returns sorted lists (arma::intersect, tree_dep.cpp:106); fall back to a scan for unsorted input
+      if (!std::binary_search(b, en, (int64_t)u) && std::find(b, en, (int64_t)u) == en) {
+        e = "children lists are inconsistent with parents lists";
+        return 1;
+      }
+    }
+    if (!block_is_reference[u] && children.len(u) > 0) { e = "a non-reference block has children"; return 4; }
+  }
+  // rows: node-major permutation
+  perm.clear();
+  perm.reserve(n_all);
+  h_m.assign(n_nodes, 0); h_row0.assign(n_nodes, 0); h_k.assign(n_nodes, 0); h_P.assign(n_nodes, 0);
+  h_chain_off.assign(n_nodes, 0); h_lastpar.assign(n_nodes, -1);
+  for (int s = 0; s < n_nodes; s++) {
+    const int u = block_of_slot[s];
+    h_row0[s] = (int)perm.size();
+    h_m[s] = (int)indexing.len(u);
+    for (int64_t t = indexing.ptr[u]; t < indexing.ptr[u + 1]; t++) perm.push_back(indexing.idx[t]);
+  }
+  if ((int64_t)perm.size() != n_all) { e = "indexing does not cover every row exactly once"; return 1; }
+  iperm.assign(n_all, -1);
+  for (int64_t i = 0; i < n_all; i++) {
+    if (iperm[perm[i]] != -1) { e = "a row belongs to two blocks"; return 1; }
+    iperm[perm[i]] = i;
+  }
+  // chains and storage offsets
+  h_chain.clear(); h_chain_poff.clear(); h_chain_boff.clear(); h_chain_uoff.clear();
+  h_goff.assign(n_nodes, 0); h_rioff.assign(n_nodes, 0); h_voff.assign(n_nodes, 0); h_uoff.assign(n_nodes, 0); h_soff.assign(n_nodes, -1);
+  g_total = ri_total = v_total = u_total = s_total = gpred_total = 0;
+  long long sd_total = 0;
+  std::vector<int> isref(n_nodes, 0);
+  for (int s = 0; s < n_nodes; s++) {
+    const int u = block_of_slot[s];
+    const bool pred = s >= n_obs_nodes;
+    const int kk = (int)parents.len(u);
+    if (kk > 32) { e = "ancestor chains longer than 32 are not supported"; return 4; }
+    h_k[s] = kk;
+    h_chain_off[s] = (int)h_chain.size();
+    int poff = 0;
+    long long boff = 0, uo = 0;
+    for (int j = 0; j < kk; j++) {
+      const int a = slot_of_block[parents.idx[parents.ptr[u] + j]];
+      h_chain.push_back(a);
+      h_chain_poff.push_back(poff);
+      h_chain_boff.push_back((int)boff);
+      h_chain_uoff.push_back((int)uo);
+      poff += h_m[a];
+      boff += pad2((long long)h_m[s] * h_m[a]);
+      uo += pad2((long long)h_m[a] * h_m[a]);
+      if (boff > 0x7fffffffLL) { e = "a block's G storage exceeds 2^31 doubles"; return 4; }
+    }
+    h_P[s] = poff;
+    if (kk) h_lastpar[s] = h_chain.back();
+    if (!pred) {
+      isref[s] = block_is_reference[u] ? 1 : 0;
+      h_goff[s] = g_total; g_total += boff;
+      h_rioff[s] = ri_total; ri_total += pad2(isref[s] ? (long long)h_m[s] * h_m[s] : h_m[s]);
+      h_voff[s] = v_total; v_total += pad2(poff);
+      h_uoff[s] = u_total; u_total += uo;
+    } else {
+      h_goff[s] = gpred_total; gpred_total += boff;
+      h_rioff[s] = sd_total; sd_total += pad2(h_m[s]);
+    }
+  }
+  // direct children among observed nodes (contiguous by construction of the slot order)
+  h_child_ptr.assign(n_nodes + 1, 0);
+  for (int s = 0; s < n_obs_nodes; s++)
+    if (h_lastpar[s] >= 0) h_child_ptr[h_lastpar[s] + 1]++;
+  for (int s = 0; s < n_nodes; s++) h_child_ptr[s + 1] += h_child_ptr[s];
+  h_child_idx.assign(h_child_ptr[n_nodes], 0);
+  {
+    std::vector<int> fill(h_child_ptr.begin(), h_child_ptr.end() - 1);
+    for (int s = 0; s < n_obs_nodes; s++)
+      if (h_lastpar[s] >= 0) h_child_idx[fill[h_lastpar[s]]++] = s;
+  }
+  for (int s = 0; s < n_obs_nodes; s++)
+    if (h_child_ptr[s + 1] > h_child_ptr[s]) { h_soff[s] = s_total; s_total += pad2((long long)h_m[s] * h_m[s]); }
+  isref_host_ = isref;
+  sd_total_ = sd_total;
+
+  // BUILD work groups: runs of siblings whose panel fits the shared-memory budget
+  h_grp_slot0.clear(); h_grp_nn.clear();
+  auto make_groups = [&](LevelInfo& L, int mode) -> int {
+    L.grp0 = (int)h_grp_slot0.size();
+    L.smem_build = 0; L.smem_gibbs = 0;
+    int s = L.slot0;
+    const int end = L.slot0 + L.nslots;
+    while (s < end) {
+      int nn = 0, NC = 0, sumsq = 0, maxmj = 1;
+      for (int j = 0; j < h_k[s]; j++) maxmj = std::max(maxmj, h_m[h_chain[h_chain_off[s] + j]]);
+      size_t need = 0;
+      while (s + nn < end && nn < 64 && h_lastpar[s + nn] == h_lastpar[s]) {
+        const int md = h_m[s + nn];
+        const int NC2 = NC + md, sq2 = sumsq + (mode == 0 ? md * md : md);
+        const size_t n2 = build_smem_bytes(mode, h_P[s], NC2, sq2, maxmj);
+        if (n2 > smem_budget || (nn > 0 && NC2 > max_group_cols)) break;
+        if (h_lastpar[s] < 0 && nn > 0) break;  // roots never share a chain
+        NC = NC2; sumsq = sq2; need = n2; nn++;
+      }
+      if (nn == 0) {
+        e = "a block needs more shared memory than the BUILD budget (m=" + std::to_string(h_m[s]) + ", P=" + std::to_string(h_P[s]) + ")";
+        return 4;
+      }
+      h_grp_slot0.push_back(s); h_grp_nn.push_back(nn);
+      L.smem_build = std::max(L.smem_build, need);
+      L.maxNC = std::max(L.maxNC, NC);
+      s += nn;
+    }
+    L.ngrp = (int)h_grp_slot0.size() - L.grp0;
+    for (int t = L.slot0; t < end; t++) {
+      L.maxP = std::max(L.maxP, h_P[t]); L.maxm = std::max(L.maxm, h_m[t]); L.maxk = std::max(L.maxk, h_k[t]);
+      L.smem_gibbs = std::max(L.smem_gibbs, gibbs_smem_bytes(L.is_ref, h_m[t], h_P[t], h_k[t]));
+    }
+    if (mode != 2 && L.smem_gibbs > 227 * 1024) { e = "a block is too large for the Gibbs kernel's shared memory"; return 4; }
+    return 0;
+  };
+  for (auto& L : levels) { int rc = make_groups(L, L.is_ref ? 0 : 1); if (rc) return rc; }
+  { int rc = make_groups(pred_level, 2); if (rc) return rc; }
+
+  // work counters per iteration (SURVEY §8d formulas on the actual tree)
+  f_alg = f_exec = n_cov = 0;
+  for (int s = 0; s < n_obs_nodes; s++) {
+    const double m = h_m[s], P = h_P[s], rho = isref[s], chi = (h_child_ptr[s + 1] > h_child_ptr[s]) ? 1.0 : 0.0;
+    const double C = (double)children.len(block_of_slot[s]);
+    const double fb = 2 * m * P * P + rho * (2 * m * m * P + m * m * m + 2 * m * P + 2 * m * m) + rho * chi * (m * m * P + std::pow(P + m, 3) / 3) + (1 - rho) * (4 * m * P);
+    const double fg = rho * (2 * P * m * m + C * m * m + 2 * m * m * m / 3 + 2 * m * P + C * m + 4 * m * m + 2 * P * P * m + 2 * P * P + 2 * P * m) +
+                      (1 - rho) * (3 * m * P + 2 * P * P * m + 2 * P * P + 2 * P * m + 10 * m);
+    const double fl = 2 * m * P + rho * 2 * m * m + (1 - rho) * 2 * m;
+    f_alg += fb + fg + fl;
+    // lean formulation actually executed: Z (mP^2) + H' (mP^2) + Z'Z (rho m^2 P, else mP) + G (rho m^2 P/ else mP) + chol/inv + Gibbs/LLW matvecs
+    f_exec += 2 * m * P * P + rho * (2 * m * m * P + m * m * P + 2 * m * m * m / 3) + (1 - rho) * 3 * m * P + 2 * m * P +
+              (4 * m * P + rho * (2 * m * m * m / 3 + 4 * m * m)) + (2 * m * P + rho * m * m);
+    n_cov += P * m + rho * m * (m + 1) / 2 + (1 - rho) * m;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------ upload
+template <class T>
+static cudaError_t dev_upload(const std::vector<T>& h, T*& d, std::vector<void*>& owned) {
+  d = nullptr;
+  const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  cudaError_t e = cudaMalloc((void**)&d, bytes);
+  if (e != cudaSuccess) return e;
+  owned.push_back(d);
+  if (!h.empty()) e = cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return e;
+}
+static cudaError_t dev_zeros(double*& d, long long n, std::vector<void*>& owned) {
+  d = nullptr;
+  const size_t bytes = (size_t)std::max<long long>(n, 1) * sizeof(double);
+  cudaError_t e = cudaMalloc((void**)&d, bytes);
+  if (e != cudaSuccess) return e;
+  owned.push_back(d);
+  return cudaMemset(d, 0, bytes);
+}
+
+int Model::upload(std::string& e) {
+  (void)e;
+  ST_CUDA(cudaSetDevice(device), "cudaSetDevice");
+  ST_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  for (auto& x : ev) ST_CUDA(cudaEventCreate(&x), "cudaEventCreate");
+  // per row
+  dvec cx(n_all), cy(n_all), yy(n_all), Xp((size_t)n_all * p), xb(n_all, 0.0);
+  std::vector<int> mvq(n_all);
+  for (int64_t i = 0; i < n_all; i++) {
+    const int64_t b = perm[i];
+    cx[i] = coords[b]; cy[i] = coords[b + n_all];
+    mvq[i] = (int)mv_id[b] - 1;
+    yy[i] = std::isfinite(y[b]) ? y[b] : 0.0;  // spamtree_model.cpp:146
+    for (int a = 0; a < p; a++) Xp[i + (size_t)a * n_all] = X[b + (size_t)a * n_all];
+    double s = 0;  // XB = X * beta_in for every outcome (:124-129)
+    for (int a = 0; a < p; a++) s += X[b + (size_t)a * n_all] * Bcoeff[a + (size_t)mvq[i] * p];
+    xb[i] = s;
+  }
+  double *d_cx, *d_cy, *d_y, *d_X;
+  int *d_mvq, *d_m, *d_row0, *d_isref, *d_k, *d_P, *d_choff, *d_cptr, *d_cidx, *d_chain, *d_cpoff, *d_cboff, *d_cuoff;
+  long long *d_goff, *d_rioff, *d_voff, *d_uoff, *d_soff;
+  ST_CUDA(dev_upload(cx, d_cx, owned), "upload cx");
+  ST_CUDA(dev_upload(cy, d_cy, owned), "upload cy");
+  ST_CUDA(dev_upload(yy, d_y, owned), "upload y");
+  ST_CUDA(dev_upload(Xp, d_X, owned), "upload X");
+  ST_CUDA(dev_upload(mvq, d_mvq, owned), "upload mv");
+  ST_CUDA(dev_upload(h_m, d_m, owned), "upload m");
+  ST_CUDA(dev_upload(h_row0, d_row0, owned), "upload row0");
+  ST_CUDA(dev_upload(isref_host_, d_isref, owned), "upload isref");
+  ST_CUDA(dev_upload(h_k, d_k, owned), "upload k");
+  ST_CUDA(dev_upload(h_P, d_P, owned), "upload P");
+  ST_CUDA(dev_upload(h_chain_off, d_choff, owned), "upload chain_off");
+  ST_CUDA(dev_upload(h_goff, d_goff, owned), "upload goff");
+  ST_CUDA(dev_upload(h_rioff, d_rioff, owned), "upload rioff");
+  ST_CUDA(dev_upload(h_voff, d_voff, owned), "upload voff");
+  ST_CUDA(dev_upload(h_uoff, d_uoff, owned), "upload uoff");
+  ST_CUDA(dev_upload(h_soff, d_soff, owned), "upload soff");
+  ST_CUDA(dev_upload(h_child_ptr, d_cptr, owned), "upload child_ptr");
+  ST_CUDA(dev_upload(h_child_idx, d_cidx, owned), "upload child_idx");
+  ST_CUDA(dev_upload(h_chain, d_chain, owned), "upload chain");
+  ST_CUDA(dev_upload(h_chain_poff, d_cpoff, owned), "upload chain_poff");
+  ST_CUDA(dev_upload(h_chain_boff, d_cboff, owned), "upload chain_boff");
+  ST_CUDA(dev_upload(h_chain_uoff, d_cuoff, owned), "upload chain_uoff");
+  ST_CUDA(dev_upload(h_grp_slot0, d_grp_slot0, owned), "upload groups");
+  ST_CUDA(dev_upload(h_grp_nn, d_grp_nn, owned), "upload groups");
+  dt.cx = d_cx; dt.cy = d_cy; dt.mvq = d_mvq; dt.y = d_y; dt.X = d_X;
+  dt.m = d_m; dt.row0 = d_row0; dt.isref = d_isref; dt.k = d_k; dt.P = d_P; dt.chain_off = d_choff;
+  dt.goff = d_goff; dt.rioff = d_rioff; dt.voff = d_voff; dt.uoff = d_uoff; dt.soff = d_soff;
+  dt.child_ptr = d_cptr; dt.child_idx = d_cidx;
+  dt.chain = d_chain; dt.chain_poff = d_cpoff; dt.chain_boff = d_cboff; dt.chain_uoff = d_cuoff;
+  for (int s = 0; s < 2; s++) {
+    ST_CUDA(dev_zeros(ds[s].G, g_total, owned), "alloc G");
+    if (keep_H) ST_CUDA(dev_zeros(ds[s].H, g_total, owned), "alloc H"); else ds[s].H = nullptr;
+    ST_CUDA(dev_zeros(ds[s].Ri, ri_total, owned), "alloc Ri");
+    ST_CUDA(dev_zeros(ds[s].logdet, n_obs_nodes, owned), "alloc logdet");
+    ST_CUDA(dev_zeros(ds[s].llcomp, n_obs_nodes, owned), "alloc llcomp");
+  }
+  ST_CUDA(dev_zeros(d_w, n_all, owned), "alloc w");
+  ST_CUDA(dev_zeros(d_z, n_all + 1, owned), "alloc z");
+  ST_CUDA(dev_upload(xb, d_xb, owned), "upload xb");
+  ST_CUDA(dev_zeros(d_V, v_total, owned), "alloc V");
+  ST_CUDA(dev_zeros(d_U, u_total, owned), "alloc U");
+  ST_CUDA(dev_zeros(d_S, s_total, owned), "alloc S");
+  ST_CUDA(dev_zeros(d_Hpred, gpred_total, owned), "alloc Hpred");
+  ST_CUDA(dev_zeros(d_sdpred, sd_total_, owned), "alloc sdpred");
+  ST_CUDA(dev_zeros(d_probe_sig, ri_total, owned), "alloc probe");
+  ST_CUDA(dev_zeros(d_probe_smu, n_all, owned), "alloc probe");
+  ST_CUDA(dev_zeros(d_scalars, 64 + kMaxStats, owned), "alloc scalars");
+  rowstat_blocks_ = (int)std::min<int64_t>(592, std::max<int64_t>(1, (n_all + 255) / 256));
+  ST_CUDA(dev_zeros(d_partial, (long long)rowstat_blocks_ * kMaxStats, owned), "alloc partial");
+  ST_CUDA(dev_upload(Bcoeff, d_bcoeff, owned), "upload beta");
+  ST_CUDA(dev_upload(tausq_inv, d_tausq_inv, owned), "upload tausq");
+  {
+    std::vector<int> z1(1, 0);
+    ST_CUDA(dev_upload(z1, d_fail, owned), "alloc fail");
+  }
+  ST_CUDA(cudaMallocHost((void**)&h_scalars, (64 + kMaxStats) * sizeof(double)), "pinned scalars");
+  ST_CUDA(cudaMallocHost((void**)&h_stage, std::max<int64_t>(n_all, 1) * sizeof(double)), "pinned stage");
+  // index used by the beta step
+  beta_widx_faithful.assign(n_all, -1);
+  beta_widx_plain.assign(n_all, -1);
+  for (int64_t s = 0; s < n_obs; s++) {
+    const int64_t i = iperm[na_ix_all[s]];
+    beta_widx_faithful[i] = (int)iperm[s];
+    beta_widx_plain[i] = (int)i;
+  }
+  {
+    std::vector<int> tmp(n_all, -1);
+    ST_CUDA(dev_upload(tmp, d_obs_widx, owned), "alloc widx");
+  }
+  beta_widx_mode = -1;
+  return 0;
+}
+
+int Model::init(std::string& e) {
+  int rc = build_bookkeeping(e);
+  if (rc) return rc;
+  if (q * (p + 1) > kMaxStats) { e = "q*(p+1) exceeds 40"; return 4; }
+  rc = build_layout(e);
+  if (rc) return rc;
+  if (n_all >= (1LL << 31)) { e = "n_all must be below 2^31"; return 4; }
+  rc = upload(e);
+  if (rc) { e = err; return rc; }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------ operations
+int Model::theta_update(int slot, const double* th) {
+  dvec& t = theta[phys(slot)];
+  std::copy(th, th + t.size(), t.begin());
+  return 0;
+}
+
+int Model::launch_build_levels(int pslot, const CovTab& tab) {
+  for (auto& L : levels) {
+    ST_CUDA(launch_build(L.is_ref ? 0 : 1, dt, ds[pslot], ds[pslot].H, ds[pslot].Ri, d_grp_slot0 + L.grp0, d_grp_nn + L.grp0,
+                         L.ngrp, d_w, tab, d_fail, keep_H ? 1 : 0, L.smem_build, stream),
+            "build_level_kernel");
+    n_launches++;
+  }
+  return 0;
+}
+
+int Model::get_loglik_comps_w(int slot, double* out3) {
+  const int ps = phys(slot);
+  CovTab tab;
+  std::string e;
+  if (!make_covtab(theta[ps].data(), (int)theta[ps].size(), q, tab, e)) { err = e; return 1; }
+  ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
+  int rc = launch_build_levels(ps, tab);
+  if (rc) return rc;
+  ST_CUDA(launch_loglik_reduce(ds[ps].logdet, ds[ps].llcomp, n_obs_nodes, d_fail, d_scalars, stream), "loglik_reduce");
+  n_launches++;
+  ST_CUDA(cudaMemcpyAsync(h_scalars, d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H scalars");
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  const bool ok = h_scalars[2] != 0.0;
+  if (ok) { loglik_w[ps] = h_scalars[0]; logdetCi[ps] = h_scalars[1]; }  // on failure the reference leaves them untouched (:971-982)
+  if (ps == cur) { gram_stale = true; pred_H_valid = false; }
+  out3[0] = loglik_w[ps]; out3[1] = logdetCi[ps]; out3[2] = ok ? 1.0 : 0.0;
+  return 0;
+}
+
+int Model::upload_rows(const double* boundary_order, double* dev) {
+  for (int64_t i = 0; i < n_all; i++) h_stage[i] = boundary_order[perm[i]];
+  ST_CUDA(cudaMemcpyAsync(dev, h_stage, n_all * sizeof(double), cudaMemcpyHostToDevice, stream), "H2D rows");
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  return 0;
+}
+
+int Model::draw_normals(uint64_t seed) {
+  ST_CUDA(launch_normals(d_z, n_all, seed, sweep_counter++, stream), "normals_kernel");
+  n_launches++;
+  return 0;
+}
+
+int Model::refresh_grams() {
+  for (int g = (int)levels.size() - 1; g >= 0; g--) {
+    ST_CUDA(launch_gram(dt, ds[cur], levels[g].slot0, levels[g].nslots, d_U, d_S, stream), "gram_level_kernel");
+    n_launches++;
+  }
+  gram_stale = false;
+  return 0;
+}
+
+int Model::gibbs_launch_only() {
+  if (gram_stale) { int rc = refresh_grams(); if (rc) return rc; }
+  for (int g = (int)levels.size() - 1; g >= 0; g--) {
+    const LevelInfo& L = levels[g];
+    ST_CUDA(launch_gibbs(L.is_ref, dt, ds[cur], L.slot0, L.nslots, d_w, d_xb, d_z, d_tausq_inv, d_S, d_V,
+                         probes ? d_probe_sig : nullptr, probes ? d_probe_smu : nullptr, d_fail, L.smem_gibbs, stream),
+            "gibbs_level_kernel");
+    n_launches++;
+  }
+  return 0;
+}
+
+int Model::deal_with_w(const double* z, uint64_t seed) {
+  if (z) { int rc = upload_rows(z, d_z); if (rc) return rc; }
+  else { int rc = draw_normals(seed); if (rc) return rc; }
+  ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
+  int rc = gibbs_launch_only();
+  if (rc) return rc;
+  int nfail = 0;
+  ST_CUDA(cudaMemcpyAsync(&nfail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H fail");
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  if (nfail) { err = "Error at gibbs_sample_w: conditional precision not positive definite"; return 3; }
+  return 0;
+}
+
+int Model::get_loglik_w(int slot, double* out2) {
+  const int ps = phys(slot);
+  ST_CUDA(launch_llw(dt, ds[ps], n_obs_nodes, d_w, stream), "llw_kernel");
+  ST_CUDA(launch_loglik_reduce(ds[ps].logdet, ds[ps].llcomp, n_obs_nodes, nullptr, d_scalars, stream), "loglik_reduce");
+  n_launches += 2;
+  ST_CUDA(cudaMemcpyAsync(h_scalars, d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H scalars");
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  loglik_w[ps] = h_scalars[0];
+  logdetCi[ps] = h_scalars[1];
+  out2[0] = loglik_w[ps]; out2[1] = logdetCi[ps];
+  return 0;
+}
+
+void Model::accept_make_change() {
+  cur = 1 - cur;
+  gram_stale = true;
+  pred_H_valid = false;
+}
+
+int Model::predict(bool theta_changed) {
+  if (pred_level.nslots == 0) return 0;
+  if (theta_changed || !pred_H_valid) {
+    CovTab tab;
+    std::string e;
+    if (!make_covtab(theta[cur].data(), (int)theta[cur].size(), q, tab, e)) { err = e; return 1; }
+    ST_CUDA(launch_build(2, dt, ds[cur], d_Hpred, d_sdpred, d_grp_slot0 + pred_level.grp0, d_grp_nn + pred_level.grp0,
+                         pred_level.ngrp, d_w, tab, d_fail, 1, pred_level.smem_build, stream),
+            "build_level_kernel(predict)");
+    n_launches++;
+    pred_H_valid = true;
+  }
+  ST_CUDA(launch_predict_sample(dt, pred_level.slot0, pred_level.nslots, d_Hpred, d_sdpred, d_w, d_z, stream), "predict_sample_kernel");
+  n_launches++;
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  return 0;
+}
+
+int Model::rowstats(bool faithful_index) {
+  const int mode = faithful_index ? 1 : 0;
+  if (beta_widx_mode != mode) {
+    const std::vector<int>& src = faithful_index ? beta_widx_faithful : beta_widx_plain;
+    ST_CUDA(cudaMemcpyAsync(d_obs_widx, src.data(), n_all * sizeof(int), cudaMemcpyHostToDevice, stream), "H2D widx");
+    ST_CUDA(cudaStreamSynchronize(stream), "sync");
+    beta_widx_mode = mode;
+  }
+  ST_CUDA(launch_rowstats(dt, d_obs_widx, n_all, p, q, d_w, d_xb, d_partial, rowstat_blocks_, d_scalars + 8, stream), "rowstats_kernel");
+  n_launches += 2;
+  ST_CUDA(cudaMemcpyAsync(h_scalars + 8, d_scalars + 8, q * (p + 1) * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H stats");
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  return 0;
+}
+
+// gibbs_sample_tausq spamtree_model.cpp:1393-1417
+int Model::gibbs_sample_tausq(const double* fixed) {
+  int rc = rowstats(beta_widx_mode != 0);
+  if (rc) return rc;
+  for (int j = 0; j < q; j++) {
+    const double bcore = h_scalars[8 + j * (p + 1) + p];
+    const double aparam = 2.01 + nobs_by_q[j] / 2.0;
+    const double bparam = 1.0 / (1.0 + .5 * bcore);
+    tausq_inv[j] = fixed ? fixed[j] : rng.gamma(aparam, bparam);
+  }
+  ST_CUDA(cudaMemcpyAsync(d_tausq_inv, tausq_inv.data(), q * sizeof(double), cudaMemcpyHostToDevice, stream), "H2D tausq");
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  return 0;
+}
+
+// gibbs_sample_beta spamtree_model.cpp:1364-1391
+int Model::gibbs_sample_beta(const double* zb, bool faithful_index) {
+  int rc = rowstats(faithful_index);
+  if (rc) return rc;
+  for (int j = 0; j < q; j++) {
+    SmallMat Si(p);
+    for (int a = 0; a < p; a++)
+      for (int b = 0; b < p; b++) Si(a, b) = tausq_inv[j] * XtX[j](a, b) + (a == b ? .01 : 0.0);  // Vi = .01 I (:157)
+    for (int a = 0; a < p; a++)
+      for (int b = 0; b < a; b++) Si(a, b) = Si(b, a);  // symmatu
+    if (!small_chol(Si)) { err = "beta step: precision not positive definite"; return 3; }
+    SmallMat Sc = small_inv_lower(Si);
+    dvec xp(p), t(p, 0.0), bmu(p, 0.0), zz(p), sz(p, 0.0);
+    for (int a = 0; a < p; a++) xp[a] = 0.0 + tausq_inv[j] * h_scalars[8 + j * (p + 1) + a];  // Vim = 0 (:158-159)
+    for (int a = 0; a < p; a++)
+      for (int b = 0; b <= a; b++) t[a] += Sc(a, b) * xp[b];
+    for (int a = 0; a < p; a++)
+      for (int b = a; b < p; b++) bmu[a] += Sc(b, a) * t[b];
+    for (int a = 0; a < p; a++) zz[a] = zb ? zb[a + (size_t)j * p] : rng.norm();
+    for (int a = 0; a < p; a++)
+      for (int b = a; b < p; b++) sz[a] += Sc(b, a) * zz[b];
+    for (int a = 0; a < p; a++) Bcoeff[a + (size_t)j * p] = bmu[a] + sz[a];
+  }
+  ST_CUDA(cudaMemcpyAsync(d_bcoeff, Bcoeff.data(), (size_t)p * q * sizeof(double), cudaMemcpyHostToDevice, stream), "H2D beta");
+  ST_CUDA(launch_xb(dt, n_all, p, d_bcoeff, d_xb, stream), "xb_kernel");
+  n_launches++;
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  return 0;
+}
+
+int Model::get_w(double* out) {
+  ST_CUDA(cudaMemcpyAsync(h_stage, d_w, n_all * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H w");
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  for (int64_t i = 0; i < n_all; i++) out[perm[i]] = h_stage[i];
+  return 0;
+}
+int Model::set_w(const double* in) { return upload_rows(in, d_w); }
+int Model::get_xb(double* out) {
+  ST_CUDA(cudaMemcpyAsync(h_stage, d_xb, n_all * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H xb");
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  for (int64_t i = 0; i < n_all; i++) out[perm[i]] = h_stage[i];
+  return 0;
+}
+int Model::set_tausq_inv(const double* t) {
+  std::copy(t, t + q, tausq_inv.begin());
+  ST_CUDA(cudaMemcpyAsync(d_tausq_inv, tausq_inv.data(), q * sizeof(double), cudaMemcpyHostToDevice, stream), "H2D tausq");
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  return 0;
+}
+int Model::sync() {
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  return 0;
+}
+
+int Model::get_node_state(int slot, int u, const std::string& which, double* out, int64_t cap, int64_t* count) {
+  const int ps = phys(slot);
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  auto emit = [&](const dvec& v) {
+    *count = (int64_t)v.size();
+    if (out) for (int64_t i = 0; i < (int64_t)v.size() && i < cap; i++) out[i] = v[i];
+    return 0;
+  };
+  if (which == "logdetCi_comps" || which == "loglik_w_comps") {
+    dvec d(n_obs_nodes), o(n_blocks, 0.0);
+    ST_CUDA(cudaMemcpy(d.data(), (which == "logdetCi_comps") ? ds[ps].logdet : ds[ps].llcomp, n_obs_nodes * sizeof(double), cudaMemcpyDeviceToHost), "D2H comps");
+    for (int s = 0; s < n_obs_nodes; s++) o[block_of_slot[s]] = d[s];
+    return emit(o);
+  }
+  if (u < 0 || u >= n_blocks) { err = "block id out of range"; return 1; }
+  const int s = slot_of_block[u];
+  const bool pred = s >= n_obs_nodes;
+  const int m = h_m[s], P = h_P[s], kk = h_k[s], coff = h_chain_off[s];
+  if (which == "H" || which == "G") {
+    const double* src = nullptr;
+    if (pred) { if (which == "G") { err = "prediction blocks have no G"; return 1; } src = d_Hpred; }
+    else if (which == "G") src = ds[ps].G;
+    else { if (!keep_H) { err = "H was not kept (keep_H = 0)"; return 1; } src = ds[ps].H; }
+    long long tot = 0;
+    for (int j = 0; j < kk; j++) tot += pad2((long long)m * h_m[h_chain[coff + j]]);
+    dvec t(std::max<long long>(tot, 1)), o((size_t)m * P);
+    if (tot) ST_CUDA(cudaMemcpy(t.data(), src + h_goff[s], tot * sizeof(double), cudaMemcpyDeviceToHost), "D2H H");
+    for (int j = 0; j < kk; j++) {
+      const int mj = h_m[h_chain[coff + j]], po = h_chain_poff[coff + j], bo = h_chain_boff[coff + j];
+      for (int r = 0; r < m; r++)
+        for (int pp = 0; pp < mj; pp++) o[r + (size_t)(po + pp) * m] = t[bo + (size_t)r * mj + pp];
+    }
+    return emit(o);
+  }
+  if (which == "Ri") {
+    if (pred) {
+      dvec o(m);
+      ST_CUDA(cudaMemcpy(o.data(), d_sdpred + h_rioff[s], m * sizeof(double), cudaMemcpyDeviceToHost), "D2H sd");
+      return emit(o);
+    }
+    if (isref_host_[s]) {
+      dvec t((size_t)m * m), o((size_t)m * m);
+      ST_CUDA(cudaMemcpy(t.data(), ds[ps].Ri + h_rioff[s], t.size() * sizeof(double), cudaMemcpyDeviceToHost), "D2H Ri");
+      for (int r = 0; r < m; r++)
+        for (int c = 0; c < m; c++) o[r + (size_t)c * m] = t[(size_t)r * m + c];
+      return emit(o);
+    }
+    dvec o(m);
+    ST_CUDA(cudaMemcpy(o.data(), ds[ps].Ri + h_rioff[s], m * sizeof(double), cudaMemcpyDeviceToHost), "D2H ri");
+    return emit(o);
+  }
+  if (which == "Sigi_tot" || which == "Smu_tot") {
+    if (pred || !probes) { err = "no Gibbs probe for this block (prediction block or probes disabled)"; return 1; }
+    if (which == "Smu_tot") {
+      dvec o(m);
+      ST_CUDA(cudaMemcpy(o.data(), d_probe_smu + h_row0[s], m * sizeof(double), cudaMemcpyDeviceToHost), "D2H smu");
+      return emit(o);
+    }
+    const size_t n = isref_host_[s] ? (size_t)m * m : (size_t)m;
+    dvec o(n);
+    ST_CUDA(cudaMemcpy(o.data(), d_probe_sig + h_rioff[s], n * sizeof(double), cudaMemcpyDeviceToHost), "D2H sig");
+    return emit(o);
+  }
+  err = "unknown state name: " + which;
+  return 1;
+}
+
+int Model::get_index(const std::string& which, int u, int c, int64_t* out, int64_t cap, int64_t* count) {
+  ivec r;
+  auto emit = [&](const ivec& v) {
+    *count = (int64_t)v.size();
+    if (out) for (int64_t i = 0; i < (int64_t)v.size() && i < cap; i++) out[i] = v[i];
+    return 0;
+  };
+  if (which == "blocks_not_empty") return emit(blocks_not_empty);
+  if (which == "blocks_predicting") return emit(blocks_predicting);
+  if (which == "block_is_reference") return emit(block_is_reference);
+  if (which == "block_ct_obs") return emit(block_ct_obs);
+  if (which == "n_actual_groups") { r.push_back(n_actual_groups); return emit(r); }
+  if (which == "u_by_block_groups") {
+    if (u < 0 || u >= n_actual_groups) { err = "group out of range"; return 1; }
+    return emit(u_by_block_groups[u]);
+  }
+  if (u < 0 || u >= n_blocks) { err = "block id out of range"; return 1; }
+  if (which == "parents_indexing") {  // init_indexing :325-335
+    for (int64_t t = parents.ptr[u]; t < parents.ptr[u + 1]; t++) {
+      const int64_t pa = parents.idx[t];
+      r.insert(r.end(), indexing.row(pa), indexing.row(pa) + indexing.len(pa));
+    }
+    return emit(r);
+  }
+  if (which == "children_indexing") {
+    for (int64_t t = children.ptr[u]; t < children.ptr[u + 1]; t++) {
+      const int64_t chd = children.idx[t];
+      r.insert(r.end(), indexing.row(chd), indexing.row(chd) + indexing.len(chd));
+    }
+    return emit(r);
+  }
+  auto dim_by_parent = [&](int b) {  // init_finalize :362-373
+    ivec d;
+    if (indexing.len(b) == 0) return d;
+    d.push_back(0);
+    for (int64_t t = parents.ptr[b]; t < parents.ptr[b + 1]; t++) d.push_back(d.back() + indexing.len(parents.idx[t]));
+    return d;
+  };
+  if (which == "dim_by_parent") return emit(dim_by_parent(u));
+  if (which == "this_is_jth_child") {  // :411-417
+    r.assign(parents.len(u), 0);
+    if (block_ct_obs[u] > 0)
+      for (int64_t t = 0; t < parents.len(u); t++) {
+        const int64_t pa = parents.idx[parents.ptr[u] + t];
+        const int64_t* b = children.row(pa);
+        r[t] = (int64_t)(std::find(b, b + children.len(pa), (int64_t)u) - b);
+      }
+    return emit(r);
+  }
+  if (which == "u_is_which_col") {  // :388-409: (firstcol, lastcol) of u inside child c's parent set
+    if (c < 0 || c >= children.len(u)) { err = "child position out of range"; return 1; }
+    const int child = (int)children.idx[children.ptr[u] + c];
+    const int64_t* b = parents.row(child);
+    const int64_t wh = std::find(b, b + parents.len(child), (int64_t)u) - b;
+    ivec d = dim_by_parent(child);
+    if (wh >= parents.len(child) || d.empty()) { err = "child does not list the block as a parent"; return 1; }
+    r.push_back(d[wh]); r.push_back(d[wh + 1]);
+    return emit(r);
+  }
+  err = "unknown index name: " + which;
+  return 1;
+}
+
+// one hot-path iteration with device normals and event timing (bench hook)
+int Model::bench_iteration(const double* theta_prop, int do_swap, uint64_t seed, double* out3, float* ms_out) {
+  const int pa = 1 - cur;
+  CovTab tab;
+  std::string e;
+  std::copy(theta_prop, theta_prop + theta[pa].size(), theta[pa].begin());
+  if (!make_covtab(theta[pa].data(), (int)theta[pa].size(), q, tab, e)) { err = e; return 1; }
+  ST_CUDA(cudaEventRecord(ev[0], stream), "event");
+  int rc = draw_normals(seed);
+  if (rc) return rc;
+  ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
+  rc = gibbs_launch_only();
+  if (rc) return rc;
+  ST_CUDA(cudaMemcpyAsync(h_scalars + 40, d_fail, sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H fail");
+  ST_CUDA(cudaEventRecord(ev[1], stream), "event");
+  ST_CUDA(launch_llw(dt, ds[cur], n_obs_nodes, d_w, stream), "llw_kernel");
+  ST_CUDA(launch_loglik_reduce(ds[cur].logdet, ds[cur].llcomp, n_obs_nodes, nullptr, d_scalars + 4, stream), "loglik_reduce");
+  n_launches += 2;
+  ST_CUDA(cudaEventRecord(ev[2], stream), "event");
+  ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
+  rc = launch_build_levels(pa, tab);
+  if (rc) return rc;
+  ST_CUDA(launch_loglik_reduce(ds[pa].logdet, ds[pa].llcomp, n_obs_nodes, d_fail, d_scalars, stream), "loglik_reduce");
+  n_launches++;
+  ST_CUDA(cudaMemcpyAsync(h_scalars, d_scalars, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H scalars");
+  ST_CUDA(cudaEventRecord(ev[3], stream), "event");
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  int nfail_gibbs;
+  std::memcpy(&nfail_gibbs, h_scalars + 40, sizeof(int));
+  if (nfail_gibbs) { err = "Error at gibbs_sample_w: conditional precision not positive definite"; return 3; }
+  loglik_w[cur] = h_scalars[4]; logdetCi[cur] = h_scalars[5];
+  const bool ok = h_scalars[2] != 0.0;
+  if (ok) { loglik_w[pa] = h_scalars[0]; logdetCi[pa] = h_scalars[1]; }
+  out3[0] = loglik_w[pa]; out3[1] = loglik_w[cur]; out3[2] = ok ? 1.0 : 0.0;
+  if (ok && do_swap) accept_make_change();
+  rc = gibbs_sample_tausq(nullptr);
+  if (rc) return rc;
+  rc = gibbs_sample_beta(nullptr, beta_widx_mode != 0);
+  if (rc) return rc;
+  ST_CUDA(cudaEventRecord(ev[4], stream), "event");
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  if (ms_out)
+    for (int i = 0; i < 4; i++) ST_CUDA(cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]), "elapsed");
+  return 0;
+}
+
+}  // namespace st

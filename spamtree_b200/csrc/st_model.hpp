@@ -1,0 +1,180 @@
+// st_model.hpp — host mirror of the reference's SpamTreeMV (src/spamtree_model.h:22-212) with its state on one GPU.
+//
+// Layout decisions:
+//  * rows are permuted ONCE into node-major order (level, node, row) so that a block's rows and each ancestor panel are
+//    contiguous; outputs are un-permuted only at the boundary (st_get_w);
+//  * per block and per theta-slot only G = Ri*H (m x P), Ri (m x m) and (optionally) H are kept — the reference's Kxc,
+//    Kxx_inv, Kxx_invchol, AK_uP_all, AK_uP_u_all and Sigi_children cubes are never materialised;
+//  * a block's parent set is its ancestor chain (tree_dep.cpp:113-119); G/H are stored as one row-major m x m_a tile per
+//    ancestor a so that a tile is one contiguous, 16-byte aligned run.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "st_common.hpp"
+
+namespace st {
+
+constexpr int kMaxQ = 8;
+
+// theta -> per outcome-pair coefficients: K(h; i, j) = c1*exp(-r1*h) + c2*exp(-r2*h)
+// (covariance_functions.cpp:113-135, :213-286; q == 1 -> cexpcov :95-111 with direct-difference distance)
+struct CovTab {
+  int q;
+  double c1[kMaxQ * kMaxQ], r1[kMaxQ * kMaxQ], c2[kMaxQ * kMaxQ], r2[kMaxQ * kMaxQ];
+};
+bool make_covtab(const double* theta, int n_theta, int q, CovTab& tab, std::string& err);
+
+// device pointers describing the tree (read-only after st_create)
+struct DevTree {
+  // per row, node-major
+  const double* cx;
+  const double* cy;
+  const int* mvq;        // 0-based outcome
+  const double* y;       // missing -> 0 (spamtree_model.cpp:146)
+  const double* X;       // n_all x p column-major, node-major rows
+  // per node (slot)
+  const int* m;
+  const int* row0;
+  const int* isref;      // 1: reference level (full m x m conditional), 0: rows conditionally independent
+  const int* k;          // chain length (#reference ancestors)
+  const int* P;          // parent-set size
+  const int* chain_off;  // into the per-chain-entry arrays
+  const long long* goff; // G / H storage offset (doubles)
+  const long long* rioff;// Ri storage offset (doubles)
+  const long long* voff; // message vector offset (P doubles)
+  const long long* uoff; // message Gram offset (tiles m_a x m_a per ancestor)
+  const long long* soff; // child-sum Gram (m x m) offset, -1 when the node has no children
+  const int* child_ptr;
+  const int* child_idx;  // direct observed children (slots)
+  // per chain entry
+  const int* chain;      // ancestor slot, root first
+  const int* chain_poff; // column offset of the ancestor inside the parent set
+  const int* chain_boff; // offset (doubles) of the ancestor's tile inside the node's G storage
+  const int* chain_uoff; // offset (doubles) of the ancestor's tile inside the node's Gram storage
+};
+
+struct DevSlot {  // everything that depends on theta (tree_utils.h:63-102, lean form)
+  double* G;
+  double* H;       // nullptr when keep_H == 0 (prediction blocks always keep theirs in Hpred)
+  double* Ri;
+  double* logdet;  // per node
+  double* llcomp;  // per node
+};
+
+struct LevelInfo {
+  int slot0 = 0, nslots = 0;  // node range
+  int is_ref = 1;
+  int grp0 = 0, ngrp = 0;     // BUILD work groups (index into grp arrays)
+  size_t smem_build = 0;      // dynamic shared memory of the BUILD kernel at this level
+  int maxP = 0, maxm = 0, maxNC = 0, maxk = 0;
+  size_t smem_gibbs = 0;
+};
+
+class Model {
+ public:
+  ~Model();
+  // ---- inputs (copied)
+  int64_t n_all = 0;
+  int p = 0, q = 0, n_blocks = 0;
+  dvec y, X, coords;
+  ivec mv_id;
+  CSR indexing, parents, children;
+  dvec block_names, block_groups;
+  ivec res_is_ref;
+  bool keep_H = true;
+  int device = 0;
+  size_t smem_budget = 200 * 1024;
+  int max_group_cols = 112;  // upper bound on the columns one BUILD work group handles
+  bool probes = true;        // record Sigi_tot / Smu_tot of the last Gibbs sweep (st_get_node_state)
+  // ---- bookkeeping, same meaning as the reference's members
+  int64_t n_obs = 0;
+  ivec na_ix_all;
+  ivec block_ct_obs, blocks_not_empty, blocks_predicting, block_is_reference;
+  std::vector<ivec> u_by_block_groups;
+  int n_gibbs_groups = 0, n_actual_groups = 0;
+  std::vector<SmallMat> XtX;  // per outcome (spamtree_model.cpp:151-155)
+  ivec nobs_by_q;
+  // ---- node-major layout
+  int n_obs_nodes = 0, n_nodes = 0;
+  std::vector<int> slot_of_block, block_of_slot;
+  std::vector<int> h_m, h_row0, h_k, h_P, h_chain_off, h_chain, h_chain_poff, h_chain_boff, h_chain_uoff, h_lastpar;
+  std::vector<long long> h_goff, h_rioff, h_voff, h_uoff, h_soff;
+  std::vector<int> h_child_ptr, h_child_idx;
+  ivec perm;   // node-major row -> boundary row
+  ivec iperm;  // boundary row -> node-major row
+  std::vector<LevelInfo> levels;  // observed levels, root first
+  LevelInfo pred_level;           // prediction blocks
+  std::vector<int> h_grp_slot0, h_grp_nn;
+  long long g_total = 0, ri_total = 0, v_total = 0, u_total = 0, s_total = 0, gpred_total = 0;
+  // ---- parameters (host copies of the small ones)
+  dvec theta[2];
+  double loglik_w[2] = {0, 0}, logdetCi[2] = {0, 0};
+  int cur = 0;  // param_data = slot `cur`
+  dvec Bcoeff;  // p x q
+  dvec tausq_inv;
+  HostRng rng;
+  bool gram_stale = true;         // message Grams depend on the param slot's theta only
+  bool pred_H_valid = false;
+  uint64_t sweep_counter = 0;
+  // ---- device
+  DevTree dt{};
+  DevSlot ds[2]{};
+  double *d_w = nullptr, *d_xb = nullptr, *d_z = nullptr, *d_V = nullptr, *d_U = nullptr, *d_S = nullptr;
+  double *d_Hpred = nullptr, *d_sdpred = nullptr;
+  double *d_probe_sig = nullptr, *d_probe_smu = nullptr;  // Sigi_tot / Smu_tot probes (rioff / row0 indexed)
+  double *d_scalars = nullptr, *h_scalars = nullptr;      // small result vector (pinned host mirror)
+  double *d_partial = nullptr;
+  double *d_bcoeff = nullptr, *d_tausq_inv = nullptr;
+  int* d_fail = nullptr;
+  int *d_grp_slot0 = nullptr, *d_grp_nn = nullptr;
+  double* h_stage = nullptr;  // pinned n_all staging buffer
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8]{};
+  std::vector<void*> owned;  // device allocations to free
+  // counters
+  double n_launches = 0, f_alg = 0, f_exec = 0, n_cov = 0;
+  std::string err;
+
+  // ---- life cycle
+  int init(std::string& e);  // bookkeeping + upload; returns st_status
+  // ---- reference-named operations (spamtree_model.cpp)
+  int theta_update(int slot, const double* th);
+  int get_loglik_comps_w(int slot, double* out3);      // BUILD  :834-998
+  int deal_with_w(const double* z, uint64_t seed);     // GIBBS  :1011-1226
+  int get_loglik_w(int slot, double* out2);            // LLW    :781-826
+  void accept_make_change();                           // :1432-1435
+  int predict(bool theta_changed);                     // :1234-1358
+  int gibbs_sample_beta(const double* zb, bool faithful_index);  // :1364-1391
+  int gibbs_sample_tausq(const double* fixed);         // :1393-1417
+  int get_w(double* out);
+  int set_w(const double* in);
+  int get_xb(double* out);
+  int set_tausq_inv(const double* t);
+  int get_node_state(int slot, int u, const std::string& which, double* out, int64_t cap, int64_t* count);
+  int get_index(const std::string& which, int u, int c, int64_t* out, int64_t cap, int64_t* count);
+  int bench_iteration(const double* theta_prop, int do_swap, uint64_t seed, double* out3, float* ms_out);
+  int sync();
+
+ private:
+  int phys(int slot) const { return slot ? 1 - cur : cur; }
+  int build_bookkeeping(std::string& e);
+  int build_layout(std::string& e);
+  int upload(std::string& e);
+  int launch_build_levels(int pslot, const CovTab& tab);
+  int refresh_grams();
+  int gibbs_launch_only();
+  int rowstats(bool faithful_index);
+  std::vector<int> isref_host_;
+  long long sd_total_ = 0;
+  int rowstat_blocks_ = 1;
+  int draw_normals(uint64_t seed);
+  int upload_rows(const double* boundary_order, double* dev);
+  int cuda_fail(cudaError_t e, const char* what);
+  std::vector<int> beta_widx_faithful, beta_widx_plain;
+  int beta_widx_mode = -1;
+  int* d_obs_widx = nullptr;
+};
+
+}  // namespace st
