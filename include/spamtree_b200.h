@@ -60,7 +60,7 @@ typedef struct {
   int32_t n_theta;
   const double* beta;          /* p start values */
   double tausq;                /* start value (the ctor receives 1/tausq, spamtree_fit.cpp:104) */
-  int32_t device;              /* CUDA device ordinal */
+  int32_t device;              /* CUDA device ordinal; < 0: host-only handle (bookkeeping for st_get_index, no compute) */
   int32_t keep_H;              /* 1: keep H = w_cond_mean_K of observed blocks on device (needed by st_get_node_state "H") */
   int64_t smem_panel_bytes;    /* 0 = default; shared-memory budget for one BUILD work group */
 } st_problem;

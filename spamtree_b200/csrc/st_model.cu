@@ -63,7 +63,8 @@ bool make_covtab(const double* theta, int n_theta, int q, CovTab& tab, std::stri
 }
 
 Model::~Model() {
-  if (device >= 0) cudaSetDevice(device);
+  if (device < 0) return;
+  cudaSetDevice(device);
   for (void* p : owned) cudaFree(p);
   if (h_scalars) cudaFreeHost(h_scalars);
   if (h_stage) cudaFreeHost(h_stage);
@@ -463,6 +464,7 @@ int Model::init(std::string& e) {
   rc = build_layout(e);
   if (rc) return rc;
   if (n_all >= (1LL << 31)) { e = "n_all must be below 2^31"; return 4; }
+  if (device < 0) return 0;  // host-only handle: bookkeeping and layout, no device state (st_get_index only)
   rc = upload(e);
   if (rc) { e = err; return rc; }
   return 0;
@@ -486,6 +488,7 @@ int Model::launch_build_levels(int pslot, const CovTab& tab) {
 }
 
 int Model::get_loglik_comps_w(int slot, double* out3) {
+  if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   const int ps = phys(slot);
   CovTab tab;
   std::string e;
@@ -505,6 +508,7 @@ int Model::get_loglik_comps_w(int slot, double* out3) {
 }
 
 int Model::upload_rows(const double* boundary_order, double* dev) {
+  if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   for (int64_t i = 0; i < n_all; i++) h_stage[i] = boundary_order[perm[i]];
   ST_CUDA(cudaMemcpyAsync(dev, h_stage, n_all * sizeof(double), cudaMemcpyHostToDevice, stream), "H2D rows");
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
@@ -539,6 +543,7 @@ int Model::gibbs_launch_only() {
 }
 
 int Model::deal_with_w(const double* z, uint64_t seed) {
+  if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   if (z) { int rc = upload_rows(z, d_z); if (rc) return rc; }
   else { int rc = draw_normals(seed); if (rc) return rc; }
   ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
@@ -552,6 +557,7 @@ int Model::deal_with_w(const double* z, uint64_t seed) {
 }
 
 int Model::get_loglik_w(int slot, double* out2) {
+  if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   const int ps = phys(slot);
   ST_CUDA(launch_llw(dt, ds[ps], n_obs_nodes, d_w, stream), "llw_kernel");
   ST_CUDA(launch_loglik_reduce(ds[ps].logdet, ds[ps].llcomp, n_obs_nodes, nullptr, d_scalars, stream), "loglik_reduce");
@@ -571,6 +577,7 @@ void Model::accept_make_change() {
 }
 
 int Model::predict(bool theta_changed) {
+  if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   if (pred_level.nslots == 0) return 0;
   if (theta_changed || !pred_H_valid) {
     CovTab tab;
@@ -589,6 +596,7 @@ int Model::predict(bool theta_changed) {
 }
 
 int Model::rowstats(bool faithful_index) {
+  if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   const int mode = faithful_index ? 1 : 0;
   if (beta_widx_mode != mode) {
     const std::vector<int>& src = faithful_index ? beta_widx_faithful : beta_widx_plain;
@@ -649,6 +657,7 @@ int Model::gibbs_sample_beta(const double* zb, bool faithful_index) {
 }
 
 int Model::get_w(double* out) {
+  if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   ST_CUDA(cudaMemcpyAsync(h_stage, d_w, n_all * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H w");
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
   for (int64_t i = 0; i < n_all; i++) out[perm[i]] = h_stage[i];
@@ -656,23 +665,27 @@ int Model::get_w(double* out) {
 }
 int Model::set_w(const double* in) { return upload_rows(in, d_w); }
 int Model::get_xb(double* out) {
+  if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   ST_CUDA(cudaMemcpyAsync(h_stage, d_xb, n_all * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H xb");
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
   for (int64_t i = 0; i < n_all; i++) out[perm[i]] = h_stage[i];
   return 0;
 }
 int Model::set_tausq_inv(const double* t) {
+  if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   std::copy(t, t + q, tausq_inv.begin());
   ST_CUDA(cudaMemcpyAsync(d_tausq_inv, tausq_inv.data(), q * sizeof(double), cudaMemcpyHostToDevice, stream), "H2D tausq");
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
   return 0;
 }
 int Model::sync() {
+  if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
   return 0;
 }
 
 int Model::get_node_state(int slot, int u, const std::string& which, double* out, int64_t cap, int64_t* count) {
+  if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   const int ps = phys(slot);
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
   auto emit = [&](const dvec& v) {
@@ -804,6 +817,7 @@ int Model::get_index(const std::string& which, int u, int c, int64_t* out, int64
 
 // one hot-path iteration with device normals and event timing (bench hook)
 int Model::bench_iteration(const double* theta_prop, int do_swap, uint64_t seed, double* out3, float* ms_out) {
+  if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   const int pa = 1 - cur;
   CovTab tab;
   std::string e;

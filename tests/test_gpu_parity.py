@@ -1,0 +1,236 @@
+"""Parity of the CUDA hot path (through the C ABI) against the CPU oracle on identical seeded inputs.
+Contract (BASELINE.json north_star / SURVEY §8c): H, Ri, log-density at fixed theta, Gibbs conditional mean and
+covariance <= 1e-9 relative (max-norm per block); w identical to <= 1e-9 given the same z."""
+import numpy as np
+import pytest
+
+import common
+from common import orc, relerr
+from dense_twin import Twin
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+CASES = [(1, 625, .1), (1, 2500, .1), (2, 2000, .1), (3, 3000, .1), (5, 4000, .15), (3, 1200, 0.0), (1, 30, .1), (2, 9, 0.0)]
+
+
+@pytest.fixture(scope="module", params=CASES, ids=lambda c: f"q{c[0]}_n{c[1]}_miss{c[2]}")
+def pair(request):
+    q, n, missing = request.param
+    pb = common.make_problem(q, n, missing=missing)
+    gm, om = common.product_model(pb), common.oracle_model(pb)
+    w0 = np.random.default_rng(7).standard_normal(n) * .5
+    gm.w = w0
+    om.w = w0
+    yield pb, gm, om
+    gm.close()
+    om.close()
+
+
+def test_build_H_Ri_logdensity(pair):
+    pb, gm, om = pair
+    nb = pb["tree"]["n_blocks"]
+    for slot in (0, 1):
+        okg, llg, ldg = gm.get_loglik_comps_w(slot)
+        oko, llo, ldo = om.get_loglik_comps_w(slot)
+        assert okg and oko
+        assert abs(llg - llo) <= TOL * abs(llo) and abs(ldg - ldo) <= TOL * abs(ldo)
+    obs, isref = om.geti("block_ct_obs"), om.geti("block_is_reference")
+    npar = np.diff(pb["tree"]["parents_ptr"])
+    for u in range(nb):
+        if obs[u] == 0:
+            continue
+        if npar[u]:
+            assert relerr(gm.node_state("H", u), om.get("H", u)) <= TOL, ("H", u)
+        ref = om.get("Ri", u) if isref[u] else om.get("ccholprecdiag", u)
+        assert relerr(gm.node_state("Ri", u), ref) <= TOL, ("Ri", u)
+    assert relerr(gm.node_state("logdetCi_comps"), om.get("logdetCi_comps")) <= TOL
+    assert relerr(gm.node_state("loglik_w_comps"), om.get("loglik_w_comps")) <= TOL
+
+
+def test_gibbs_conditionals_and_draw(pair):
+    pb, gm, om = pair
+    n, nb = pb["n"], pb["tree"]["n_blocks"]
+    gm.get_loglik_comps_w(0)
+    om.get_loglik_comps_w(0)
+    obs, isref = om.geti("block_ct_obs"), om.geti("block_is_reference")
+    rng = np.random.default_rng(8)
+    for sweep in range(3):
+        z = rng.standard_normal(n)
+        gm.deal_with_w(z)
+        om.deal_with_w(z)
+        assert relerr(gm.w, om.w) <= TOL
+        for u in range(nb):
+            if obs[u] == 0:
+                continue
+            Sg, So = gm.node_state("Sigi_tot", u), om.get("Sigi_tot", u)
+            Mg, Mo = gm.node_state("Smu_tot", u), om.get("Smu_tot", u)
+            assert relerr(Sg, So) <= TOL and relerr(Mg, Mo) <= 10 * TOL
+            if isref[u]:  # conditional covariance Sigi_tot^-1 and mean Sigi_tot^-1 Smu_tot
+                m = Mo.size
+                Cg, Co = np.linalg.inv(Sg.reshape(m, m)), np.linalg.inv(So.reshape(m, m))
+                assert relerr(Cg, Co) <= 100 * TOL  # conditioning of Sigi_tot enters here
+                assert relerr(Cg @ Mg, Co @ Mo) <= 100 * TOL
+            else:
+                assert relerr(Mg / Sg, Mo / So) <= TOL
+        lg, lo = gm.get_loglik_w(0), om.get_loglik_w(0)
+        assert abs(lg[0] - lo[0]) <= TOL * abs(lo[0]) and abs(lg[1] - lo[1]) <= TOL * abs(lo[1])
+
+
+def test_predict_beta_tausq(pair):
+    pb, gm, om = pair
+    q = pb["q"]
+    rng = np.random.default_rng(9)
+    z = rng.standard_normal(pb["n"])
+    gm.deal_with_w(z)
+    om.deal_with_w(z)
+    gm.predict(True)
+    om.predict(True)
+    assert relerr(gm.w, om.w) <= TOL
+    gm.predict(False)   # H of the prediction blocks is reused (spamtree_model.cpp:1256)
+    om.predict(False)
+    assert relerr(gm.w, om.w) <= TOL
+    t = np.linspace(3, 9, q)
+    gm.gibbs_sample_tausq(t)
+    om.gibbs_sample_tausq(t)
+    zb = rng.standard_normal((3, q))
+    gm.gibbs_sample_beta(zb, True)   # reference indexing quirk
+    om.gibbs_sample_beta(zb)
+    pg, po = gm.params(), om.params()
+    assert relerr(pg["Bcoeff"], po["Bcoeff"]) <= TOL and relerr(pg["XB"], po["XB"]) <= TOL
+    gm.seed(5)
+    om.seed(5)
+    gm.gibbs_sample_tausq()
+    om.gibbs_sample_tausq()
+    assert relerr(gm.params()["tausq_inv"], om.params()["tausq_inv"]) <= TOL
+    # corrected beta indexing against an oracle built with that flag
+    om2 = common.oracle_model(pb, flags=orc.FLAG_PROBES | orc.FLAG_CORRECT_BETA_INDEX)
+    om2.w = gm.w
+    om2.set_tausq_inv(gm.params()["tausq_inv"])
+    gm.gibbs_sample_beta(zb, False)
+    om2.gibbs_sample_beta(zb)
+    assert relerr(gm.params()["Bcoeff"], om2.params()["Bcoeff"]) <= TOL
+    om2.close()
+
+
+def test_swap_and_two_slots(pair):
+    pb, gm, om = pair
+    th2 = pb["theta"] * (1 + .01 * np.random.default_rng(3).standard_normal(pb["theta"].size))
+    for m in (gm, om):
+        m.theta_update(1, th2)
+    rg, ro = gm.get_loglik_comps_w(1), om.get_loglik_comps_w(1)
+    assert rg[0] and ro[0] and abs(rg[1] - ro[1]) <= TOL * abs(ro[1])
+    for m in (gm, om):
+        m.accept_make_change()
+    lg, lo = gm.get_loglik_w(0), om.get_loglik_w(0)   # param_data is now the theta-2 state
+    assert abs(lg[0] - rg[1]) <= 1e-12 * abs(rg[1])
+    assert abs(lg[0] - lo[0]) <= TOL * abs(lo[0])
+    z = np.random.default_rng(4).standard_normal(pb["n"])
+    gm.deal_with_w(z)
+    om.deal_with_w(z)
+    assert relerr(gm.w, om.w) <= TOL
+    for m in (gm, om):
+        m.accept_make_change()
+
+
+def test_lockstep_chain_matches_oracle_chain():
+    """spamtree_mv_mcmc (spamtree_fit.cpp:167-391) run on both sides with the same host random stream"""
+    from spamtree_b200 import synth
+    for q, n in [(1, 625), (2, 1500)]:
+        pb = common.make_problem(q, n)
+        pb["theta"] = synth.default_bounds(q).mean(axis=1) if q == 1 else pb["theta"]
+        gm, om = common.product_model(pb), common.oracle_model(pb)
+        npar = pb["theta"].size
+        bounds = synth.default_bounds(q)
+        kw = dict(keep=15, burn=70, thin=2, adapting=True, seed=21)
+        rg = gm.mcmc(bounds, np.eye(npar) * .01, rng_mode=0, **kw)
+        ro = om.mcmc(bounds, np.eye(npar) * .01, **kw)
+        assert rg["n_accepted"] == ro["n_accepted"] and rg["n_accepted"] > 0
+        assert relerr(rg["theta_mcmc"], ro["theta_mcmc"]) <= 1e-8
+        assert relerr(rg["beta_mcmc"], ro["beta_mcmc"]) <= 1e-7
+        assert relerr(rg["tausq_mcmc"], ro["tausq_mcmc"]) <= 1e-7
+        assert relerr(rg["w_mcmc"], ro["w_mcmc"]) <= 1e-6
+        assert relerr(rg["yhat_mcmc"], ro["yhat_mcmc"]) <= 1e-6
+        assert relerr(rg["paramsd"], ro["paramsd"]) <= 1e-7
+        gm.close()
+        om.close()
+
+
+def test_cholesky_failure_rejects_without_error():
+    """BUILD returns ok = 0 (spamtree_model.cpp:971-982) and the slot recovers; never an exception"""
+    pb = common.make_problem(3, 900)
+    gm, om = common.product_model(pb), common.oracle_model(pb)
+    assert gm.get_loglik_comps_w(0)[0]
+    ll_before = gm.get_loglik_comps_w(1)[1]
+    bad = pb["theta"].copy()
+    bad[12:] = [1e-3, 1e-3, 999.0]
+    bad[0:3] = [30, -30, 30]
+    for m in (gm, om):
+        m.theta_update(1, bad)
+    okg, llg, _ = gm.get_loglik_comps_w(1)
+    oko = om.get_loglik_comps_w(1)[0]
+    assert okg == oko
+    if not okg:
+        assert llg == ll_before  # loglik_w of the slot is left untouched on failure
+    gm.theta_update(1, pb["theta"])
+    assert gm.get_loglik_comps_w(1)[0]
+    z = np.random.default_rng(1).standard_normal(pb["n"])
+    gm.deal_with_w(z)   # the param slot was never touched
+    gm.close()
+    om.close()
+
+
+def test_cross_covariance_ag10_on_gpu():
+    import spamtree_b200 as sb
+    xl = np.linspace(0, 1, 10)
+    g = np.array([(a, b) for b in xl for a in xl])
+    coords = np.vstack([g, g])
+    mv = np.r_[np.ones(100, int), 2 * np.ones(100, int)]
+    args = ([1, 1.5], [.1, .51], [1, 2], [5.0], np.array([[0, 1.0], [1.0, 0]]))
+    CC = sb.CrossCovarianceAG10(coords, mv, coords, mv, *args)
+    assert np.allclose(np.diag(CC)[:100], 1.01, rtol=0, atol=1e-14) and np.allclose(np.diag(CC)[100:], 2.5101, rtol=0, atol=1e-14)
+    assert relerr(CC, orc.cross_covariance_ag10(coords, mv, coords, mv, *args)) <= 1e-13
+    rng = np.random.default_rng(0)
+    c1, c2 = rng.random((57, 2)), rng.random((31, 2))
+    m1, m2 = rng.integers(1, 4, 57), rng.integers(1, 4, 31)
+    D = np.array([[0, 1, 2], [1, 0, 1.5], [2, 1.5, 0.0]])
+    a3 = ([1, 1.5, .8], [.1, .51, .3], [1, 2, 3], [2, .5, 5.0], D)
+    assert relerr(sb.CrossCovarianceAG10(c1, m1, c2, m2, *a3), orc.cross_covariance_ag10(c1, m1, c2, m2, *a3)) <= 1e-13
+    with pytest.raises(sb.SpamTreeError):
+        sb.CrossCovarianceAG10(c1, np.ones(57, int), c2, np.ones(31, int), [1], [1], [1], [1], np.zeros((1, 1)))
+
+
+def test_gpu_matches_dense_math_directly():
+    """independent of the oracle: H, Ri, log-density against scipy-free dense numpy on a small tree"""
+    pb = common.make_problem(3, 900)
+    gm, tw = common.product_model(pb), Twin(pb)
+    w = np.random.default_rng(2).standard_normal(900)
+    gm.w = w
+    ok, ll, _ = gm.get_loglik_comps_w(0)
+    assert ok and abs(ll - tw.loglik(w)) <= TOL * abs(ll)
+    for u in range(tw.nb):
+        if tw.obs[u] == 0:
+            continue
+        H, Ri = tw.block(u)
+        m = tw.rows[u].size
+        if H.shape[1]:
+            assert relerr(gm.node_state("H", u).reshape(-1, m).T, H) <= 10 * TOL
+        got = gm.node_state("Ri", u)
+        assert relerr(got.reshape(m, m).T if tw.isref[u] else got, Ri) <= 10 * TOL
+    gm.close()
+
+
+def test_unsupported_inputs_fail_loudly():
+    import spamtree_b200 as sb
+    pb = common.make_problem(1, 625)
+    d, t = pb["d"], pb["tree"]
+    with pytest.raises(sb.SpamTreeError) as e:
+        sb.SpamTreeMV(d["y"], d["X"], d["coords"], d["mv_id"], t["res_is_ref"], None, None, True, t["block_names"],
+                      t["block_groups"], None, pb["beta"], pb["theta"], pb["tausq"], csr=pb["csr"])
+    assert e.value.code == 4
+    bad = list(pb["csr"])
+    bad[3] = bad[3].copy()
+    bad[3][-1] = 0  # break a parent chain
+    with pytest.raises(sb.SpamTreeError):
+        sb.SpamTreeMV(d["y"], d["X"], d["coords"], d["mv_id"], t["res_is_ref"], None, None, False, t["block_names"],
+                      t["block_groups"], None, pb["beta"], pb["theta"], pb["tausq"], csr=tuple(bad))
