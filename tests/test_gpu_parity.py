@@ -111,6 +111,9 @@ def test_predict_beta_tausq(pair):
     om2.gibbs_sample_beta(zb)
     assert relerr(gm.params()["Bcoeff"], om2.params()["Bcoeff"]) <= TOL
     om2.close()
+    gm.gibbs_sample_beta(zb, True)   # leave the pair in the same state for the tests that follow
+    om.gibbs_sample_beta(zb)
+    assert relerr(gm.params()["XB"], om.params()["XB"]) <= TOL
 
 
 def test_swap_and_two_slots(pair):
@@ -138,14 +141,14 @@ def test_lockstep_chain_matches_oracle_chain():
     from spamtree_b200 import synth
     for q, n in [(1, 625), (2, 1500)]:
         pb = common.make_problem(q, n)
-        pb["theta"] = synth.default_bounds(q).mean(axis=1) if q == 1 else pb["theta"]
         gm, om = common.product_model(pb), common.oracle_model(pb)
         npar = pb["theta"].size
         bounds = synth.default_bounds(q)
         kw = dict(keep=15, burn=70, thin=2, adapting=True, seed=21)
-        rg = gm.mcmc(bounds, np.eye(npar) * .01, rng_mode=0, **kw)
-        ro = om.mcmc(bounds, np.eye(npar) * .01, **kw)
-        assert rg["n_accepted"] == ro["n_accepted"] and rg["n_accepted"] > 0
+        sd = np.eye(npar) * (.01 if q == 1 else 2e-4)
+        rg = gm.mcmc(bounds, sd, rng_mode=0, **kw)
+        ro = om.mcmc(bounds, sd, **kw)
+        assert rg["n_accepted"] == ro["n_accepted"] and rg["n_accepted"] > 3
         assert relerr(rg["theta_mcmc"], ro["theta_mcmc"]) <= 1e-8
         assert relerr(rg["beta_mcmc"], ro["beta_mcmc"]) <= 1e-7
         assert relerr(rg["tausq_mcmc"], ro["tausq_mcmc"]) <= 1e-7
