@@ -1,0 +1,489 @@
+// st_build.cu — build_level_kernel: BUILD of one tree level (get_loglik_comps_w_std, spamtree_model.cpp:834-998) and
+// of the prediction blocks (predict_std, :1234-1358).
+//
+// One CTA per work group = a run of blocks that share their ancestor chain (siblings), or share all but the deepest
+// ancestor (cousins; the deepest ancestor is then "family specific").  Per group, entirely in shared memory:
+//   1. K = K_{pa,u}: cross-covariance panel, one column per row of the group's blocks (Covariancef_inplace, :885)
+//   2. Z = L^-1 K : the chain's inverse Cholesky factor is never stored; its block row j is [-G_a | Ri_a] of ancestor
+//                   a = chain[j] (tree_utils.cpp:204-206), so Z is formed tile by tile, deepest ancestor first, in place
+//   3. R = K_uu - Z'Z (= Kcc - H Kxc, :896-897), Ri = chol(R)^-1 in place (non-reference levels: diagonal only, :931-948)
+//   4. H' = L^-T Z, shallowest ancestor first, in place  (H = Kxc' Kxx_inv, :887, without ever forming Kxx_inv)
+//   5. G = Ri H, e = w - H w_pa, wcore, logdet (:888, :912-913, :966-968)
+// The operand tiles (G_a, Ri_a of the ancestors) stream from global/L2 through a 3-stage cp.async ring so that the
+// register-tiled FP64 FMA loops read both operands from shared memory.
+#include <cuda_pipeline.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "st_device.cuh"
+#include "st_kernels.cuh"
+
+namespace st {
+
+namespace {
+constexpr int TR = kBuildTR, TC = kBuildTC;
+constexpr int F_RI = 1, F_TRANS = 2, F_PERFAM = 4, F_FIRST = 8, F_LAST = 16;
+constexpr int kDescInts = 6;  // flags, chain index of the operand's owner (-1: family parent), tile index, brow, orow0, ochain
+}  // namespace
+
+template <int MODE>
+__global__ void __launch_bounds__(kBuildThreads, 1)
+build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __restrict__ outRi,
+                   const int* __restrict__ grp_slot0, const int* __restrict__ grp_nn, const int* __restrict__ grp_share,
+                   const double* __restrict__ w, CovTab tab, int* __restrict__ fail, int keep_H) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ CovTabS ct;
+  __shared__ int s_chain[kMaxChain], s_cm[kMaxChain], s_crow[kMaxChain + 1], s_crow0g[kMaxChain];
+  __shared__ int s_nm[kMaxGroupNodes], s_nc0[kMaxGroupNodes], s_nR0[kMaxGroupNodes], s_nfam[kMaxGroupNodes];
+  __shared__ int s_fpar[kMaxFam], s_fm[kMaxFam], s_fc0[kMaxFam + 1], s_frow0g[kMaxFam];
+  __shared__ BuildShape sh;
+  __shared__ BuildPlan pl;
+  __shared__ int s_nfwd;
+
+  const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+  const int s0 = grp_slot0[blockIdx.x], nn = grp_nn[blockIdx.x];
+  const int k = T.k[s0];
+
+  load_covtab(ct, tab);
+  if (tid == 0) {
+    const int share = grp_share[blockIdx.x];
+    const int coff = T.chain_off[s0];
+    const int kc = share ? k - 1 : k;
+    int maxm = 1;
+    for (int j = 0; j < kc; j++) {
+      const int a = T.chain[coff + j];
+      s_chain[j] = a;
+      s_cm[j] = T.m[a];
+      s_crow[j] = T.chain_poff[coff + j];
+      s_crow0g[j] = T.row0[a];
+      maxm = max(maxm, s_cm[j]);
+    }
+    const int Pc = (kc < k) ? T.chain_poff[coff + kc] : T.P[s0];
+    s_crow[kc] = Pc;
+    int F = 0, c = 0, sumR = 0, maxmd = 1, mmaxs = 0, prevpar = -2;
+    for (int d = 0; d < nn; d++) {
+      const int par = T.lastpar[s0 + d], md = T.m[s0 + d];
+      if (d == 0 || (share && par != prevpar)) {
+        c = (c + 3) & ~3;
+        s_fpar[F] = par;
+        s_fm[F] = share ? T.m[par] : 0;
+        s_frow0g[F] = share ? T.row0[par] : 0;
+        s_fc0[F] = c;
+        mmaxs = max(mmaxs, s_fm[F]);
+        F++;
+        prevpar = par;
+      }
+      s_nfam[d] = F - 1;
+      s_nc0[d] = c;
+      s_nm[d] = md;
+      s_nR0[d] = sumR;
+      c += md;
+      sumR += md * tile_rs(md);
+      maxmd = max(maxmd, md);
+    }
+    const int NCp = (c + 3) & ~3;
+    s_fc0[F] = NCp;
+    maxm = max(maxm, mmaxs);
+    sh.mode = MODE; sh.share = share; sh.kc = kc; sh.Pc = Pc; sh.mmaxs = mmaxs; sh.F = F; sh.NCp = NCp; sh.sumR = sumR;
+    sh.maxtile = maxm * tile_rs(maxm); sh.maxmd = maxmd;
+    pl = build_plan(sh);
+    s_nfwd = (share ? kc + 1 : 0) + kc * (kc + 1) / 2;
+  }
+  __syncthreads();
+  const int share = sh.share, kc = sh.kc, Pc = sh.Pc, mmaxs = sh.mmaxs, F = sh.F, NCp = sh.NCp, maxtile = sh.maxtile;
+  const int LD = pl.LD, Ppad = pl.Ppad, nsets = pl.nsets, Fst = pl.Fst, nfwd = s_nfwd;
+  double* base = reinterpret_cast<double*>(smem_raw);
+  double* panel = base + pl.o_panel;
+  double* Rb = base + pl.o_R;
+  double* ring = base + pl.o_ring;
+  double* pxs = base + pl.o_pxs;
+  double* pys = base + pl.o_pys;
+  double* wpa = base + pl.o_wpa;
+  double* cxs = base + pl.o_cxs;
+  double* cys = base + pl.o_cys;
+  double* ecol = base + pl.o_ecol;
+  double* vtmp = base + pl.o_vtmp;
+  int* pq = reinterpret_cast<int*>(base + pl.o_pq);
+  int* cq = reinterpret_cast<int*>(base + pl.o_cq);
+  int* colnode = reinterpret_cast<int*>(base + pl.o_colnode);
+  int* cgfam = reinterpret_cast<int*>(base + pl.o_cgfam);
+  int* desc = reinterpret_cast<int*>(base + pl.o_desc);
+
+  // ---- operand-tile descriptors of the whole group, in execution order (forward sweep, then backward sweep)
+  if (tid == 0) {
+    int n = 0;
+    auto put = [&](int flags, int owner, int tidx, int brow, int orow0, int ochain) {
+      int* d = desc + n * kDescInts;
+      d[0] = flags; d[1] = owner; d[2] = tidx; d[3] = brow; d[4] = orow0; d[5] = ochain;
+      n++;
+    };
+    if (share) {  // Z of the family-specific (deepest) ancestor
+      for (int i2 = 0; i2 < kc; i2++) put(F_PERFAM | (i2 == 0 ? F_FIRST : 0), -1, i2, s_crow[i2], Pc, -1);
+      put(F_RI | F_PERFAM | F_LAST | (kc == 0 ? F_FIRST : 0), -1, 0, Pc, Pc, -1);
+    }
+    for (int j = kc - 1; j >= 0; j--) {
+      for (int i2 = 0; i2 < j; i2++) put(i2 == 0 ? F_FIRST : 0, j, i2, s_crow[i2], s_crow[j], j);
+      put(F_RI | F_LAST | (j == 0 ? F_FIRST : 0), j, 0, s_crow[j], s_crow[j], j);
+    }
+    for (int i = 0; i < kc; i++) {
+      const bool more = (i + 1 < kc) || share;
+      put(F_RI | F_TRANS | F_FIRST | (more ? 0 : F_LAST), i, 0, s_crow[i], s_crow[i], i);
+      for (int j = i + 1; j < kc; j++) put(F_TRANS | ((j + 1 == kc && !share) ? F_LAST : 0), j, i, s_crow[j], s_crow[i], i);
+      if (share) put(F_TRANS | F_PERFAM | F_LAST, -1, i, Pc, s_crow[i], i);
+    }
+    if (share) put(F_RI | F_TRANS | F_PERFAM | F_FIRST | F_LAST, -1, 0, Pc, Pc, -1);
+  }
+
+  // ---- phase 1: coordinates (ancestor rows are contiguous in the node-major layout)
+  for (int j = 0; j < kc; j++) {
+    const int r0 = s_crow0g[j], po = s_crow[j];
+    for (int t = tid; t < s_cm[j]; t += nth) {
+      pxs[po + t] = T.cx[r0 + t]; pys[po + t] = T.cy[r0 + t]; pq[po + t] = T.mvq[r0 + t]; wpa[po + t] = w[r0 + t];
+    }
+  }
+  if (share)
+    for (int f = 0; f < F; f++) {
+      const int r0 = s_frow0g[f], po = Pc + f * mmaxs;
+      for (int t = tid; t < s_fm[f]; t += nth) {
+        pxs[po + t] = T.cx[r0 + t]; pys[po + t] = T.cy[r0 + t]; pq[po + t] = T.mvq[r0 + t]; wpa[po + t] = w[r0 + t];
+      }
+    }
+  for (int c = tid; c < LD; c += nth) { cxs[c] = 0; cys[c] = 0; cq[c] = 0; colnode[c] = -1; }
+  for (int cg = tid; cg < NCp / 4; cg += nth) {
+    int f = 0;
+    while (f + 1 < F && 4 * cg >= s_fc0[f + 1]) f++;
+    cgfam[cg] = f;
+  }
+  __syncthreads();
+  for (int d = 0; d < nn; d++) {
+    const int r0 = T.row0[s0 + d], c0 = s_nc0[d];
+    for (int t = tid; t < s_nm[d]; t += nth) {
+      cxs[c0 + t] = T.cx[r0 + t]; cys[c0 + t] = T.cy[r0 + t]; cq[c0 + t] = T.mvq[r0 + t]; colnode[c0 + t] = d;
+    }
+  }
+  __syncthreads();
+
+  // ---- cp.async ring over the operand tiles
+  auto tile_geom = [&](const int* d, int f, int& slot, int& rows, int& cols) {
+    if (d[0] & F_PERFAM) { slot = s_fpar[f]; rows = s_fm[f]; } else { slot = s_chain[d[1]]; rows = s_cm[d[1]]; }
+    cols = (d[0] & F_RI) ? rows : s_cm[d[2]];
+  };
+  auto issue = [&](int s) {
+    const int* d = desc + s * kDescInts;
+    const int nf = (d[0] & F_PERFAM) ? F : 1;
+    double* dst0 = ring + (size_t)(s % kBuildStages) * Fst * maxtile;
+    for (int f = 0; f < nf; f++) {
+      int slot, rows, cols;
+      tile_geom(d, f, slot, rows, cols);
+      const double* src = (d[0] & F_RI) ? S.Ri + T.rioff[slot] : S.G + T.goff[slot] + T.chain_boff[T.chain_off[slot] + d[2]];
+      const int n16 = rows * tile_rs(cols) / 2;  // 16-byte chunks (tile sizes are even)
+      double* dst = dst0 + (size_t)f * maxtile;
+      for (int c = tid; c < n16; c += nth) __pipeline_memcpy_async(dst + 2 * c, src + 2 * c, 16);
+    }
+  };
+  if (nsets > 0) { issue(0); }
+  __pipeline_commit();
+  if (nsets > 1) { issue(1); }
+  __pipeline_commit();
+
+  // ---- phase 2: covariance panel K_{pa,u} and K_uu
+  for (int idx = tid; idx < Pc * LD; idx += nth) {
+    const int i = idx / LD, c = idx - i * LD;
+    panel[idx] = (c < NCp && colnode[c] >= 0) ? cov_eval(ct, pxs[i], pys[i], pq[i], cxs[c], cys[c], cq[c]) : 0.0;
+  }
+  if (share)
+    for (int idx = tid; idx < mmaxs * LD; idx += nth) {
+      const int t = idx / LD, c = idx - t * LD;
+      double v = 0.0;
+      if (c < NCp && colnode[c] >= 0) {
+        const int f = cgfam[c >> 2];
+        if (t < s_fm[f]) {
+          const int pi = Pc + f * mmaxs + t;
+          v = cov_eval(ct, pxs[pi], pys[pi], pq[pi], cxs[c], cys[c], cq[c]);
+        }
+      }
+      panel[(size_t)(Pc + t) * LD + c] = v;
+    }
+  if (MODE == 0) {
+    for (int d = 0; d < nn; d++) {
+      const int md = s_nm[d], c0 = s_nc0[d], rsd = tile_rs(md);
+      double* Kuu = Rb + s_nR0[d];
+      for (int e = tid; e < md * rsd; e += nth) {
+        const int r = e / rsd, r2 = e - r * rsd;
+        Kuu[e] = (r2 < md) ? cov_eval(ct, cxs[c0 + r], cys[c0 + r], cq[c0 + r], cxs[c0 + r2], cys[c0 + r2], cq[c0 + r2]) : 0.0;
+      }
+    }
+  } else {
+    for (int c = tid; c < LD; c += nth) Rb[c] = (c < NCp && colnode[c] >= 0) ? cov_eval(ct, cxs[c], cys[c], cq[c], cxs[c], cys[c], cq[c]) : 1.0;
+  }
+  // (the first __syncthreads of the sweep below publishes the panel)
+
+  // ---- phases 3 and 6: one generic sweep over descriptor range [s_begin, s_end)
+  const int n_cg = NCp / TC;
+  double acc[TR][TC];
+  int it_r0 = 0, it_c0 = 0, it_fam = 0, it_orows = 0;
+  bool it_active = false;
+  auto sweep = [&](int s_begin, int s_end) {
+    for (int s = s_begin; s < s_end; s++) {
+      const int* d = desc + s * kDescInts;
+      const int flags = d[0];
+      __pipeline_wait_prior(kBuildStages - 2);
+      __syncthreads();
+      if (s + 2 < nsets) issue(s + 2);
+      __pipeline_commit();
+      if (flags & F_FIRST) {  // new output block: map one register tile to this thread
+        const int omax = (d[5] < 0) ? mmaxs : s_cm[d[5]];
+        const int n_rg = (omax + TR - 1) / TR;
+        it_active = tid < n_rg * n_cg;
+        if (it_active) {
+          const int rg = tid % n_rg, cg = tid / n_rg;
+          it_r0 = rg * TR;
+          it_c0 = cg * TC;
+          it_fam = cgfam[cg];
+          it_orows = (d[5] < 0) ? s_fm[it_fam] : omax;
+          it_active = it_r0 < it_orows;
+        }
+#pragma unroll
+        for (int tr = 0; tr < TR; tr++)
+#pragma unroll
+          for (int tc = 0; tc < TC; tc++) acc[tr][tc] = 0.0;
+      }
+      if (it_active) {
+        const int fi = (flags & F_PERFAM) ? it_fam : 0;
+        int slot, rows, cols;
+        tile_geom(d, fi, slot, rows, cols);
+        const int rs = tile_rs(cols);
+        const double* tile = ring + ((size_t)(s % kBuildStages) * Fst + fi) * maxtile;
+        const double* Bp = panel + (size_t)d[3] * LD + it_c0;
+        const bool trans = flags & F_TRANS;
+        const int K = trans ? rows : cols;
+        const int astride = trans ? rs : 1;
+        int aoff[TR];
+#pragma unroll
+        for (int tr = 0; tr < TR; tr++) aoff[tr] = min(it_r0 + tr, it_orows - 1) * (trans ? 1 : rs);
+        const double sgn = (flags & F_RI) ? -1.0 : 1.0;  // acc = sum G*B - Ri*B ; the block written out is -acc
+#pragma unroll 2
+        for (int kk = 0; kk < K; kk++) {
+          const double2 b01 = *reinterpret_cast<const double2*>(Bp + (size_t)kk * LD);
+          const double2 b23 = *reinterpret_cast<const double2*>(Bp + (size_t)kk * LD + 2);
+          const double* ap = tile + kk * astride;
+          double av[TR];
+#pragma unroll
+          for (int tr = 0; tr < TR; tr++) av[tr] = ap[aoff[tr]];
+          if (flags & F_RI) {
+#pragma unroll
+            for (int tr = 0; tr < TR; tr++) av[tr] *= sgn;
+          }
+#pragma unroll
+          for (int tr = 0; tr < TR; tr++) {
+            acc[tr][0] = fma(av[tr], b01.x, acc[tr][0]);
+            acc[tr][1] = fma(av[tr], b01.y, acc[tr][1]);
+            acc[tr][2] = fma(av[tr], b23.x, acc[tr][2]);
+            acc[tr][3] = fma(av[tr], b23.y, acc[tr][3]);
+          }
+        }
+      }
+      if (flags & F_LAST) {  // every thread has finished reading the rows that are about to be overwritten
+        __syncthreads();
+        if (it_active) {
+#pragma unroll
+          for (int tr = 0; tr < TR; tr++)
+            if (it_r0 + tr < it_orows) {
+              double* o = panel + (size_t)(d[4] + it_r0 + tr) * LD + it_c0;
+              *reinterpret_cast<double2*>(o) = make_double2(-acc[tr][0], -acc[tr][1]);
+              *reinterpret_cast<double2*>(o + 2) = make_double2(-acc[tr][2], -acc[tr][3]);
+            }
+        }
+      }
+    }
+    __syncthreads();
+  };
+
+  __syncthreads();
+  sweep(0, nfwd);  // Z = L^-1 K
+
+  // ---- phase 4/5: Schur complement and its inverse Cholesky factor
+  if (MODE == 0) {
+    int total = 0;
+    for (int d = 0; d < nn; d++) total += ((s_nm[d] + TR - 1) / TR) * ((s_nm[d] + TC - 1) / TC);
+    for (int item = tid; item < total; item += nth) {
+      int d = 0, rem = item;
+      for (;; d++) {
+        const int cnt = ((s_nm[d] + TR - 1) / TR) * ((s_nm[d] + TC - 1) / TC);
+        if (rem < cnt) break;
+        rem -= cnt;
+      }
+      const int md = s_nm[d], c0d = s_nc0[d], rsd = tile_rs(md);
+      const int nrg = (md + TR - 1) / TR;
+      const int r0 = (rem % nrg) * TR, c0 = (rem / nrg) * TC;
+      double a2[TR][TC];
+#pragma unroll
+      for (int tr = 0; tr < TR; tr++)
+#pragma unroll
+        for (int tc = 0; tc < TC; tc++) a2[tr][tc] = 0.0;
+      int ro[TR], co[TC];
+#pragma unroll
+      for (int tr = 0; tr < TR; tr++) ro[tr] = c0d + min(r0 + tr, md - 1);
+#pragma unroll
+      for (int tc = 0; tc < TC; tc++) co[tc] = c0d + min(c0 + tc, md - 1);
+#pragma unroll 2
+      for (int pp = 0; pp < Ppad; pp++) {
+        const double* row = panel + (size_t)pp * LD;
+        double a[TR], b[TC];
+#pragma unroll
+        for (int tr = 0; tr < TR; tr++) a[tr] = row[ro[tr]];
+#pragma unroll
+        for (int tc = 0; tc < TC; tc++) b[tc] = row[co[tc]];
+#pragma unroll
+        for (int tr = 0; tr < TR; tr++)
+#pragma unroll
+          for (int tc = 0; tc < TC; tc++) a2[tr][tc] = fma(a[tr], b[tc], a2[tr][tc]);
+      }
+      double* R = Rb + s_nR0[d];
+#pragma unroll
+      for (int tr = 0; tr < TR; tr++)
+#pragma unroll
+        for (int tc = 0; tc < TC; tc++)
+          if (r0 + tr < md && c0 + tc < md) R[(r0 + tr) * rsd + c0 + tc] -= a2[tr][tc];
+    }
+    __syncthreads();
+    for (int d = warp; d < nn; d += nwarps) {
+      const int md = s_nm[d], rsd = tile_rs(md);
+      double* R = Rb + s_nR0[d];
+      if (warp_chol(R, md, rsd, lane)) {
+        warp_inv_lower_inplace(R, md, rsd, vtmp + warp * (sh.maxmd + 2), lane);
+      } else {
+        if (lane == 0) atomicAdd(fail, 1);
+        for (int e = lane; e < md * rsd; e += 32) R[e] = 0.0;
+      }
+    }
+    __syncthreads();
+  } else {
+    for (int c = tid; c < NCp; c += nth) {
+      if (colnode[c] < 0) continue;
+      double s = 0;
+      for (int pp = 0; pp < Ppad; pp++) { const double z = panel[(size_t)pp * LD + c]; s = fma(z, z, s); }
+      const double R = Rb[c] - s;
+      const bool ok = (R > 0.0) && isfinite(R);
+      if (MODE == 1) {
+        if (!ok) atomicAdd(fail, 1);
+        Rb[c] = ok ? 1.0 / sqrt(R) : 0.0;  // ccholprecdiag (:945)
+      } else {
+        Rb[c] = ok ? sqrt(R) : 0.0;  // predict_std zeroes the sd when the Cholesky fails (:1316-1322)
+      }
+    }
+    __syncthreads();
+  }
+
+  sweep(nfwd, nsets);  // H' = L^-T Z
+
+  // ---- phase 7: outputs.  panel[p][c] = H(c, p)
+  for (int c = tid; c < NCp; c += nth) {
+    const int d = colnode[c];
+    if (d < 0) continue;
+    double s = w[T.row0[s0 + d] + (c - s_nc0[d])];
+    for (int pp = 0; pp < Pc; pp++) s = fma(-panel[(size_t)pp * LD + c], wpa[pp], s);
+    if (share) {
+      const int f = s_nfam[d];
+      for (int t = 0; t < s_fm[f]; t++) s = fma(-panel[(size_t)(Pc + t) * LD + c], wpa[Pc + f * mmaxs + t], s);
+    }
+    ecol[c] = s;  // e = w_x - H w_pa (:888)
+  }
+  __syncthreads();
+  for (int d = 0; d < nn; d++) {
+    const int sd = s0 + d, md = s_nm[d], c0d = s_nc0[d], f = s_nfam[d], rsd = tile_rs(md);
+    const long long go = T.goff[sd];
+    const int ncoff = T.chain_off[sd];
+    const double* Rid = Rb + ((MODE == 0) ? s_nR0[d] : c0d);
+    const int nrg = (md + TR - 1) / TR;
+    for (int j = 0; j < k; j++) {
+      const int mj = (j < kc) ? s_cm[j] : s_fm[f];
+      const int prow = (j < kc) ? s_crow[j] : Pc;
+      const int rsj = tile_rs(mj);
+      const long long bo = go + T.chain_boff[ncoff + j];
+      for (int e = tid; e < mj * nrg; e += nth) {
+        const int pp = e % mj, r0 = (e / mj) * TR;
+        const double* hp = panel + (size_t)(prow + pp) * LD + c0d;
+        if (MODE == 0) {
+          double g[TR];
+#pragma unroll
+          for (int tr = 0; tr < TR; tr++) g[tr] = 0.0;
+          const int rmax = min(r0 + TR, md);
+          for (int r2 = 0; r2 < rmax; r2++) {
+            const double b = hp[r2];
+#pragma unroll
+            for (int tr = 0; tr < TR; tr++) g[tr] = fma(Rid[min(r0 + tr, md - 1) * rsd + r2], b, g[tr]);
+          }
+#pragma unroll
+          for (int tr = 0; tr < TR; tr++)
+            if (r0 + tr < md) {
+              S.G[bo + (size_t)(r0 + tr) * rsj + pp] = g[tr];  // G = Ri H (bottom-left block of Kxx_invchol, tree_utils.cpp:205)
+              if (keep_H) outH[bo + (size_t)(r0 + tr) * rsj + pp] = hp[r0 + tr];
+            }
+        } else {
+#pragma unroll
+          for (int tr = 0; tr < TR; tr++)
+            if (r0 + tr < md) {
+              const double h = hp[r0 + tr];
+              if (MODE == 1) {
+                S.G[bo + (size_t)(r0 + tr) * rsj + pp] = Rid[r0 + tr] * h;
+                if (keep_H) outH[bo + (size_t)(r0 + tr) * rsj + pp] = h;
+              } else {
+                outH[bo + (size_t)(r0 + tr) * rsj + pp] = h;
+              }
+            }
+        }
+      }
+    }
+    const long long ro = T.rioff[sd];
+    for (int e = tid; e < ((MODE == 0) ? md * rsd : md); e += nth) outRi[ro + e] = Rid[e];
+    if (MODE != 2 && warp == (d % nwarps)) {
+      // wcore = e' prec e = |Ri e|^2 (:913 / :950) ; logdet = sum log diag(Ri) (:966)
+      double wc = 0, ld = 0;
+      for (int r = lane; r < md; r += 32) {
+        double t;
+        if (MODE == 0) {
+          t = 0;
+          for (int r2 = 0; r2 <= r; r2++) t = fma(Rid[r * rsd + r2], ecol[c0d + r2], t);
+          ld += log(Rid[r * rsd + r]);
+        } else {
+          t = Rid[r] * ecol[c0d + r];
+          ld += log(Rid[r]);
+        }
+        wc = fma(t, t, wc);
+      }
+      wc = warp_sum(wc);
+      ld = warp_sum(ld);
+      if (lane == 0) {
+        S.logdet[sd] = ld;
+        S.llcomp[sd] = (double)md * kHl2pi - 0.5 * wc;  // :967-968
+      }
+    }
+  }
+}
+
+template <int MODE>
+static cudaError_t launch_build_t(const DevTree& T, const DevSlot& S, double* outH, double* outRi, const int* grp_slot0,
+                                  const int* grp_nn, const int* grp_share, int ngrp, const double* w, const CovTab& tab,
+                                  int* fail, int keep_H, size_t smem, cudaStream_t st) {
+  auto kern = build_level_kernel<MODE>;
+  static size_t configured[3] = {0, 0, 0};
+  if (smem > configured[MODE]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured[MODE] = smem;
+  }
+  kern<<<ngrp, kBuildThreads, smem, st>>>(T, S, outH, outRi, grp_slot0, grp_nn, grp_share, w, tab, fail, keep_H);
+  return cudaGetLastError();
+}
+cudaError_t launch_build(int mode, const DevTree& T, const DevSlot& S, double* outH, double* outRi, const int* grp_slot0,
+                         const int* grp_nn, const int* grp_share, int ngrp, const double* w, const CovTab& tab, int* fail,
+                         int keep_H, size_t smem, cudaStream_t st) {
+  if (ngrp <= 0) return cudaSuccess;
+  if (mode == 0) return launch_build_t<0>(T, S, outH, outRi, grp_slot0, grp_nn, grp_share, ngrp, w, tab, fail, keep_H, smem, st);
+  if (mode == 1) return launch_build_t<1>(T, S, outH, outRi, grp_slot0, grp_nn, grp_share, ngrp, w, tab, fail, keep_H, smem, st);
+  return launch_build_t<2>(T, S, outH, outRi, grp_slot0, grp_nn, grp_share, ngrp, w, tab, fail, keep_H, smem, st);
+}
+
+}  // namespace st

@@ -1,0 +1,79 @@
+// st_device.cuh — device helpers shared by the kernels (covariance evaluation, warp-level dense routines)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "st_kernels.cuh"
+
+namespace st {
+
+struct CovTabS {  // shared-memory copy of CovTab
+  int q;
+  double c1[kMaxQ * kMaxQ], r1[kMaxQ * kMaxQ], c2[kMaxQ * kMaxQ], r2[kMaxQ * kMaxQ];
+};
+__device__ __forceinline__ void load_covtab(CovTabS& s, const CovTab& t) {
+  if (threadIdx.x == 0) s.q = t.q;
+  for (int i = threadIdx.x; i < t.q * t.q; i += blockDim.x) {
+    s.c1[i] = t.c1[i]; s.r1[i] = t.r1[i]; s.c2[i] = t.c2[i]; s.r2[i] = t.r2[i];
+  }
+}
+// mvCovAG20107_inplace / cexpcov (covariance_functions.cpp:95-111, :213-286): see make_covtab() for (c1, r1, c2, r2)
+__device__ __forceinline__ double cov_eval(const CovTabS& t, double x1, double y1, int q1, double x2, double y2, int q2) {
+  const double dx = x1 - x2, dy = y1 - y2;
+  const double h = sqrt(dx * dx + dy * dy);
+  const int ix = q1 * t.q + q2;
+  double v = t.c1[ix] * exp(-t.r1[ix] * h);
+  const double c2 = t.c2[ix];
+  if (c2 != 0.0) v += c2 * exp(-t.r2[ix] * h);
+  return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// in-place lower Cholesky of the symmetric m x m matrix A (row-major, leading dimension ld) by one warp;
+// reads the lower triangle only; false on a non-positive or non-finite pivot (dpotrf's info > 0)
+__device__ inline bool warp_chol(double* A, int m, int ld, int lane) {
+  for (int c = 0; c < m; c++) {
+    __syncwarp();
+    double d = A[c * ld + c];
+    if (!(d > 0.0) || !isfinite(d)) return false;
+    d = sqrt(d);
+    const double inv = 1.0 / d;
+    __syncwarp();
+    for (int r = c + lane; r < m; r += 32) A[r * ld + c] = (r == c) ? d : A[r * ld + c] * inv;
+    __syncwarp();
+    for (int r = c + 1 + lane; r < m; r += 32) {
+      const double lrc = A[r * ld + c];
+      for (int c2 = c + 1; c2 <= r; c2++) A[r * ld + c2] -= lrc * A[c2 * ld + c];
+    }
+  }
+  __syncwarp();
+  return true;
+}
+// L <- L^-1 in place for a lower-triangular L (dtrtri); v: m doubles of scratch owned by the warp.
+// The strict upper triangle is zero-filled afterwards so that the result can be used as a dense tile.
+__device__ inline void warp_inv_lower_inplace(double* L, int m, int ld, double* v, int lane) {
+  for (int j = m - 1; j >= 0; j--) {
+    __syncwarp();
+    const double ajj = 1.0 / L[j * ld + j];
+    for (int r = j + 1 + lane; r < m; r += 32) v[r] = L[r * ld + j];
+    __syncwarp();
+    for (int r = j + 1 + lane; r < m; r += 32) {
+      double s = 0;
+      for (int kk = j + 1; kk <= r; kk++) s = fma(L[r * ld + kk], v[kk], s);
+      L[r * ld + j] = -s * ajj;
+    }
+    if (lane == 0) L[j * ld + j] = ajj;
+  }
+  __syncwarp();
+  for (int e = lane; e < m * m; e += 32) {
+    const int r = e / m, c = e - r * m;
+    if (c > r) L[r * ld + c] = 0.0;
+  }
+  __syncwarp();
+}
+
+}  // namespace st

@@ -253,7 +253,7 @@ int Model::build_layout(std::string& e) {
       h_chain_boff.push_back((int)boff);
       h_chain_uoff.push_back((int)uo);
       poff += h_m[a];
-      boff += pad2((long long)h_m[s] * h_m[a]);
+      boff += (long long)h_m[s] * tile_rs(h_m[a]);
       uo += pad2((long long)h_m[a] * h_m[a]);
       if (boff > 0x7fffffffLL) { e = "a block's G storage exceeds 2^31 doubles"; return 4; }
     }
@@ -262,7 +262,7 @@ int Model::build_layout(std::string& e) {
     if (!pred) {
       isref[s] = block_is_reference[u] ? 1 : 0;
       h_goff[s] = g_total; g_total += boff;
-      h_rioff[s] = ri_total; ri_total += pad2(isref[s] ? (long long)h_m[s] * h_m[s] : h_m[s]);
+      h_rioff[s] = ri_total; ri_total += isref[s] ? (long long)h_m[s] * tile_rs(h_m[s]) : pad2(h_m[s]);
       h_voff[s] = v_total; v_total += pad2(poff);
       h_uoff[s] = u_total; u_total += uo;
     } else {
@@ -286,32 +286,73 @@ int Model::build_layout(std::string& e) {
   isref_host_ = isref;
   sd_total_ = sd_total;
 
-  // BUILD work groups: runs of siblings whose panel fits the shared-memory budget
-  h_grp_slot0.clear(); h_grp_nn.clear();
+  // BUILD work groups: runs of blocks that share their ancestor chain (siblings) or all of it but the deepest ancestor
+  // (cousins, when sibling sets are too narrow to fill a CTA), sized to the shared-memory budget
+  h_grp_slot0.clear(); h_grp_nn.clear(); h_grp_share.clear();
+  auto shape_of = [&](int s, int nn, int share, int mode) {
+    BuildShape sh{};
+    const int k = h_k[s], coff = h_chain_off[s], kc = share ? k - 1 : k;
+    int maxm = 1;
+    for (int j = 0; j < kc; j++) maxm = std::max(maxm, h_m[h_chain[coff + j]]);
+    sh.mode = mode; sh.share = share; sh.kc = kc;
+    sh.Pc = (kc < k) ? h_chain_poff[coff + kc] : h_P[s];
+    int F = 0, c = 0, sumR = 0, maxmd = 1, mmaxs = 0, prevpar = -2;
+    for (int d = 0; d < nn; d++) {
+      const int par = h_lastpar[s + d], md = h_m[s + d];
+      if (d == 0 || (share && par != prevpar)) {
+        c = (c + 3) & ~3;
+        if (share) mmaxs = std::max(mmaxs, h_m[par]);
+        F++;
+        prevpar = par;
+      }
+      c += md;
+      sumR += md * tile_rs(md);
+      maxmd = std::max(maxmd, md);
+    }
+    maxm = std::max(maxm, mmaxs);
+    sh.mmaxs = mmaxs; sh.F = F; sh.NCp = (c + 3) & ~3; sh.sumR = sumR; sh.maxtile = maxm * tile_rs(maxm); sh.maxmd = maxmd;
+    return sh;
+  };
+  auto fits = [&](const BuildShape& sh) {
+    if (sh.F > kMaxFam) return false;
+    const int omax = std::max(sh.mmaxs, 1);
+    (void)omax;
+    return build_plan(sh).total <= smem_budget;
+  };
   auto make_groups = [&](LevelInfo& L, int mode) -> int {
     L.grp0 = (int)h_grp_slot0.size();
     L.smem_build = 0; L.smem_gibbs = 0;
-    int s = L.slot0;
     const int end = L.slot0 + L.nslots;
+    // cousins when the sibling sets of this level are narrow
+    long long cols = 0, fams = 0;
+    for (int t = L.slot0; t < end; t++) { cols += h_m[t]; if (t == L.slot0 || h_lastpar[t] != h_lastpar[t - 1]) fams++; }
+    const int share = (L.nslots > 0 && h_k[L.slot0] >= 1 && fams > 0 && cols / fams < cousin_threshold) ? 1 : 0;
+    auto gpar = [&](int t) { const int p1 = h_lastpar[t]; return p1 < 0 ? -2 : h_lastpar[p1]; };
+    int s = L.slot0;
     while (s < end) {
-      int nn = 0, NC = 0, sumsq = 0, maxmj = 1;
+      int nn = 0;
+      BuildShape best{};
+      int maxmj = 1;
       for (int j = 0; j < h_k[s]; j++) maxmj = std::max(maxmj, h_m[h_chain[h_chain_off[s] + j]]);
-      size_t need = 0;
-      while (s + nn < end && nn < 64 && h_lastpar[s + nn] == h_lastpar[s]) {
-        const int md = h_m[s + nn];
-        const int NC2 = NC + md, sq2 = sumsq + (mode == 0 ? md * md : md);
-        const size_t n2 = build_smem_bytes(mode, h_P[s], NC2, sq2, maxmj);
-        if (n2 > smem_budget || (nn > 0 && NC2 > max_group_cols)) break;
-        if (h_lastpar[s] < 0 && nn > 0) break;  // roots never share a chain
-        NC = NC2; sumsq = sq2; need = n2; nn++;
+      while (s + nn < end && nn < kMaxGroupNodes) {
+        const int t = s + nn;
+        if (nn > 0) {
+          if (h_lastpar[s] < 0) break;  // roots never share a chain
+          if (share ? (gpar(t) != gpar(s)) : (h_lastpar[t] != h_lastpar[s])) break;
+        }
+        BuildShape sh = shape_of(s, nn + 1, share, mode);
+        const int n_rg = (std::max(maxmj, sh.mmaxs) + kBuildTR - 1) / kBuildTR;
+        if (!fits(sh) || n_rg * (sh.NCp / kBuildTC) > kBuildThreads || (nn > 0 && sh.NCp > max_group_cols)) break;
+        best = sh;
+        nn++;
       }
       if (nn == 0) {
-        e = "a block needs more shared memory than the BUILD budget (m=" + std::to_string(h_m[s]) + ", P=" + std::to_string(h_P[s]) + ")";
+        e = "a block is too large for one BUILD work group (m=" + std::to_string(h_m[s]) + ", P=" + std::to_string(h_P[s]) + ")";
         return 4;
       }
-      h_grp_slot0.push_back(s); h_grp_nn.push_back(nn);
-      L.smem_build = std::max(L.smem_build, need);
-      L.maxNC = std::max(L.maxNC, NC);
+      h_grp_slot0.push_back(s); h_grp_nn.push_back(nn); h_grp_share.push_back(share);
+      L.smem_build = std::max(L.smem_build, build_plan(best).total);
+      L.maxNC = std::max(L.maxNC, best.NCp);
       s += nn;
     }
     L.ngrp = (int)h_grp_slot0.size() - L.grp0;
@@ -394,6 +435,8 @@ int Model::upload(std::string& e) {
   ST_CUDA(dev_upload(isref_host_, d_isref, owned), "upload isref");
   ST_CUDA(dev_upload(h_k, d_k, owned), "upload k");
   ST_CUDA(dev_upload(h_P, d_P, owned), "upload P");
+  int* d_lastpar;
+  ST_CUDA(dev_upload(h_lastpar, d_lastpar, owned), "upload lastpar");
   ST_CUDA(dev_upload(h_chain_off, d_choff, owned), "upload chain_off");
   ST_CUDA(dev_upload(h_goff, d_goff, owned), "upload goff");
   ST_CUDA(dev_upload(h_rioff, d_rioff, owned), "upload rioff");
@@ -408,8 +451,9 @@ int Model::upload(std::string& e) {
   ST_CUDA(dev_upload(h_chain_uoff, d_cuoff, owned), "upload chain_uoff");
   ST_CUDA(dev_upload(h_grp_slot0, d_grp_slot0, owned), "upload groups");
   ST_CUDA(dev_upload(h_grp_nn, d_grp_nn, owned), "upload groups");
+  ST_CUDA(dev_upload(h_grp_share, d_grp_share, owned), "upload groups");
   dt.cx = d_cx; dt.cy = d_cy; dt.mvq = d_mvq; dt.y = d_y; dt.X = d_X;
-  dt.m = d_m; dt.row0 = d_row0; dt.isref = d_isref; dt.k = d_k; dt.P = d_P; dt.chain_off = d_choff;
+  dt.m = d_m; dt.row0 = d_row0; dt.isref = d_isref; dt.k = d_k; dt.P = d_P; dt.lastpar = d_lastpar; dt.chain_off = d_choff;
   dt.goff = d_goff; dt.rioff = d_rioff; dt.voff = d_voff; dt.uoff = d_uoff; dt.soff = d_soff;
   dt.child_ptr = d_cptr; dt.child_idx = d_cidx;
   dt.chain = d_chain; dt.chain_poff = d_cpoff; dt.chain_boff = d_cboff; dt.chain_uoff = d_cuoff;
@@ -480,7 +524,7 @@ int Model::theta_update(int slot, const double* th) {
 int Model::launch_build_levels(int pslot, const CovTab& tab) {
   for (auto& L : levels) {
     ST_CUDA(launch_build(L.is_ref ? 0 : 1, dt, ds[pslot], ds[pslot].H, ds[pslot].Ri, d_grp_slot0 + L.grp0, d_grp_nn + L.grp0,
-                         L.ngrp, d_w, tab, d_fail, keep_H ? 1 : 0, L.smem_build, stream),
+                         d_grp_share + L.grp0, L.ngrp, d_w, tab, d_fail, keep_H ? 1 : 0, L.smem_build, stream),
             "build_level_kernel");
     n_launches++;
   }
@@ -584,7 +628,7 @@ int Model::predict(bool theta_changed) {
     std::string e;
     if (!make_covtab(theta[cur].data(), (int)theta[cur].size(), q, tab, e)) { err = e; return 1; }
     ST_CUDA(launch_build(2, dt, ds[cur], d_Hpred, d_sdpred, d_grp_slot0 + pred_level.grp0, d_grp_nn + pred_level.grp0,
-                         pred_level.ngrp, d_w, tab, d_fail, 1, pred_level.smem_build, stream),
+                         d_grp_share + pred_level.grp0, pred_level.ngrp, d_w, tab, d_fail, 1, pred_level.smem_build, stream),
             "build_level_kernel(predict)");
     n_launches++;
     pred_H_valid = true;
@@ -709,13 +753,13 @@ int Model::get_node_state(int slot, int u, const std::string& which, double* out
     else if (which == "G") src = ds[ps].G;
     else { if (!keep_H) { err = "H was not kept (keep_H = 0)"; return 1; } src = ds[ps].H; }
     long long tot = 0;
-    for (int j = 0; j < kk; j++) tot += pad2((long long)m * h_m[h_chain[coff + j]]);
+    for (int j = 0; j < kk; j++) tot += (long long)m * tile_rs(h_m[h_chain[coff + j]]);
     dvec t(std::max<long long>(tot, 1)), o((size_t)m * P);
     if (tot) ST_CUDA(cudaMemcpy(t.data(), src + h_goff[s], tot * sizeof(double), cudaMemcpyDeviceToHost), "D2H H");
     for (int j = 0; j < kk; j++) {
       const int mj = h_m[h_chain[coff + j]], po = h_chain_poff[coff + j], bo = h_chain_boff[coff + j];
       for (int r = 0; r < m; r++)
-        for (int pp = 0; pp < mj; pp++) o[r + (size_t)(po + pp) * m] = t[bo + (size_t)r * mj + pp];
+        for (int pp = 0; pp < mj; pp++) o[r + (size_t)(po + pp) * m] = t[bo + (size_t)r * tile_rs(mj) + pp];
     }
     return emit(o);
   }
@@ -726,10 +770,11 @@ int Model::get_node_state(int slot, int u, const std::string& which, double* out
       return emit(o);
     }
     if (isref_host_[s]) {
-      dvec t((size_t)m * m), o((size_t)m * m);
+      const int rsm = tile_rs(m);
+      dvec t((size_t)m * rsm), o((size_t)m * m);
       ST_CUDA(cudaMemcpy(t.data(), ds[ps].Ri + h_rioff[s], t.size() * sizeof(double), cudaMemcpyDeviceToHost), "D2H Ri");
       for (int r = 0; r < m; r++)
-        for (int c = 0; c < m; c++) o[r + (size_t)c * m] = t[(size_t)r * m + c];
+        for (int c = 0; c < m; c++) o[r + (size_t)c * m] = t[(size_t)r * rsm + c];
       return emit(o);
     }
     dvec o(m);

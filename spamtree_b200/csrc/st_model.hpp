@@ -40,6 +40,7 @@ struct DevTree {
   const int* isref;      // 1: reference level (full m x m conditional), 0: rows conditionally independent
   const int* k;          // chain length (#reference ancestors)
   const int* P;          // parent-set size
+  const int* lastpar;    // slot of the last (deepest) parent, -1 for roots
   const int* chain_off;  // into the per-chain-entry arrays
   const long long* goff; // G / H storage offset (doubles)
   const long long* rioff;// Ri storage offset (doubles)
@@ -85,8 +86,9 @@ class Model {
   ivec res_is_ref;
   bool keep_H = true;
   int device = 0;
-  size_t smem_budget = 200 * 1024;
-  int max_group_cols = 112;  // upper bound on the columns one BUILD work group handles
+  size_t smem_budget = 221 * 1024;  // dynamic; the kernel also holds ~4 KB of static shared memory (227 KB per CTA)
+  int max_group_cols = 104;  // upper bound on the columns one BUILD work group handles
+  int cousin_threshold = 48; // sibling sets narrower than this (columns) are merged into cousin groups
   bool probes = true;        // record Sigi_tot / Smu_tot of the last Gibbs sweep (st_get_node_state)
   // ---- bookkeeping, same meaning as the reference's members
   int64_t n_obs = 0;
@@ -106,7 +108,7 @@ class Model {
   ivec iperm;  // boundary row -> node-major row
   std::vector<LevelInfo> levels;  // observed levels, root first
   LevelInfo pred_level;           // prediction blocks
-  std::vector<int> h_grp_slot0, h_grp_nn;
+  std::vector<int> h_grp_slot0, h_grp_nn, h_grp_share;
   long long g_total = 0, ri_total = 0, v_total = 0, u_total = 0, s_total = 0, gpred_total = 0;
   // ---- parameters (host copies of the small ones)
   dvec theta[2];
@@ -128,7 +130,7 @@ class Model {
   double *d_partial = nullptr;
   double *d_bcoeff = nullptr, *d_tausq_inv = nullptr;
   int* d_fail = nullptr;
-  int *d_grp_slot0 = nullptr, *d_grp_nn = nullptr;
+  int *d_grp_slot0 = nullptr, *d_grp_nn = nullptr, *d_grp_share = nullptr;
   double* h_stage = nullptr;  // pinned n_all staging buffer
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8]{};

@@ -24,7 +24,8 @@ def main():
     csr = (tree["indexing_ptr"], tree["indexing_idx"], tree["parents_ptr"], tree["parents_idx"], tree["children_ptr"], tree["children_idx"])
     theta = synth.theta_for(q)
     gm = sb.SpamTreeMV(d["y"], d["X"], d["coords"], d["mv_id"], tree["res_is_ref"], None, None, False, tree["block_names"],
-                       tree["block_groups"], None, np.zeros(3), theta, 0.1, csr=csr, keep_H=False)
+                       tree["block_groups"], None, np.zeros(3), theta, 0.1, csr=csr, keep_H=False,
+                       smem_panel_bytes=int(os.environ.get("ST_SMEM_BUDGET", "0")))
     t3 = time.time()
     print(f"{name}: n={d['y'].size} q={q} blocks={tree['n_blocks']} data {t1 - t0:.1f}s tree {t2 - t1:.1f}s create {t3 - t2:.1f}s", flush=True)
     print("initial builds", gm.get_loglik_comps_w(0), gm.get_loglik_comps_w(1), flush=True)
