@@ -27,16 +27,60 @@ constexpr int F_RI = 1, F_TRANS = 2, F_PERFAM = 4, F_FIRST = 8, F_LAST = 16;
 constexpr int kDescInts = 6;  // flags, chain index of the operand's owner (-1: family parent), tile index, brow, orow0, ochain
 }  // namespace
 
+// acc[tr][tc] (+/-)= A(tr, kk) * B(kk, tc) for kk in [0, n).  Both operands are in shared memory.
+// mac_rows: A(tr, kk) = pa[tr][kk] (tile rows, stride 1 along kk); mac_cols: A(tr, kk) = pt[kk * rs + tr] (transposed use)
+template <bool NEG>
+__device__ __forceinline__ void mac_rows(double (&acc)[TR][TC], const double* (&pa)[TR], const double* __restrict__ Bp,
+                                         int LD, int n) {
+#pragma unroll 4
+  for (int kk = 0; kk < n; kk++) {
+    const double2 b01 = *reinterpret_cast<const double2*>(Bp);
+    const double2 b23 = *reinterpret_cast<const double2*>(Bp + 2);
+    Bp += LD;
+#pragma unroll
+    for (int tr = 0; tr < TR; tr++) {
+      const double a = NEG ? -pa[tr][kk] : pa[tr][kk];
+      acc[tr][0] = fma(a, b01.x, acc[tr][0]);
+      acc[tr][1] = fma(a, b01.y, acc[tr][1]);
+      acc[tr][2] = fma(a, b23.x, acc[tr][2]);
+      acc[tr][3] = fma(a, b23.y, acc[tr][3]);
+    }
+  }
+}
+template <bool NEG>
+__device__ __forceinline__ void mac_cols(double (&acc)[TR][TC], const double* __restrict__ pt, int rs,
+                                         const double* __restrict__ Bp, int LD, int n) {
+#pragma unroll 4
+  for (int kk = 0; kk < n; kk++) {
+    const double2 b01 = *reinterpret_cast<const double2*>(Bp);
+    const double2 b23 = *reinterpret_cast<const double2*>(Bp + 2);
+    Bp += LD;
+#pragma unroll
+    for (int tr = 0; tr < TR; tr++) {
+      const double a = NEG ? -pt[tr] : pt[tr];  // rows past the block's end read padding; their accumulators are never stored
+      acc[tr][0] = fma(a, b01.x, acc[tr][0]);
+      acc[tr][1] = fma(a, b01.y, acc[tr][1]);
+      acc[tr][2] = fma(a, b23.x, acc[tr][2]);
+      acc[tr][3] = fma(a, b23.y, acc[tr][3]);
+    }
+    pt += rs;
+  }
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(kBuildThreads, 1)
+__global__ void __launch_bounds__(kBuildThreads)
 build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __restrict__ outRi,
                    const int* __restrict__ grp_slot0, const int* __restrict__ grp_nn, const int* __restrict__ grp_share,
-                   const double* __restrict__ w, CovTab tab, int* __restrict__ fail, int keep_H) {
+                   const double* __restrict__ w, CovTab tab, int* __restrict__ fail, int keep_H,
+                   unsigned long long* __restrict__ prof) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ CovTabS ct;
   __shared__ int s_chain[kMaxChain], s_cm[kMaxChain], s_crow[kMaxChain + 1], s_crow0g[kMaxChain];
   __shared__ int s_nm[kMaxGroupNodes], s_nc0[kMaxGroupNodes], s_nR0[kMaxGroupNodes], s_nfam[kMaxGroupNodes];
   __shared__ int s_fpar[kMaxFam], s_fm[kMaxFam], s_fc0[kMaxFam + 1], s_frow0g[kMaxFam];
+  __shared__ int s_npar[kMaxGroupNodes], s_nrow0[kMaxGroupNodes], s_rspref[kMaxChain + 1];
+  __shared__ long long s_cgoff[kMaxChain], s_crioff[kMaxChain], s_fgoff[kMaxFam], s_frioff[kMaxFam];
+  __shared__ long long s_ngoff[kMaxGroupNodes], s_nrioff[kMaxGroupNodes];
   __shared__ BuildShape sh;
   __shared__ BuildPlan pl;
   __shared__ int s_nfwd;
@@ -45,38 +89,42 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
   const int s0 = grp_slot0[blockIdx.x], nn = grp_nn[blockIdx.x];
   const int k = T.k[s0];
 
+  long long tprev = clock64();
+  auto mark = [&](int ph) {
+    if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + ph, (unsigned long long)(t - tprev)); tprev = t; }
+  };
   load_covtab(ct, tab);
+  // ---- setup: metadata of the chain and of the group's blocks, loaded in parallel (no dependent global loads later)
+  {
+    const int coff = T.chain_off[s0];
+    for (int j = tid; j < k; j += nth) {
+      const int a = T.chain[coff + j];
+      s_chain[j] = a; s_cm[j] = T.m[a]; s_crow[j] = T.chain_poff[coff + j]; s_crow0g[j] = T.row0[a];
+      s_cgoff[j] = T.goff[a]; s_crioff[j] = T.rioff[a];
+    }
+    for (int d = tid; d < nn; d += nth) {
+      s_nm[d] = T.m[s0 + d]; s_npar[d] = T.lastpar[s0 + d]; s_nrow0[d] = T.row0[s0 + d];
+      s_ngoff[d] = T.goff[s0 + d]; s_nrioff[d] = T.rioff[s0 + d];
+    }
+  }
+  __syncthreads();
   if (tid == 0) {
     const int share = grp_share[blockIdx.x];
-    const int coff = T.chain_off[s0];
     const int kc = share ? k - 1 : k;
-    int maxm = 1;
-    for (int j = 0; j < kc; j++) {
-      const int a = T.chain[coff + j];
-      s_chain[j] = a;
-      s_cm[j] = T.m[a];
-      s_crow[j] = T.chain_poff[coff + j];
-      s_crow0g[j] = T.row0[a];
-      maxm = max(maxm, s_cm[j]);
-    }
-    const int Pc = (kc < k) ? T.chain_poff[coff + kc] : T.P[s0];
+    const int Pc = (kc < k) ? s_crow[kc] : T.P[s0];
     s_crow[kc] = Pc;
-    int F = 0, c = 0, sumR = 0, maxmd = 1, mmaxs = 0, prevpar = -2;
+    int F = 0, c = 0, sumR = 0, maxmd = 1, prevpar = -2;
     for (int d = 0; d < nn; d++) {
-      const int par = T.lastpar[s0 + d], md = T.m[s0 + d];
+      const int par = s_npar[d], md = s_nm[d];
       if (d == 0 || (share && par != prevpar)) {
         c = (c + 3) & ~3;
         s_fpar[F] = par;
-        s_fm[F] = share ? T.m[par] : 0;
-        s_frow0g[F] = share ? T.row0[par] : 0;
         s_fc0[F] = c;
-        mmaxs = max(mmaxs, s_fm[F]);
         F++;
         prevpar = par;
       }
       s_nfam[d] = F - 1;
       s_nc0[d] = c;
-      s_nm[d] = md;
       s_nR0[d] = sumR;
       c += md;
       sumR += md * tile_rs(md);
@@ -84,11 +132,29 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
     }
     const int NCp = (c + 3) & ~3;
     s_fc0[F] = NCp;
+    sh.mode = MODE; sh.share = share; sh.kc = kc; sh.Pc = Pc; sh.F = F; sh.NCp = NCp; sh.sumR = sumR; sh.maxmd = maxmd;
+    int acc_rs = 0;
+    for (int j = 0; j <= kc && j < kMaxChain; j++) { s_rspref[j] = acc_rs; if (j < kc) acc_rs += tile_rs(s_cm[j]); }
+  }
+  __syncthreads();
+  if (tid < sh.F) {
+    const int par = s_fpar[tid];
+    const bool sp = sh.share != 0;
+    s_fm[tid] = sp ? T.m[par] : 0;
+    s_frow0g[tid] = sp ? T.row0[par] : 0;
+    s_fgoff[tid] = sp ? T.goff[par] : 0;
+    s_frioff[tid] = sp ? T.rioff[par] : 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int maxm = 1, mmaxs = 0;
+    for (int j = 0; j < sh.kc; j++) maxm = max(maxm, s_cm[j]);
+    for (int f = 0; f < sh.F; f++) mmaxs = max(mmaxs, s_fm[f]);
     maxm = max(maxm, mmaxs);
-    sh.mode = MODE; sh.share = share; sh.kc = kc; sh.Pc = Pc; sh.mmaxs = mmaxs; sh.F = F; sh.NCp = NCp; sh.sumR = sumR;
-    sh.maxtile = maxm * tile_rs(maxm); sh.maxmd = maxmd;
+    sh.mmaxs = mmaxs;
+    sh.maxtile = maxm * tile_rs(maxm);
     pl = build_plan(sh);
-    s_nfwd = (share ? kc + 1 : 0) + kc * (kc + 1) / 2;
+    s_nfwd = (sh.share ? sh.kc + 1 : 0) + sh.kc * (sh.kc + 1) / 2;
   }
   __syncthreads();
   const int share = sh.share, kc = sh.kc, Pc = sh.Pc, mmaxs = sh.mmaxs, F = sh.F, NCp = sh.NCp, maxtile = sh.maxtile;
@@ -157,13 +223,14 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
   }
   __syncthreads();
   for (int d = 0; d < nn; d++) {
-    const int r0 = T.row0[s0 + d], c0 = s_nc0[d];
+    const int r0 = s_nrow0[d], c0 = s_nc0[d];
     for (int t = tid; t < s_nm[d]; t += nth) {
       cxs[c0 + t] = T.cx[r0 + t]; cys[c0 + t] = T.cy[r0 + t]; cq[c0 + t] = T.mvq[r0 + t]; colnode[c0 + t] = d;
     }
   }
   __syncthreads();
 
+  mark(0);
   // ---- cp.async ring over the operand tiles
   auto tile_geom = [&](const int* d, int f, int& slot, int& rows, int& cols) {
     if (d[0] & F_PERFAM) { slot = s_fpar[f]; rows = s_fm[f]; } else { slot = s_chain[d[1]]; rows = s_cm[d[1]]; }
@@ -176,7 +243,9 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
     for (int f = 0; f < nf; f++) {
       int slot, rows, cols;
       tile_geom(d, f, slot, rows, cols);
-      const double* src = (d[0] & F_RI) ? S.Ri + T.rioff[slot] : S.G + T.goff[slot] + T.chain_boff[T.chain_off[slot] + d[2]];
+      const bool pf = d[0] & F_PERFAM;
+      const double* src = (d[0] & F_RI) ? S.Ri + (pf ? s_frioff[f] : s_crioff[d[1]])
+                                        : S.G + (pf ? s_fgoff[f] : s_cgoff[d[1]]) + (long long)rows * s_rspref[d[2]];
       const int n16 = rows * tile_rs(cols) / 2;  // 16-byte chunks (tile sizes are even)
       double* dst = dst0 + (size_t)f * maxtile;
       for (int c = tid; c < n16; c += nth) __pipeline_memcpy_async(dst + 2 * c, src + 2 * c, 16);
@@ -188,23 +257,33 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
   __pipeline_commit();
 
   // ---- phase 2: covariance panel K_{pa,u} and K_uu
-  for (int idx = tid; idx < Pc * LD; idx += nth) {
-    const int i = idx / LD, c = idx - i * LD;
-    panel[idx] = (c < NCp && colnode[c] >= 0) ? cov_eval(ct, pxs[i], pys[i], pq[i], cxs[c], cys[c], cq[c]) : 0.0;
-  }
-  if (share)
-    for (int idx = tid; idx < mmaxs * LD; idx += nth) {
-      const int t = idx / LD, c = idx - t * LD;
-      double v = 0.0;
-      if (c < NCp && colnode[c] >= 0) {
-        const int f = cgfam[c >> 2];
-        if (t < s_fm[f]) {
-          const int pi = Pc + f * mmaxs + t;
-          v = cov_eval(ct, pxs[pi], pys[pi], pq[pi], cxs[c], cys[c], cq[c]);
-        }
-      }
-      panel[(size_t)(Pc + t) * LD + c] = v;
+  for (int c = lane; c < LD; c += 32) {
+    const bool real = (c < NCp) && colnode[c] >= 0;
+    const double xc = cxs[c], yc = cys[c];
+    const int qc = cq[c];
+    int i = warp;
+    for (; i + 3 * nwarps < Pc; i += 4 * nwarps) {  // four independent evaluations in flight per thread
+      const int i1 = i + nwarps, i2 = i + 2 * nwarps, i3 = i + 3 * nwarps;
+      const double v0 = cov_eval(ct, pxs[i], pys[i], pq[i], xc, yc, qc);
+      const double v1 = cov_eval(ct, pxs[i1], pys[i1], pq[i1], xc, yc, qc);
+      const double v2 = cov_eval(ct, pxs[i2], pys[i2], pq[i2], xc, yc, qc);
+      const double v3 = cov_eval(ct, pxs[i3], pys[i3], pq[i3], xc, yc, qc);
+      panel[(size_t)i * LD + c] = real ? v0 : 0.0;
+      panel[(size_t)i1 * LD + c] = real ? v1 : 0.0;
+      panel[(size_t)i2 * LD + c] = real ? v2 : 0.0;
+      panel[(size_t)i3 * LD + c] = real ? v3 : 0.0;
     }
+    for (; i < Pc; i += nwarps)
+      panel[(size_t)i * LD + c] = real ? cov_eval(ct, pxs[i], pys[i], pq[i], xc, yc, qc) : 0.0;
+    if (share) {
+      const int f = real ? cgfam[c >> 2] : 0;
+      const int mf = real ? s_fm[f] : 0;
+      for (int t = warp; t < mmaxs; t += nwarps) {
+        const int pi = Pc + f * mmaxs + t;
+        panel[(size_t)(Pc + t) * LD + c] = (t < mf) ? cov_eval(ct, pxs[pi], pys[pi], pq[pi], xc, yc, qc) : 0.0;
+      }
+    }
+  }
   if (MODE == 0) {
     for (int d = 0; d < nn; d++) {
       const int md = s_nm[d], c0 = s_nc0[d], rsd = tile_rs(md);
@@ -219,8 +298,13 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
   }
   // (the first __syncthreads of the sweep below publishes the panel)
 
-  // ---- phases 3 and 6: one generic sweep over descriptor range [s_begin, s_end)
+  // ---- phases 3 and 6: one generic sweep over descriptor range [s_begin, s_end).
+  // The CTA's threads form two halves: both map to the same register tiles and each half takes one half of every
+  // tile's reduction range (split-K), so that all warps issue FP64 work; the halves are summed through the panel.
   const int n_cg = NCp / TC;
+  const int half = nth >> 1;
+  const int htid = (tid < half) ? tid : tid - half;
+  const int hgrp = (tid < half) ? 0 : 1;
   double acc[TR][TC];
   int it_r0 = 0, it_c0 = 0, it_fam = 0, it_orows = 0;
   bool it_active = false;
@@ -228,16 +312,20 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
     for (int s = s_begin; s < s_end; s++) {
       const int* d = desc + s * kDescInts;
       const int flags = d[0];
+      long long tq0 = 0;
+      if (prof && tid == 0) tq0 = clock64();
       __pipeline_wait_prior(kBuildStages - 2);
       __syncthreads();
+      if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + 8, (unsigned long long)(t - tq0)); tq0 = t; }
       if (s + 2 < nsets) issue(s + 2);
       __pipeline_commit();
+      if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + 9, (unsigned long long)(t - tq0)); tq0 = t; }
       if (flags & F_FIRST) {  // new output block: map one register tile to this thread
         const int omax = (d[5] < 0) ? mmaxs : s_cm[d[5]];
         const int n_rg = (omax + TR - 1) / TR;
-        it_active = tid < n_rg * n_cg;
+        it_active = htid < n_rg * n_cg;
         if (it_active) {
-          const int rg = tid % n_rg, cg = tid / n_rg;
+          const int rg = htid % n_rg, cg = htid / n_rg;
           it_r0 = rg * TR;
           it_c0 = cg * TC;
           it_fam = cgfam[cg];
@@ -255,38 +343,28 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
         tile_geom(d, fi, slot, rows, cols);
         const int rs = tile_rs(cols);
         const double* tile = ring + ((size_t)(s % kBuildStages) * Fst + fi) * maxtile;
-        const double* Bp = panel + (size_t)d[3] * LD + it_c0;
         const bool trans = flags & F_TRANS;
         const int K = trans ? rows : cols;
-        const int astride = trans ? rs : 1;
-        int aoff[TR];
+        const int kmid = (K + 1) >> 1;
+        const int kk0 = hgrp ? kmid : 0, kk1 = hgrp ? K : kmid;
+        const double* Bp = panel + (size_t)(d[3] + kk0) * LD + it_c0;
+        // acc = sum G*B - Ri*B ; the block written out is -acc
+        if (!trans) {
+          const double* pa[TR];
 #pragma unroll
-        for (int tr = 0; tr < TR; tr++) aoff[tr] = min(it_r0 + tr, it_orows - 1) * (trans ? 1 : rs);
-        const double sgn = (flags & F_RI) ? -1.0 : 1.0;  // acc = sum G*B - Ri*B ; the block written out is -acc
-#pragma unroll 2
-        for (int kk = 0; kk < K; kk++) {
-          const double2 b01 = *reinterpret_cast<const double2*>(Bp + (size_t)kk * LD);
-          const double2 b23 = *reinterpret_cast<const double2*>(Bp + (size_t)kk * LD + 2);
-          const double* ap = tile + kk * astride;
-          double av[TR];
-#pragma unroll
-          for (int tr = 0; tr < TR; tr++) av[tr] = ap[aoff[tr]];
-          if (flags & F_RI) {
-#pragma unroll
-            for (int tr = 0; tr < TR; tr++) av[tr] *= sgn;
-          }
-#pragma unroll
-          for (int tr = 0; tr < TR; tr++) {
-            acc[tr][0] = fma(av[tr], b01.x, acc[tr][0]);
-            acc[tr][1] = fma(av[tr], b01.y, acc[tr][1]);
-            acc[tr][2] = fma(av[tr], b23.x, acc[tr][2]);
-            acc[tr][3] = fma(av[tr], b23.y, acc[tr][3]);
-          }
+          for (int tr = 0; tr < TR; tr++) pa[tr] = tile + min(it_r0 + tr, it_orows - 1) * rs + kk0;
+          if (flags & F_RI) mac_rows<true>(acc, pa, Bp, LD, kk1 - kk0);
+          else mac_rows<false>(acc, pa, Bp, LD, kk1 - kk0);
+        } else {
+          const double* pt = tile + kk0 * rs + it_r0;
+          if (flags & F_RI) mac_cols<true>(acc, pt, rs, Bp, LD, kk1 - kk0);
+          else mac_cols<false>(acc, pt, rs, Bp, LD, kk1 - kk0);
         }
       }
+      if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + 10, (unsigned long long)(t - tq0)); tq0 = t; }
       if (flags & F_LAST) {  // every thread has finished reading the rows that are about to be overwritten
         __syncthreads();
-        if (it_active) {
+        if (it_active && hgrp == 1) {
 #pragma unroll
           for (int tr = 0; tr < TR; tr++)
             if (it_r0 + tr < it_orows) {
@@ -295,13 +373,27 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
               *reinterpret_cast<double2*>(o + 2) = make_double2(-acc[tr][2], -acc[tr][3]);
             }
         }
+        __syncthreads();
+        if (it_active && hgrp == 0) {
+#pragma unroll
+          for (int tr = 0; tr < TR; tr++)
+            if (it_r0 + tr < it_orows) {
+              double* o = panel + (size_t)(d[4] + it_r0 + tr) * LD + it_c0;
+              const double2 p01 = *reinterpret_cast<const double2*>(o), p23 = *reinterpret_cast<const double2*>(o + 2);
+              *reinterpret_cast<double2*>(o) = make_double2(p01.x - acc[tr][0], p01.y - acc[tr][1]);
+              *reinterpret_cast<double2*>(o + 2) = make_double2(p23.x - acc[tr][2], p23.y - acc[tr][3]);
+            }
+        }
+        if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + 11, (unsigned long long)(t - tq0)); tq0 = t; }
       }
     }
     __syncthreads();
   };
 
   __syncthreads();
+  mark(1);
   sweep(0, nfwd);  // Z = L^-1 K
+  mark(2);
 
   // ---- phase 4/5: Schur complement and its inverse Cholesky factor
   if (MODE == 0) {
@@ -348,13 +440,15 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
           if (r0 + tr < md && c0 + tc < md) R[(r0 + tr) * rsd + c0 + tc] -= a2[tr][tc];
     }
     __syncthreads();
+    mark(3);
     for (int d = warp; d < nn; d += nwarps) {
       const int md = s_nm[d], rsd = tile_rs(md);
       double* R = Rb + s_nR0[d];
-      if (warp_chol(R, md, rsd, lane)) {
-        warp_inv_lower_inplace(R, md, rsd, vtmp + warp * (sh.maxmd + 2), lane);
-      } else {
+      bool okc = warp_chol(R, md, rsd, lane);
+      if (okc) warp_inv_lower_inplace(R, md, rsd, vtmp + warp * (sh.maxmd + 2), lane);
+      if (!okc) {
         if (lane == 0) atomicAdd(fail, 1);
+        __syncwarp();
         for (int e = lane; e < md * rsd; e += 32) R[e] = 0.0;
       }
     }
@@ -376,13 +470,15 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
     __syncthreads();
   }
 
+  mark(4);
   sweep(nfwd, nsets);  // H' = L^-T Z
+  mark(5);
 
   // ---- phase 7: outputs.  panel[p][c] = H(c, p)
   for (int c = tid; c < NCp; c += nth) {
     const int d = colnode[c];
     if (d < 0) continue;
-    double s = w[T.row0[s0 + d] + (c - s_nc0[d])];
+    double s = w[s_nrow0[d] + (c - s_nc0[d])];
     for (int pp = 0; pp < Pc; pp++) s = fma(-panel[(size_t)pp * LD + c], wpa[pp], s);
     if (share) {
       const int f = s_nfam[d];
@@ -393,15 +489,14 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
   __syncthreads();
   for (int d = 0; d < nn; d++) {
     const int sd = s0 + d, md = s_nm[d], c0d = s_nc0[d], f = s_nfam[d], rsd = tile_rs(md);
-    const long long go = T.goff[sd];
-    const int ncoff = T.chain_off[sd];
+    const long long go = s_ngoff[d];
     const double* Rid = Rb + ((MODE == 0) ? s_nR0[d] : c0d);
     const int nrg = (md + TR - 1) / TR;
     for (int j = 0; j < k; j++) {
       const int mj = (j < kc) ? s_cm[j] : s_fm[f];
       const int prow = (j < kc) ? s_crow[j] : Pc;
       const int rsj = tile_rs(mj);
-      const long long bo = go + T.chain_boff[ncoff + j];
+      const long long bo = go + (long long)md * s_rspref[j];
       for (int e = tid; e < mj * nrg; e += nth) {
         const int pp = e % mj, r0 = (e / mj) * TR;
         const double* hp = panel + (size_t)(prow + pp) * LD + c0d;
@@ -436,7 +531,7 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
         }
       }
     }
-    const long long ro = T.rioff[sd];
+    const long long ro = s_nrioff[d];
     for (int e = tid; e < ((MODE == 0) ? md * rsd : md); e += nth) outRi[ro + e] = Rid[e];
     if (MODE != 2 && warp == (d % nwarps)) {
       // wcore = e' prec e = |Ri e|^2 (:913 / :950) ; logdet = sum log diag(Ri) (:966)
@@ -461,12 +556,14 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
       }
     }
   }
+  __syncthreads();
+  mark(6);
 }
 
 template <int MODE>
 static cudaError_t launch_build_t(const DevTree& T, const DevSlot& S, double* outH, double* outRi, const int* grp_slot0,
                                   const int* grp_nn, const int* grp_share, int ngrp, const double* w, const CovTab& tab,
-                                  int* fail, int keep_H, size_t smem, cudaStream_t st) {
+                                  int* fail, int keep_H, size_t smem, cudaStream_t st, unsigned long long* prof, int nthreads) {
   auto kern = build_level_kernel<MODE>;
   static size_t configured[3] = {0, 0, 0};
   if (smem > configured[MODE]) {
@@ -474,16 +571,16 @@ static cudaError_t launch_build_t(const DevTree& T, const DevSlot& S, double* ou
     if (e != cudaSuccess) return e;
     configured[MODE] = smem;
   }
-  kern<<<ngrp, kBuildThreads, smem, st>>>(T, S, outH, outRi, grp_slot0, grp_nn, grp_share, w, tab, fail, keep_H);
+  kern<<<ngrp, nthreads, smem, st>>>(T, S, outH, outRi, grp_slot0, grp_nn, grp_share, w, tab, fail, keep_H, prof);
   return cudaGetLastError();
 }
 cudaError_t launch_build(int mode, const DevTree& T, const DevSlot& S, double* outH, double* outRi, const int* grp_slot0,
                          const int* grp_nn, const int* grp_share, int ngrp, const double* w, const CovTab& tab, int* fail,
-                         int keep_H, size_t smem, cudaStream_t st) {
+                         int keep_H, size_t smem, cudaStream_t st, unsigned long long* prof, int nthreads) {
   if (ngrp <= 0) return cudaSuccess;
-  if (mode == 0) return launch_build_t<0>(T, S, outH, outRi, grp_slot0, grp_nn, grp_share, ngrp, w, tab, fail, keep_H, smem, st);
-  if (mode == 1) return launch_build_t<1>(T, S, outH, outRi, grp_slot0, grp_nn, grp_share, ngrp, w, tab, fail, keep_H, smem, st);
-  return launch_build_t<2>(T, S, outH, outRi, grp_slot0, grp_nn, grp_share, ngrp, w, tab, fail, keep_H, smem, st);
+  if (mode == 0) return launch_build_t<0>(T, S, outH, outRi, grp_slot0, grp_nn, grp_share, ngrp, w, tab, fail, keep_H, smem, st, prof, nthreads);
+  if (mode == 1) return launch_build_t<1>(T, S, outH, outRi, grp_slot0, grp_nn, grp_share, ngrp, w, tab, fail, keep_H, smem, st, prof, nthreads);
+  return launch_build_t<2>(T, S, outH, outRi, grp_slot0, grp_nn, grp_share, ngrp, w, tab, fail, keep_H, smem, st, prof, nthreads);
 }
 
 }  // namespace st

@@ -21,10 +21,8 @@ __device__ __forceinline__ double cov_eval(const CovTabS& t, double x1, double y
   const double dx = x1 - x2, dy = y1 - y2;
   const double h = sqrt(dx * dx + dy * dy);
   const int ix = q1 * t.q + q2;
-  double v = t.c1[ix] * exp(-t.r1[ix] * h);
-  const double c2 = t.c2[ix];
-  if (c2 != 0.0) v += c2 * exp(-t.r2[ix] * h);
-  return v;
+  // branch-free (c2 = r2 = 0 for cross-outcome pairs): lets several evaluations per thread overlap their latencies
+  return fma(t.c2[ix], exp(-t.r2[ix] * h), t.c1[ix] * exp(-t.r1[ix] * h));
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -47,7 +45,8 @@ __device__ inline bool warp_chol(double* A, int m, int ld, int lane) {
     __syncwarp();
     for (int r = c + 1 + lane; r < m; r += 32) {
       const double lrc = A[r * ld + c];
-      for (int c2 = c + 1; c2 <= r; c2++) A[r * ld + c2] -= lrc * A[c2 * ld + c];
+#pragma unroll 4
+      for (int c2 = c + 1; c2 <= r; c2++) A[r * ld + c2] = fma(-lrc, A[c2 * ld + c], A[r * ld + c2]);
     }
   }
   __syncwarp();
@@ -62,8 +61,11 @@ __device__ inline void warp_inv_lower_inplace(double* L, int m, int ld, double* 
     for (int r = j + 1 + lane; r < m; r += 32) v[r] = L[r * ld + j];
     __syncwarp();
     for (int r = j + 1 + lane; r < m; r += 32) {
-      double s = 0;
-      for (int kk = j + 1; kk <= r; kk++) s = fma(L[r * ld + kk], v[kk], s);
+      double s0 = 0, s1 = 0;
+      int kk = j + 1;
+      for (; kk + 1 <= r; kk += 2) { s0 = fma(L[r * ld + kk], v[kk], s0); s1 = fma(L[r * ld + kk + 1], v[kk + 1], s1); }
+      if (kk <= r) s0 = fma(L[r * ld + kk], v[kk], s0);
+      const double s = s0 + s1;
       L[r * ld + j] = -s * ajj;
     }
     if (lane == 0) L[j * ld + j] = ajj;

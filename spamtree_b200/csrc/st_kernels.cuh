@@ -58,7 +58,7 @@ __host__ __device__ inline BuildPlan build_plan(const BuildShape& s) {
   auto take = [&](size_t n_doubles) { size_t r = o; o += ((n_doubles + 1) & ~(size_t)1); return r; };
   p.o_panel = take((size_t)p.Ppad * p.LD);
   p.o_R = take(s.mode == 0 ? (size_t)s.sumR : (size_t)p.LD);
-  p.o_ring = take((size_t)kBuildStages * p.Fst * s.maxtile);
+  p.o_ring = take((size_t)kBuildStages * p.Fst * s.maxtile + 8);  // +8: mac_cols may read past the last row of a tile
   p.o_pxs = take(p.Pv); p.o_pys = take(p.Pv); p.o_wpa = take(p.Pv);
   p.o_cxs = take(p.LD); p.o_cys = take(p.LD); p.o_ecol = take(p.LD);
   p.o_vtmp = take((size_t)(kBuildThreads / 32) * (s.maxmd + 2));
@@ -74,7 +74,8 @@ inline size_t gibbs_smem_bytes(int is_ref, int m, int P, int k) {
 
 cudaError_t launch_build(int mode, const DevTree& T, const DevSlot& S, double* outH, double* outRi, const int* grp_slot0,
                          const int* grp_nn, const int* grp_share, int ngrp, const double* w, const CovTab& tab, int* fail,
-                         int keep_H, size_t smem, cudaStream_t st);
+                         int keep_H, size_t smem, cudaStream_t st, unsigned long long* prof = nullptr,
+                         int nthreads = kBuildThreads);
 cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlot& S, int slot0, int nslots, double* w,
                          const double* xb, const double* z, const double* tausq_inv, const double* SigS, double* V,
                          double* probe_sig, double* probe_smu, int* fail, size_t smem, cudaStream_t st);

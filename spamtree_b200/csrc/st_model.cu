@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -342,7 +343,7 @@ int Model::build_layout(std::string& e) {
         }
         BuildShape sh = shape_of(s, nn + 1, share, mode);
         const int n_rg = (std::max(maxmj, sh.mmaxs) + kBuildTR - 1) / kBuildTR;
-        if (!fits(sh) || n_rg * (sh.NCp / kBuildTC) > kBuildThreads || (nn > 0 && sh.NCp > max_group_cols)) break;
+        if (!fits(sh) || n_rg * (sh.NCp / kBuildTC) > build_threads / 2 || (nn > 0 && sh.NCp > max_group_cols)) break;
         best = sh;
         nn++;
       }
@@ -502,6 +503,11 @@ int Model::upload(std::string& e) {
 }
 
 int Model::init(std::string& e) {
+  // development overrides of the BUILD tiling
+  if (const char* v = getenv("ST_BUILD_THREADS")) build_threads = atoi(v);
+  if (const char* v = getenv("ST_MAX_COLS")) max_group_cols = atoi(v);
+  if (const char* v = getenv("ST_COUSIN")) cousin_threshold = atoi(v);
+  if (const char* v = getenv("ST_SMEM_BUDGET")) smem_budget = (size_t)atol(v);
   int rc = build_bookkeeping(e);
   if (rc) return rc;
   if (q * (p + 1) > kMaxStats) { e = "q*(p+1) exceeds 40"; return 4; }
@@ -522,12 +528,31 @@ int Model::theta_update(int slot, const double* th) {
 }
 
 int Model::launch_build_levels(int pslot, const CovTab& tab) {
+  // ST_PROFILE_BUILD=1: per-phase clock64() totals of build_level_kernel, printed per level (development aid)
+  static const bool profile = getenv("ST_PROFILE_BUILD") != nullptr;
+  unsigned long long* d_prof = nullptr;
+  if (profile) {
+    cudaMalloc((void**)&d_prof, 16 * sizeof(unsigned long long));
+  }
   for (auto& L : levels) {
+    if (profile) cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), stream);
     ST_CUDA(launch_build(L.is_ref ? 0 : 1, dt, ds[pslot], ds[pslot].H, ds[pslot].Ri, d_grp_slot0 + L.grp0, d_grp_nn + L.grp0,
-                         d_grp_share + L.grp0, L.ngrp, d_w, tab, d_fail, keep_H ? 1 : 0, L.smem_build, stream),
+                         d_grp_share + L.grp0, L.ngrp, d_w, tab, d_fail, keep_H ? 1 : 0, L.smem_build, stream, d_prof, build_threads),
             "build_level_kernel");
     n_launches++;
+    if (profile) {
+      unsigned long long h[16];
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+      double tot = 0;
+      for (int i = 0; i < 7; i++) tot += (double)h[i];
+      fprintf(stderr, "[build profile] level slot0=%d groups=%d ref=%d cycles/group=%.0f : setup %.1f%% cov %.1f%% fwd %.1f%% ZtZ %.1f%% chol %.1f%% bwd %.1f%% out %.1f%%\n",
+              L.slot0, L.ngrp, L.is_ref, tot / std::max(1, L.ngrp), 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot,
+              100 * h[4] / tot, 100 * h[5] / tot, 100 * h[6] / tot);
+      fprintf(stderr, "      sweeps (thread 0): wait+sync %.1f%% issue %.1f%% compute %.1f%% step-end %.1f%% of kernel\n", 100 * h[8] / tot, 100 * h[9] / tot, 100 * h[10] / tot, 100 * h[11] / tot);
+    }
   }
+  if (profile) cudaFree(d_prof);
   return 0;
 }
 
@@ -628,7 +653,7 @@ int Model::predict(bool theta_changed) {
     std::string e;
     if (!make_covtab(theta[cur].data(), (int)theta[cur].size(), q, tab, e)) { err = e; return 1; }
     ST_CUDA(launch_build(2, dt, ds[cur], d_Hpred, d_sdpred, d_grp_slot0 + pred_level.grp0, d_grp_nn + pred_level.grp0,
-                         d_grp_share + pred_level.grp0, pred_level.ngrp, d_w, tab, d_fail, 1, pred_level.smem_build, stream),
+                         d_grp_share + pred_level.grp0, pred_level.ngrp, d_w, tab, d_fail, 1, pred_level.smem_build, stream, nullptr, build_threads),
             "build_level_kernel(predict)");
     n_launches++;
     pred_H_valid = true;

@@ -86,7 +86,8 @@ class Model {
   ivec res_is_ref;
   bool keep_H = true;
   int device = 0;
-  size_t smem_budget = 221 * 1024;  // dynamic; the kernel also holds ~4 KB of static shared memory (227 KB per CTA)
+  size_t smem_budget = 220 * 1024;  // dynamic; the kernel also holds ~4 KB of static shared memory (227 KB per CTA)
+  int build_threads = 256;   // CTA size of build_level_kernel (two split-K halves)
   int max_group_cols = 104;  // upper bound on the columns one BUILD work group handles
   int cousin_threshold = 48; // sibling sets narrower than this (columns) are merged into cousin groups
   bool probes = true;        // record Sigi_tot / Smu_tot of the last Gibbs sweep (st_get_node_state)
