@@ -32,6 +32,23 @@ typedef enum {
   ST_ERR_NAN = 5        /* NaN log-likelihood at the current theta (reference: `throw 1`, spamtree_fit.cpp:234-237) */
 } st_status;
 
+/* Multi-GPU: one problem cut into subtrees, one rank (process + GPU) per run of subtrees (the reference is
+ * single-process).  Every rank creates its handle from ITS blocks: the blocks of the first n_top_levels tree levels are
+ * present on every rank (replicated, computed redundantly), the rest are the rank's own subtrees.  The library calls
+ * `allreduce` (in-place sum over ranks of `count` doubles at a DEVICE pointer, after synchronising its stream) for the
+ * three scalars of the log-density, the messages of the cut-level blocks to the replicated blocks, and the beta / tausq
+ * sufficient statistics.  spamtree_b200/partition.py builds these inputs; the callback is torch.distributed (NCCL). */
+typedef int (*st_allreduce_fn)(void* ctx, void* device_ptr, int64_t count);
+typedef struct {
+  int32_t rank, nranks;
+  int32_t n_top_levels;         /* replicated levels (0: the ranks hold disjoint trees) */
+  int64_t rng_row_offset;       /* rows owned by lower ranks: keeps the device normal streams of the ranks disjoint */
+  int64_t n_global_rows;        /* rows of the whole problem */
+  const int64_t* global_rows;   /* n_all: global row of every local row (host-RNG mode draws for all global rows) */
+  st_allreduce_fn allreduce;
+  void* ctx;
+} st_partition;
+
 /* Inputs of the SpamTreeMV constructor (spamtree_model.cpp:8-37), i.e. the arguments
  * spamtree_mv_mcmc receives from R (spamtree_fit.cpp:5-54).  Lists of uvec are CSR.
  * Accepted-and-ignored reference arguments (Z values, blocking, gix_block, start_w,
@@ -63,6 +80,7 @@ typedef struct {
   int32_t device;              /* CUDA device ordinal; < 0: host-only handle (bookkeeping for st_get_index, no compute) */
   int32_t keep_H;              /* 1: keep H = w_cond_mean_K of observed blocks on device (needed by st_get_node_state "H") */
   int64_t smem_panel_bytes;    /* 0 = default; shared-memory budget for one BUILD work group */
+  const st_partition* partition; /* NULL: the whole problem on one GPU */
 } st_problem;
 
 /* SpamTreeMV::SpamTreeMV — spamtree_model.cpp:8-192 (+ init_indexing :315, na_study :303,

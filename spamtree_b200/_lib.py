@@ -20,6 +20,17 @@ c_int64_p = C.POINTER(C.c_int64)
 c_float_p = C.POINTER(C.c_float)
 
 
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
+
+
+class StPartition(C.Structure):
+    _fields_ = [
+        ("rank", C.c_int32), ("nranks", C.c_int32), ("n_top_levels", C.c_int32),
+        ("rng_row_offset", C.c_int64), ("n_global_rows", C.c_int64), ("global_rows", c_int64_p),
+        ("allreduce", ALLREDUCE_FN), ("ctx", C.c_void_p),
+    ]
+
+
 class StProblem(C.Structure):
     _fields_ = [
         ("n_all", C.c_int64), ("p", C.c_int32), ("q", C.c_int32),
@@ -33,6 +44,7 @@ class StProblem(C.Structure):
         ("theta", c_double_p), ("n_theta", C.c_int32),
         ("beta", c_double_p), ("tausq", C.c_double),
         ("device", C.c_int32), ("keep_H", C.c_int32), ("smem_panel_bytes", C.c_int64),
+        ("partition", C.POINTER(StPartition)),
     ]
 
 

@@ -186,13 +186,14 @@ class SpamTreeMV:
     """src/spamtree_model.h:22-212.  Constructor arguments follow spamtree_model.cpp:8-37 (lists are 0-based id lists)."""
 
     def __init__(self, y, X, coords, mv_id, res_is_ref, parents, children, limited_tree, block_names, block_groups,
-                 indexing, beta, theta, tausq, device=0, keep_H=True, smem_panel_bytes=0, csr=None):
+                 indexing, beta, theta, tausq, device=0, keep_H=True, smem_panel_bytes=0, csr=None, partition=None,
+                 q=None):
         self.y = _f64(y).reshape(-1)
         self.n_all = self.y.size
         Xa = np.asarray(X, dtype=np.float64).reshape(self.n_all, -1)
         self.p = Xa.shape[1]
         self.mv_id = _i64(mv_id).reshape(-1)
-        self.q = int(np.unique(self.mv_id).size)
+        self.q = int(np.unique(self.mv_id).size) if q is None else int(q)
         self._X, self._coords = _colmajor(Xa), _colmajor(np.asarray(coords, dtype=np.float64))
         if csr is not None:
             ip_, ii, pp, pi, cp, ci = [_i64(a) for a in csr]
@@ -218,6 +219,26 @@ class SpamTreeMV:
         pr.theta, pr.n_theta = _dp(self._theta), self.npar
         pr.beta, pr.tausq = _dp(self._beta), float(tausq)
         pr.device, pr.keep_H, pr.smem_panel_bytes = int(device), int(bool(keep_H)), int(smem_panel_bytes)
+        if partition is not None and partition["nranks"] > 1:
+            # partition: a sub-problem dict from spamtree_b200.partition.subproblem plus "allreduce": callable(ptr, count)
+            fn = partition["allreduce"]
+
+            def _cb(ctx, ptr, count):
+                try:
+                    fn(ptr, count)
+                    return 0
+                except Exception as ex:  # never let an exception cross the C boundary
+                    print(f"spamtree_b200: allreduce callback failed: {ex}", flush=True)
+                    return 1
+
+            self._cb = _lib.ALLREDUCE_FN(_cb)
+            self._grows = _i64(partition["global_rows"])
+            pt = _lib.StPartition()
+            pt.rank, pt.nranks, pt.n_top_levels = int(partition["rank"]), int(partition["nranks"]), int(partition["n_top_levels"])
+            pt.rng_row_offset, pt.n_global_rows = int(partition["rng_row_offset"]), int(partition["n_global_rows"])
+            pt.global_rows, pt.allreduce, pt.ctx = _ip(self._grows), self._cb, None
+            self._pt = pt
+            pr.partition = C.pointer(pt)
         h = C.c_void_p()
         rc = lib.st_create(C.byref(pr), C.byref(h))
         if rc:

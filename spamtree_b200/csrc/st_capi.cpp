@@ -77,6 +77,15 @@ int st_create(const st_problem* pr, st_handle** out) {
       for (int a = 0; a < pr->p; a++) M.Bcoeff[a + (size_t)j * pr->p] = pr->beta[a];  // spamtree_model.cpp:124-129
     M.tausq_inv.assign(pr->q, 1.0 / pr->tausq);                                         // :118
     M.rng.seed(1);
+    if (pr->partition && pr->partition->nranks > 1) {
+      const st_partition& pt = *pr->partition;
+      if (!pt.allreduce || pt.rank < 0 || pt.rank >= pt.nranks) { g_create_error = "partition: bad rank or missing allreduce callback"; delete h; return ST_ERR_INVALID; }
+      M.part = true;
+      M.rank = pt.rank; M.nranks = pt.nranks; M.n_top_levels = pt.n_top_levels;
+      M.rng_row_offset = pt.rng_row_offset; M.n_global_rows = pt.n_global_rows;
+      if (pt.global_rows) M.global_rows.assign(pt.global_rows, pt.global_rows + pr->n_all);
+      M.allreduce_fn = pt.allreduce; M.allreduce_ctx = pt.ctx;
+    }
     {
       st::CovTab tab;
       std::string e;

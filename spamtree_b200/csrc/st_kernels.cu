@@ -269,11 +269,12 @@ cudaError_t launch_llw(const DevTree& T, const DevSlot& S, int nslots, const dou
 // out[0] = sum(logdet) + sum(llcomp), out[1] = sum(logdet), out[2] = (fail == 0)  (:987-988 / :815-816).
 // Fixed summation order: deterministic run to run.
 __global__ void __launch_bounds__(1024) loglik_reduce_kernel(const double* __restrict__ logdet,
-                                                             const double* __restrict__ llcomp, int n,
-                                                             const int* __restrict__ fail, double* __restrict__ out) {
+                                                             const double* __restrict__ llcomp, int first, int n,
+                                                             const int* __restrict__ fail, int fail_as_count,
+                                                             double* __restrict__ out) {
   __shared__ double sa[1024], sb[1024];
   double a = 0, b = 0;
-  for (int i = threadIdx.x; i < n; i += 1024) { a += logdet[i]; b += llcomp[i]; }
+  for (int i = first + threadIdx.x; i < first + n; i += 1024) { a += logdet[i]; b += llcomp[i]; }
   sa[threadIdx.x] = a;
   sb[threadIdx.x] = b;
   __syncthreads();
@@ -284,12 +285,39 @@ __global__ void __launch_bounds__(1024) loglik_reduce_kernel(const double* __res
   if (threadIdx.x == 0) {
     out[0] = sa[0] + sb[0];
     out[1] = sa[0];
-    out[2] = (fail == nullptr || *fail == 0) ? 1.0 : 0.0;
+    if (fail_as_count) out[2] = fail ? (double)*fail : 0.0;
+    else out[2] = (fail == nullptr || *fail == 0) ? 1.0 : 0.0;
   }
 }
-cudaError_t launch_loglik_reduce(const double* logdet, const double* llcomp, int n, const int* fail, double* out,
-                                 cudaStream_t st) {
-  loglik_reduce_kernel<<<1, 1024, 0, st>>>(logdet, llcomp, n, fail, out);
+cudaError_t launch_loglik_reduce(const double* logdet, const double* llcomp, int first, int n, const int* fail,
+                                 int fail_as_count, double* out, cudaStream_t st) {
+  loglik_reduce_kernel<<<1, 1024, 0, st>>>(logdet, llcomp, first, n, fail, fail_as_count, out);
+  return cudaGetLastError();
+}
+
+// partition only: sums of the messages of a replicated block's LOCAL children into its pseudo child, which is then
+// all-reduced over the ranks (the replicated block pulls from the pseudo child like from any child)
+__global__ void frontier_sum_kernel(DevTree T, const int* __restrict__ pseudo, const int* __restrict__ c0,
+                                    const int* __restrict__ c1, const int* __restrict__ vlen, const int* __restrict__ ulen,
+                                    double* __restrict__ V, double* __restrict__ U, int do_v, int do_u) {
+  const int i = blockIdx.x, ps = pseudo[i];
+  if (do_v)
+    for (int e = threadIdx.x; e < vlen[i]; e += blockDim.x) {
+      double s = 0;
+      for (int c = c0[i]; c < c1[i]; c++) s += V[T.voff[c] + e];
+      V[T.voff[ps] + e] = s;
+    }
+  if (do_u)
+    for (int e = threadIdx.x; e < ulen[i]; e += blockDim.x) {
+      double s = 0;
+      for (int c = c0[i]; c < c1[i]; c++) s += U[T.uoff[c] + e];
+      U[T.uoff[ps] + e] = s;
+    }
+}
+cudaError_t launch_frontier_sum(const DevTree& T, int n, const int* pseudo, const int* c0, const int* c1, const int* vlen,
+                                const int* ulen, double* V, double* U, int do_v, int do_u, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  frontier_sum_kernel<<<n, 256, 0, st>>>(T, pseudo, c0, c1, vlen, ulen, V, U, do_v, do_u);
   return cudaGetLastError();
 }
 
@@ -326,26 +354,26 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
   const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
   c[0] = hi1 ^ c[1] ^ k0; c[1] = lo1; c[2] = hi0 ^ c[3] ^ k1; c[3] = lo0;
 }
-__global__ void normals_kernel(double* __restrict__ z, long long n, uint64_t seed, uint64_t counter) {
+__global__ void normals_kernel(double* __restrict__ z, long long n, uint64_t seed, uint64_t counter, long long n_shared,
+                               long long offset) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long pair = i;  // each thread produces z[2i], z[2i+1]
-  if (2 * pair >= n) return;
-  uint32_t c[4] = {(uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)counter, (uint32_t)(counter >> 32)};
+  if (i >= n) return;
+  // rows replicated on every rank (i < n_shared) use the same key everywhere; the others are shifted by the rank's offset
+  const unsigned long long key = (unsigned long long)(i < n_shared ? i : i + offset);
+  uint32_t c[4] = {(uint32_t)key, (uint32_t)(key >> 32), (uint32_t)counter, (uint32_t)(counter >> 32)};
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
   for (int r = 0; r < 10; r++) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
   const double u1 = ((((uint64_t)c[0] << 32 | c[1]) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
   const double u2 = ((((uint64_t)c[2] << 32 | c[3]) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
-  const double rad = sqrt(-2.0 * log(u1));
   double sn, cs;
   sincospi(2.0 * u2, &sn, &cs);
-  z[2 * pair] = rad * cs;
-  if (2 * pair + 1 < n) z[2 * pair + 1] = rad * sn;
+  z[i] = sqrt(-2.0 * log(u1)) * cs;
 }
-cudaError_t launch_normals(double* z, long long n, uint64_t seed, uint64_t counter, cudaStream_t st) {
-  const long long pairs = (n + 1) / 2;
-  if (pairs <= 0) return cudaSuccess;
-  normals_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(z, n, seed, counter);
+cudaError_t launch_normals(double* z, long long n, uint64_t seed, uint64_t counter, long long n_shared, long long offset,
+                           cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  normals_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z, n, seed, counter, n_shared, offset);
   return cudaGetLastError();
 }
 

@@ -82,11 +82,14 @@ cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlot& S, int slo
 cudaError_t launch_gram(const DevTree& T, const DevSlot& S, int slot0, int nslots, double* U, double* SigS,
                         cudaStream_t st);
 cudaError_t launch_llw(const DevTree& T, const DevSlot& S, int nslots, const double* w, cudaStream_t st);
-cudaError_t launch_loglik_reduce(const double* logdet, const double* llcomp, int n, const int* fail, double* out,
-                                 cudaStream_t st);
+cudaError_t launch_loglik_reduce(const double* logdet, const double* llcomp, int first, int n, const int* fail,
+                                 int fail_as_count, double* out, cudaStream_t st);
+cudaError_t launch_frontier_sum(const DevTree& T, int n, const int* pseudo, const int* c0, const int* c1, const int* vlen,
+                                const int* ulen, double* V, double* U, int do_v, int do_u, cudaStream_t st);
 cudaError_t launch_predict_sample(const DevTree& T, int slot0, int nslots, const double* Hpred, const double* sdpred,
                                   double* w, const double* z, cudaStream_t st);
-cudaError_t launch_normals(double* z, long long n, uint64_t seed, uint64_t counter, cudaStream_t st);
+cudaError_t launch_normals(double* z, long long n, uint64_t seed, uint64_t counter, long long n_shared, long long offset,
+                           cudaStream_t st);
 cudaError_t launch_rowstats(const DevTree& T, const int* widx, long long n_all, int p, int q, const double* w,
                             const double* xb, double* partial, int nblocks, double* out, cudaStream_t st);
 cudaError_t launch_xb(const DevTree& T, long long n_all, int p, const double* bcoeff, double* xb, cudaStream_t st);

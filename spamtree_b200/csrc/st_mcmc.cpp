@@ -77,8 +77,10 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
   out.n_accepted = out.n_chol_fail = 0;
   auto lo = [&](int j) { return o.set_unif_bounds[j]; };
   auto hi = [&](int j) { return o.set_unif_bounds[j + npar]; };
-  dvec zbuf, wbuf, xbbuf;
+  dvec zbuf, wbuf, xbbuf, zglob;
   if (o.rng_mode == 0) zbuf.resize(M.n_all);
+  const bool pglob = M.part && !M.global_rows.empty();  // partitioned: draw for every row of the problem, keep ours
+  if (pglob) zglob.resize(M.n_global_rows);
   const auto t0 = std::chrono::steady_clock::now();
   for (int m = 0; m < mcmc; m++) {
     bool predicting = false;
@@ -86,7 +88,12 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
     if (mx >= 0 && mx % o.thin == 0) predicting = true;
     if (o.sample_w) {  // :183-187
       if (o.rng_mode == 0) {
-        for (int64_t i = 0; i < M.n_all; i++) zbuf[i] = M.rng.norm();  // bigrnorm (:1018)
+        if (pglob) {
+          for (int64_t i = 0; i < M.n_global_rows; i++) zglob[i] = M.rng.norm();
+          for (int64_t i = 0; i < M.n_all; i++) zbuf[i] = zglob[M.global_rows[i]];
+        } else {
+          for (int64_t i = 0; i < M.n_all; i++) zbuf[i] = M.rng.norm();  // bigrnorm (:1018)
+        }
         rc = M.deal_with_w(zbuf.data(), 0);
       } else {
         rc = M.deal_with_w(nullptr, o.seed);
@@ -166,9 +173,11 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
         rc = M.get_xb(xbbuf.data());
         if (rc) return rc;
       }
+      if (pglob && o.rng_mode == 0)
+        for (int64_t i = 0; i < M.n_global_rows; i++) zglob[i] = M.rng.norm();
       if (o.rng_mode == 0 || out.yhat_mcmc)
         for (int64_t i = 0; i < M.n_all; i++) {
-          const double e = M.rng.norm();  // arma::randn(n) of :384
+          const double e = (pglob && o.rng_mode == 0) ? zglob[M.global_rows[i]] : M.rng.norm();  // arma::randn(n) of :384
           if (out.yhat_mcmc)
             out.yhat_mcmc[i + (size_t)msaved * M.n_all] = xbbuf[i] + wbuf[i] + std::pow(M.tausq_inv[M.mv_id[i] - 1], -.5) * e;
         }

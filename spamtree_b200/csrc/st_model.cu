@@ -271,16 +271,63 @@ int Model::build_layout(std::string& e) {
       h_rioff[s] = sd_total; sd_total += pad2(h_m[s]);
     }
   }
+  // partition: the deepest replicated level pulls its children's messages through one pseudo child per block, filled
+  // by an all-reduce over the ranks (its real children live on several ranks)
+  n_slots_total = n_nodes;
+  n_top_slots = 0;
+  std::vector<char> is_front(n_nodes, 0);
+  h_front_pseudo.clear(); h_front_c0.clear(); h_front_c1.clear(); h_front_vlen.clear(); h_front_ulen.clear();
+  v_front0 = v_total; u_front0 = u_total;
+  if (part) {
+    if (n_top_levels < 0 || n_top_levels >= (int)levels.size()) { e = "partition: n_top_levels out of range"; return 1; }
+    for (int g = 0; g < n_top_levels; g++) n_top_slots += levels[g].nslots;
+    n_top_rows = (n_top_slots < n_nodes) ? h_row0[n_top_slots] : (int)n_all;
+    if (n_top_levels >= 1) {
+      const LevelInfo& FL = levels[n_top_levels - 1];
+      const LevelInfo& CL = levels[n_top_levels];
+      if (!FL.is_ref) { e = "partition: the deepest replicated level must be a reference level"; return 1; }
+      int c = CL.slot0;
+      for (int dd = FL.slot0; dd < FL.slot0 + FL.nslots; dd++) {
+        is_front[dd] = 1;
+        const int ps = n_slots_total++;
+        const int c0 = c;
+        while (c < CL.slot0 + CL.nslots && h_lastpar[c] == dd) c++;
+        // the pseudo child looks like a child of dd with no rows: chain = chain(dd) + dd
+        h_m.push_back(0); h_row0.push_back(0); isref.push_back(0); h_lastpar.push_back(dd);
+        h_k.push_back(h_k[dd] + 1);
+        h_chain_off.push_back((int)h_chain.size());
+        int poff = 0;
+        long long uo = 0;
+        for (int j = 0; j <= h_k[dd]; j++) {
+          const int a = (j < h_k[dd]) ? h_chain[h_chain_off[dd] + j] : dd;
+          h_chain.push_back(a); h_chain_poff.push_back(poff); h_chain_boff.push_back(0); h_chain_uoff.push_back((int)uo);
+          poff += h_m[a];
+          uo += pad2((long long)h_m[a] * h_m[a]);
+        }
+        h_P.push_back(poff);
+        h_goff.push_back(0); h_rioff.push_back(0); h_soff.push_back(-1);
+        h_voff.push_back(v_total); v_total += pad2(poff);
+        h_uoff.push_back(u_total); u_total += uo;
+        h_front_pseudo.push_back(ps); h_front_c0.push_back(c0); h_front_c1.push_back(c);
+        h_front_vlen.push_back(poff); h_front_ulen.push_back((int)uo);
+      }
+      if (c != CL.slot0 + CL.nslots) { e = "partition: a block of the cut level has no replicated parent"; return 1; }
+    }
+    v_front_len = v_total - v_front0;
+    u_front_len = u_total - u_front0;
+  }
   // direct children among observed nodes (contiguous by construction of the slot order)
-  h_child_ptr.assign(n_nodes + 1, 0);
+  h_child_ptr.assign(n_slots_total + 1, 0);
   for (int s = 0; s < n_obs_nodes; s++)
-    if (h_lastpar[s] >= 0) h_child_ptr[h_lastpar[s] + 1]++;
-  for (int s = 0; s < n_nodes; s++) h_child_ptr[s + 1] += h_child_ptr[s];
-  h_child_idx.assign(h_child_ptr[n_nodes], 0);
+    if (h_lastpar[s] >= 0 && !is_front[h_lastpar[s]]) h_child_ptr[h_lastpar[s] + 1]++;
+  for (size_t i = 0; i < h_front_pseudo.size(); i++) h_child_ptr[h_lastpar[h_front_pseudo[i]] + 1]++;
+  for (int s = 0; s < n_slots_total; s++) h_child_ptr[s + 1] += h_child_ptr[s];
+  h_child_idx.assign(h_child_ptr[n_slots_total], 0);
   {
     std::vector<int> fill(h_child_ptr.begin(), h_child_ptr.end() - 1);
     for (int s = 0; s < n_obs_nodes; s++)
-      if (h_lastpar[s] >= 0) h_child_idx[fill[h_lastpar[s]]++] = s;
+      if (h_lastpar[s] >= 0 && !is_front[h_lastpar[s]]) h_child_idx[fill[h_lastpar[s]]++] = s;
+    for (size_t i = 0; i < h_front_pseudo.size(); i++) h_child_idx[fill[h_lastpar[h_front_pseudo[i]]]++] = h_front_pseudo[i];
   }
   for (int s = 0; s < n_obs_nodes; s++)
     if (h_child_ptr[s + 1] > h_child_ptr[s]) { h_soff[s] = s_total; s_total += pad2((long long)h_m[s] * h_m[s]); }
@@ -453,6 +500,11 @@ int Model::upload(std::string& e) {
   ST_CUDA(dev_upload(h_grp_slot0, d_grp_slot0, owned), "upload groups");
   ST_CUDA(dev_upload(h_grp_nn, d_grp_nn, owned), "upload groups");
   ST_CUDA(dev_upload(h_grp_share, d_grp_share, owned), "upload groups");
+  ST_CUDA(dev_upload(h_front_pseudo, d_front_pseudo, owned), "upload frontier");
+  ST_CUDA(dev_upload(h_front_c0, d_front_c0, owned), "upload frontier");
+  ST_CUDA(dev_upload(h_front_c1, d_front_c1, owned), "upload frontier");
+  ST_CUDA(dev_upload(h_front_vlen, d_front_vlen, owned), "upload frontier");
+  ST_CUDA(dev_upload(h_front_ulen, d_front_ulen, owned), "upload frontier");
   dt.cx = d_cx; dt.cy = d_cy; dt.mvq = d_mvq; dt.y = d_y; dt.X = d_X;
   dt.m = d_m; dt.row0 = d_row0; dt.isref = d_isref; dt.k = d_k; dt.P = d_P; dt.lastpar = d_lastpar; dt.chain_off = d_choff;
   dt.goff = d_goff; dt.rioff = d_rioff; dt.voff = d_voff; dt.uoff = d_uoff; dt.soff = d_soff;
@@ -475,7 +527,7 @@ int Model::upload(std::string& e) {
   ST_CUDA(dev_zeros(d_sdpred, sd_total_, owned), "alloc sdpred");
   ST_CUDA(dev_zeros(d_probe_sig, ri_total, owned), "alloc probe");
   ST_CUDA(dev_zeros(d_probe_smu, n_all, owned), "alloc probe");
-  ST_CUDA(dev_zeros(d_scalars, 64 + kMaxStats, owned), "alloc scalars");
+  ST_CUDA(dev_zeros(d_scalars, 64 + kMaxStats + 1024, owned), "alloc scalars");
   rowstat_blocks_ = (int)std::min<int64_t>(592, std::max<int64_t>(1, (n_all + 255) / 256));
   ST_CUDA(dev_zeros(d_partial, (long long)rowstat_blocks_ * kMaxStats, owned), "alloc partial");
   ST_CUDA(dev_upload(Bcoeff, d_bcoeff, owned), "upload beta");
@@ -484,13 +536,14 @@ int Model::upload(std::string& e) {
     std::vector<int> z1(1, 0);
     ST_CUDA(dev_upload(z1, d_fail, owned), "alloc fail");
   }
-  ST_CUDA(cudaMallocHost((void**)&h_scalars, (64 + kMaxStats) * sizeof(double)), "pinned scalars");
+  ST_CUDA(cudaMallocHost((void**)&h_scalars, (64 + kMaxStats + 1024) * sizeof(double)), "pinned scalars");
   ST_CUDA(cudaMallocHost((void**)&h_stage, std::max<int64_t>(n_all, 1) * sizeof(double)), "pinned stage");
   // index used by the beta step
   beta_widx_faithful.assign(n_all, -1);
   beta_widx_plain.assign(n_all, -1);
   for (int64_t s = 0; s < n_obs; s++) {
     const int64_t i = iperm[na_ix_all[s]];
+    if (part && rank > 0 && i < n_top_rows) continue;  // replicated rows are counted by rank 0 only
     beta_widx_faithful[i] = (int)iperm[s];
     beta_widx_plain[i] = (int)i;
   }
@@ -517,10 +570,71 @@ int Model::init(std::string& e) {
   if (device < 0) return 0;  // host-only handle: bookkeeping and layout, no device state (st_get_index only)
   rc = upload(e);
   if (rc) { e = err; return rc; }
+  if (part) {
+    // XtX and the per-outcome counts are sums over ALL observed rows of the problem: replicated rows once, then all-reduce
+    const int nx = q * p * p + q;
+    if (nx > 1024) { e = "partition: q*p*p too large"; return 4; }
+    for (auto& M : XtX) std::fill(M.a.begin(), M.a.end(), 0.0);
+    std::fill(nobs_by_q.begin(), nobs_by_q.end(), 0);
+    for (int64_t b : na_ix_all) {
+      if (rank > 0 && iperm[b] < n_top_rows) continue;
+      const int j = (int)mv_id[b] - 1;
+      nobs_by_q[j]++;
+      for (int a = 0; a < p; a++)
+        for (int c = 0; c < p; c++) XtX[j](a, c) += X[b + (size_t)a * n_all] * X[b + (size_t)c * n_all];
+    }
+    double* hb = h_scalars + 64 + kMaxStats;
+    for (int j = 0; j < q; j++) {
+      std::copy(XtX[j].a.begin(), XtX[j].a.end(), hb + (size_t)j * p * p);
+      hb[q * p * p + j] = (double)nobs_by_q[j];
+    }
+    double* db = d_scalars + 64 + kMaxStats;
+    ST_CUDA(cudaMemcpyAsync(db, hb, nx * sizeof(double), cudaMemcpyHostToDevice, stream), "H2D XtX");
+    rc = allreduce_dev(db, nx);
+    if (rc) { e = err; return rc; }
+    ST_CUDA(cudaMemcpyAsync(hb, db, nx * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H XtX");
+    ST_CUDA(cudaStreamSynchronize(stream), "sync");
+    for (int j = 0; j < q; j++) {
+      std::copy(hb + (size_t)j * p * p, hb + (size_t)(j + 1) * p * p, XtX[j].a.begin());
+      nobs_by_q[j] = (int64_t)std::llround(hb[q * p * p + j]);
+    }
+  }
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------------------ operations
+int Model::allreduce_dev(double* dptr, int64_t n) {
+  if (!part || nranks <= 1 || n <= 0) return 0;
+  ST_CUDA(cudaStreamSynchronize(stream), "sync before allreduce");
+  if (!allreduce_fn || allreduce_fn(allreduce_ctx, dptr, n) != 0) { err = "partition: the allreduce callback failed"; return 1; }
+  return 0;
+}
+
+// sum of the per-block log-density pieces (:987-988 / :815-816).  Partitioned: replicated blocks once + all-reduced rest.
+// out3_host = {loglik_w, logdetCi, number of failed Cholesky factorisations}
+int Model::reduce_loglik(int ps, const int* fail, double* out3_host) {
+  if (!part) {
+    ST_CUDA(launch_loglik_reduce(ds[ps].logdet, ds[ps].llcomp, 0, n_obs_nodes, fail, 1, d_scalars, stream), "loglik_reduce");
+    n_launches++;
+    ST_CUDA(cudaMemcpyAsync(h_scalars, d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H scalars");
+    ST_CUDA(cudaStreamSynchronize(stream), "sync");
+    out3_host[0] = h_scalars[0]; out3_host[1] = h_scalars[1]; out3_host[2] = h_scalars[2];
+    return 0;
+  }
+  ST_CUDA(launch_loglik_reduce(ds[ps].logdet, ds[ps].llcomp, 0, n_top_slots, nullptr, 1, d_scalars, stream), "loglik_reduce");
+  ST_CUDA(launch_loglik_reduce(ds[ps].logdet, ds[ps].llcomp, n_top_slots, n_obs_nodes - n_top_slots, fail, 1, d_scalars + 4, stream), "loglik_reduce");
+  n_launches += 2;
+  int rc = allreduce_dev(d_scalars + 4, 3);
+  if (rc) return rc;
+  ST_CUDA(cudaMemcpyAsync(h_scalars, d_scalars, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H scalars");
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  // out[0] of the kernel is logdet + llcomp, out[1] logdet
+  out3_host[0] = h_scalars[0] + h_scalars[4];
+  out3_host[1] = h_scalars[1] + h_scalars[5];
+  out3_host[2] = h_scalars[6];
+  return 0;
+}
+
 int Model::theta_update(int slot, const double* th) {
   dvec& t = theta[phys(slot)];
   std::copy(th, th + t.size(), t.begin());
@@ -565,12 +679,11 @@ int Model::get_loglik_comps_w(int slot, double* out3) {
   ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
   int rc = launch_build_levels(ps, tab);
   if (rc) return rc;
-  ST_CUDA(launch_loglik_reduce(ds[ps].logdet, ds[ps].llcomp, n_obs_nodes, d_fail, d_scalars, stream), "loglik_reduce");
-  n_launches++;
-  ST_CUDA(cudaMemcpyAsync(h_scalars, d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H scalars");
-  ST_CUDA(cudaStreamSynchronize(stream), "sync");
-  const bool ok = h_scalars[2] != 0.0;
-  if (ok) { loglik_w[ps] = h_scalars[0]; logdetCi[ps] = h_scalars[1]; }  // on failure the reference leaves them untouched (:971-982)
+  double r3[3];
+  rc = reduce_loglik(ps, d_fail, r3);
+  if (rc) return rc;
+  const bool ok = r3[2] == 0.0;
+  if (ok) { loglik_w[ps] = r3[0]; logdetCi[ps] = r3[1]; }  // on failure the reference leaves them untouched (:971-982)
   if (ps == cur) { gram_stale = true; pred_H_valid = false; }
   out3[0] = loglik_w[ps]; out3[1] = logdetCi[ps]; out3[2] = ok ? 1.0 : 0.0;
   return 0;
@@ -585,13 +698,20 @@ int Model::upload_rows(const double* boundary_order, double* dev) {
 }
 
 int Model::draw_normals(uint64_t seed) {
-  ST_CUDA(launch_normals(d_z, n_all, seed, sweep_counter++, stream), "normals_kernel");
+  ST_CUDA(launch_normals(d_z, n_all, seed, sweep_counter++, part ? n_top_rows : n_all, part ? rng_row_offset : 0, stream), "normals_kernel");
   n_launches++;
   return 0;
 }
 
 int Model::refresh_grams() {
   for (int g = (int)levels.size() - 1; g >= 0; g--) {
+    if (part && n_top_levels >= 1 && g == n_top_levels - 1) {  // children of this level live on several ranks
+      ST_CUDA(launch_frontier_sum(dt, (int)h_front_pseudo.size(), d_front_pseudo, d_front_c0, d_front_c1, d_front_vlen, d_front_ulen,
+                                  d_V, d_U, 0, 1, stream), "frontier_sum_kernel");
+      n_launches++;
+      int rc = allreduce_dev(d_U + u_front0, u_front_len);
+      if (rc) return rc;
+    }
     ST_CUDA(launch_gram(dt, ds[cur], levels[g].slot0, levels[g].nslots, d_U, d_S, stream), "gram_level_kernel");
     n_launches++;
   }
@@ -603,6 +723,13 @@ int Model::gibbs_launch_only() {
   if (gram_stale) { int rc = refresh_grams(); if (rc) return rc; }
   for (int g = (int)levels.size() - 1; g >= 0; g--) {
     const LevelInfo& L = levels[g];
+    if (part && n_top_levels >= 1 && g == n_top_levels - 1) {
+      ST_CUDA(launch_frontier_sum(dt, (int)h_front_pseudo.size(), d_front_pseudo, d_front_c0, d_front_c1, d_front_vlen, d_front_ulen,
+                                  d_V, d_U, 1, 0, stream), "frontier_sum_kernel");
+      n_launches++;
+      int rc = allreduce_dev(d_V + v_front0, v_front_len);
+      if (rc) return rc;
+    }
     ST_CUDA(launch_gibbs(L.is_ref, dt, ds[cur], L.slot0, L.nslots, d_w, d_xb, d_z, d_tausq_inv, d_S, d_V,
                          probes ? d_probe_sig : nullptr, probes ? d_probe_smu : nullptr, d_fail, L.smem_gibbs, stream),
             "gibbs_level_kernel");
@@ -621,6 +748,15 @@ int Model::deal_with_w(const double* z, uint64_t seed) {
   int nfail = 0;
   ST_CUDA(cudaMemcpyAsync(&nfail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H fail");
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  if (part) {  // every rank must take the same exit
+    h_scalars[48] = nfail;
+    ST_CUDA(cudaMemcpyAsync(d_scalars + 48, h_scalars + 48, sizeof(double), cudaMemcpyHostToDevice, stream), "H2D");
+    rc = allreduce_dev(d_scalars + 48, 1);
+    if (rc) return rc;
+    ST_CUDA(cudaMemcpyAsync(h_scalars + 48, d_scalars + 48, sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H");
+    ST_CUDA(cudaStreamSynchronize(stream), "sync");
+    nfail = h_scalars[48] != 0.0;
+  }
   if (nfail) { err = "Error at gibbs_sample_w: conditional precision not positive definite"; return 3; }
   return 0;
 }
@@ -629,12 +765,12 @@ int Model::get_loglik_w(int slot, double* out2) {
   if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   const int ps = phys(slot);
   ST_CUDA(launch_llw(dt, ds[ps], n_obs_nodes, d_w, stream), "llw_kernel");
-  ST_CUDA(launch_loglik_reduce(ds[ps].logdet, ds[ps].llcomp, n_obs_nodes, nullptr, d_scalars, stream), "loglik_reduce");
-  n_launches += 2;
-  ST_CUDA(cudaMemcpyAsync(h_scalars, d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H scalars");
-  ST_CUDA(cudaStreamSynchronize(stream), "sync");
-  loglik_w[ps] = h_scalars[0];
-  logdetCi[ps] = h_scalars[1];
+  n_launches++;
+  double r3[3];
+  int rc = reduce_loglik(ps, nullptr, r3);
+  if (rc) return rc;
+  loglik_w[ps] = r3[0];
+  logdetCi[ps] = r3[1];
   out2[0] = loglik_w[ps]; out2[1] = logdetCi[ps];
   return 0;
 }
@@ -675,6 +811,10 @@ int Model::rowstats(bool faithful_index) {
   }
   ST_CUDA(launch_rowstats(dt, d_obs_widx, n_all, p, q, d_w, d_xb, d_partial, rowstat_blocks_, d_scalars + 8, stream), "rowstats_kernel");
   n_launches += 2;
+  {
+    int rc = allreduce_dev(d_scalars + 8, q * (p + 1));
+    if (rc) return rc;
+  }
   ST_CUDA(cudaMemcpyAsync(h_scalars + 8, d_scalars + 8, q * (p + 1) * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H stats");
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
   return 0;
@@ -682,7 +822,8 @@ int Model::rowstats(bool faithful_index) {
 
 // gibbs_sample_tausq spamtree_model.cpp:1393-1417
 int Model::gibbs_sample_tausq(const double* fixed) {
-  int rc = rowstats(beta_widx_mode != 0);
+  if (part && beta_widx_mode == -1) beta_widx_mode = -2;
+  int rc = rowstats(part ? false : (beta_widx_mode != 0));
   if (rc) return rc;
   for (int j = 0; j < q; j++) {
     const double bcore = h_scalars[8 + j * (p + 1) + p];
@@ -697,6 +838,11 @@ int Model::gibbs_sample_tausq(const double* fixed) {
 
 // gibbs_sample_beta spamtree_model.cpp:1364-1391
 int Model::gibbs_sample_beta(const double* zb, bool faithful_index) {
+  if (part && faithful_index) {
+    err = "partitioned runs support only the corrected beta row index (faithful_index = 0): the reference's mis-indexing "
+          "(SURVEY App. D #12) mixes rows that live on different ranks";
+    return 4;
+  }
   int rc = rowstats(faithful_index);
   if (rc) return rc;
   for (int j = 0; j < q; j++) {
@@ -902,28 +1048,28 @@ int Model::bench_iteration(const double* theta_prop, int do_swap, uint64_t seed,
   ST_CUDA(cudaMemcpyAsync(h_scalars + 40, d_fail, sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H fail");
   ST_CUDA(cudaEventRecord(ev[1], stream), "event");
   ST_CUDA(launch_llw(dt, ds[cur], n_obs_nodes, d_w, stream), "llw_kernel");
-  ST_CUDA(launch_loglik_reduce(ds[cur].logdet, ds[cur].llcomp, n_obs_nodes, nullptr, d_scalars + 4, stream), "loglik_reduce");
-  n_launches += 2;
+  n_launches++;
+  double rl[3], rb[3];
+  rc = reduce_loglik(cur, nullptr, rl);
+  if (rc) return rc;
+  int nfail_gibbs;
+  std::memcpy(&nfail_gibbs, h_scalars + 40, sizeof(int));
+  if (nfail_gibbs) { err = "Error at gibbs_sample_w: conditional precision not positive definite"; return 3; }
   ST_CUDA(cudaEventRecord(ev[2], stream), "event");
   ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
   rc = launch_build_levels(pa, tab);
   if (rc) return rc;
-  ST_CUDA(launch_loglik_reduce(ds[pa].logdet, ds[pa].llcomp, n_obs_nodes, d_fail, d_scalars, stream), "loglik_reduce");
-  n_launches++;
-  ST_CUDA(cudaMemcpyAsync(h_scalars, d_scalars, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H scalars");
+  rc = reduce_loglik(pa, d_fail, rb);
+  if (rc) return rc;
   ST_CUDA(cudaEventRecord(ev[3], stream), "event");
-  ST_CUDA(cudaStreamSynchronize(stream), "sync");
-  int nfail_gibbs;
-  std::memcpy(&nfail_gibbs, h_scalars + 40, sizeof(int));
-  if (nfail_gibbs) { err = "Error at gibbs_sample_w: conditional precision not positive definite"; return 3; }
-  loglik_w[cur] = h_scalars[4]; logdetCi[cur] = h_scalars[5];
-  const bool ok = h_scalars[2] != 0.0;
-  if (ok) { loglik_w[pa] = h_scalars[0]; logdetCi[pa] = h_scalars[1]; }
+  loglik_w[cur] = rl[0]; logdetCi[cur] = rl[1];
+  const bool ok = rb[2] == 0.0;
+  if (ok) { loglik_w[pa] = rb[0]; logdetCi[pa] = rb[1]; }
   out3[0] = loglik_w[pa]; out3[1] = loglik_w[cur]; out3[2] = ok ? 1.0 : 0.0;
   if (ok && do_swap) accept_make_change();
   rc = gibbs_sample_tausq(nullptr);
   if (rc) return rc;
-  rc = gibbs_sample_beta(nullptr, beta_widx_mode != 0);
+  rc = gibbs_sample_beta(nullptr, part ? false : (beta_widx_mode != 0));
   if (rc) return rc;
   ST_CUDA(cudaEventRecord(ev[4], stream), "event");
   ST_CUDA(cudaStreamSynchronize(stream), "sync");

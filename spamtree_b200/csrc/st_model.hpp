@@ -111,6 +111,19 @@ class Model {
   LevelInfo pred_level;           // prediction blocks
   std::vector<int> h_grp_slot0, h_grp_nn, h_grp_share;
   long long g_total = 0, ri_total = 0, v_total = 0, u_total = 0, s_total = 0, gpred_total = 0;
+  // ---- multi-GPU partition (include/spamtree_b200.h: st_partition)
+  bool part = false;
+  int rank = 0, nranks = 1, n_top_levels = 0;
+  int64_t rng_row_offset = 0, n_global_rows = 0;
+  ivec global_rows;
+  int (*allreduce_fn)(void*, void*, int64_t) = nullptr;
+  void* allreduce_ctx = nullptr;
+  int n_top_slots = 0, n_top_rows = 0, n_slots_total = 0;
+  std::vector<int> h_front_pseudo, h_front_c0, h_front_c1, h_front_vlen, h_front_ulen;
+  int *d_front_pseudo = nullptr, *d_front_c0 = nullptr, *d_front_c1 = nullptr, *d_front_vlen = nullptr, *d_front_ulen = nullptr;
+  long long v_front0 = 0, v_front_len = 0, u_front0 = 0, u_front_len = 0;
+  int allreduce_dev(double* dptr, int64_t n);
+  int reduce_loglik(int ps, const int* fail, double* out3_host);
   // ---- parameters (host copies of the small ones)
   dvec theta[2];
   double loglik_w[2] = {0, 0}, logdetCi[2] = {0, 0};
