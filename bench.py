@@ -5,9 +5,9 @@
   python bench.py --impl reference --gpus N ...            # the reference algorithm on the host cores (CPU oracle)
 
 A "step" is one MCMC iteration of the hot path (spamtree_fit.cpp:167-330 minus predict/save): GIBBS sweep over w + LLW +
-BUILD at a proposed theta + accept/swap + tausq + beta.  At N=1 the workload is BASELINE config C4 (q=3, n=1M); at N>1
-every rank runs its own C4-sized replica of independent subtrees ("weak" scaling over partitions).
-Prints ONE JSON line on rank 0.
+BUILD at a proposed theta + accept/swap + tausq + beta.  The workload is BASELINE config C4 (q=3, n=1M) at every N: at
+N>1 the ONE problem is cut into subtrees (spamtree_b200/partition.py), one rank per GPU, NCCL carrying the log-density
+scalars, the cut-level messages and the beta/tausq statistics ("strong" scaling).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -136,7 +136,7 @@ def run_reference(args, rank, world):
     ts = [om.timed_iteration(props[warm + i], do_swap=(i % 4 == 3)) for i in range(steps)]
     v = steps / float(np.sum(ts))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-            "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "n": int(d["y"].size), "q": int(d["q"]), "blocks": int(t["n_blocks"]),
                        "note": "reference algorithm (CPU oracle port, OpenMP over the blocks of a level) on the host cores; "
                                "steps clamped to --ref-steps so that the run ends within minutes"},
@@ -175,10 +175,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # every rank owns an independent partition: the same C4-shaped problem with its own seed (weak scaling)
-    d, t, csr, theta = build_problem(args.workload, 2021 + rank)
-    gm = sb.SpamTreeMV(d["y"], d["X"], d["coords"], d["mv_id"], t["res_is_ref"], None, None, False, t["block_names"], t["block_groups"],
-                       None, np.zeros(3), theta, 0.1, csr=csr, keep_H=False, device=local_rank)
+    # one problem; at N > 1 every rank builds the same tree and keeps its subtrees plus the replicated top levels
+    d, t, csr, theta = build_problem(args.workload, 2021)
+    if world > 1:
+        from spamtree_b200 import dist as sdist
+        gm, sp, pl = sdist.partitioned_model(d, t, theta, np.zeros(3), 0.1, rank, world, local_rank, sdist.make_allreduce(dev))
+    else:
+        sp, pl = None, None
+        gm = sb.SpamTreeMV(d["y"], d["X"], d["coords"], d["mv_id"], t["res_is_ref"], None, None, False, t["block_names"], t["block_groups"],
+                           None, np.zeros(3), theta, 0.1, csr=csr, keep_H=False, device=local_rank)
     gm.get_loglik_comps_w(0)
     gm.get_loglik_comps_w(1)
     props = proposals(theta, args.warmup + args.steps, 99)
@@ -214,7 +219,7 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     elapsed_max, dev_s_max = float(tt[0]), float(tt[1])
-    value = world * args.steps / elapsed_max
+    value = args.steps / elapsed_max  # one chain: iterations of the whole job per second
 
     # end-to-end leg: the public driver (spamtree_mv_mcmc loop) with host buffers; every iteration is a saved one
     # (theta', tausq, beta go host->device; the 3 log-density scalars, the sufficient statistics and w come back)
@@ -224,39 +229,46 @@ def main():
     npar = theta.size
     barrier()
     res = gm.mcmc(bounds, np.eye(npar) * 1e-4, keep=e2e_steps, burn=0, thin=1, adapting=True, rng_mode=1, seed=5,
-                  sample_predicts=False, save_w=True, save_yhat=False)
+                  sample_predicts=False, save_w=True, save_yhat=False, faithful_beta_index=(world == 1))
     te = torch.tensor([res["mcmc_time"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps / float(te[0])
+    e2e_value = e2e_steps / float(te[0])
+    cnt = gm.counters()
+    tw = torch.tensor([cnt["f_alg"], cnt["f_exec"], c1["launches"] - c0["launches"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tw)  # work and launches of the whole job (replicated top levels counted on every rank)
     n_all, q, p = int(d["y"].size), int(d["q"]), 3
+    n_local = n_all if sp is None else int(sp["y"].size)
     h2d = 8 * (npar + q + p * q)
-    d2h = 8 * (n_all + 3 + 3 + 2 * q * (p + 1)) + 4
+    d2h = 8 * (n_local + 3 + 3 + 2 * q * (p + 1)) + 4  # per rank
 
     if rank == 0:
         hbm_peak, peak_src = load_peaks()
-        cnt = gm.counters()
         build_ms = float(phase[2]) / args.steps
         # BUILD share of the SURVEY §8d flop count: F_alg minus the Gibbs/LLW terms is not separable from counters alone,
         # so the roofline of the dominant kernel is quoted on the executed-formulation flops of BUILD
-        f_alg, f_exec = cnt["f_alg"], cnt["f_exec"]
+        f_alg, f_exec = float(tw[0]), float(tw[1])
+        fp64_peak_job = fp64_peak * world
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * elapsed_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * elapsed_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "n": n_all, "q": q, "p": p, "blocks": int(t["n_blocks"]),
                        "levels": int(len(t["res_is_ref"])), "theta": "fixed parity point, 0.2% random-walk proposals, every 4th accepted",
                        "l2": "working set (G, Ri of both theta slots, >3 GB) is larger than the 126 MB L2; no flush needed",
-                       "parallelism": f"{world} independent partition(s), one per GPU, no data-path collective"},
+                       "parallelism": ("single GPU" if world == 1 else
+                                       f"{world} ranks, subtree partition below tree level {pl['gc']} (levels above replicated); NCCL all-reduce of "
+                                       "3 log-density scalars (x2), cut-level messages and beta/tausq statistics per iteration")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "path": "SpamTreeMV.mcmc -> st_mcmc_run (spamtree_mv_mcmc loop), every iteration saved (w copied to the host)"},
-            "gpu_launches": int(c1["launches"] - c0["launches"]),
+            "gpu_launches": int(tw[2]),
             "device_ms_per_step": {"gibbs": float(phase[0]) / args.steps, "llw": float(phase[1]) / args.steps,
                                    "build": build_ms, "beta_tausq": float(phase[3]) / args.steps, "max_over_ranks_total": 1e3 * dev_s_max / args.steps},
             "roofline": {"bound": "tensor", "pipe": "FP64 DFMA (sm_100a has no tcgen05 FP64 kind)", "kernel": "build_level_kernel (all levels of one BUILD)",
                          "achieved": None,
-                         "peak": fp64_peak, "unit": "TFLOP/s",
+                         "peak": fp64_peak_job, "unit": "TFLOP/s",
                          "frac": None, "traffic": None,
                          "achieved_executed": None,
                          "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure); HBM peak " + peak_src,
@@ -266,8 +278,8 @@ def main():
         step_s = elapsed_max / args.steps
         line["roofline"]["achieved"] = f_alg / step_s / 1e12
         line["roofline"]["achieved_executed"] = f_exec / step_s / 1e12
-        line["roofline"]["frac"] = line["roofline"]["achieved"] / fp64_peak if fp64_peak else None
-        line["roofline"]["frac_executed"] = line["roofline"]["achieved_executed"] / fp64_peak if fp64_peak else None
+        line["roofline"]["frac"] = line["roofline"]["achieved"] / fp64_peak_job if fp64_peak else None
+        line["roofline"]["frac_executed"] = line["roofline"]["achieved_executed"] / fp64_peak_job if fp64_peak else None
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cb, _ = cpu_baseline_sample(args.workload, d, t, csr, theta, iters=1)

@@ -28,7 +28,8 @@ def plan(tree, y, nranks):
         return {"gc": 0, "levels": levels, "owner": np.zeros(nb, dtype=np.int64), "top": np.zeros(nb, dtype=bool)}
     gc = None
     for i, L in enumerate(levels):
-        if np.count_nonzero(obs & (lev == L)) >= nranks:
+        cnt = np.count_nonzero(obs & (lev == L))
+        if cnt >= nranks and (cnt % nranks == 0 or cnt >= 4 * nranks):   # enough subtrees to balance the ranks
             gc = i
             break
     if gc is None:
@@ -54,12 +55,18 @@ def plan(tree, y, nranks):
         if root[u] >= 0:
             weight[root[u]] += len(rows[u]) * (1 + len(par[u]))  # ~ BUILD cost of the block's rows
     w = np.array([weight[u] for u in cut_blocks])
-    bounds = np.searchsorted(np.cumsum(w), np.linspace(0, w.sum(), nranks + 1)[1:-1], side="left")
+    cs = np.cumsum(w)
     owner_of_cut = np.zeros(len(cut_blocks), dtype=np.int64)
     prev = 0
-    for r, b in enumerate(list(bounds) + [len(cut_blocks)]):
-        b = max(b, prev + 1) if r < nranks - 1 else len(cut_blocks)   # every rank gets at least one subtree
-        b = min(b, len(cut_blocks) - (nranks - 1 - r))
+    for r in range(nranks):
+        if r == nranks - 1:
+            b = len(cut_blocks)
+        else:
+            target = cs[-1] * (r + 1) / nranks
+            i = int(np.searchsorted(cs, target, side="left"))            # cs[i] is the first prefix sum >= target
+            below = cs[i - 1] if i > 0 else 0.0
+            b = i if (i > 0 and target - below <= cs[min(i, len(cs) - 1)] - target) else i + 1   # nearer boundary
+            b = min(max(b, prev + 1), len(cut_blocks) - (nranks - 1 - r))  # every rank gets at least one subtree
         owner_of_cut[prev:b] = r
         prev = b
     omap = {u: owner_of_cut[i] for i, u in enumerate(cut_blocks)}

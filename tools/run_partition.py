@@ -70,7 +70,7 @@ def main():
     bounds = synth.default_bounds(q)
     npar = theta.size
     kw = dict(keep=8, burn=40, thin=1, adapting=True, seed=17, rng_mode=0, faithful_beta_index=False)
-    sd = np.eye(npar) * (.01 if q == 1 else 2e-4)
+    sd = np.eye(npar) * (.01 if q == 1 else 1e-5)
     gm2, sp2, _ = sdist.partitioned_model(d, tree, theta, beta, tausq, rank, world, lrank, ar)
     full2 = sb.SpamTreeMV(d["y"], d["X"], d["coords"], d["mv_id"], tree["res_is_ref"], None, None, False, tree["block_names"],
                           tree["block_groups"], None, beta, theta, tausq, csr=csr, device=lrank)
