@@ -47,21 +47,31 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
   const double* Rig = S.Ri + T.rioff[sd];
   const int nch = T.child_ptr[sd + 1] - T.child_ptr[sd];
   const int* ch = T.child_idx + T.child_ptr[sd];
-
+  // chain metadata once, in parallel (no dependent global loads inside the loops below)
+  __shared__ int c_m[32], c_po[32], c_bo[32], c_r0[32];
+  __shared__ long long c_voff[16];
+  if (tid < k) {
+    const int a = T.chain[coff + tid];
+    c_m[tid] = T.m[a]; c_po[tid] = T.chain_poff[coff + tid]; c_bo[tid] = T.chain_boff[coff + tid]; c_r0[tid] = T.row0[a];
+  }
+  if (tid >= 32 && tid < 32 + min(nch, 16)) c_voff[tid - 32] = T.voff[ch[tid - 32]];
   for (int e = tid; e < msq; e += nth) RiS[e] = Rig[e];
+  __syncthreads();
   for (int j = 0; j < k; j++) {
-    const int a = T.chain[coff + j], po = T.chain_poff[coff + j], r0 = T.row0[a], ma = T.m[a];
+    const int po = c_po[j], r0 = c_r0[j], ma = c_m[j];
     for (int t = tid; t < ma; t += nth) wpa[po + t] = w[r0 + t];
   }
   __syncthreads();
   // gwj[j][r] = G_j(r,:) w_{a_j}   (pieces of H w_pa scaled by Ri; :1063 / :1103)
   for (int e = tid; e < k * m; e += nth) {
     const int j = e / m, r = e - j * m;
-    const int mj = T.m[T.chain[coff + j]], po = T.chain_poff[coff + j];
-    const double* g = G + T.chain_boff[coff + j] + (size_t)r * tile_rs(mj);
-    double s = 0;
-    for (int pp = 0; pp < mj; pp++) s = fma(g[pp], wpa[po + pp], s);
-    gwj[e] = s;
+    const int mj = c_m[j], po = c_po[j];
+    const double* g = G + c_bo[j] + (size_t)r * tile_rs(mj);
+    double s0 = 0, s1 = 0;
+    int pp = 0;
+    for (; pp + 1 < mj; pp += 2) { s0 = fma(g[pp], wpa[po + pp], s0); s1 = fma(g[pp + 1], wpa[po + pp + 1], s1); }
+    if (pp < mj) s0 = fma(g[pp], wpa[po + pp], s0);
+    gwj[e] = s0 + s1;
   }
   __syncthreads();
   for (int r = tid; r < m; r += nth) {
@@ -87,7 +97,7 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
     for (int a = tid; a < m; a += nth) {
       double s = 0;
       for (int r = a; r < m; r++) s = fma(RiS[r * rsm + a], gw[r], s);
-      for (int c = 0; c < nch; c++) s += V[T.voff[ch[c]] + P + a];
+      for (int c = 0; c < nch; c++) s += V[(c < 16 ? c_voff[c] : T.voff[ch[c]]) + P + a];
       s += tausq_inv[T.mvq[row0 + a]] * (T.y[row0 + a] - xb[row0 + a]);
       smu[a] = s;
       if (probe_smu) probe_smu[row0 + a] = s;
@@ -150,17 +160,20 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
   for (int e = tid; e < k * m; e += nth) gwj[e] += rr[e % m];
   __syncthreads();
   double* Vd = V + T.voff[sd];
-  for (int j = 0; j < k; j++) {
-    const int mj = T.m[T.chain[coff + j]], po = T.chain_poff[coff + j];
-    const double* g = G + T.chain_boff[coff + j];
+  // all (ancestor, column) pairs at once: P independent dot products over the block's rows
+  for (int e = tid; e < P; e += nth) {
+    int j = 0;
+    while (j + 1 < k && e >= c_po[j + 1]) j++;
+    const int mj = c_m[j], po = c_po[j], pp = e - po, rsj = tile_rs(mj);
+    const double* g = G + c_bo[j] + pp;
     const double* vj = gwj + (size_t)j * m;
-    const int rsj = tile_rs(mj);
-    for (int pp = tid; pp < mj; pp += nth) {
-      double s = 0;
-      for (int r = 0; r < m; r++) s = fma(g[(size_t)r * rsj + pp], vj[r], s);
-      for (int c = 0; c < nch; c++) s += V[T.voff[ch[c]] + po + pp];
-      Vd[po + pp] = s;
-    }
+    double s0 = 0, s1 = 0;
+    int r = 0;
+    for (; r + 1 < m; r += 2) { s0 = fma(g[(size_t)r * rsj], vj[r], s0); s1 = fma(g[(size_t)(r + 1) * rsj], vj[r + 1], s1); }
+    if (r < m) s0 = fma(g[(size_t)r * rsj], vj[r], s0);
+    double s = s0 + s1;
+    for (int c = 0; c < nch; c++) s += V[(c < 16 ? c_voff[c] : T.voff[ch[c]]) + e];
+    Vd[e] = s;
   }
 }
 
@@ -241,17 +254,26 @@ llw_kernel(DevTree T, DevSlot S, int nslots, const double* __restrict__ w) {
   const bool ref = T.isref[sd] != 0;
   const double* G = S.G + T.goff[sd];
   const double* Ri = S.Ri + T.rioff[sd];
+  const int rsm = tile_rs(m);
+  // lane j keeps the metadata of ancestor j (k <= 32): no dependent global loads inside the row loop
+  int a_m = 0, a_bo = 0, a_r0 = 0;
+  if (lane < k) {
+    const int a = T.chain[coff + lane];
+    a_m = T.m[a];
+    a_bo = T.chain_boff[coff + lane];
+    a_r0 = T.row0[a];
+  }
   double wc = 0;
   for (int r = 0; r < m; r++) {
     double s = 0;
     if (ref) {
-      for (int r2 = lane; r2 <= r; r2 += 32) s = fma(Ri[r * tile_rs(m) + r2], w[row0 + r2], s);
+      for (int r2 = lane; r2 <= r; r2 += 32) s = fma(Ri[r * rsm + r2], w[row0 + r2], s);
     } else if (lane == 0) {
       s = Ri[r] * w[row0 + r];
     }
     for (int j = 0; j < k; j++) {
-      const int a = T.chain[coff + j], mj = T.m[a], ar0 = T.row0[a];
-      const double* g = G + T.chain_boff[coff + j] + (size_t)r * tile_rs(mj);
+      const int mj = __shfl_sync(0xffffffffu, a_m, j), bo = __shfl_sync(0xffffffffu, a_bo, j), ar0 = __shfl_sync(0xffffffffu, a_r0, j);
+      const double* g = G + bo + (size_t)r * tile_rs(mj);
       for (int pp = lane; pp < mj; pp += 32) s = fma(-g[pp], w[ar0 + pp], s);
     }
     s = warp_sum(s);

@@ -15,6 +15,7 @@ constexpr int kBuildTC = 4;
 constexpr int kGibbsThreads = 128;
 constexpr int kGramThreads = 128;
 constexpr int kLlwThreads = 128;
+constexpr int kLlwMaxP = 1024;  // parent-set rows the LLW kernel stages per warp (checked at st_create)
 constexpr int kMaxStats = 40;  // q * (p + 1)
 constexpr double kHl2pi = -0.91893853320467274178;  // -0.5 * log(2 pi)  (spamtree_model.h:20)
 

@@ -238,11 +238,17 @@ int Model::build_layout(std::string& e) {
   g_total = ri_total = v_total = u_total = s_total = gpred_total = 0;
   long long sd_total = 0;
   std::vector<int> isref(n_nodes, 0);
+  auto poff_check = [&](int u) {
+    long long t = 0;
+    for (int64_t x = parents.ptr[u]; x < parents.ptr[u + 1]; x++) t += indexing.len(parents.idx[x]);
+    return t;
+  };
   for (int s = 0; s < n_nodes; s++) {
     const int u = block_of_slot[s];
     const bool pred = s >= n_obs_nodes;
     const int kk = (int)parents.len(u);
     if (kk > 32) { e = "ancestor chains longer than 32 are not supported"; return 4; }
+    if (!pred && poff_check(u) > kLlwMaxP) { e = "a parent set larger than 1024 rows is not supported"; return 4; }
     h_k[s] = kk;
     h_chain_off[s] = (int)h_chain.size();
     int poff = 0;
