@@ -251,10 +251,7 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
       for (int c = tid; c < n16; c += nth) __pipeline_memcpy_async(dst + 2 * c, src + 2 * c, 16);
     }
   };
-  if (nsets > 0) { issue(0); }
-  __pipeline_commit();
-  if (nsets > 1) { issue(1); }
-  __pipeline_commit();
+  // (each sweep primes the ring itself: between the sweeps the ring doubles as scratch for the triangular inverses)
 
   // ---- phase 2: covariance panel K_{pa,u} and K_uu
   for (int c = lane; c < LD; c += 32) {
@@ -309,6 +306,10 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
   int it_r0 = 0, it_c0 = 0, it_fam = 0, it_orows = 0;
   bool it_active = false;
   auto sweep = [&](int s_begin, int s_end) {
+    if (s_begin < s_end) issue(s_begin);
+    __pipeline_commit();
+    if (s_begin + 1 < s_end) issue(s_begin + 1);
+    __pipeline_commit();
     for (int s = s_begin; s < s_end; s++) {
       const int* d = desc + s * kDescInts;
       const int flags = d[0];
@@ -317,7 +318,7 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
       __pipeline_wait_prior(kBuildStages - 2);
       __syncthreads();
       if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + 8, (unsigned long long)(t - tq0)); tq0 = t; }
-      if (s + 2 < nsets) issue(s + 2);
+      if (s + 2 < s_end) issue(s + 2);
       __pipeline_commit();
       if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + 9, (unsigned long long)(t - tq0)); tq0 = t; }
       if (flags & F_FIRST) {  // new output block: map one register tile to this thread
@@ -444,8 +445,21 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
     for (int d = warp; d < nn; d += nwarps) {
       const int md = s_nm[d], rsd = tile_rs(md);
       double* R = Rb + s_nR0[d];
+      long long tc0 = 0;
+      if (prof && tid == 0) tc0 = clock64();
       bool okc = warp_chol(R, md, rsd, lane);
-      if (okc) warp_inv_lower_inplace(R, md, rsd, vtmp + warp * (sh.maxmd + 2), lane);
+      if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + 12, (unsigned long long)(t - tc0)); tc0 = t; }
+      if (okc) {
+        if ((size_t)kBuildStages * Fst * maxtile >= (size_t)sh.sumR) {  // the idle ring holds the inverse (column-parallel)
+          double* X = ring + s_nR0[d];
+          warp_inv_lower_cols(R, X, md, rsd, vtmp + warp * (sh.maxmd + 2), lane);
+          for (int e = lane; e < md * rsd; e += 32) R[e] = X[e];
+          __syncwarp();
+        } else {
+          warp_inv_lower_inplace(R, md, rsd, vtmp + warp * (sh.maxmd + 2), lane);
+        }
+      }
+      if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + 13, (unsigned long long)(t - tc0)); }
       if (!okc) {
         if (lane == 0) atomicAdd(fail, 1);
         __syncwarp();
@@ -475,62 +489,93 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
   mark(5);
 
   // ---- phase 7: outputs.  panel[p][c] = H(c, p)
-  for (int c = tid; c < NCp; c += nth) {
-    const int d = colnode[c];
-    if (d < 0) continue;
-    double s = w[s_nrow0[d] + (c - s_nc0[d])];
-    for (int pp = 0; pp < Pc; pp++) s = fma(-panel[(size_t)pp * LD + c], wpa[pp], s);
-    if (share) {
-      const int f = s_nfam[d];
-      for (int t = 0; t < s_fm[f]; t++) s = fma(-panel[(size_t)(Pc + t) * LD + c], wpa[Pc + f * mmaxs + t], s);
-    }
-    ecol[c] = s;  // e = w_x - H w_pa (:888)
-  }
-  __syncthreads();
-  for (int d = 0; d < nn; d++) {
-    const int sd = s0 + d, md = s_nm[d], c0d = s_nc0[d], f = s_nfam[d], rsd = tile_rs(md);
-    const long long go = s_ngoff[d];
-    const double* Rid = Rb + ((MODE == 0) ? s_nR0[d] : c0d);
-    const int nrg = (md + TR - 1) / TR;
-    for (int j = 0; j < k; j++) {
-      const int mj = (j < kc) ? s_cm[j] : s_fm[f];
-      const int prow = (j < kc) ? s_crow[j] : Pc;
-      const int rsj = tile_rs(mj);
-      const long long bo = go + (long long)md * s_rspref[j];
-      for (int e = tid; e < mj * nrg; e += nth) {
-        const int pp = e % mj, r0 = (e / mj) * TR;
-        const double* hp = panel + (size_t)(prow + pp) * LD + c0d;
-        if (MODE == 0) {
-          double g[TR];
-#pragma unroll
-          for (int tr = 0; tr < TR; tr++) g[tr] = 0.0;
-          const int rmax = min(r0 + TR, md);
-          for (int r2 = 0; r2 < rmax; r2++) {
-            const double b = hp[r2];
-#pragma unroll
-            for (int tr = 0; tr < TR; tr++) g[tr] = fma(Rid[min(r0 + tr, md - 1) * rsd + r2], b, g[tr]);
-          }
-#pragma unroll
-          for (int tr = 0; tr < TR; tr++)
-            if (r0 + tr < md) {
-              S.G[bo + (size_t)(r0 + tr) * rsj + pp] = g[tr];  // G = Ri H (bottom-left block of Kxx_invchol, tree_utils.cpp:205)
-              if (keep_H) outH[bo + (size_t)(r0 + tr) * rsj + pp] = hp[r0 + tr];
-            }
-        } else {
-#pragma unroll
-          for (int tr = 0; tr < TR; tr++)
-            if (r0 + tr < md) {
-              const double h = hp[r0 + tr];
-              if (MODE == 1) {
-                S.G[bo + (size_t)(r0 + tr) * rsj + pp] = Rid[r0 + tr] * h;
-                if (keep_H) outH[bo + (size_t)(r0 + tr) * rsj + pp] = h;
-              } else {
-                outH[bo + (size_t)(r0 + tr) * rsj + pp] = h;
-              }
-            }
-        }
+  {
+    const int parts = max(1, min(4, nth / max(NCp, 1)));  // threads per column
+    for (int c = NCp + tid; c < LD; c += nth) ecol[c] = 0.0;
+    for (int c = tid; c < NCp; c += nth) ecol[c] = (colnode[c] >= 0) ? w[s_nrow0[colnode[c]] + (c - s_nc0[colnode[c]])] : 0.0;
+    __syncthreads();
+    const int c = tid % NCp, part = tid / NCp;
+    double s = 0;
+    if (part < parts && colnode[c] >= 0) {
+      const int lo = (int)((long long)Pc * part / parts), hi = (int)((long long)Pc * (part + 1) / parts);
+      double s1 = 0;
+      int pp = lo;
+      for (; pp + 1 < hi; pp += 2) {
+        s = fma(panel[(size_t)pp * LD + c], wpa[pp], s);
+        s1 = fma(panel[(size_t)(pp + 1) * LD + c], wpa[pp + 1], s1);
+      }
+      if (pp < hi) s = fma(panel[(size_t)pp * LD + c], wpa[pp], s);
+      s += s1;
+      if (share && part == 0) {
+        const int f = s_nfam[colnode[c]];
+        for (int t = 0; t < s_fm[f]; t++) s = fma(panel[(size_t)(Pc + t) * LD + c], wpa[Pc + f * mmaxs + t], s);
       }
     }
+    // fixed-order combination of the partial sums (deterministic): part 0 first, then 1, 2, 3
+    for (int q2 = 0; q2 < parts; q2++) {
+      if (part == q2 && part < parts && colnode[c] >= 0) ecol[c] -= s;  // e = w_x - H w_pa (:888)
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  // G = Ri H (bottom-left block of Kxx_invchol(u), tree_utils.cpp:205) and H, one (block, row group, parent column)
+  // item per thread pass, parent column fastest so that the global writes of a warp are contiguous
+  {
+    int total = 0;
+    for (int d = 0; d < nn; d++) total += ((s_nm[d] + TR - 1) / TR) * (Pc + (share ? s_fm[s_nfam[d]] : 0));
+    for (int item = tid; item < total; item += nth) {
+      int d = 0, rem = item;
+      for (;; d++) {
+        const int cnt = ((s_nm[d] + TR - 1) / TR) * (Pc + (share ? s_fm[s_nfam[d]] : 0));
+        if (rem < cnt) break;
+        rem -= cnt;
+      }
+      const int md = s_nm[d], c0d = s_nc0[d], f = s_nfam[d], rsd = tile_rs(md);
+      const int Pd = Pc + (share ? s_fm[f] : 0);
+      const int pcol = rem % Pd, r0 = (rem / Pd) * TR;
+      int j = 0, mj, prow;
+      if (pcol >= Pc) { j = kc; mj = s_fm[f]; prow = Pc; }
+      else { while (j + 1 < kc && pcol >= s_crow[j + 1]) j++; mj = s_cm[j]; prow = s_crow[j]; }
+      const int pp = pcol - prow, rsj = tile_rs(mj);
+      const long long bo = s_ngoff[d] + (long long)md * s_rspref[j] + pp;
+      const double* hp = panel + (size_t)(prow + pp) * LD + c0d;
+      const double* Rid = Rb + ((MODE == 0) ? s_nR0[d] : c0d);
+      if (MODE == 0) {
+        double g[TR];
+        int ro_[TR];
+#pragma unroll
+        for (int tr = 0; tr < TR; tr++) { g[tr] = 0.0; ro_[tr] = min(r0 + tr, md - 1) * rsd; }
+        const int rmax = min(r0 + TR, md);
+#pragma unroll 4
+        for (int r2 = 0; r2 < rmax; r2++) {
+          const double bv = hp[r2];
+#pragma unroll
+          for (int tr = 0; tr < TR; tr++) g[tr] = fma(Rid[ro_[tr] + r2], bv, g[tr]);
+        }
+#pragma unroll
+        for (int tr = 0; tr < TR; tr++)
+          if (r0 + tr < md) {
+            S.G[bo + (size_t)(r0 + tr) * rsj] = g[tr];
+            if (keep_H) outH[bo + (size_t)(r0 + tr) * rsj] = hp[r0 + tr];
+          }
+      } else {
+#pragma unroll
+        for (int tr = 0; tr < TR; tr++)
+          if (r0 + tr < md) {
+            const double h = hp[r0 + tr];
+            if (MODE == 1) {
+              S.G[bo + (size_t)(r0 + tr) * rsj] = Rid[r0 + tr] * h;  // non-reference rows: G_i = H_i / sqrt(R_ii)
+              if (keep_H) outH[bo + (size_t)(r0 + tr) * rsj] = h;
+            } else {
+              outH[bo + (size_t)(r0 + tr) * rsj] = h;
+            }
+          }
+      }
+    }
+  }
+  for (int d = 0; d < nn; d++) {
+    const int sd = s0 + d, md = s_nm[d], c0d = s_nc0[d], rsd = tile_rs(md);
+    const double* Rid = Rb + ((MODE == 0) ? s_nR0[d] : c0d);
     const long long ro = s_nrioff[d];
     for (int e = tid; e < ((MODE == 0) ? md * rsd : md); e += nth) outRi[ro + e] = Rid[e];
     if (MODE != 2 && warp == (d % nwarps)) {

@@ -32,7 +32,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // in-place lower Cholesky of the symmetric m x m matrix A (row-major, leading dimension ld) by one warp;
-// reads the lower triangle only; false on a non-positive or non-finite pivot (dpotrf's info > 0)
+// reads the lower triangle only; false on a non-positive or non-finite pivot (dpotrf's info > 0).
+// Lane r owns row r; the trailing update is batched 8 columns at a time (loads, FMAs, stores) so that the
+// shared-memory latencies overlap instead of chaining.
 __device__ inline bool warp_chol(double* A, int m, int ld, int lane) {
   for (int c = 0; c < m; c++) {
     __syncwarp();
@@ -45,8 +47,16 @@ __device__ inline bool warp_chol(double* A, int m, int ld, int lane) {
     __syncwarp();
     for (int r = c + 1 + lane; r < m; r += 32) {
       const double lrc = A[r * ld + c];
-#pragma unroll 4
-      for (int c2 = c + 1; c2 <= r; c2++) A[r * ld + c2] = fma(-lrc, A[c2 * ld + c], A[r * ld + c2]);
+      double* row = A + r * ld;
+      int c2 = c + 1;
+      for (; c2 + 7 <= r; c2 += 8) {
+        double x[8], l[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { x[u] = row[c2 + u]; l[u] = A[(c2 + u) * ld + c]; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) row[c2 + u] = fma(-lrc, l[u], x[u]);
+      }
+      for (; c2 <= r; c2++) row[c2] = fma(-lrc, A[c2 * ld + c], row[c2]);
     }
   }
   __syncwarp();
@@ -61,12 +71,18 @@ __device__ inline void warp_inv_lower_inplace(double* L, int m, int ld, double* 
     for (int r = j + 1 + lane; r < m; r += 32) v[r] = L[r * ld + j];
     __syncwarp();
     for (int r = j + 1 + lane; r < m; r += 32) {
-      double s0 = 0, s1 = 0;
+      const double* row = L + r * ld;
+      double s[4] = {0, 0, 0, 0};
       int kk = j + 1;
-      for (; kk + 1 <= r; kk += 2) { s0 = fma(L[r * ld + kk], v[kk], s0); s1 = fma(L[r * ld + kk + 1], v[kk + 1], s1); }
-      if (kk <= r) s0 = fma(L[r * ld + kk], v[kk], s0);
-      const double s = s0 + s1;
-      L[r * ld + j] = -s * ajj;
+      for (; kk + 7 <= r; kk += 8) {
+        double x[8], y[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { x[u] = row[kk + u]; y[u] = v[kk + u]; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) s[u & 3] = fma(x[u], y[u], s[u & 3]);
+      }
+      for (; kk <= r; kk++) s[0] = fma(row[kk], v[kk], s[0]);
+      L[r * ld + j] = -((s[0] + s[1]) + (s[2] + s[3])) * ajj;
     }
     if (lane == 0) L[j * ld + j] = ajj;
   }
@@ -74,6 +90,32 @@ __device__ inline void warp_inv_lower_inplace(double* L, int m, int ld, double* 
   for (int e = lane; e < m * m; e += 32) {
     const int r = e / m, c = e - r * m;
     if (c > r) L[r * ld + c] = 0.0;
+  }
+  __syncwarp();
+}
+
+// X = L^-1 for a lower-triangular L, column c by lane c with no inter-lane dependency (forward substitution on e_c);
+// X has the layout of L and must not alias it; dinv: m doubles of scratch (1 / diag(L)); strict upper part zeroed.
+__device__ inline void warp_inv_lower_cols(const double* L, double* X, int m, int ld, double* dinv, int lane) {
+  for (int r = lane; r < m; r += 32) dinv[r] = 1.0 / L[r * ld + r];
+  __syncwarp();
+  for (int c = lane; c < m; c += 32) {
+    for (int r = 0; r < c; r++) X[r * ld + c] = 0.0;
+    X[c * ld + c] = dinv[c];
+    for (int r = c + 1; r < m; r++) {
+      const double* row = L + r * ld;
+      double s[4] = {0, 0, 0, 0};
+      int kk = c;
+      for (; kk + 7 < r; kk += 8) {
+        double x[8], y[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { x[u] = row[kk + u]; y[u] = X[(kk + u) * ld + c]; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) s[u & 3] = fma(x[u], y[u], s[u & 3]);
+      }
+      for (; kk < r; kk++) s[0] = fma(row[kk], X[kk * ld + c], s[0]);
+      X[r * ld + c] = -((s[0] + s[1]) + (s[2] + s[3])) * dinv[r];
+    }
   }
   __syncwarp();
 }

@@ -670,6 +670,7 @@ int Model::launch_build_levels(int pslot, const CovTab& tab) {
               L.slot0, L.ngrp, L.is_ref, tot / std::max(1, L.ngrp), 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot,
               100 * h[4] / tot, 100 * h[5] / tot, 100 * h[6] / tot);
       fprintf(stderr, "      sweeps (thread 0): wait+sync %.1f%% issue %.1f%% compute %.1f%% step-end %.1f%% of kernel\n", 100 * h[8] / tot, 100 * h[9] / tot, 100 * h[10] / tot, 100 * h[11] / tot);
+      fprintf(stderr, "      chol (warp 0): factorise %.1f%% invert %.1f%% of kernel\n", 100 * h[12] / tot, 100 * h[13] / tot);
     }
   }
   if (profile) cudaFree(d_prof);
