@@ -1,16 +1,18 @@
 // st_build.cu — build_level_kernel: BUILD of one tree level (get_loglik_comps_w_std, spamtree_model.cpp:834-998) and
 // of the prediction blocks (predict_std, :1234-1358).
 //
-// One CTA per work group = a run of blocks that share their ancestor chain (siblings), or share all but the deepest
-// ancestor (cousins; the deepest ancestor is then "family specific").  Per group, entirely in shared memory:
+// One CTA per work group = a run of sibling blocks (they share their ancestor chain).  Per group, in shared memory:
 //   1. K = K_{pa,u}: cross-covariance panel, one column per row of the group's blocks (Covariancef_inplace, :885)
-//   2. Z = L^-1 K : the chain's inverse Cholesky factor is never stored; its block row j is [-G_a | Ri_a] of ancestor
-//                   a = chain[j] (tree_utils.cpp:204-206), so Z is formed tile by tile, deepest ancestor first, in place
-//   3. R = K_uu - Z'Z (= Kcc - H Kxc, :896-897), Ri = chol(R)^-1 in place (non-reference levels: diagonal only, :931-948)
-//   4. H' = L^-T Z, shallowest ancestor first, in place  (H = Kxc' Kxx_inv, :887, without ever forming Kxx_inv)
-//   5. G = Ri H, e = w - H w_pa, wcore, logdet (:888, :912-913, :966-968)
-// The operand tiles (G_a, Ri_a of the ancestors) stream from global/L2 through a 3-stage cp.async ring so that the
-// register-tiled FP64 FMA loops read both operands from shared memory.
+//   2. Z = L^-1 K : the chain's inverse Cholesky factor L^-1 (Kxx_invchol of the parent, :882) is never stored as a
+//                   matrix; its rows are the row blocks [G_a | -Ri_a] (sign flipped, tree_utils.cpp:204-206) that every
+//                   ancestor a wrote when its own level was built.  16 rows at a time are staged with cp.async and
+//                   multiplied into the panel in place, bottom rows first.
+//   3. R = K_uu - Z'Z (= Kcc - H Kxc, :896-897), Ri = chol(R)^-1 (non-reference levels: diagonal only, :931-948)
+//   4. Y' = Z Ri' in place, then G' = L^-T Y' (= (Ri H)', :887-888 without ever forming Kxx_inv): 16 columns of L^-1
+//      at a time are staged; the accumulators go straight to global memory, and G w_pa is accumulated on the way
+//   5. wcore = |Ri w_u - G w_pa|^2, logdet (:912-913, :966-968)
+// All dense contractions are FP64 tensor-core MMAs (mma.sync m8n8k4): one warp owns 8 panel columns, so that the
+// in-place updates need no inter-warp synchronisation, and reuses every B fragment for two m-tiles.
 #include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 
@@ -22,244 +24,174 @@
 namespace st {
 
 namespace {
-constexpr int TR = kBuildTR, TC = kBuildTC;
-constexpr int F_RI = 1, F_TRANS = 2, F_PERFAM = 4, F_FIRST = 8, F_LAST = 16;
-constexpr int kDescInts = 6;  // flags, chain index of the operand's owner (-1: family parent), tile index, brow, orow0, ochain
+constexpr int RS = kBuildRS, ST = kBuildST;
+
+// D(8x8) += A(8x4, row) * B(4x8, col); lane l holds A[l>>2][l&3], B[l&3][l>>2], D[l>>2][2*(l&3) + {0,1}]
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// R (row-major, stride rs, lower triangle valid, m <= 32) <- chol(R)^-1 (lower; strict upper zeroed) by one warp.
+// The factorisation keeps row `lane` in registers and broadcasts the pivot column through cb (2 x 32 doubles);
+// the inverse is one forward substitution per lane (column `lane`), reading L by broadcast.  dv: 32 doubles (1/diag).
+__device__ __forceinline__ bool warp_chol_inv32(double* R, int m, int rs, double* cb, double* dv, int lane) {
+  bool ok = true;
+  {
+    double a[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) a[j] = (lane < m && j <= lane) ? R[lane * rs + j] : 0.0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      if (j < m) {
+        double d = __shfl_sync(0xffffffffu, a[j], j);
+        if (!(d > 0.0) || !isfinite(d)) { ok = false; d = 1.0; }  // dpotrf info > 0
+        const double sd = sqrt(d), inv = 1.0 / sd;
+        a[j] = (lane == j) ? sd : a[j] * inv;
+        double* c = cb + (j & 1) * 32;
+        c[lane] = a[j];
+        if (lane == 0) dv[j] = inv;
+        __syncwarp();
+#pragma unroll
+        for (int c2 = j + 1; c2 < 32; c2++)
+          if (c2 < m) a[c2] = fma(-a[j], c[c2], a[c2]);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 32; j++)
+      if (j < m && lane < m && j <= lane) R[lane * rs + j] = a[j];
+  }
+  __syncwarp();
+  double x[32];
+#pragma unroll
+  for (int r = 0; r < 32; r++) {
+    x[r] = 0.0;
+    if (r < m) {
+      double s0 = (r == lane) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+      for (int kx = 0; kx + 1 < r; kx += 2) {
+        const double2 l = *reinterpret_cast<const double2*>(R + r * rs + kx);
+        s0 = fma(-l.x, x[kx], s0);
+        s1 = fma(-l.y, x[kx + 1], s1);
+      }
+      if (r & 1) s0 = fma(-R[r * rs + r - 1], x[r - 1], s0);
+      x[r] = (s0 + s1) * dv[r];
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 32; r++)
+    if (r < m && lane < m) R[r * rs + lane] = x[r];  // x[r] = 0 for lane > r
+  __syncwarp();
+  return ok;
+}
 }  // namespace
 
-// acc[tr][tc] (+/-)= A(tr, kk) * B(kk, tc) for kk in [0, n).  Both operands are in shared memory.
-// mac_rows: A(tr, kk) = pa[tr][kk] (tile rows, stride 1 along kk); mac_cols: A(tr, kk) = pt[kk * rs + tr] (transposed use)
-template <bool NEG>
-__device__ __forceinline__ void mac_rows(double (&acc)[TR][TC], const double* (&pa)[TR], const double* __restrict__ Bp,
-                                         int LD, int n) {
-#pragma unroll 4
-  for (int kk = 0; kk < n; kk++) {
-    const double2 b01 = *reinterpret_cast<const double2*>(Bp);
-    const double2 b23 = *reinterpret_cast<const double2*>(Bp + 2);
-    Bp += LD;
-#pragma unroll
-    for (int tr = 0; tr < TR; tr++) {
-      const double a = NEG ? -pa[tr][kk] : pa[tr][kk];
-      acc[tr][0] = fma(a, b01.x, acc[tr][0]);
-      acc[tr][1] = fma(a, b01.y, acc[tr][1]);
-      acc[tr][2] = fma(a, b23.x, acc[tr][2]);
-      acc[tr][3] = fma(a, b23.y, acc[tr][3]);
-    }
-  }
-}
-template <bool NEG>
-__device__ __forceinline__ void mac_cols(double (&acc)[TR][TC], const double* __restrict__ pt, int rs,
-                                         const double* __restrict__ Bp, int LD, int n) {
-#pragma unroll 4
-  for (int kk = 0; kk < n; kk++) {
-    const double2 b01 = *reinterpret_cast<const double2*>(Bp);
-    const double2 b23 = *reinterpret_cast<const double2*>(Bp + 2);
-    Bp += LD;
-#pragma unroll
-    for (int tr = 0; tr < TR; tr++) {
-      const double a = NEG ? -pt[tr] : pt[tr];  // rows past the block's end read padding; their accumulators are never stored
-      acc[tr][0] = fma(a, b01.x, acc[tr][0]);
-      acc[tr][1] = fma(a, b01.y, acc[tr][1]);
-      acc[tr][2] = fma(a, b23.x, acc[tr][2]);
-      acc[tr][3] = fma(a, b23.y, acc[tr][3]);
-    }
-    pt += rs;
-  }
-}
-
+// MODE 0: reference level, 1: non-reference level, 2: prediction blocks (outG = Hpred receives H, outRi = sd)
 template <int MODE>
-__global__ void __launch_bounds__(kBuildThreads)
-build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __restrict__ outRi,
-                   const int* __restrict__ grp_slot0, const int* __restrict__ grp_nn, const int* __restrict__ grp_share,
-                   const double* __restrict__ w, CovTab tab, int* __restrict__ fail, int keep_H,
-                   unsigned long long* __restrict__ prof) {
+__global__ void __launch_bounds__(kBuildMaxThreads)
+build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __restrict__ outH, double* __restrict__ outRi,
+                   const int* __restrict__ grp_slot0, const int* __restrict__ grp_nn, const double* __restrict__ w,
+                   CovTab tab, int* __restrict__ fail, int ns, unsigned long long* __restrict__ prof) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ CovTabS ct;
-  __shared__ int s_chain[kMaxChain], s_cm[kMaxChain], s_crow[kMaxChain + 1], s_crow0g[kMaxChain];
-  __shared__ int s_nm[kMaxGroupNodes], s_nc0[kMaxGroupNodes], s_nR0[kMaxGroupNodes], s_nfam[kMaxGroupNodes];
-  __shared__ int s_fpar[kMaxFam], s_fm[kMaxFam], s_fc0[kMaxFam + 1], s_frow0g[kMaxFam];
-  __shared__ int s_npar[kMaxGroupNodes], s_nrow0[kMaxGroupNodes], s_rspref[kMaxChain + 1];
-  __shared__ long long s_cgoff[kMaxChain], s_crioff[kMaxChain], s_fgoff[kMaxFam], s_frioff[kMaxFam];
+  __shared__ int s_cm[kMaxChain], s_crow[kMaxChain + 1], s_crow0g[kMaxChain], s_cgs[kMaxChain];
+  __shared__ long long s_cgoff[kMaxChain];
+  __shared__ int s_nm[kMaxGroupNodes], s_nc0[kMaxGroupNodes + 1], s_nrow0[kMaxGroupNodes], s_ngs[kMaxGroupNodes], s_nRb[kMaxGroupNodes];
   __shared__ long long s_ngoff[kMaxGroupNodes], s_nrioff[kMaxGroupNodes];
-  __shared__ BuildShape sh;
-  __shared__ BuildPlan pl;
-  __shared__ int s_nfwd;
+  __shared__ double s_nlogdet[kMaxGroupNodes];
+  __shared__ int s_sumRb, s_maxmd;
 
   const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
   const int s0 = grp_slot0[blockIdx.x], nn = grp_nn[blockIdx.x];
-  const int k = T.k[s0];
+  const int k = T.k[s0], P = T.P[s0];
 
   long long tprev = clock64();
   auto mark = [&](int ph) {
     if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + ph, (unsigned long long)(t - tprev)); tprev = t; }
   };
   load_covtab(ct, tab);
-  // ---- setup: metadata of the chain and of the group's blocks, loaded in parallel (no dependent global loads later)
+  // ---- setup: metadata of the chain and of the group's blocks
   {
     const int coff = T.chain_off[s0];
     for (int j = tid; j < k; j += nth) {
       const int a = T.chain[coff + j];
-      s_chain[j] = a; s_cm[j] = T.m[a]; s_crow[j] = T.chain_poff[coff + j]; s_crow0g[j] = T.row0[a];
-      s_cgoff[j] = T.goff[a]; s_crioff[j] = T.rioff[a];
+      s_cm[j] = T.m[a]; s_crow[j] = T.chain_poff[coff + j]; s_crow0g[j] = T.row0[a]; s_cgoff[j] = T.goff[a]; s_cgs[j] = T.gs[a];
     }
     for (int d = tid; d < nn; d += nth) {
-      s_nm[d] = T.m[s0 + d]; s_npar[d] = T.lastpar[s0 + d]; s_nrow0[d] = T.row0[s0 + d];
-      s_ngoff[d] = T.goff[s0 + d]; s_nrioff[d] = T.rioff[s0 + d];
+      s_nm[d] = T.m[s0 + d]; s_nrow0[d] = T.row0[s0 + d]; s_ngoff[d] = T.goff[s0 + d]; s_ngs[d] = T.gs[s0 + d];
+      s_nrioff[d] = T.rioff[s0 + d];
     }
   }
   __syncthreads();
   if (tid == 0) {
-    const int share = grp_share[blockIdx.x];
-    const int kc = share ? k - 1 : k;
-    const int Pc = (kc < k) ? s_crow[kc] : T.P[s0];
-    s_crow[kc] = Pc;
-    int F = 0, c = 0, sumR = 0, maxmd = 1, prevpar = -2;
+    int c = 0, rb = 0, mx = 1;
     for (int d = 0; d < nn; d++) {
-      const int par = s_npar[d], md = s_nm[d];
-      if (d == 0 || (share && par != prevpar)) {
-        c = (c + 3) & ~3;
-        s_fpar[F] = par;
-        s_fc0[F] = c;
-        F++;
-        prevpar = par;
-      }
-      s_nfam[d] = F - 1;
-      s_nc0[d] = c;
-      s_nR0[d] = sumR;
-      c += md;
-      sumR += md * tile_rs(md);
-      maxmd = max(maxmd, md);
+      s_nc0[d] = c; s_nRb[d] = rb;
+      c += s_nm[d];
+      if (MODE == 0) rb += rb_doubles(s_nm[d]);
+      mx = max(mx, s_nm[d]);
     }
-    const int NCp = (c + 3) & ~3;
-    s_fc0[F] = NCp;
-    sh.mode = MODE; sh.share = share; sh.kc = kc; sh.Pc = Pc; sh.F = F; sh.NCp = NCp; sh.sumR = sumR; sh.maxmd = maxmd;
-    int acc_rs = 0;
-    for (int j = 0; j <= kc && j < kMaxChain; j++) { s_rspref[j] = acc_rs; if (j < kc) acc_rs += tile_rs(s_cm[j]); }
+    s_nc0[nn] = c; s_sumRb = rb; s_maxmd = mx; s_crow[k] = P;
   }
   __syncthreads();
-  if (tid < sh.F) {
-    const int par = s_fpar[tid];
-    const bool sp = sh.share != 0;
-    s_fm[tid] = sp ? T.m[par] : 0;
-    s_frow0g[tid] = sp ? T.row0[par] : 0;
-    s_fgoff[tid] = sp ? T.goff[par] : 0;
-    s_frioff[tid] = sp ? T.rioff[par] : 0;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int maxm = 1, mmaxs = 0;
-    for (int j = 0; j < sh.kc; j++) maxm = max(maxm, s_cm[j]);
-    for (int f = 0; f < sh.F; f++) mmaxs = max(mmaxs, s_fm[f]);
-    maxm = max(maxm, mmaxs);
-    sh.mmaxs = mmaxs;
-    sh.maxtile = maxm * tile_rs(maxm);
-    pl = build_plan(sh);
-    s_nfwd = (sh.share ? sh.kc + 1 : 0) + sh.kc * (sh.kc + 1) / 2;
-  }
-  __syncthreads();
-  const int share = sh.share, kc = sh.kc, Pc = sh.Pc, mmaxs = sh.mmaxs, F = sh.F, NCp = sh.NCp, maxtile = sh.maxtile;
-  const int LD = pl.LD, Ppad = pl.Ppad, nsets = pl.nsets, Fst = pl.Fst, nfwd = s_nfwd;
+  const int ncols = s_nc0[nn];
+  const BuildPlan pl = build_plan(P, ncols, s_sumRb, s_maxmd, ns, (MODE == 0) ? min(nn, kBuildMaxThreads / 32) : 0);
+  const int Ppad = pl.Ppad, NCp = pl.NCp, NT = pl.NT, LD = pl.LD, SA = pl.SA, slotsz = pl.slot;
   double* base = reinterpret_cast<double*>(smem_raw);
   double* panel = base + pl.o_panel;
-  double* Rb = base + pl.o_R;
   double* ring = base + pl.o_ring;
+  double* Rb = ring;  // the Schur complements live in the ring while it is idle (between the sweeps)
   double* pxs = base + pl.o_pxs;
   double* pys = base + pl.o_pys;
   double* wpa = base + pl.o_wpa;
   double* cxs = base + pl.o_cxs;
   double* cys = base + pl.o_cys;
-  double* ecol = base + pl.o_ecol;
+  double* wcol = base + pl.o_wcol;
+  double* tvec = base + pl.o_tvec;
+  double* gw = base + pl.o_gw;
+  double* rdiag = base + pl.o_rdiag;
+  long long* rowsrc = reinterpret_cast<long long*>(base + pl.o_rowsrc);
+  long long* colbase = reinterpret_cast<long long*>(base + pl.o_colbase);
   double* vtmp = base + pl.o_vtmp;
+  double* s_cb = base + pl.o_cb;
   int* pq = reinterpret_cast<int*>(base + pl.o_pq);
+  int* rowlen = reinterpret_cast<int*>(base + pl.o_rowlen);
   int* cq = reinterpret_cast<int*>(base + pl.o_cq);
   int* colnode = reinterpret_cast<int*>(base + pl.o_colnode);
-  int* cgfam = reinterpret_cast<int*>(base + pl.o_cgfam);
-  int* desc = reinterpret_cast<int*>(base + pl.o_desc);
 
-  // ---- operand-tile descriptors of the whole group, in execution order (forward sweep, then backward sweep)
-  if (tid == 0) {
-    int n = 0;
-    auto put = [&](int flags, int owner, int tidx, int brow, int orow0, int ochain) {
-      int* d = desc + n * kDescInts;
-      d[0] = flags; d[1] = owner; d[2] = tidx; d[3] = brow; d[4] = orow0; d[5] = ochain;
-      n++;
-    };
-    if (share) {  // Z of the family-specific (deepest) ancestor
-      for (int i2 = 0; i2 < kc; i2++) put(F_PERFAM | (i2 == 0 ? F_FIRST : 0), -1, i2, s_crow[i2], Pc, -1);
-      put(F_RI | F_PERFAM | F_LAST | (kc == 0 ? F_FIRST : 0), -1, 0, Pc, Pc, -1);
-    }
-    for (int j = kc - 1; j >= 0; j--) {
-      for (int i2 = 0; i2 < j; i2++) put(i2 == 0 ? F_FIRST : 0, j, i2, s_crow[i2], s_crow[j], j);
-      put(F_RI | F_LAST | (j == 0 ? F_FIRST : 0), j, 0, s_crow[j], s_crow[j], j);
-    }
-    for (int i = 0; i < kc; i++) {
-      const bool more = (i + 1 < kc) || share;
-      put(F_RI | F_TRANS | F_FIRST | (more ? 0 : F_LAST), i, 0, s_crow[i], s_crow[i], i);
-      for (int j = i + 1; j < kc; j++) put(F_TRANS | ((j + 1 == kc && !share) ? F_LAST : 0), j, i, s_crow[j], s_crow[i], i);
-      if (share) put(F_TRANS | F_PERFAM | F_LAST, -1, i, Pc, s_crow[i], i);
-    }
-    if (share) put(F_RI | F_TRANS | F_PERFAM | F_FIRST | F_LAST, -1, 0, Pc, Pc, -1);
-  }
-
-  // ---- phase 1: coordinates (ancestor rows are contiguous in the node-major layout)
-  for (int j = 0; j < kc; j++) {
-    const int r0 = s_crow0g[j], po = s_crow[j];
-    for (int t = tid; t < s_cm[j]; t += nth) {
-      pxs[po + t] = T.cx[r0 + t]; pys[po + t] = T.cy[r0 + t]; pq[po + t] = T.mvq[r0 + t]; wpa[po + t] = w[r0 + t];
+  // ---- phase 1: per parent row (= row of the chain's factor) and per column metadata
+  for (int j = 0; j < k; j++) {
+    const int r0g = s_crow0g[j], po = s_crow[j], mj = s_cm[j], gsj = s_cgs[j];
+    const long long go = s_cgoff[j];
+    for (int t = tid; t < mj; t += nth) {
+      pxs[po + t] = T.cx[r0g + t]; pys[po + t] = T.cy[r0g + t]; pq[po + t] = T.mvq[r0g + t]; wpa[po + t] = w[r0g + t];
+      rowsrc[po + t] = go + (long long)t * gsj;
+      rowlen[po + t] = po + mj;  // [G_a | -Ri_a]: the entries above Ri's diagonal are stored zeros
     }
   }
-  if (share)
-    for (int f = 0; f < F; f++) {
-      const int r0 = s_frow0g[f], po = Pc + f * mmaxs;
-      for (int t = tid; t < s_fm[f]; t += nth) {
-        pxs[po + t] = T.cx[r0 + t]; pys[po + t] = T.cy[r0 + t]; pq[po + t] = T.mvq[r0 + t]; wpa[po + t] = w[r0 + t];
-      }
-    }
-  for (int c = tid; c < LD; c += nth) { cxs[c] = 0; cys[c] = 0; cq[c] = 0; colnode[c] = -1; }
-  for (int cg = tid; cg < NCp / 4; cg += nth) {
-    int f = 0;
-    while (f + 1 < F && 4 * cg >= s_fc0[f + 1]) f++;
-    cgfam[cg] = f;
-  }
+  for (int r = P + tid; r < Ppad; r += nth) { pxs[r] = 0; pys[r] = 0; pq[r] = 0; wpa[r] = 0; rowsrc[r] = 0; rowlen[r] = 0; }
+  for (int c = tid; c < LD; c += nth) { cxs[c] = 0; cys[c] = 0; cq[c] = 0; colnode[c] = -1; colbase[c] = -1; wcol[c] = 0; tvec[c] = 0; gw[c] = 0; rdiag[c] = 0; }
   __syncthreads();
   for (int d = 0; d < nn; d++) {
-    const int r0 = s_nrow0[d], c0 = s_nc0[d];
+    const int r0g = s_nrow0[d], c0 = s_nc0[d], gsd = s_ngs[d];
+    const long long go = s_ngoff[d];
     for (int t = tid; t < s_nm[d]; t += nth) {
-      cxs[c0 + t] = T.cx[r0 + t]; cys[c0 + t] = T.cy[r0 + t]; cq[c0 + t] = T.mvq[r0 + t]; colnode[c0 + t] = d;
+      cxs[c0 + t] = T.cx[r0g + t]; cys[c0 + t] = T.cy[r0g + t]; cq[c0 + t] = T.mvq[r0g + t]; colnode[c0 + t] = d;
+      colbase[c0 + t] = go + (long long)t * gsd;
+      wcol[c0 + t] = (MODE == 2) ? 0.0 : w[r0g + t];
     }
   }
   __syncthreads();
-
   mark(0);
-  // ---- cp.async ring over the operand tiles
-  auto tile_geom = [&](const int* d, int f, int& slot, int& rows, int& cols) {
-    if (d[0] & F_PERFAM) { slot = s_fpar[f]; rows = s_fm[f]; } else { slot = s_chain[d[1]]; rows = s_cm[d[1]]; }
-    cols = (d[0] & F_RI) ? rows : s_cm[d[2]];
-  };
-  auto issue = [&](int s) {
-    const int* d = desc + s * kDescInts;
-    const int nf = (d[0] & F_PERFAM) ? F : 1;
-    double* dst0 = ring + (size_t)(s % kBuildStages) * Fst * maxtile;
-    for (int f = 0; f < nf; f++) {
-      int slot, rows, cols;
-      tile_geom(d, f, slot, rows, cols);
-      const bool pf = d[0] & F_PERFAM;
-      const double* src = (d[0] & F_RI) ? S.Ri + (pf ? s_frioff[f] : s_crioff[d[1]])
-                                        : S.G + (pf ? s_fgoff[f] : s_cgoff[d[1]]) + (long long)rows * s_rspref[d[2]];
-      const int n16 = rows * tile_rs(cols) / 2;  // 16-byte chunks (tile sizes are even)
-      double* dst = dst0 + (size_t)f * maxtile;
-      for (int c = tid; c < n16; c += nth) __pipeline_memcpy_async(dst + 2 * c, src + 2 * c, 16);
-    }
-  };
-  // (each sweep primes the ring itself: between the sweeps the ring doubles as scratch for the triangular inverses)
 
-  // ---- phase 2: covariance panel K_{pa,u} and K_uu
+  // ---- phase 2: covariance panel K_{pa,u}; rows >= P and columns past the group's are zero
   for (int c = lane; c < LD; c += 32) {
-    const bool real = (c < NCp) && colnode[c] >= 0;
+    const bool real = colnode[c] >= 0;
     const double xc = cxs[c], yc = cys[c];
     const int qc = cq[c];
     int i = warp;
-    for (; i + 3 * nwarps < Pc; i += 4 * nwarps) {  // four independent evaluations in flight per thread
+    for (; i + 3 * nwarps < P; i += 4 * nwarps) {  // four independent evaluations in flight per thread
       const int i1 = i + nwarps, i2 = i + 2 * nwarps, i3 = i + 3 * nwarps;
       const double v0 = cov_eval(ct, pxs[i], pys[i], pq[i], xc, yc, qc);
       const double v1 = cov_eval(ct, pxs[i1], pys[i1], pq[i1], xc, yc, qc);
@@ -270,345 +202,303 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outH, double* __re
       panel[(size_t)i2 * LD + c] = real ? v2 : 0.0;
       panel[(size_t)i3 * LD + c] = real ? v3 : 0.0;
     }
-    for (; i < Pc; i += nwarps)
+    for (; i < P; i += nwarps)
       panel[(size_t)i * LD + c] = real ? cov_eval(ct, pxs[i], pys[i], pq[i], xc, yc, qc) : 0.0;
-    if (share) {
-      const int f = real ? cgfam[c >> 2] : 0;
-      const int mf = real ? s_fm[f] : 0;
-      for (int t = warp; t < mmaxs; t += nwarps) {
-        const int pi = Pc + f * mmaxs + t;
-        panel[(size_t)(Pc + t) * LD + c] = (t < mf) ? cov_eval(ct, pxs[pi], pys[pi], pq[pi], xc, yc, qc) : 0.0;
-      }
-    }
-  }
-  if (MODE == 0) {
-    for (int d = 0; d < nn; d++) {
-      const int md = s_nm[d], c0 = s_nc0[d], rsd = tile_rs(md);
-      double* Kuu = Rb + s_nR0[d];
-      for (int e = tid; e < md * rsd; e += nth) {
-        const int r = e / rsd, r2 = e - r * rsd;
-        Kuu[e] = (r2 < md) ? cov_eval(ct, cxs[c0 + r], cys[c0 + r], cq[c0 + r], cxs[c0 + r2], cys[c0 + r2], cq[c0 + r2]) : 0.0;
-      }
-    }
-  } else {
-    for (int c = tid; c < LD; c += nth) Rb[c] = (c < NCp && colnode[c] >= 0) ? cov_eval(ct, cxs[c], cys[c], cq[c], cxs[c], cys[c], cq[c]) : 1.0;
+    for (i = P + warp; i < Ppad; i += nwarps) panel[(size_t)i * LD + c] = 0.0;
   }
   // (the first __syncthreads of the sweep below publishes the panel)
+  mark(1);
 
-  // ---- phases 3 and 6: one generic sweep over descriptor range [s_begin, s_end).
-  // The CTA's threads form two halves: both map to the same register tiles and each half takes one half of every
-  // tile's reduction range (split-K), so that all warps issue FP64 work; the halves are summed through the panel.
-  const int n_cg = NCp / TC;
-  const int half = nth >> 1;
-  const int htid = (tid < half) ? tid : tid - half;
-  const int hgrp = (tid < half) ? 0 : 1;
-  double acc[TR][TC];
-  int it_r0 = 0, it_c0 = 0, it_fam = 0, it_orows = 0;
-  bool it_active = false;
-  auto sweep = [&](int s_begin, int s_end) {
-    if (s_begin < s_end) issue(s_begin);
-    __pipeline_commit();
-    if (s_begin + 1 < s_end) issue(s_begin + 1);
-    __pipeline_commit();
-    for (int s = s_begin; s < s_end; s++) {
-      const int* d = desc + s * kDescInts;
-      const int flags = d[0];
-      long long tq0 = 0;
-      if (prof && tid == 0) tq0 = clock64();
-      __pipeline_wait_prior(kBuildStages - 2);
-      __syncthreads();
-      if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + 8, (unsigned long long)(t - tq0)); tq0 = t; }
-      if (s + 2 < s_end) issue(s + 2);
-      __pipeline_commit();
-      if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + 9, (unsigned long long)(t - tq0)); tq0 = t; }
-      if (flags & F_FIRST) {  // new output block: map one register tile to this thread
-        const int omax = (d[5] < 0) ? mmaxs : s_cm[d[5]];
-        const int n_rg = (omax + TR - 1) / TR;
-        it_active = htid < n_rg * n_cg;
-        if (it_active) {
-          const int rg = htid % n_rg, cg = htid / n_rg;
-          it_r0 = rg * TR;
-          it_c0 = cg * TC;
-          it_fam = cgfam[cg];
-          it_orows = (d[5] < 0) ? s_fm[it_fam] : omax;
-          it_active = it_r0 < it_orows;
-        }
-#pragma unroll
-        for (int tr = 0; tr < TR; tr++)
-#pragma unroll
-          for (int tc = 0; tc < TC; tc++) acc[tr][tc] = 0.0;
-      }
-      if (it_active) {
-        const int fi = (flags & F_PERFAM) ? it_fam : 0;
-        int slot, rows, cols;
-        tile_geom(d, fi, slot, rows, cols);
-        const int rs = tile_rs(cols);
-        const double* tile = ring + ((size_t)(s % kBuildStages) * Fst + fi) * maxtile;
-        const bool trans = flags & F_TRANS;
-        const int K = trans ? rows : cols;
-        const int kmid = (K + 1) >> 1;
-        const int kk0 = hgrp ? kmid : 0, kk1 = hgrp ? K : kmid;
-        const double* Bp = panel + (size_t)(d[3] + kk0) * LD + it_c0;
-        // acc = sum G*B - Ri*B ; the block written out is -acc
-        if (!trans) {
-          const double* pa[TR];
-#pragma unroll
-          for (int tr = 0; tr < TR; tr++) pa[tr] = tile + min(it_r0 + tr, it_orows - 1) * rs + kk0;
-          if (flags & F_RI) mac_rows<true>(acc, pa, Bp, LD, kk1 - kk0);
-          else mac_rows<false>(acc, pa, Bp, LD, kk1 - kk0);
-        } else {
-          const double* pt = tile + kk0 * rs + it_r0;
-          if (flags & F_RI) mac_cols<true>(acc, pt, rs, Bp, LD, kk1 - kk0);
-          else mac_cols<false>(acc, pt, rs, Bp, LD, kk1 - kk0);
-        }
-      }
-      if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + 10, (unsigned long long)(t - tq0)); tq0 = t; }
-      if (flags & F_LAST) {  // every thread has finished reading the rows that are about to be overwritten
-        __syncthreads();
-        if (it_active && hgrp == 1) {
-#pragma unroll
-          for (int tr = 0; tr < TR; tr++)
-            if (it_r0 + tr < it_orows) {
-              double* o = panel + (size_t)(d[4] + it_r0 + tr) * LD + it_c0;
-              *reinterpret_cast<double2*>(o) = make_double2(-acc[tr][0], -acc[tr][1]);
-              *reinterpret_cast<double2*>(o + 2) = make_double2(-acc[tr][2], -acc[tr][3]);
-            }
-        }
-        __syncthreads();
-        if (it_active && hgrp == 0) {
-#pragma unroll
-          for (int tr = 0; tr < TR; tr++)
-            if (it_r0 + tr < it_orows) {
-              double* o = panel + (size_t)(d[4] + it_r0 + tr) * LD + it_c0;
-              const double2 p01 = *reinterpret_cast<const double2*>(o), p23 = *reinterpret_cast<const double2*>(o + 2);
-              *reinterpret_cast<double2*>(o) = make_double2(p01.x - acc[tr][0], p01.y - acc[tr][1]);
-              *reinterpret_cast<double2*>(o + 2) = make_double2(p23.x - acc[tr][2], p23.y - acc[tr][3]);
-            }
-        }
-        if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + 11, (unsigned long long)(t - tq0)); tq0 = t; }
-      }
+  const int nstg = Ppad / RS;
+  // stage of the forward sweep: rows [r0, r0 + 16) of the chain's factor, columns [0, r0 + 16)
+  auto issue_fwd = [&](int st, double* slot) {
+    const int r0 = st * RS, nch = (r0 + RS) >> 1;  // 16-byte chunks per row
+    for (int idx = tid; idx < RS * nch; idx += nth) {
+      const int rr = idx / nch, c2 = (idx - rr * nch) * 2;
+      const int r = r0 + rr;
+      const int valid = min(max(rowlen[r] - c2, 0), 2);
+      const double* src = S.G + rowsrc[r] + (valid ? c2 : 0);
+      __pipeline_memcpy_async(slot + rr * SA + c2, src, 16, 16 - 8 * valid);
     }
-    __syncthreads();
+  };
+  // stage of the backward sweep: columns [r0, r0 + 16) of rows [r0, Ppad)
+  auto issue_bwd = [&](int st, double* slot) {
+    const int r0 = st * RS, nrow = Ppad - r0;
+    for (int idx = tid; idx < nrow * 8; idx += nth) {
+      const int rr = idx >> 3, c2 = (idx & 7) * 2;
+      const int r = r0 + rr;
+      const int valid = min(max(rowlen[r] - (r0 + c2), 0), 2);
+      const double* src = S.G + rowsrc[r] + (valid ? r0 + c2 : 0);
+      __pipeline_memcpy_async(slot + rr * ST + c2, src, 16, 16 - 8 * valid);
+    }
   };
 
+  // ---- phase 3: Z = L^-1 K in place, bottom rows first (row r of Z needs rows <= r of K)
+  if (ns == 2 && nstg > 0) issue_fwd(nstg - 1, ring);
+  for (int i = 0; i < nstg; i++) {
+    const int st = nstg - 1 - i;
+    double* slot = ring + ((ns == 2) ? (i & 1) * slotsz : 0);
+    if (ns == 1) issue_fwd(st, slot);
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    if (ns == 2 && i + 1 < nstg) issue_fwd(st - 1, ring + ((i + 1) & 1) * slotsz);
+    if (warp < NT) {
+      const int r0 = st * RS;
+      const double* ap = slot + (lane >> 2) * SA + (lane & 3);
+      const double* bp = panel + (size_t)(lane & 3) * LD + 8 * warp + (lane >> 2);
+      double c0[2] = {0, 0}, c1[2] = {0, 0}, d0[2] = {0, 0}, d1[2] = {0, 0};
+      const int K0 = r0 + 8;  // the upper m-tile (rows r0 .. r0+7) has no entries past column r0 + 7
+#pragma unroll 2
+      for (int kk = 0; kk < K0; kk += 8) {
+        const double a0 = ap[kk], a1 = ap[8 * SA + kk], b0 = bp[(size_t)kk * LD];
+        const double a2 = ap[kk + 4], a3 = ap[8 * SA + kk + 4], b1 = bp[(size_t)(kk + 4) * LD];
+        dmma(c0, a0, b0); dmma(c1, a1, b0); dmma(d0, a2, b1); dmma(d1, a3, b1);
+      }
+      {
+        const double a1 = ap[8 * SA + K0], b0 = bp[(size_t)K0 * LD];
+        const double a3 = ap[8 * SA + K0 + 4], b1 = bp[(size_t)(K0 + 4) * LD];
+        dmma(c1, a1, b0); dmma(d1, a3, b1);
+      }
+      // the staged rows are [G | -Ri] = -L^-1
+      double* o = panel + (size_t)(r0 + (lane >> 2)) * LD + 8 * warp + 2 * (lane & 3);
+      *reinterpret_cast<double2*>(o) = make_double2(-(c0[0] + d0[0]), -(c0[1] + d0[1]));
+      *reinterpret_cast<double2*>(o + (size_t)8 * LD) = make_double2(-(c1[0] + d1[0]), -(c1[1] + d1[1]));
+    }
+    if (ns == 1) __syncthreads();
+  }
   __syncthreads();
-  mark(1);
-  sweep(0, nfwd);  // Z = L^-1 K
   mark(2);
 
   // ---- phase 4/5: Schur complement and its inverse Cholesky factor
   if (MODE == 0) {
+    const int sumRb = s_sumRb;
+    for (int e = tid; e < sumRb; e += nth) Rb[e] = 0.0;
+    __syncthreads();
     int total = 0;
-    for (int d = 0; d < nn; d++) total += ((s_nm[d] + TR - 1) / TR) * ((s_nm[d] + TC - 1) / TC);
-    for (int item = tid; item < total; item += nth) {
+    for (int d = 0; d < nn; d++) { const int mt = (s_nm[d] + 7) >> 3; total += mt * (mt + 1) / 2; }
+    for (int item = warp; item < total; item += nwarps) {
       int d = 0, rem = item;
       for (;; d++) {
-        const int cnt = ((s_nm[d] + TR - 1) / TR) * ((s_nm[d] + TC - 1) / TC);
+        const int mt = (s_nm[d] + 7) >> 3, cnt = mt * (mt + 1) / 2;
         if (rem < cnt) break;
         rem -= cnt;
       }
-      const int md = s_nm[d], c0d = s_nc0[d], rsd = tile_rs(md);
-      const int nrg = (md + TR - 1) / TR;
-      const int r0 = (rem % nrg) * TR, c0 = (rem / nrg) * TC;
-      double a2[TR][TC];
-#pragma unroll
-      for (int tr = 0; tr < TR; tr++)
-#pragma unroll
-        for (int tc = 0; tc < TC; tc++) a2[tr][tc] = 0.0;
-      int ro[TR], co[TC];
-#pragma unroll
-      for (int tr = 0; tr < TR; tr++) ro[tr] = c0d + min(r0 + tr, md - 1);
-#pragma unroll
-      for (int tc = 0; tc < TC; tc++) co[tc] = c0d + min(c0 + tc, md - 1);
+      int ti = 0;
+      while ((ti + 1) * (ti + 2) / 2 <= rem) ti++;
+      const int tj = rem - ti * (ti + 1) / 2;
+      const int md = s_nm[d], c0d = s_nc0[d], rs = rb_stride(md);
+      const double* ap = panel + (size_t)(lane & 3) * LD + min(c0d + 8 * ti + (lane >> 2), LD - 1);
+      const double* bp = panel + (size_t)(lane & 3) * LD + min(c0d + 8 * tj + (lane >> 2), LD - 1);
+      double c0[2] = {0, 0}, d0[2] = {0, 0};
 #pragma unroll 2
-      for (int pp = 0; pp < Ppad; pp++) {
-        const double* row = panel + (size_t)pp * LD;
-        double a[TR], b[TC];
-#pragma unroll
-        for (int tr = 0; tr < TR; tr++) a[tr] = row[ro[tr]];
-#pragma unroll
-        for (int tc = 0; tc < TC; tc++) b[tc] = row[co[tc]];
-#pragma unroll
-        for (int tr = 0; tr < TR; tr++)
-#pragma unroll
-          for (int tc = 0; tc < TC; tc++) a2[tr][tc] = fma(a[tr], b[tc], a2[tr][tc]);
+      for (int kk = 0; kk < Ppad; kk += 8) {
+        dmma(c0, ap[(size_t)kk * LD], bp[(size_t)kk * LD]);
+        dmma(d0, ap[(size_t)(kk + 4) * LD], bp[(size_t)(kk + 4) * LD]);
       }
-      double* R = Rb + s_nR0[d];
+      const int i = 8 * ti + (lane >> 2), j = 8 * tj + 2 * (lane & 3);
+      double* R = Rb + s_nRb[d];
 #pragma unroll
-      for (int tr = 0; tr < TR; tr++)
-#pragma unroll
-        for (int tc = 0; tc < TC; tc++)
-          if (r0 + tr < md && c0 + tc < md) R[(r0 + tr) * rsd + c0 + tc] -= a2[tr][tc];
+      for (int e = 0; e < 2; e++)
+        if (i < md && j + e <= i)
+          R[i * rs + j + e] = cov_eval(ct, cxs[c0d + i], cys[c0d + i], cq[c0d + i], cxs[c0d + j + e], cys[c0d + j + e], cq[c0d + j + e]) - (c0[e] + d0[e]);
     }
     __syncthreads();
     mark(3);
     for (int d = warp; d < nn; d += nwarps) {
-      const int md = s_nm[d], rsd = tile_rs(md);
-      double* R = Rb + s_nR0[d];
-      long long tc0 = 0;
-      if (prof && tid == 0) tc0 = clock64();
-      bool okc = warp_chol(R, md, rsd, lane);
-      if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + 12, (unsigned long long)(t - tc0)); tc0 = t; }
-      if (okc) {
-        if ((size_t)kBuildStages * Fst * maxtile >= (size_t)sh.sumR) {  // the idle ring holds the inverse (column-parallel)
-          double* X = ring + s_nR0[d];
-          warp_inv_lower_cols(R, X, md, rsd, vtmp + warp * (sh.maxmd + 2), lane);
-          for (int e = lane; e < md * rsd; e += 32) R[e] = X[e];
-          __syncwarp();
-        } else {
-          warp_inv_lower_inplace(R, md, rsd, vtmp + warp * (sh.maxmd + 2), lane);
-        }
+      const int md = s_nm[d], c0d = s_nc0[d], rs = rb_stride(md);
+      double* R = Rb + s_nRb[d];
+      bool okc;
+      if (md <= 32) {
+        okc = warp_chol_inv32(R, md, rs, s_cb + warp * 96, s_cb + warp * 96 + 64, lane);
+      } else {
+        okc = warp_chol(R, md, rs, lane);
+        if (okc) warp_inv_lower_inplace(R, md, rs, vtmp + warp * (s_maxmd + 2), lane);
       }
-      if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + 13, (unsigned long long)(t - tc0)); }
       if (!okc) {
         if (lane == 0) atomicAdd(fail, 1);
         __syncwarp();
-        for (int e = lane; e < md * rsd; e += 32) R[e] = 0.0;
+        for (int e = lane; e < md * rs; e += 32) R[e] = 0.0;
       }
+      __syncwarp();
+      // Ri to global memory: the stand-alone tile (Gibbs, LLW) and the [G | -Ri] row block (children's BUILD)
+      const int trs = tile_rs(md);
+      double* ori = outRi + s_nrioff[d];
+      for (int e = lane; e < md * trs; e += 32) {
+        const int r = e / trs, c = e - r * trs;
+        ori[e] = (c < md) ? R[r * rs + c] : 0.0;
+      }
+      double* og = outG + s_ngoff[d] + P;
+      const int gsd = s_ngs[d];
+      for (int e = lane; e < md * md; e += 32) {
+        const int r = e / md, c = e - r * md;
+        og[(size_t)r * gsd + c] = -R[r * rs + c];
+      }
+      // t = Ri w_u (:912-913 via e = w_u - H w_pa: Ri e = Ri w_u - G w_pa) and logdet = sum log diag(Ri) (:966)
+      double ld = 0;
+      for (int r = lane; r < md; r += 32) {
+        double t = 0;
+        for (int c = 0; c <= r; c++) t = fma(R[r * rs + c], wcol[c0d + c], t);
+        tvec[c0d + r] = t;
+        ld += okc ? log(R[r * rs + r]) : 0.0;
+      }
+      ld = warp_sum(ld);
+      if (lane == 0) s_nlogdet[d] = ld;
     }
     __syncthreads();
   } else {
     for (int c = tid; c < NCp; c += nth) {
-      if (colnode[c] < 0) continue;
-      double s = 0;
-      for (int pp = 0; pp < Ppad; pp++) { const double z = panel[(size_t)pp * LD + c]; s = fma(z, z, s); }
-      const double R = Rb[c] - s;
+      const int d = colnode[c];
+      if (d < 0) continue;
+      double q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+      for (int pp = 0; pp < Ppad; pp += 4) {
+        const double z0 = panel[(size_t)pp * LD + c], z1 = panel[(size_t)(pp + 1) * LD + c];
+        const double z2 = panel[(size_t)(pp + 2) * LD + c], z3 = panel[(size_t)(pp + 3) * LD + c];
+        q0 = fma(z0, z0, q0); q1 = fma(z1, z1, q1); q2 = fma(z2, z2, q2); q3 = fma(z3, z3, q3);
+      }
+      const double R = cov_eval(ct, cxs[c], cys[c], cq[c], cxs[c], cys[c], cq[c]) - ((q0 + q1) + (q2 + q3));
       const bool ok = (R > 0.0) && isfinite(R);
+      const int t = c - s_nc0[d];
       if (MODE == 1) {
         if (!ok) atomicAdd(fail, 1);
-        Rb[c] = ok ? 1.0 / sqrt(R) : 0.0;  // ccholprecdiag (:945)
+        const double ri = ok ? 1.0 / sqrt(R) : 0.0;  // ccholprecdiag (:945)
+        rdiag[c] = ri;
+        outRi[s_nrioff[d] + t] = ri;
+        tvec[c] = ri * wcol[c];
       } else {
-        Rb[c] = ok ? sqrt(R) : 0.0;  // predict_std zeroes the sd when the Cholesky fails (:1316-1322)
+        outRi[s_nrioff[d] + t] = ok ? sqrt(R) : 0.0;  // predict_std zeroes the sd when the Cholesky fails (:1316-1322)
       }
     }
     __syncthreads();
+    mark(3);
   }
-
   mark(4);
-  sweep(nfwd, nsets);  // H' = L^-T Z
-  mark(5);
 
-  // ---- phase 7: outputs.  panel[p][c] = H(c, p)
-  {
-    const int parts = max(1, min(4, nth / max(NCp, 1)));  // threads per column
-    for (int c = NCp + tid; c < LD; c += nth) ecol[c] = 0.0;
-    for (int c = tid; c < NCp; c += nth) ecol[c] = (colnode[c] >= 0) ? w[s_nrow0[colnode[c]] + (c - s_nc0[colnode[c]])] : 0.0;
-    __syncthreads();
-    const int c = tid % NCp, part = tid / NCp;
-    double s = 0;
-    if (part < parts && colnode[c] >= 0) {
-      const int lo = (int)((long long)Pc * part / parts), hi = (int)((long long)Pc * (part + 1) / parts);
-      double s1 = 0;
-      int pp = lo;
-      for (; pp + 1 < hi; pp += 2) {
-        s = fma(panel[(size_t)pp * LD + c], wpa[pp], s);
-        s1 = fma(panel[(size_t)(pp + 1) * LD + c], wpa[pp + 1], s1);
-      }
-      if (pp < hi) s = fma(panel[(size_t)pp * LD + c], wpa[pp], s);
-      s += s1;
-      if (share && part == 0) {
-        const int f = s_nfam[colnode[c]];
-        for (int t = 0; t < s_fm[f]; t++) s = fma(panel[(size_t)(Pc + t) * LD + c], wpa[Pc + f * mmaxs + t], s);
-      }
-    }
-    // fixed-order combination of the partial sums (deterministic): part 0 first, then 1, 2, 3
-    for (int q2 = 0; q2 < parts; q2++) {
-      if (part == q2 && part < parts && colnode[c] >= 0) ecol[c] -= s;  // e = w_x - H w_pa (:888)
+  // ---- backward sweep: out' = L^-T panel, written straight to global memory (row block layout of the group's blocks)
+  auto bwd_sweep = [&](double* __restrict__ out, bool do_gw) {
+    double gacc[2] = {0, 0};
+    if (ns == 2 && nstg > 0) issue_bwd(0, ring);
+    for (int i = 0; i < nstg; i++) {
+      double* slot = ring + ((ns == 2) ? (i & 1) * slotsz : 0);
+      if (ns == 1) issue_bwd(i, slot);
+      __pipeline_commit();
+      __pipeline_wait_prior(0);
       __syncthreads();
-    }
-  }
-  __syncthreads();
-  // G = Ri H (bottom-left block of Kxx_invchol(u), tree_utils.cpp:205) and H, one (block, row group, parent column)
-  // item per thread pass, parent column fastest so that the global writes of a warp are contiguous
-  {
-    int total = 0;
-    for (int d = 0; d < nn; d++) total += ((s_nm[d] + TR - 1) / TR) * (Pc + (share ? s_fm[s_nfam[d]] : 0));
-    for (int item = tid; item < total; item += nth) {
-      int d = 0, rem = item;
-      for (;; d++) {
-        const int cnt = ((s_nm[d] + TR - 1) / TR) * (Pc + (share ? s_fm[s_nfam[d]] : 0));
-        if (rem < cnt) break;
-        rem -= cnt;
-      }
-      const int md = s_nm[d], c0d = s_nc0[d], f = s_nfam[d], rsd = tile_rs(md);
-      const int Pd = Pc + (share ? s_fm[f] : 0);
-      const int pcol = rem % Pd, r0 = (rem / Pd) * TR;
-      int j = 0, mj, prow;
-      if (pcol >= Pc) { j = kc; mj = s_fm[f]; prow = Pc; }
-      else { while (j + 1 < kc && pcol >= s_crow[j + 1]) j++; mj = s_cm[j]; prow = s_crow[j]; }
-      const int pp = pcol - prow, rsj = tile_rs(mj);
-      const long long bo = s_ngoff[d] + (long long)md * s_rspref[j] + pp;
-      const double* hp = panel + (size_t)(prow + pp) * LD + c0d;
-      const double* Rid = Rb + ((MODE == 0) ? s_nR0[d] : c0d);
-      if (MODE == 0) {
-        double g[TR];
-        int ro_[TR];
-#pragma unroll
-        for (int tr = 0; tr < TR; tr++) { g[tr] = 0.0; ro_[tr] = min(r0 + tr, md - 1) * rsd; }
-        const int rmax = min(r0 + TR, md);
-#pragma unroll 4
-        for (int r2 = 0; r2 < rmax; r2++) {
-          const double bv = hp[r2];
-#pragma unroll
-          for (int tr = 0; tr < TR; tr++) g[tr] = fma(Rid[ro_[tr] + r2], bv, g[tr]);
+      if (ns == 2 && i + 1 < nstg) issue_bwd(i + 1, ring + ((i + 1) & 1) * slotsz);
+      if (warp < NT) {
+        const int r0 = i * RS, nk = Ppad - r0;
+        const double* ap = slot + (lane & 3) * ST + (lane >> 2);  // A[m][k] = stage[k][m] (transposed use)
+        const double* bp = panel + (size_t)(r0 + (lane & 3)) * LD + 8 * warp + (lane >> 2);
+        double c0[2] = {0, 0}, c1[2] = {0, 0}, d0[2] = {0, 0}, d1[2] = {0, 0};
+        // rows r0 .. r0+7 of the stage have no entries in columns r0+8 .. r0+15 (lower-triangular factor)
+        dmma(c0, ap[0], bp[0]);
+        dmma(d0, ap[4 * ST], bp[(size_t)4 * LD]);
+#pragma unroll 2
+        for (int kk = 8; kk < nk; kk += 8) {
+          const double a0 = ap[kk * ST], a1 = ap[kk * ST + 8], b0 = bp[(size_t)kk * LD];
+          const double a2 = ap[(kk + 4) * ST], a3 = ap[(kk + 4) * ST + 8], b1 = bp[(size_t)(kk + 4) * LD];
+          dmma(c0, a0, b0); dmma(c1, a1, b0); dmma(d0, a2, b1); dmma(d1, a3, b1);
         }
+        const int r = r0 + (lane >> 2), c = 8 * warp + 2 * (lane & 3);
+        const long long cb0 = colbase[c], cb1 = colbase[c + 1];
+        const double v00 = -(c0[0] + d0[0]), v01 = -(c0[1] + d0[1]), v10 = -(c1[0] + d1[0]), v11 = -(c1[1] + d1[1]);
+        if (r < P) {
+          if (cb0 >= 0) out[cb0 + r] = v00;
+          if (cb1 >= 0) out[cb1 + r] = v01;
+        }
+        if (r + 8 < P) {
+          if (cb0 >= 0) out[cb0 + r + 8] = v10;
+          if (cb1 >= 0) out[cb1 + r + 8] = v11;
+        }
+        if (do_gw) {
+          const double w0 = wpa[r], w1 = wpa[r + 8];  // zero past P
+          gacc[0] = fma(v00, w0, fma(v10, w1, gacc[0]));
+          gacc[1] = fma(v01, w0, fma(v11, w1, gacc[1]));
+        }
+      }
+      if (ns == 1) __syncthreads();
+    }
+    if (do_gw && warp < NT) {  // G w_pa per column: fixed-order reduction over the lanes that share the column
 #pragma unroll
-        for (int tr = 0; tr < TR; tr++)
-          if (r0 + tr < md) {
-            S.G[bo + (size_t)(r0 + tr) * rsj] = g[tr];
-            if (keep_H) outH[bo + (size_t)(r0 + tr) * rsj] = hp[r0 + tr];
-          }
-      } else {
-#pragma unroll
-        for (int tr = 0; tr < TR; tr++)
-          if (r0 + tr < md) {
-            const double h = hp[r0 + tr];
-            if (MODE == 1) {
-              S.G[bo + (size_t)(r0 + tr) * rsj] = Rid[r0 + tr] * h;  // non-reference rows: G_i = H_i / sqrt(R_ii)
-              if (keep_H) outH[bo + (size_t)(r0 + tr) * rsj] = h;
-            } else {
-              outH[bo + (size_t)(r0 + tr) * rsj] = h;
-            }
-          }
+      for (int o = 4; o < 32; o <<= 1) {
+        gacc[0] += __shfl_xor_sync(0xffffffffu, gacc[0], o);
+        gacc[1] += __shfl_xor_sync(0xffffffffu, gacc[1], o);
+      }
+      if ((lane >> 2) == 0) { gw[8 * warp + 2 * lane] = gacc[0]; gw[8 * warp + 2 * lane + 1] = gacc[1]; }
+    }
+    __syncthreads();
+  };
+
+  if (MODE == 2) {
+    bwd_sweep(outG, false);  // H of the prediction blocks
+  } else {
+    if (outH != nullptr) {
+      bwd_sweep(outH, false);  // H = K_{u,pa} Kxx_inv (:887), kept only on request
+      if (MODE == 0) {  // the sweep used the ring: reload Ri
+        const int sumRb = s_sumRb;
+        for (int e = tid; e < sumRb; e += nth) Rb[e] = 0.0;
+        __syncthreads();
+        for (int d = 0; d < nn; d++) {
+          const int md = s_nm[d], rs = rb_stride(md), trs = tile_rs(md);
+          const double* ori = outRi + s_nrioff[d];
+          double* R = Rb + s_nRb[d];
+          for (int e = tid; e < md * md; e += nth) { const int r = e / md, c = e - r * md; R[r * rs + c] = ori[r * trs + c]; }
+        }
+        __syncthreads();
       }
     }
-  }
-  for (int d = 0; d < nn; d++) {
-    const int sd = s0 + d, md = s_nm[d], c0d = s_nc0[d], rsd = tile_rs(md);
-    const double* Rid = Rb + ((MODE == 0) ? s_nR0[d] : c0d);
-    const long long ro = s_nrioff[d];
-    for (int e = tid; e < ((MODE == 0) ? md * rsd : md); e += nth) outRi[ro + e] = Rid[e];
-    if (MODE != 2 && warp == (d % nwarps)) {
-      // wcore = e' prec e = |Ri e|^2 (:913 / :950) ; logdet = sum log diag(Ri) (:966)
+    // Y' = Z Ri' in place
+    if (MODE == 0) {
+      const int npt = Ppad >> 3;
+      for (int item = warp; item < npt * nn; item += nwarps) {
+        const int d = item / npt, pt = item - d * npt;
+        const int md = s_nm[d], c0d = s_nc0[d], rs = rb_stride(md);
+        const double* R = Rb + s_nRb[d];
+        const double* ap = panel + (size_t)(8 * pt + (lane >> 2)) * LD;
+        for (int it = ((md + 7) >> 3) - 1; it >= 0; it--) {  // descending: tile `it` reads columns < 8 it + 8, writes [8 it, 8 it + 8)
+          const int Kx = min(8 * it + 8, (md + 3) & ~3);
+          const double* bp = R + (8 * it + (lane >> 2)) * rs + (lane & 3);
+          double c0[2] = {0, 0};
+          for (int kk = 0; kk < Kx; kk += 4) dmma(c0, ap[min(c0d + kk + (lane & 3), LD - 1)], bp[kk]);
+          const int jl = 8 * it + 2 * (lane & 3);
+          double* o = panel + (size_t)(8 * pt + (lane >> 2)) * LD + c0d + jl;
+          if (jl < md) o[0] = c0[0];
+          if (jl + 1 < md) o[1] = c0[1];
+        }
+      }
+    } else {
+      for (int e = tid; e < Ppad * NCp; e += nth) {
+        const int pp = e / NCp, c = e - pp * NCp;
+        panel[(size_t)pp * LD + c] *= rdiag[c];  // non-reference rows: G_i = H_i / sqrt(R_ii)
+      }
+    }
+    __syncthreads();
+    mark(5);
+    bwd_sweep(outG, true);  // G = Ri H (bottom-left block of Kxx_invchol(u), tree_utils.cpp:205)
+    // wcore = e' prec e = |Ri w_u - G w_pa|^2 (:913 / :950) ; logdet = sum log diag(Ri) (:966)
+    for (int d = warp; d < nn; d += nwarps) {
+      const int md = s_nm[d], c0d = s_nc0[d];
       double wc = 0, ld = 0;
       for (int r = lane; r < md; r += 32) {
-        double t;
-        if (MODE == 0) {
-          t = 0;
-          for (int r2 = 0; r2 <= r; r2++) t = fma(Rid[r * rsd + r2], ecol[c0d + r2], t);
-          ld += log(Rid[r * rsd + r]);
-        } else {
-          t = Rid[r] * ecol[c0d + r];
-          ld += log(Rid[r]);
-        }
+        const double t = tvec[c0d + r] - gw[c0d + r];
         wc = fma(t, t, wc);
+        if (MODE == 1) ld += log(rdiag[c0d + r]);
       }
       wc = warp_sum(wc);
-      ld = warp_sum(ld);
+      if (MODE == 1) ld = warp_sum(ld); else ld = s_nlogdet[d];
       if (lane == 0) {
-        S.logdet[sd] = ld;
-        S.llcomp[sd] = (double)md * kHl2pi - 0.5 * wc;  // :967-968
+        S.logdet[s0 + d] = ld;
+        S.llcomp[s0 + d] = (double)md * kHl2pi - 0.5 * wc;  // :967-968
       }
     }
   }
-  __syncthreads();
   mark(6);
 }
 
 template <int MODE>
-static cudaError_t launch_build_t(const DevTree& T, const DevSlot& S, double* outH, double* outRi, const int* grp_slot0,
-                                  const int* grp_nn, const int* grp_share, int ngrp, const double* w, const CovTab& tab,
-                                  int* fail, int keep_H, size_t smem, cudaStream_t st, unsigned long long* prof, int nthreads) {
+static cudaError_t launch_build_t(const DevTree& T, const DevSlot& S, double* outG, double* outH, double* outRi,
+                                  const int* grp_slot0, const int* grp_nn, int ngrp, const double* w, const CovTab& tab,
+                                  int* fail, int ns, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof) {
   auto kern = build_level_kernel<MODE>;
   static size_t configured[3] = {0, 0, 0};
   if (smem > configured[MODE]) {
@@ -616,16 +506,16 @@ static cudaError_t launch_build_t(const DevTree& T, const DevSlot& S, double* ou
     if (e != cudaSuccess) return e;
     configured[MODE] = smem;
   }
-  kern<<<ngrp, nthreads, smem, st>>>(T, S, outH, outRi, grp_slot0, grp_nn, grp_share, w, tab, fail, keep_H, prof);
+  kern<<<ngrp, nthreads, smem, st>>>(T, S, outG, outH, outRi, grp_slot0, grp_nn, w, tab, fail, ns, prof);
   return cudaGetLastError();
 }
-cudaError_t launch_build(int mode, const DevTree& T, const DevSlot& S, double* outH, double* outRi, const int* grp_slot0,
-                         const int* grp_nn, const int* grp_share, int ngrp, const double* w, const CovTab& tab, int* fail,
-                         int keep_H, size_t smem, cudaStream_t st, unsigned long long* prof, int nthreads) {
+cudaError_t launch_build(int mode, const DevTree& T, const DevSlot& S, double* outG, double* outH, double* outRi,
+                         const int* grp_slot0, const int* grp_nn, int ngrp, const double* w, const CovTab& tab, int* fail,
+                         int ns, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof) {
   if (ngrp <= 0) return cudaSuccess;
-  if (mode == 0) return launch_build_t<0>(T, S, outH, outRi, grp_slot0, grp_nn, grp_share, ngrp, w, tab, fail, keep_H, smem, st, prof, nthreads);
-  if (mode == 1) return launch_build_t<1>(T, S, outH, outRi, grp_slot0, grp_nn, grp_share, ngrp, w, tab, fail, keep_H, smem, st, prof, nthreads);
-  return launch_build_t<2>(T, S, outH, outRi, grp_slot0, grp_nn, grp_share, ngrp, w, tab, fail, keep_H, smem, st, prof, nthreads);
+  if (mode == 0) return launch_build_t<0>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, smem, st, nthreads, prof);
+  if (mode == 1) return launch_build_t<1>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, smem, st, nthreads, prof);
+  return launch_build_t<2>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, smem, st, nthreads, prof);
 }
 
 }  // namespace st

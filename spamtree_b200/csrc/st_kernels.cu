@@ -34,7 +34,7 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
   const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int sd = slot0 + blockIdx.x;
   const int m = T.m[sd], k = T.k[sd], P = T.P[sd], coff = T.chain_off[sd], row0 = T.row0[sd];
-  const int rsm = tile_rs(m);
+  const int rsm = tile_rs(m), gs = T.gs[sd];
   const int msq = REF ? m * rsm : m;
   double* RiS = reinterpret_cast<double*>(smem_raw);
   double* Sig = RiS + msq;
@@ -48,11 +48,11 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
   const int nch = T.child_ptr[sd + 1] - T.child_ptr[sd];
   const int* ch = T.child_idx + T.child_ptr[sd];
   // chain metadata once, in parallel (no dependent global loads inside the loops below)
-  __shared__ int c_m[32], c_po[32], c_bo[32], c_r0[32];
+  __shared__ int c_m[32], c_po[32], c_r0[32];
   __shared__ long long c_voff[16];
   if (tid < k) {
     const int a = T.chain[coff + tid];
-    c_m[tid] = T.m[a]; c_po[tid] = T.chain_poff[coff + tid]; c_bo[tid] = T.chain_boff[coff + tid]; c_r0[tid] = T.row0[a];
+    c_m[tid] = T.m[a]; c_po[tid] = T.chain_poff[coff + tid]; c_r0[tid] = T.row0[a];
   }
   if (tid >= 32 && tid < 32 + min(nch, 16)) c_voff[tid - 32] = T.voff[ch[tid - 32]];
   for (int e = tid; e < msq; e += nth) RiS[e] = Rig[e];
@@ -66,7 +66,7 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
   for (int e = tid; e < k * m; e += nth) {
     const int j = e / m, r = e - j * m;
     const int mj = c_m[j], po = c_po[j];
-    const double* g = G + c_bo[j] + (size_t)r * tile_rs(mj);
+    const double* g = G + (size_t)r * gs + po;
     double s0 = 0, s1 = 0;
     int pp = 0;
     for (; pp + 1 < mj; pp += 2) { s0 = fma(g[pp], wpa[po + pp], s0); s1 = fma(g[pp + 1], wpa[po + pp + 1], s1); }
@@ -164,8 +164,8 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
   for (int e = tid; e < P; e += nth) {
     int j = 0;
     while (j + 1 < k && e >= c_po[j + 1]) j++;
-    const int mj = c_m[j], po = c_po[j], pp = e - po, rsj = tile_rs(mj);
-    const double* g = G + c_bo[j] + pp;
+    const int rsj = gs;
+    const double* g = G + e;
     const double* vj = gwj + (size_t)j * m;
     double s0 = 0, s1 = 0;
     int r = 0;
@@ -213,12 +213,13 @@ gram_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ U, doubl
   const int nch = T.child_ptr[sd + 1] - T.child_ptr[sd];
   const int* ch = T.child_idx + T.child_ptr[sd];
   const double* G = S.G + T.goff[sd];
+  const int gs = T.gs[sd];
   double* Ud = U + T.uoff[sd];
   for (int j = 0; j < k; j++) {
     const int mj = T.m[T.chain[coff + j]];
-    const double* g = G + T.chain_boff[coff + j];
+    const double* g = G + T.chain_poff[coff + j];
     const int uo = T.chain_uoff[coff + j];
-    const int rsj = tile_rs(mj);
+    const int rsj = gs;
     for (int e = tid; e < mj * mj; e += nth) {
       const int a = e / mj, b = e - a * mj;
       double s = 0;
@@ -254,13 +255,13 @@ llw_kernel(DevTree T, DevSlot S, int nslots, const double* __restrict__ w) {
   const bool ref = T.isref[sd] != 0;
   const double* G = S.G + T.goff[sd];
   const double* Ri = S.Ri + T.rioff[sd];
-  const int rsm = tile_rs(m);
+  const int rsm = tile_rs(m), gs = T.gs[sd];
   // lane j keeps the metadata of ancestor j (k <= 32): no dependent global loads inside the row loop
-  int a_m = 0, a_bo = 0, a_r0 = 0;
+  int a_m = 0, a_po = 0, a_r0 = 0;
   if (lane < k) {
     const int a = T.chain[coff + lane];
     a_m = T.m[a];
-    a_bo = T.chain_boff[coff + lane];
+    a_po = T.chain_poff[coff + lane];
     a_r0 = T.row0[a];
   }
   double wc = 0;
@@ -272,8 +273,8 @@ llw_kernel(DevTree T, DevSlot S, int nslots, const double* __restrict__ w) {
       s = Ri[r] * w[row0 + r];
     }
     for (int j = 0; j < k; j++) {
-      const int mj = __shfl_sync(0xffffffffu, a_m, j), bo = __shfl_sync(0xffffffffu, a_bo, j), ar0 = __shfl_sync(0xffffffffu, a_r0, j);
-      const double* g = G + bo + (size_t)r * tile_rs(mj);
+      const int mj = __shfl_sync(0xffffffffu, a_m, j), po = __shfl_sync(0xffffffffu, a_po, j), ar0 = __shfl_sync(0xffffffffu, a_r0, j);
+      const double* g = G + (size_t)r * gs + po;
       for (int pp = lane; pp < mj; pp += 32) s = fma(-g[pp], w[ar0 + pp], s);
     }
     s = warp_sum(s);
@@ -351,12 +352,13 @@ __global__ void predict_sample_kernel(DevTree T, int slot0, int nslots, const do
   const int sd = slot0 + blockIdx.x;
   const int m = T.m[sd], k = T.k[sd], coff = T.chain_off[sd], row0 = T.row0[sd];
   const double* H = Hpred + T.goff[sd];
+  const int gs = T.gs[sd];
   const double* sdv = sdpred + T.rioff[sd];
   for (int r = threadIdx.x; r < m; r += blockDim.x) {
     double s = 0;
     for (int j = 0; j < k; j++) {
       const int a = T.chain[coff + j], mj = T.m[a], ar0 = T.row0[a];
-      const double* h = H + T.chain_boff[coff + j] + (size_t)r * tile_rs(mj);
+      const double* h = H + (size_t)r * gs + T.chain_poff[coff + j];
       for (int pp = 0; pp < mj; pp++) s = fma(h[pp], w[ar0 + pp], s);
     }
     w[row0 + r] = s + sdv[r] * z[row0 + r];

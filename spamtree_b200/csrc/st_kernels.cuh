@@ -9,9 +9,12 @@
 
 namespace st {
 
-constexpr int kBuildThreads = 256;
-constexpr int kBuildTR = 5;  // register tile rows: blocks have ~25 rows (5 x 5 knots per cell, R/spamtree_fit.R:229-233)
-constexpr int kBuildTC = 4;
+constexpr int kBuildMaxThreads = 512;  // build_level_kernel: one warp per 8 panel columns (at most 16 warps)
+constexpr int kBuildRS = 16;     // rows of the chain's inverse Cholesky factor staged per step (two DMMA m-tiles)
+constexpr int kBuildST = 20;     // row stride of a backward stage: 16 columns + 4 (conflict-free fragment reads)
+constexpr int kMaxGroupCols = 128;
+constexpr int kMaxGroupNodes = 32;
+constexpr int kMaxChain = 32;
 constexpr int kGibbsThreads = 128;
 constexpr int kGramThreads = 128;
 constexpr int kLlwThreads = 128;
@@ -19,52 +22,53 @@ constexpr int kLlwMaxP = 1024;  // parent-set rows the LLW kernel stages per war
 constexpr int kMaxStats = 40;  // q * (p + 1)
 constexpr double kHl2pi = -0.91893853320467274178;  // -0.5 * log(2 pi)  (spamtree_model.h:20)
 
-// row stride of a stored tile with `cols` columns: even (16-byte rows) and = 2 mod 4 (conflict-free 5-row gathers)
+// row stride of a stored m x m Ri tile with `cols` columns: even (16-byte rows) and = 2 mod 4
 __host__ __device__ inline int tile_rs(int cols) {
   int r = (cols + 1) & ~1;
   if ((r & 3) == 0) r += 2;
   return r;
 }
+// Row stride of a block's row block of the chain's inverse Cholesky factor: [ G (P) | -Ri (m, reference blocks) | 0 ].
+// (tree_utils.cpp:204-206 stores [-Ri H | Ri]; the sign is flipped here so that consumers read G directly.)
+__host__ __device__ inline int g_stride(int P, int m, int isref) { return (P + (isref ? m : 0) + 3) & ~3; }
+// shared-memory layout of a block's m x m Schur complement inside build_level_kernel: stride = 4 mod 8, rows padded to 8
+__host__ __device__ inline int rb_stride(int m) {
+  int r = (m + 3) & ~3;
+  if ((r & 7) == 0) r += 4;
+  return r;
+}
+__host__ __device__ inline int rb_doubles(int m) { return ((m + 7) & ~7) * rb_stride(m); }
 
-// ---- shared-memory plan of build_level_kernel (one work group)
-constexpr int kBuildStages = 3;   // cp.async ring depth
-constexpr int kMaxFam = 8;        // sibling sets ("families") per work group
-constexpr int kMaxGroupNodes = 64;
-constexpr int kMaxChain = 32;
-struct BuildShape {
-  int mode;    // 0 reference level, 1 non-reference level, 2 prediction blocks
-  int share;   // 1: the deepest ancestor differs per family (cousin group)
-  int kc;      // ancestors common to the whole group
-  int Pc;      // rows of the common ancestors
-  int mmaxs;   // max rows of the family-specific ancestor (0 when share == 0)
-  int F;       // families
-  int NCp;     // panel columns, every family padded to a multiple of 4
-  int sumR;    // mode 0: sum of m_d * tile_rs(m_d) over the group's blocks
-  int maxtile; // doubles of the largest operand tile
-  int maxmd;   // largest block of the group
-};
+// ---- shared-memory plan of build_level_kernel (one work group = a run of sibling blocks)
 struct BuildPlan {
-  int LD, Ppad, Pv, nsets, Fst;
-  size_t o_panel, o_R, o_ring, o_pxs, o_pys, o_wpa, o_cxs, o_cys, o_ecol, o_vtmp, o_pq, o_cq, o_colnode, o_cgfam, o_desc, total;
+  int Ppad, NCp, NT, LD, SA, slot, ring;
+  size_t o_panel, o_ring, o_pxs, o_pys, o_wpa, o_cxs, o_cys, o_wcol, o_tvec, o_gw, o_rdiag, o_rowsrc, o_colbase, o_vtmp, o_cb,
+      o_pq, o_rowlen, o_cq, o_colnode, total;
 };
-__host__ __device__ inline int build_nsets(int kc, int share) { return kc * (kc + 1) + share * (2 * kc + 2); }
-__host__ __device__ inline BuildPlan build_plan(const BuildShape& s) {
+// P parent rows, ncols rows in the group's blocks, sumRb = sum of rb_doubles over its blocks (reference levels),
+// maxmd = largest block, ns = ring depth (1 or 2), nchol = warps factorising at once (reference levels: min(blocks, 16))
+__host__ __device__ inline BuildPlan build_plan(int P, int ncols, int sumRb, int maxmd, int ns, int nchol) {
   BuildPlan p;
-  p.LD = s.NCp + 2;
-  p.Ppad = s.Pc + (s.share ? s.mmaxs : 0);
-  p.Pv = s.Pc + (s.share ? s.F * s.mmaxs : 0);
-  p.nsets = build_nsets(s.kc, s.share);
-  p.Fst = s.share ? s.F : 1;
+  p.Ppad = (P + 15) & ~15;
+  p.NCp = (ncols + 7) & ~7;
+  p.NT = p.NCp >> 3;
+  p.LD = p.NCp + 4;   // = 4 or 12 mod 16: the 4 x 8 and 8 x 4 DMMA fragment reads hit 16 distinct banks per half-warp
+  p.SA = p.Ppad + 4;  // = 4 mod 16, same reason
+  const int fw = kBuildRS * p.SA, bw = p.Ppad * kBuildST;
+  p.slot = fw > bw ? fw : bw;
+  p.ring = ns * p.slot > sumRb ? ns * p.slot : sumRb;
   size_t o = 0;
   auto take = [&](size_t n_doubles) { size_t r = o; o += ((n_doubles + 1) & ~(size_t)1); return r; };
   p.o_panel = take((size_t)p.Ppad * p.LD);
-  p.o_R = take(s.mode == 0 ? (size_t)s.sumR : (size_t)p.LD);
-  p.o_ring = take((size_t)kBuildStages * p.Fst * s.maxtile + 8);  // +8: mac_cols may read past the last row of a tile
-  p.o_pxs = take(p.Pv); p.o_pys = take(p.Pv); p.o_wpa = take(p.Pv);
-  p.o_cxs = take(p.LD); p.o_cys = take(p.LD); p.o_ecol = take(p.LD);
-  p.o_vtmp = take((size_t)(kBuildThreads / 32) * (s.maxmd + 2));
-  p.o_pq = take((p.Pv + 1) / 2); p.o_cq = take((p.LD + 1) / 2); p.o_colnode = take((p.LD + 1) / 2); p.o_cgfam = take((p.LD / 4 + 2) / 2);
-  p.o_desc = take((size_t)p.nsets * 4);
+  p.o_ring = take((size_t)p.ring);
+  p.o_pxs = take(p.Ppad); p.o_pys = take(p.Ppad); p.o_wpa = take(p.Ppad);
+  p.o_cxs = take(p.LD); p.o_cys = take(p.LD); p.o_wcol = take(p.LD); p.o_tvec = take(p.LD); p.o_gw = take(p.LD);
+  p.o_rdiag = take(p.LD);
+  p.o_rowsrc = take(p.Ppad); p.o_colbase = take(p.LD);
+  p.o_vtmp = take(maxmd > 32 ? (size_t)(kBuildMaxThreads / 32) * (maxmd + 2) : 0);
+  p.o_cb = take((size_t)nchol * 96);  // per factorising warp: pivot columns (2 x 32) and 1 / diag (32)
+  p.o_pq = take((p.Ppad + 1) / 2); p.o_rowlen = take((p.Ppad + 1) / 2);
+  p.o_cq = take((p.LD + 1) / 2); p.o_colnode = take((p.LD + 1) / 2);
   p.total = o * 8 + 16;
   return p;
 }
@@ -73,10 +77,9 @@ inline size_t gibbs_smem_bytes(int is_ref, int m, int P, int k) {
   return 8 * (msq + (size_t)P + (size_t)(k + 1) * m + 3 * (size_t)m) + 16;
 }
 
-cudaError_t launch_build(int mode, const DevTree& T, const DevSlot& S, double* outH, double* outRi, const int* grp_slot0,
-                         const int* grp_nn, const int* grp_share, int ngrp, const double* w, const CovTab& tab, int* fail,
-                         int keep_H, size_t smem, cudaStream_t st, unsigned long long* prof = nullptr,
-                         int nthreads = kBuildThreads);
+cudaError_t launch_build(int mode, const DevTree& T, const DevSlot& S, double* outG, double* outH, double* outRi,
+                         const int* grp_slot0, const int* grp_nn, int ngrp, const double* w, const CovTab& tab, int* fail,
+                         int ns, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof = nullptr);
 cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlot& S, int slot0, int nslots, double* w,
                          const double* xb, const double* z, const double* tausq_inv, const double* SigS, double* V,
                          double* probe_sig, double* probe_smu, int* fail, size_t smem, cudaStream_t st);

@@ -233,7 +233,8 @@ int Model::build_layout(std::string& e) {
     iperm[perm[i]] = i;
   }
   // chains and storage offsets
-  h_chain.clear(); h_chain_poff.clear(); h_chain_boff.clear(); h_chain_uoff.clear();
+  h_chain.clear(); h_chain_poff.clear(); h_chain_uoff.clear();
+  h_gs.assign(n_nodes, 0);
   h_goff.assign(n_nodes, 0); h_rioff.assign(n_nodes, 0); h_voff.assign(n_nodes, 0); h_uoff.assign(n_nodes, 0); h_soff.assign(n_nodes, -1);
   g_total = ri_total = v_total = u_total = s_total = gpred_total = 0;
   long long sd_total = 0;
@@ -252,19 +253,19 @@ int Model::build_layout(std::string& e) {
     h_k[s] = kk;
     h_chain_off[s] = (int)h_chain.size();
     int poff = 0;
-    long long boff = 0, uo = 0;
+    long long uo = 0;
     for (int j = 0; j < kk; j++) {
       const int a = slot_of_block[parents.idx[parents.ptr[u] + j]];
       h_chain.push_back(a);
       h_chain_poff.push_back(poff);
-      h_chain_boff.push_back((int)boff);
       h_chain_uoff.push_back((int)uo);
       poff += h_m[a];
-      boff += (long long)h_m[s] * tile_rs(h_m[a]);
       uo += pad2((long long)h_m[a] * h_m[a]);
-      if (boff > 0x7fffffffLL) { e = "a block's G storage exceeds 2^31 doubles"; return 4; }
     }
     h_P[s] = poff;
+    // the block's rows of the chain's inverse Cholesky factor: [ G (P) | -Ri (m, reference blocks) | 0 ]
+    h_gs[s] = g_stride(poff, h_m[s], (!pred && block_is_reference[u]) ? 1 : 0);
+    const long long boff = (long long)h_m[s] * h_gs[s];
     if (kk) h_lastpar[s] = h_chain.back();
     if (!pred) {
       isref[s] = block_is_reference[u] ? 1 : 0;
@@ -306,12 +307,12 @@ int Model::build_layout(std::string& e) {
         long long uo = 0;
         for (int j = 0; j <= h_k[dd]; j++) {
           const int a = (j < h_k[dd]) ? h_chain[h_chain_off[dd] + j] : dd;
-          h_chain.push_back(a); h_chain_poff.push_back(poff); h_chain_boff.push_back(0); h_chain_uoff.push_back((int)uo);
+          h_chain.push_back(a); h_chain_poff.push_back(poff); h_chain_uoff.push_back((int)uo);
           poff += h_m[a];
           uo += pad2((long long)h_m[a] * h_m[a]);
         }
         h_P.push_back(poff);
-        h_goff.push_back(0); h_rioff.push_back(0); h_soff.push_back(-1);
+        h_goff.push_back(0); h_rioff.push_back(0); h_soff.push_back(-1); h_gs.push_back(0);
         h_voff.push_back(v_total); v_total += pad2(poff);
         h_uoff.push_back(u_total); u_total += uo;
         h_front_pseudo.push_back(ps); h_front_c0.push_back(c0); h_front_c1.push_back(c);
@@ -340,76 +341,56 @@ int Model::build_layout(std::string& e) {
   isref_host_ = isref;
   sd_total_ = sd_total;
 
-  // BUILD work groups: runs of blocks that share their ancestor chain (siblings) or all of it but the deepest ancestor
-  // (cousins, when sibling sets are too narrow to fill a CTA), sized to the shared-memory budget
-  h_grp_slot0.clear(); h_grp_nn.clear(); h_grp_share.clear();
-  auto shape_of = [&](int s, int nn, int share, int mode) {
-    BuildShape sh{};
-    const int k = h_k[s], coff = h_chain_off[s], kc = share ? k - 1 : k;
-    int maxm = 1;
-    for (int j = 0; j < kc; j++) maxm = std::max(maxm, h_m[h_chain[coff + j]]);
-    sh.mode = mode; sh.share = share; sh.kc = kc;
-    sh.Pc = (kc < k) ? h_chain_poff[coff + kc] : h_P[s];
-    int F = 0, c = 0, sumR = 0, maxmd = 1, mmaxs = 0, prevpar = -2;
+  // BUILD work groups: runs of sibling blocks (they share their ancestor chain), at most max_group_cols columns
+  // (one warp per 8 columns) and sized to the shared-memory budget
+  h_grp_slot0.clear(); h_grp_nn.clear();
+  auto group_plan = [&](int s, int nn, int mode, int ns) {
+    int ncols = 0, sumRb = 0, maxmd = 1;
     for (int d = 0; d < nn; d++) {
-      const int par = h_lastpar[s + d], md = h_m[s + d];
-      if (d == 0 || (share && par != prevpar)) {
-        c = (c + 3) & ~3;
-        if (share) mmaxs = std::max(mmaxs, h_m[par]);
-        F++;
-        prevpar = par;
-      }
-      c += md;
-      sumR += md * tile_rs(md);
-      maxmd = std::max(maxmd, md);
+      ncols += h_m[s + d];
+      if (mode == 0) sumRb += rb_doubles(h_m[s + d]);
+      maxmd = std::max(maxmd, h_m[s + d]);
     }
-    maxm = std::max(maxm, mmaxs);
-    sh.mmaxs = mmaxs; sh.F = F; sh.NCp = (c + 3) & ~3; sh.sumR = sumR; sh.maxtile = maxm * tile_rs(maxm); sh.maxmd = maxmd;
-    return sh;
-  };
-  auto fits = [&](const BuildShape& sh) {
-    if (sh.F > kMaxFam) return false;
-    const int omax = std::max(sh.mmaxs, 1);
-    (void)omax;
-    return build_plan(sh).total <= smem_budget;
+    return build_plan(h_P[s], ncols, sumRb, maxmd, ns, mode == 0 ? std::min(nn, kBuildMaxThreads / 32) : 0);
   };
   auto make_groups = [&](LevelInfo& L, int mode) -> int {
     L.grp0 = (int)h_grp_slot0.size();
     L.smem_build = 0; L.smem_gibbs = 0;
     const int end = L.slot0 + L.nslots;
-    // cousins when the sibling sets of this level are narrow
-    long long cols = 0, fams = 0;
-    for (int t = L.slot0; t < end; t++) { cols += h_m[t]; if (t == L.slot0 || h_lastpar[t] != h_lastpar[t - 1]) fams++; }
-    const int share = (L.nslots > 0 && h_k[L.slot0] >= 1 && fams > 0 && cols / fams < cousin_threshold) ? 1 : 0;
-    auto gpar = [&](int t) { const int p1 = h_lastpar[t]; return p1 < 0 ? -2 : h_lastpar[p1]; };
-    int s = L.slot0;
+    const int col_cap = std::min(max_group_cols, kMaxGroupCols);
+    int s = L.slot0, maxNT = 1;
+    size_t need1 = 0, need2 = 0;
     while (s < end) {
       int nn = 0;
-      BuildShape best{};
-      int maxmj = 1;
-      for (int j = 0; j < h_k[s]; j++) maxmj = std::max(maxmj, h_m[h_chain[h_chain_off[s] + j]]);
+      BuildPlan best{};
       while (s + nn < end && nn < kMaxGroupNodes) {
         const int t = s + nn;
-        if (nn > 0) {
-          if (h_lastpar[s] < 0) break;  // roots never share a chain
-          if (share ? (gpar(t) != gpar(s)) : (h_lastpar[t] != h_lastpar[s])) break;
-        }
-        BuildShape sh = shape_of(s, nn + 1, share, mode);
-        const int n_rg = (std::max(maxmj, sh.mmaxs) + kBuildTR - 1) / kBuildTR;
-        if (!fits(sh) || n_rg * (sh.NCp / kBuildTC) > build_threads / 2 || (nn > 0 && sh.NCp > max_group_cols)) break;
-        best = sh;
+        if (nn > 0 && (h_lastpar[s] < 0 || h_lastpar[t] != h_lastpar[s])) break;  // roots never share a chain
+        const BuildPlan pl = group_plan(s, nn + 1, mode, 1);
+        if (pl.total > smem_budget || pl.NCp > kMaxGroupCols || (nn > 0 && pl.NCp > col_cap)) break;
+        best = pl;
         nn++;
       }
       if (nn == 0) {
         e = "a block is too large for one BUILD work group (m=" + std::to_string(h_m[s]) + ", P=" + std::to_string(h_P[s]) + ")";
         return 4;
       }
-      h_grp_slot0.push_back(s); h_grp_nn.push_back(nn); h_grp_share.push_back(share);
-      L.smem_build = std::max(L.smem_build, build_plan(best).total);
+      h_grp_slot0.push_back(s); h_grp_nn.push_back(nn);
+      need1 = std::max(need1, best.total);
+      need2 = std::max(need2, group_plan(s, nn, mode, 2).total);
+      maxNT = std::max(maxNT, best.NT);
       L.maxNC = std::max(L.maxNC, best.NCp);
       s += nn;
     }
     L.ngrp = (int)h_grp_slot0.size() - L.grp0;
+    // ring depth: double-buffered when it fits; single-buffered when that lets two CTAs share an SM (they overlap instead)
+    const size_t half_sm = (size_t)113 * 1024;
+    if (force_build_ns == 1 || force_build_ns == 2) L.build_ns = (force_build_ns == 2 && need2 <= smem_budget) ? 2 : 1;
+    else if (need2 <= half_sm) L.build_ns = 2;
+    else if (need1 <= half_sm) L.build_ns = 1;
+    else L.build_ns = (need2 <= smem_budget) ? 2 : 1;
+    L.smem_build = (L.build_ns == 2) ? need2 : need1;
+    L.build_threads = 32 * std::min(kBuildMaxThreads / 32, std::max(4, maxNT));
     for (int t = L.slot0; t < end; t++) {
       L.maxP = std::max(L.maxP, h_P[t]); L.maxm = std::max(L.maxm, h_m[t]); L.maxk = std::max(L.maxk, h_k[t]);
       L.smem_gibbs = std::max(L.smem_gibbs, gibbs_smem_bytes(L.is_ref, h_m[t], h_P[t], h_k[t]));
@@ -477,7 +458,7 @@ int Model::upload(std::string& e) {
     xb[i] = s;
   }
   double *d_cx, *d_cy, *d_y, *d_X;
-  int *d_mvq, *d_m, *d_row0, *d_isref, *d_k, *d_P, *d_choff, *d_cptr, *d_cidx, *d_chain, *d_cpoff, *d_cboff, *d_cuoff;
+  int *d_mvq, *d_m, *d_row0, *d_isref, *d_k, *d_P, *d_choff, *d_cptr, *d_cidx, *d_chain, *d_cpoff, *d_cuoff, *d_gs;
   long long *d_goff, *d_rioff, *d_voff, *d_uoff, *d_soff;
   ST_CUDA(dev_upload(cx, d_cx, owned), "upload cx");
   ST_CUDA(dev_upload(cy, d_cy, owned), "upload cy");
@@ -493,6 +474,7 @@ int Model::upload(std::string& e) {
   ST_CUDA(dev_upload(h_lastpar, d_lastpar, owned), "upload lastpar");
   ST_CUDA(dev_upload(h_chain_off, d_choff, owned), "upload chain_off");
   ST_CUDA(dev_upload(h_goff, d_goff, owned), "upload goff");
+  ST_CUDA(dev_upload(h_gs, d_gs, owned), "upload gs");
   ST_CUDA(dev_upload(h_rioff, d_rioff, owned), "upload rioff");
   ST_CUDA(dev_upload(h_voff, d_voff, owned), "upload voff");
   ST_CUDA(dev_upload(h_uoff, d_uoff, owned), "upload uoff");
@@ -501,11 +483,9 @@ int Model::upload(std::string& e) {
   ST_CUDA(dev_upload(h_child_idx, d_cidx, owned), "upload child_idx");
   ST_CUDA(dev_upload(h_chain, d_chain, owned), "upload chain");
   ST_CUDA(dev_upload(h_chain_poff, d_cpoff, owned), "upload chain_poff");
-  ST_CUDA(dev_upload(h_chain_boff, d_cboff, owned), "upload chain_boff");
   ST_CUDA(dev_upload(h_chain_uoff, d_cuoff, owned), "upload chain_uoff");
   ST_CUDA(dev_upload(h_grp_slot0, d_grp_slot0, owned), "upload groups");
   ST_CUDA(dev_upload(h_grp_nn, d_grp_nn, owned), "upload groups");
-  ST_CUDA(dev_upload(h_grp_share, d_grp_share, owned), "upload groups");
   ST_CUDA(dev_upload(h_front_pseudo, d_front_pseudo, owned), "upload frontier");
   ST_CUDA(dev_upload(h_front_c0, d_front_c0, owned), "upload frontier");
   ST_CUDA(dev_upload(h_front_c1, d_front_c1, owned), "upload frontier");
@@ -513,9 +493,9 @@ int Model::upload(std::string& e) {
   ST_CUDA(dev_upload(h_front_ulen, d_front_ulen, owned), "upload frontier");
   dt.cx = d_cx; dt.cy = d_cy; dt.mvq = d_mvq; dt.y = d_y; dt.X = d_X;
   dt.m = d_m; dt.row0 = d_row0; dt.isref = d_isref; dt.k = d_k; dt.P = d_P; dt.lastpar = d_lastpar; dt.chain_off = d_choff;
-  dt.goff = d_goff; dt.rioff = d_rioff; dt.voff = d_voff; dt.uoff = d_uoff; dt.soff = d_soff;
+  dt.goff = d_goff; dt.gs = d_gs; dt.rioff = d_rioff; dt.voff = d_voff; dt.uoff = d_uoff; dt.soff = d_soff;
   dt.child_ptr = d_cptr; dt.child_idx = d_cidx;
-  dt.chain = d_chain; dt.chain_poff = d_cpoff; dt.chain_boff = d_cboff; dt.chain_uoff = d_cuoff;
+  dt.chain = d_chain; dt.chain_poff = d_cpoff; dt.chain_uoff = d_cuoff;
   for (int s = 0; s < 2; s++) {
     ST_CUDA(dev_zeros(ds[s].G, g_total, owned), "alloc G");
     if (keep_H) ST_CUDA(dev_zeros(ds[s].H, g_total, owned), "alloc H"); else ds[s].H = nullptr;
@@ -563,9 +543,8 @@ int Model::upload(std::string& e) {
 
 int Model::init(std::string& e) {
   // development overrides of the BUILD tiling
-  if (const char* v = getenv("ST_BUILD_THREADS")) build_threads = atoi(v);
+  if (const char* v = getenv("ST_BUILD_NS")) force_build_ns = atoi(v);
   if (const char* v = getenv("ST_MAX_COLS")) max_group_cols = atoi(v);
-  if (const char* v = getenv("ST_COUSIN")) cousin_threshold = atoi(v);
   if (const char* v = getenv("ST_SMEM_BUDGET")) smem_budget = (size_t)atol(v);
   int rc = build_bookkeeping(e);
   if (rc) return rc;
@@ -656,8 +635,9 @@ int Model::launch_build_levels(int pslot, const CovTab& tab) {
   }
   for (auto& L : levels) {
     if (profile) cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), stream);
-    ST_CUDA(launch_build(L.is_ref ? 0 : 1, dt, ds[pslot], ds[pslot].H, ds[pslot].Ri, d_grp_slot0 + L.grp0, d_grp_nn + L.grp0,
-                         d_grp_share + L.grp0, L.ngrp, d_w, tab, d_fail, keep_H ? 1 : 0, L.smem_build, stream, d_prof, build_threads),
+    ST_CUDA(launch_build(L.is_ref ? 0 : 1, dt, ds[pslot], ds[pslot].G, keep_H ? ds[pslot].H : nullptr, ds[pslot].Ri,
+                         d_grp_slot0 + L.grp0, d_grp_nn + L.grp0, L.ngrp, d_w, tab, d_fail, L.build_ns, L.smem_build, stream,
+                         L.build_threads, d_prof),
             "build_level_kernel");
     n_launches++;
     if (profile) {
@@ -666,11 +646,9 @@ int Model::launch_build_levels(int pslot, const CovTab& tab) {
       cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
       double tot = 0;
       for (int i = 0; i < 7; i++) tot += (double)h[i];
-      fprintf(stderr, "[build profile] level slot0=%d groups=%d ref=%d cycles/group=%.0f : setup %.1f%% cov %.1f%% fwd %.1f%% ZtZ %.1f%% chol %.1f%% bwd %.1f%% out %.1f%%\n",
+      fprintf(stderr, "[build profile] level slot0=%d groups=%d ref=%d cycles/group=%.0f : setup %.1f%% cov %.1f%% fwd %.1f%% ZtZ %.1f%% chol %.1f%% Y %.1f%% bwd+out %.1f%%\n",
               L.slot0, L.ngrp, L.is_ref, tot / std::max(1, L.ngrp), 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot,
               100 * h[4] / tot, 100 * h[5] / tot, 100 * h[6] / tot);
-      fprintf(stderr, "      sweeps (thread 0): wait+sync %.1f%% issue %.1f%% compute %.1f%% step-end %.1f%% of kernel\n", 100 * h[8] / tot, 100 * h[9] / tot, 100 * h[10] / tot, 100 * h[11] / tot);
-      fprintf(stderr, "      chol (warp 0): factorise %.1f%% invert %.1f%% of kernel\n", 100 * h[12] / tot, 100 * h[13] / tot);
     }
   }
   if (profile) cudaFree(d_prof);
@@ -795,8 +773,9 @@ int Model::predict(bool theta_changed) {
     CovTab tab;
     std::string e;
     if (!make_covtab(theta[cur].data(), (int)theta[cur].size(), q, tab, e)) { err = e; return 1; }
-    ST_CUDA(launch_build(2, dt, ds[cur], d_Hpred, d_sdpred, d_grp_slot0 + pred_level.grp0, d_grp_nn + pred_level.grp0,
-                         d_grp_share + pred_level.grp0, pred_level.ngrp, d_w, tab, d_fail, 1, pred_level.smem_build, stream, nullptr, build_threads),
+    ST_CUDA(launch_build(2, dt, ds[cur], d_Hpred, nullptr, d_sdpred, d_grp_slot0 + pred_level.grp0, d_grp_nn + pred_level.grp0,
+                         pred_level.ngrp, d_w, tab, d_fail, pred_level.build_ns, pred_level.smem_build, stream,
+                         pred_level.build_threads, nullptr),
             "build_level_kernel(predict)");
     n_launches++;
     pred_H_valid = true;
@@ -924,21 +903,18 @@ int Model::get_node_state(int slot, int u, const std::string& which, double* out
   if (u < 0 || u >= n_blocks) { err = "block id out of range"; return 1; }
   const int s = slot_of_block[u];
   const bool pred = s >= n_obs_nodes;
-  const int m = h_m[s], P = h_P[s], kk = h_k[s], coff = h_chain_off[s];
+  const int m = h_m[s], P = h_P[s];
   if (which == "H" || which == "G") {
     const double* src = nullptr;
     if (pred) { if (which == "G") { err = "prediction blocks have no G"; return 1; } src = d_Hpred; }
     else if (which == "G") src = ds[ps].G;
     else { if (!keep_H) { err = "H was not kept (keep_H = 0)"; return 1; } src = ds[ps].H; }
-    long long tot = 0;
-    for (int j = 0; j < kk; j++) tot += (long long)m * tile_rs(h_m[h_chain[coff + j]]);
+    const int gs = h_gs[s];
+    const long long tot = (long long)m * gs;
     dvec t(std::max<long long>(tot, 1)), o((size_t)m * P);
     if (tot) ST_CUDA(cudaMemcpy(t.data(), src + h_goff[s], tot * sizeof(double), cudaMemcpyDeviceToHost), "D2H H");
-    for (int j = 0; j < kk; j++) {
-      const int mj = h_m[h_chain[coff + j]], po = h_chain_poff[coff + j], bo = h_chain_boff[coff + j];
-      for (int r = 0; r < m; r++)
-        for (int pp = 0; pp < mj; pp++) o[r + (size_t)(po + pp) * m] = t[bo + (size_t)r * tile_rs(mj) + pp];
-    }
+    for (int r = 0; r < m; r++)
+      for (int pp = 0; pp < P; pp++) o[r + (size_t)pp * m] = t[(size_t)r * gs + pp];
     return emit(o);
   }
   if (which == "Ri") {

@@ -5,8 +5,8 @@
 //    contiguous; outputs are un-permuted only at the boundary (st_get_w);
 //  * per block and per theta-slot only G = Ri*H (m x P), Ri (m x m) and (optionally) H are kept — the reference's Kxc,
 //    Kxx_inv, Kxx_invchol, AK_uP_all, AK_uP_u_all and Sigi_children cubes are never materialised;
-//  * a block's parent set is its ancestor chain (tree_dep.cpp:113-119); G/H are stored as one row-major m x m_a tile per
-//    ancestor a so that a tile is one contiguous, 16-byte aligned run.
+//  * a block's parent set is its ancestor chain (tree_dep.cpp:113-119); G is stored as the block's rows of the chain's
+//    inverse Cholesky factor, [ G | -Ri | 0 ] row-major, so that BUILD of the descendants streams contiguous rows.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -42,7 +42,8 @@ struct DevTree {
   const int* P;          // parent-set size
   const int* lastpar;    // slot of the last (deepest) parent, -1 for roots
   const int* chain_off;  // into the per-chain-entry arrays
-  const long long* goff; // G / H storage offset (doubles)
+  const long long* goff; // G / H storage offset (doubles) of the block's row block
+  const int* gs;         // row stride of that row block: [ G (P) | -Ri (m, reference blocks) | 0 ], g_stride()
   const long long* rioff;// Ri storage offset (doubles)
   const long long* voff; // message vector offset (P doubles)
   const long long* uoff; // message Gram offset (tiles m_a x m_a per ancestor)
@@ -52,7 +53,6 @@ struct DevTree {
   // per chain entry
   const int* chain;      // ancestor slot, root first
   const int* chain_poff; // column offset of the ancestor inside the parent set
-  const int* chain_boff; // offset (doubles) of the ancestor's tile inside the node's G storage
   const int* chain_uoff; // offset (doubles) of the ancestor's tile inside the node's Gram storage
 };
 
@@ -69,6 +69,8 @@ struct LevelInfo {
   int is_ref = 1;
   int grp0 = 0, ngrp = 0;     // BUILD work groups (index into grp arrays)
   size_t smem_build = 0;      // dynamic shared memory of the BUILD kernel at this level
+  int build_threads = 128;    // 32 x (8-column tiles of the widest group), at least 4 warps
+  int build_ns = 2;           // depth of the cp.async ring (1 when that lets two CTAs share an SM, or 2 does not fit)
   int maxP = 0, maxm = 0, maxNC = 0, maxk = 0;
   size_t smem_gibbs = 0;
 };
@@ -86,10 +88,9 @@ class Model {
   ivec res_is_ref;
   bool keep_H = true;
   int device = 0;
-  size_t smem_budget = 220 * 1024;  // dynamic; the kernel also holds ~4 KB of static shared memory (227 KB per CTA)
-  int build_threads = 256;   // CTA size of build_level_kernel (two split-K halves)
-  int max_group_cols = 104;  // upper bound on the columns one BUILD work group handles
-  int cousin_threshold = 48; // sibling sets narrower than this (columns) are merged into cousin groups
+  size_t smem_budget = 227 * 1024 - 5 * 1024;  // dynamic; the kernel also holds ~4.5 KB of static shared memory (227 KB per CTA)
+  int force_build_ns = 0;    // development override of the ring depth (ST_BUILD_NS)
+  int max_group_cols = 104;  // upper bound on the columns one BUILD work group handles (one warp per 8 columns)
   bool probes = true;        // record Sigi_tot / Smu_tot of the last Gibbs sweep (st_get_node_state)
   // ---- bookkeeping, same meaning as the reference's members
   int64_t n_obs = 0;
@@ -102,14 +103,14 @@ class Model {
   // ---- node-major layout
   int n_obs_nodes = 0, n_nodes = 0;
   std::vector<int> slot_of_block, block_of_slot;
-  std::vector<int> h_m, h_row0, h_k, h_P, h_chain_off, h_chain, h_chain_poff, h_chain_boff, h_chain_uoff, h_lastpar;
+  std::vector<int> h_m, h_row0, h_k, h_P, h_chain_off, h_chain, h_chain_poff, h_chain_uoff, h_lastpar, h_gs;
   std::vector<long long> h_goff, h_rioff, h_voff, h_uoff, h_soff;
   std::vector<int> h_child_ptr, h_child_idx;
   ivec perm;   // node-major row -> boundary row
   ivec iperm;  // boundary row -> node-major row
   std::vector<LevelInfo> levels;  // observed levels, root first
   LevelInfo pred_level;           // prediction blocks
-  std::vector<int> h_grp_slot0, h_grp_nn, h_grp_share;
+  std::vector<int> h_grp_slot0, h_grp_nn;
   long long g_total = 0, ri_total = 0, v_total = 0, u_total = 0, s_total = 0, gpred_total = 0;
   // ---- multi-GPU partition (include/spamtree_b200.h: st_partition)
   bool part = false;
@@ -144,7 +145,7 @@ class Model {
   double *d_partial = nullptr;
   double *d_bcoeff = nullptr, *d_tausq_inv = nullptr;
   int* d_fail = nullptr;
-  int *d_grp_slot0 = nullptr, *d_grp_nn = nullptr, *d_grp_share = nullptr;
+  int *d_grp_slot0 = nullptr, *d_grp_nn = nullptr;
   double* h_stage = nullptr;  // pinned n_all staging buffer
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8]{};
