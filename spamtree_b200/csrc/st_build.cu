@@ -34,7 +34,7 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 // R (row-major, stride rs, lower triangle valid, m <= 32) <- chol(R)^-1 (lower; strict upper zeroed) by one warp.
 // The factorisation keeps row `lane` in registers and broadcasts the pivot column through cb (2 x 32 doubles);
 // the inverse is one forward substitution per lane (column `lane`), reading L by broadcast.  dv: 32 doubles (1/diag).
-__device__ __forceinline__ bool warp_chol_inv32(double* R, int m, int rs, double* cb, double* dv, int lane) {
+__device__ __forceinline__ bool warp_chol_inv32(double* R, int m, int rs, double* cb, double* dv, int lane, long long* tmid) {
   bool ok = true;
   {
     double a[32];
@@ -45,7 +45,7 @@ __device__ __forceinline__ bool warp_chol_inv32(double* R, int m, int rs, double
       if (j < m) {
         double d = __shfl_sync(0xffffffffu, a[j], j);
         if (!(d > 0.0) || !isfinite(d)) { ok = false; d = 1.0; }  // dpotrf info > 0
-        const double sd = sqrt(d), inv = 1.0 / sd;
+        const double inv = rsqrt(d), sd = d * inv;
         a[j] = (lane == j) ? sd : a[j] * inv;
         double* c = cb + (j & 1) * 32;
         c[lane] = a[j];
@@ -62,6 +62,7 @@ __device__ __forceinline__ bool warp_chol_inv32(double* R, int m, int rs, double
       if (j < m && lane < m && j <= lane) R[lane * rs + j] = a[j];
   }
   __syncwarp();
+  if (tmid) *tmid = clock64();
   double x[32];
 #pragma unroll
   for (int r = 0; r < 32; r++) {
@@ -160,26 +161,30 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
   int* cq = reinterpret_cast<int*>(base + pl.o_cq);
   int* colnode = reinterpret_cast<int*>(base + pl.o_colnode);
 
-  // ---- phase 1: per parent row (= row of the chain's factor) and per column metadata
-  for (int j = 0; j < k; j++) {
-    const int r0g = s_crow0g[j], po = s_crow[j], mj = s_cm[j], gsj = s_cgs[j];
-    const long long go = s_cgoff[j];
-    for (int t = tid; t < mj; t += nth) {
-      pxs[po + t] = T.cx[r0g + t]; pys[po + t] = T.cy[r0g + t]; pq[po + t] = T.mvq[r0g + t]; wpa[po + t] = w[r0g + t];
-      rowsrc[po + t] = go + (long long)t * gsj;
-      rowlen[po + t] = po + mj;  // [G_a | -Ri_a]: the entries above Ri's diagonal are stored zeros
+  // ---- phase 1: per parent row (= row of the chain's factor) and per column metadata, one pass (independent loads)
+  for (int r = tid; r < Ppad; r += nth) {
+    if (r < P) {
+      int j = 0;
+      while (j + 1 < k && r >= s_crow[j + 1]) j++;
+      const int t = r - s_crow[j], g = s_crow0g[j] + t;
+      pxs[r] = T.cx[g]; pys[r] = T.cy[g]; pq[r] = T.mvq[g]; wpa[r] = w[g];
+      rowsrc[r] = s_cgoff[j] + (long long)t * s_cgs[j];
+      rowlen[r] = s_crow[j] + s_cm[j];  // [G_a | -Ri_a]: the entries above Ri's diagonal are stored zeros
+    } else {
+      pxs[r] = 0; pys[r] = 0; pq[r] = 0; wpa[r] = 0; rowsrc[r] = 0; rowlen[r] = 0;
     }
   }
-  for (int r = P + tid; r < Ppad; r += nth) { pxs[r] = 0; pys[r] = 0; pq[r] = 0; wpa[r] = 0; rowsrc[r] = 0; rowlen[r] = 0; }
-  for (int c = tid; c < LD; c += nth) { cxs[c] = 0; cys[c] = 0; cq[c] = 0; colnode[c] = -1; colbase[c] = -1; wcol[c] = 0; tvec[c] = 0; gw[c] = 0; rdiag[c] = 0; }
-  __syncthreads();
-  for (int d = 0; d < nn; d++) {
-    const int r0g = s_nrow0[d], c0 = s_nc0[d], gsd = s_ngs[d];
-    const long long go = s_ngoff[d];
-    for (int t = tid; t < s_nm[d]; t += nth) {
-      cxs[c0 + t] = T.cx[r0g + t]; cys[c0 + t] = T.cy[r0g + t]; cq[c0 + t] = T.mvq[r0g + t]; colnode[c0 + t] = d;
-      colbase[c0 + t] = go + (long long)t * gsd;
-      wcol[c0 + t] = (MODE == 2) ? 0.0 : w[r0g + t];
+  for (int c = tid; c < LD; c += nth) {
+    tvec[c] = 0; gw[c] = 0; rdiag[c] = 0;
+    if (c < ncols) {
+      int d = 0;
+      while (d + 1 < nn && c >= s_nc0[d + 1]) d++;
+      const int t = c - s_nc0[d], g = s_nrow0[d] + t;
+      cxs[c] = T.cx[g]; cys[c] = T.cy[g]; cq[c] = T.mvq[g]; colnode[c] = d;
+      colbase[c] = s_ngoff[d] + (long long)t * s_ngs[d];
+      wcol[c] = (MODE == 2) ? 0.0 : w[g];
+    } else {
+      cxs[c] = 0; cys[c] = 0; cq[c] = 0; colnode[c] = -1; colbase[c] = -1; wcol[c] = 0;
     }
   }
   __syncthreads();
@@ -275,9 +280,12 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
     const int sumRb = s_sumRb;
     for (int e = tid; e < sumRb; e += nth) Rb[e] = 0.0;
     __syncthreads();
+    // one 8 x 8 tile of the lower triangle per item; the FP64 pipe is per SM sub-partition, so the items are dealt to a
+    // multiple of four warps
+    const int nwe = (nwarps >= 4) ? (nwarps & ~3) : nwarps;
     int total = 0;
     for (int d = 0; d < nn; d++) { const int mt = (s_nm[d] + 7) >> 3; total += mt * (mt + 1) / 2; }
-    for (int item = warp; item < total; item += nwarps) {
+    for (int item = warp; item < total && warp < nwe; item += nwe) {
       int d = 0, rem = item;
       for (;; d++) {
         const int mt = (s_nm[d] + 7) >> 3, cnt = mt * (mt + 1) / 2;
@@ -290,27 +298,32 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
       const int md = s_nm[d], c0d = s_nc0[d], rs = rb_stride(md);
       const double* ap = panel + (size_t)(lane & 3) * LD + min(c0d + 8 * ti + (lane >> 2), LD - 1);
       const double* bp = panel + (size_t)(lane & 3) * LD + min(c0d + 8 * tj + (lane >> 2), LD - 1);
-      double c0[2] = {0, 0}, d0[2] = {0, 0};
+      double c0[2] = {0, 0}, d0[2] = {0, 0}, c1[2] = {0, 0}, d1[2] = {0, 0};
 #pragma unroll 2
-      for (int kk = 0; kk < Ppad; kk += 8) {
+      for (int kk = 0; kk < Ppad; kk += 16) {
         dmma(c0, ap[(size_t)kk * LD], bp[(size_t)kk * LD]);
         dmma(d0, ap[(size_t)(kk + 4) * LD], bp[(size_t)(kk + 4) * LD]);
+        dmma(c1, ap[(size_t)(kk + 8) * LD], bp[(size_t)(kk + 8) * LD]);
+        dmma(d1, ap[(size_t)(kk + 12) * LD], bp[(size_t)(kk + 12) * LD]);
       }
       const int i = 8 * ti + (lane >> 2), j = 8 * tj + 2 * (lane & 3);
       double* R = Rb + s_nRb[d];
 #pragma unroll
       for (int e = 0; e < 2; e++)
         if (i < md && j + e <= i)
-          R[i * rs + j + e] = cov_eval(ct, cxs[c0d + i], cys[c0d + i], cq[c0d + i], cxs[c0d + j + e], cys[c0d + j + e], cq[c0d + j + e]) - (c0[e] + d0[e]);
+          R[i * rs + j + e] = cov_eval(ct, cxs[c0d + i], cys[c0d + i], cq[c0d + i], cxs[c0d + j + e], cys[c0d + j + e], cq[c0d + j + e]) - ((c0[e] + d0[e]) + (c1[e] + d1[e]));
     }
     __syncthreads();
     mark(3);
     for (int d = warp; d < nn; d += nwarps) {
-      const int md = s_nm[d], c0d = s_nc0[d], rs = rb_stride(md);
+      const int md = s_nm[d], rs = rb_stride(md);
       double* R = Rb + s_nRb[d];
       bool okc;
+      long long tc0 = 0, tc1 = 0;
+      if (prof && tid == 0) tc0 = clock64();
       if (md <= 32) {
-        okc = warp_chol_inv32(R, md, rs, s_cb + warp * 96, s_cb + warp * 96 + 64, lane);
+        okc = warp_chol_inv32(R, md, rs, s_cb + warp * 96, s_cb + warp * 96 + 64, lane, (prof && tid == 0) ? &tc1 : nullptr);
+        if (prof && tid == 0) { atomicAdd(prof + 8, (unsigned long long)(tc1 - tc0)); atomicAdd(prof + 9, (unsigned long long)(clock64() - tc1)); }
       } else {
         okc = warp_chol(R, md, rs, lane);
         if (okc) warp_inv_lower_inplace(R, md, rs, vtmp + warp * (s_maxmd + 2), lane);
@@ -320,29 +333,42 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
         __syncwarp();
         for (int e = lane; e < md * rs; e += 32) R[e] = 0.0;
       }
-      __syncwarp();
-      // Ri to global memory: the stand-alone tile (Gibbs, LLW) and the [G | -Ri] row block (children's BUILD)
-      const int trs = tile_rs(md);
+      if (lane == 0) s_nlogdet[d] = okc ? 0.0 : -1.0;  // flag, replaced by the log-determinant below
+    }
+    __syncthreads();
+    mark(4);
+    // Ri to global memory: the stand-alone tile (Gibbs, LLW) and the [G | -Ri] row block (children's BUILD)
+    for (int d = 0; d < nn; d++) {
+      const int md = s_nm[d], rs = rb_stride(md), trs = tile_rs(md), gsd = s_ngs[d];
+      const double* R = Rb + s_nRb[d];
       double* ori = outRi + s_nrioff[d];
-      for (int e = lane; e < md * trs; e += 32) {
-        const int r = e / trs, c = e - r * trs;
-        ori[e] = (c < md) ? R[r * rs + c] : 0.0;
-      }
       double* og = outG + s_ngoff[d] + P;
-      const int gsd = s_ngs[d];
-      for (int e = lane; e < md * md; e += 32) {
-        const int r = e / md, c = e - r * md;
-        og[(size_t)r * gsd + c] = -R[r * rs + c];
+      for (int e = tid; e < md * trs; e += nth) {
+        const int r = e / trs, c = e - r * trs;
+        const double v = (c < md) ? R[r * rs + c] : 0.0;
+        ori[e] = v;
+        if (c < md) og[(size_t)r * gsd + c] = -v;
       }
-      // t = Ri w_u (:912-913 via e = w_u - H w_pa: Ri e = Ri w_u - G w_pa) and logdet = sum log diag(Ri) (:966)
+    }
+    // t = Ri w_u (:912-913 via e = w_u - H w_pa: Ri e = Ri w_u - G w_pa) and logdet = sum log diag(Ri) (:966)
+    for (int c = tid; c < ncols; c += nth) {
+      const int d = colnode[c], c0d = s_nc0[d], r = c - c0d;
+      const double* Rr = Rb + s_nRb[d] + r * rb_stride(s_nm[d]);
+      double t0 = 0, t1 = 0;
+      int c2 = 0;
+      for (; c2 + 1 <= r; c2 += 2) { t0 = fma(Rr[c2], wcol[c0d + c2], t0); t1 = fma(Rr[c2 + 1], wcol[c0d + c2 + 1], t1); }
+      if (c2 <= r) t0 = fma(Rr[c2], wcol[c0d + c2], t0);
+      tvec[c] = t0 + t1;
+    }
+    __syncthreads();
+    for (int d = warp; d < nn; d += nwarps) {
+      const int md = s_nm[d], rs = rb_stride(md);
+      const double* R = Rb + s_nRb[d];
+      const bool okc = s_nlogdet[d] == 0.0;
       double ld = 0;
-      for (int r = lane; r < md; r += 32) {
-        double t = 0;
-        for (int c = 0; c <= r; c++) t = fma(R[r * rs + c], wcol[c0d + c], t);
-        tvec[c0d + r] = t;
-        ld += okc ? log(R[r * rs + r]) : 0.0;
-      }
+      for (int r = lane; r < md; r += 32) ld += okc ? log(R[r * rs + r]) : 0.0;
       ld = warp_sum(ld);
+      __syncwarp();
       if (lane == 0) s_nlogdet[d] = ld;
     }
     __syncthreads();
@@ -371,8 +397,8 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
     }
     __syncthreads();
     mark(3);
+    mark(4);
   }
-  mark(4);
 
   // ---- backward sweep: out' = L^-T panel, written straight to global memory (row block layout of the group's blocks)
   auto bwd_sweep = [&](double* __restrict__ out, bool do_gw) {
@@ -450,20 +476,33 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
     // Y' = Z Ri' in place
     if (MODE == 0) {
       const int npt = Ppad >> 3;
-      for (int item = warp; item < npt * nn; item += nwarps) {
+      const int nwe = (nwarps >= 4) ? (nwarps & ~3) : nwarps;
+      for (int item = warp; item < npt * nn && warp < nwe; item += nwe) {
         const int d = item / npt, pt = item - d * npt;
         const int md = s_nm[d], c0d = s_nc0[d], rs = rb_stride(md);
         const double* R = Rb + s_nRb[d];
         const double* ap = panel + (size_t)(8 * pt + (lane >> 2)) * LD;
-        for (int it = ((md + 7) >> 3) - 1; it >= 0; it--) {  // descending: tile `it` reads columns < 8 it + 8, writes [8 it, 8 it + 8)
-          const int Kx = min(8 * it + 8, (md + 3) & ~3);
-          const double* bp = R + (8 * it + (lane >> 2)) * rs + (lane & 3);
-          double c0[2] = {0, 0};
-          for (int kk = 0; kk < Kx; kk += 4) dmma(c0, ap[min(c0d + kk + (lane & 3), LD - 1)], bp[kk]);
-          const int jl = 8 * it + 2 * (lane & 3);
-          double* o = panel + (size_t)(8 * pt + (lane >> 2)) * LD + c0d + jl;
-          if (jl < md) o[0] = c0[0];
-          if (jl + 1 < md) o[1] = c0[1];
+        const int mt = (md + 7) >> 3, Kmax = (md + 3) & ~3;
+        // chunks of four column tiles, last chunk first: a chunk reads columns below its end and writes only its own
+        for (int it0 = ((mt - 1) >> 2) << 2; it0 >= 0; it0 -= 4) {
+          const int nt = min(4, mt - it0);
+          const int Kc = min(8 * (it0 + nt), Kmax);
+          const double* bp = R + (8 * it0 + (lane >> 2)) * rs + (lane & 3);
+          double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+          for (int kk = 0; kk < Kc; kk += 4) {
+            const double a = ap[min(c0d + kk + (lane & 3), LD - 1)];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+              if (u < nt && kk < 8 * (it0 + u) + 8) dmma(acc[u], a, bp[u * 8 * rs + kk]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (u >= nt) continue;
+            const int jl = 8 * (it0 + u) + 2 * (lane & 3);
+            double* o = panel + (size_t)(8 * pt + (lane >> 2)) * LD + c0d + jl;
+            if (jl < md) o[0] = acc[u][0];
+            if (jl + 1 < md) o[1] = acc[u][1];
+          }
         }
       }
     } else {

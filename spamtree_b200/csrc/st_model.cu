@@ -355,11 +355,13 @@ int Model::build_layout(std::string& e) {
   };
   auto make_groups = [&](LevelInfo& L, int mode) -> int {
     L.grp0 = (int)h_grp_slot0.size();
-    L.smem_build = 0; L.smem_gibbs = 0;
+    L.smem_gibbs = 0;
+    L.build_launches.clear();
     const int end = L.slot0 + L.nslots;
     const int col_cap = std::min(max_group_cols, kMaxGroupCols);
-    int s = L.slot0, maxNT = 1;
-    size_t need1 = 0, need2 = 0;
+    struct Grp { int s, nn, NT; size_t need1, need2; };
+    std::vector<Grp> gs;
+    int s = L.slot0;
     while (s < end) {
       int nn = 0;
       BuildPlan best{};
@@ -375,22 +377,35 @@ int Model::build_layout(std::string& e) {
         e = "a block is too large for one BUILD work group (m=" + std::to_string(h_m[s]) + ", P=" + std::to_string(h_P[s]) + ")";
         return 4;
       }
-      h_grp_slot0.push_back(s); h_grp_nn.push_back(nn);
-      need1 = std::max(need1, best.total);
-      need2 = std::max(need2, group_plan(s, nn, mode, 2).total);
-      maxNT = std::max(maxNT, best.NT);
+      gs.push_back({s, nn, best.NT, best.total, group_plan(s, nn, mode, 2).total});
       L.maxNC = std::max(L.maxNC, best.NCp);
       s += nn;
     }
-    L.ngrp = (int)h_grp_slot0.size() - L.grp0;
-    // ring depth: double-buffered when it fits; single-buffered when that lets two CTAs share an SM (they overlap instead)
+    // buckets by width: up to 4, 8, 16 tiles of 8 columns
     const size_t half_sm = (size_t)113 * 1024;
-    if (force_build_ns == 1 || force_build_ns == 2) L.build_ns = (force_build_ns == 2 && need2 <= smem_budget) ? 2 : 1;
-    else if (need2 <= half_sm) L.build_ns = 2;
-    else if (need1 <= half_sm) L.build_ns = 1;
-    else L.build_ns = (need2 <= smem_budget) ? 2 : 1;
-    L.smem_build = (L.build_ns == 2) ? need2 : need1;
-    L.build_threads = 32 * std::min(kBuildMaxThreads / 32, std::max(4, maxNT));
+    for (int b = 0; b < 3; b++) {
+      const int lo = (b == 0) ? 0 : (b == 1 ? 4 : 8), hi = (b == 0) ? 4 : (b == 1 ? 8 : 16);
+      LevelInfo::BuildLaunch bl;
+      bl.grp0 = (int)h_grp_slot0.size();
+      size_t need1 = 0, need2 = 0;
+      int maxNT = 1;
+      for (const Grp& g : gs)
+        if (g.NT > lo && g.NT <= hi) {
+          h_grp_slot0.push_back(g.s); h_grp_nn.push_back(g.nn);
+          need1 = std::max(need1, g.need1); need2 = std::max(need2, g.need2); maxNT = std::max(maxNT, g.NT);
+        }
+      bl.ngrp = (int)h_grp_slot0.size() - bl.grp0;
+      if (bl.ngrp == 0) continue;
+      // ring depth: double-buffered when it fits; single-buffered when that lets two CTAs share an SM (they overlap instead)
+      if (force_build_ns == 1 || force_build_ns == 2) bl.ns = (force_build_ns == 2 && need2 <= smem_budget) ? 2 : 1;
+      else if (need2 <= half_sm) bl.ns = 2;
+      else if (need1 <= half_sm) bl.ns = 1;
+      else bl.ns = (need2 <= smem_budget) ? 2 : 1;
+      bl.smem = (bl.ns == 2) ? need2 : need1;
+      bl.threads = 32 * std::min(kBuildMaxThreads / 32, std::max(4, maxNT));
+      L.build_launches.push_back(bl);
+    }
+    L.ngrp = (int)h_grp_slot0.size() - L.grp0;
     for (int t = L.slot0; t < end; t++) {
       L.maxP = std::max(L.maxP, h_P[t]); L.maxm = std::max(L.maxm, h_m[t]); L.maxk = std::max(L.maxk, h_k[t]);
       L.smem_gibbs = std::max(L.smem_gibbs, gibbs_smem_bytes(L.is_ref, h_m[t], h_P[t], h_k[t]));
@@ -634,21 +649,32 @@ int Model::launch_build_levels(int pslot, const CovTab& tab) {
     cudaMalloc((void**)&d_prof, 16 * sizeof(unsigned long long));
   }
   for (auto& L : levels) {
-    if (profile) cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), stream);
-    ST_CUDA(launch_build(L.is_ref ? 0 : 1, dt, ds[pslot], ds[pslot].G, keep_H ? ds[pslot].H : nullptr, ds[pslot].Ri,
-                         d_grp_slot0 + L.grp0, d_grp_nn + L.grp0, L.ngrp, d_w, tab, d_fail, L.build_ns, L.smem_build, stream,
-                         L.build_threads, d_prof),
-            "build_level_kernel");
-    n_launches++;
-    if (profile) {
-      unsigned long long h[16];
-      cudaStreamSynchronize(stream);
-      cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
-      double tot = 0;
-      for (int i = 0; i < 7; i++) tot += (double)h[i];
-      fprintf(stderr, "[build profile] level slot0=%d groups=%d ref=%d cycles/group=%.0f : setup %.1f%% cov %.1f%% fwd %.1f%% ZtZ %.1f%% chol %.1f%% Y %.1f%% bwd+out %.1f%%\n",
-              L.slot0, L.ngrp, L.is_ref, tot / std::max(1, L.ngrp), 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot,
-              100 * h[4] / tot, 100 * h[5] / tot, 100 * h[6] / tot);
+    for (const auto& B : L.build_launches) {
+      cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+      if (profile) {
+        cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), stream);
+        cudaEventCreate(&pe0); cudaEventCreate(&pe1);
+        cudaEventRecord(pe0, stream);
+      }
+      ST_CUDA(launch_build(L.is_ref ? 0 : 1, dt, ds[pslot], ds[pslot].G, keep_H ? ds[pslot].H : nullptr, ds[pslot].Ri,
+                           d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w, tab, d_fail, B.ns, B.smem, stream, B.threads, d_prof),
+              "build_level_kernel");
+      n_launches++;
+      if (profile) {
+        unsigned long long h[16];
+        cudaEventRecord(pe1, stream);
+        cudaStreamSynchronize(stream);
+        float pms = 0;
+        cudaEventElapsedTime(&pms, pe0, pe1);
+        cudaEventDestroy(pe0); cudaEventDestroy(pe1);
+        cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+        double tot = 0;
+        for (int i = 0; i < 7; i++) tot += (double)h[i];
+        fprintf(stderr, "[build profile] level slot0=%d groups=%d ref=%d threads=%d ns=%d smem=%zu  %.3f ms  cycles/group=%.0f : setup %.1f%% cov %.1f%% fwd %.1f%% ZtZ %.1f%% chol %.1f%% Y %.1f%% bwd+out %.1f%%\n",
+                L.slot0, B.ngrp, L.is_ref, B.threads, B.ns, B.smem, pms, tot / std::max(1, B.ngrp), 100 * h[0] / tot, 100 * h[1] / tot,
+                100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, 100 * h[5] / tot, 100 * h[6] / tot);
+        if (L.is_ref) fprintf(stderr, "      chol (warp 0): factorise %.1f%% invert %.1f%% of kernel\n", 100 * h[8] / tot, 100 * h[9] / tot);
+      }
     }
   }
   if (profile) cudaFree(d_prof);
@@ -773,11 +799,12 @@ int Model::predict(bool theta_changed) {
     CovTab tab;
     std::string e;
     if (!make_covtab(theta[cur].data(), (int)theta[cur].size(), q, tab, e)) { err = e; return 1; }
-    ST_CUDA(launch_build(2, dt, ds[cur], d_Hpred, nullptr, d_sdpred, d_grp_slot0 + pred_level.grp0, d_grp_nn + pred_level.grp0,
-                         pred_level.ngrp, d_w, tab, d_fail, pred_level.build_ns, pred_level.smem_build, stream,
-                         pred_level.build_threads, nullptr),
-            "build_level_kernel(predict)");
-    n_launches++;
+    for (const auto& B : pred_level.build_launches) {
+      ST_CUDA(launch_build(2, dt, ds[cur], d_Hpred, nullptr, d_sdpred, d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w, tab,
+                           d_fail, B.ns, B.smem, stream, B.threads, nullptr),
+              "build_level_kernel(predict)");
+      n_launches++;
+    }
     pred_H_valid = true;
   }
   ST_CUDA(launch_predict_sample(dt, pred_level.slot0, pred_level.nslots, d_Hpred, d_sdpred, d_w, d_z, stream), "predict_sample_kernel");

@@ -68,9 +68,15 @@ struct LevelInfo {
   int slot0 = 0, nslots = 0;  // node range
   int is_ref = 1;
   int grp0 = 0, ngrp = 0;     // BUILD work groups (index into grp arrays)
-  size_t smem_build = 0;      // dynamic shared memory of the BUILD kernel at this level
-  int build_threads = 128;    // 32 x (8-column tiles of the widest group), at least 4 warps
-  int build_ns = 2;           // depth of the cp.async ring (1 when that lets two CTAs share an SM, or 2 does not fit)
+  // the groups of a level are bucketed by width (8-column tiles) so that narrow groups are not launched with the
+  // shared memory and CTA size of the widest one
+  struct BuildLaunch {
+    int grp0 = 0, ngrp = 0;
+    size_t smem = 0;          // dynamic shared memory of build_level_kernel
+    int threads = 128;        // 32 x (8-column tiles of the widest group in the bucket), at least 4 warps
+    int ns = 2;               // depth of the cp.async ring (1 when that lets two CTAs share an SM, or when 2 does not fit)
+  };
+  std::vector<BuildLaunch> build_launches;
   int maxP = 0, maxm = 0, maxNC = 0, maxk = 0;
   size_t smem_gibbs = 0;
 };
