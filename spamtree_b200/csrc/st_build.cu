@@ -32,58 +32,51 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 }
 
 // R (row-major, stride rs, lower triangle valid, m <= 32) <- chol(R)^-1 (lower; strict upper zeroed) by one warp.
-// The factorisation keeps row `lane` in registers and broadcasts the pivot column through cb (2 x 32 doubles);
-// the inverse is one forward substitution per lane (column `lane`), reading L by broadcast.  dv: 32 doubles (1/diag).
+// Factorisation: lane i keeps row i in registers, rotated so that the pivot column is always a[0] (the loop stays
+// rolled: the trailing update writes a[i] <- a[i+1] - l_i * l_(j+1+i)); the pivot column is broadcast through cb
+// (2 x 64 doubles).  Inverse: row r of L^-1 overwrites row r of L (lane c solves for column c).  dv: 32 doubles (1/diag).
 __device__ __forceinline__ bool warp_chol_inv32(double* R, int m, int rs, double* cb, double* dv, int lane, long long* tmid) {
   bool ok = true;
   {
     double a[32];
 #pragma unroll
     for (int j = 0; j < 32; j++) a[j] = (lane < m && j <= lane) ? R[lane * rs + j] : 0.0;
+    cb[32 + lane] = 0.0;
+    cb[96 + lane] = 0.0;
+    for (int j = 0; j < m; j++) {
+      double d = __shfl_sync(0xffffffffu, a[0], j);
+      if (!(d > 0.0) || !isfinite(d)) { ok = false; d = 1.0; }  // dpotrf info > 0
+      const double inv = rsqrt(d), sd = d * inv;
+      const double l = (lane == j) ? sd : ((lane > j) ? a[0] * inv : 0.0);
+      double* c = cb + (j & 1) * 64;
+      c[lane] = l;
+      if (lane >= j && lane < m) R[lane * rs + j] = l;
+      if (lane == 0) dv[j] = inv;
+      __syncwarp();
+      const double* cj = c + j + 1;  // l of rows j+1 ..; entries past row 31 are never used by a valid element
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
-      if (j < m) {
-        double d = __shfl_sync(0xffffffffu, a[j], j);
-        if (!(d > 0.0) || !isfinite(d)) { ok = false; d = 1.0; }  // dpotrf info > 0
-        const double inv = rsqrt(d), sd = d * inv;
-        a[j] = (lane == j) ? sd : a[j] * inv;
-        double* c = cb + (j & 1) * 32;
-        c[lane] = a[j];
-        if (lane == 0) dv[j] = inv;
-        __syncwarp();
-#pragma unroll
-        for (int c2 = j + 1; c2 < 32; c2++)
-          if (c2 < m) a[c2] = fma(-a[j], c[c2], a[c2]);
-      }
+      for (int i = 0; i < 31; i++) a[i] = fma(-l, cj[i], a[i + 1]);
+      a[31] = 0.0;
     }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 32; j++)
-      if (j < m && lane < m && j <= lane) R[lane * rs + j] = a[j];
   }
   __syncwarp();
   if (tmid) *tmid = clock64();
-  double x[32];
-#pragma unroll
-  for (int r = 0; r < 32; r++) {
-    x[r] = 0.0;
-    if (r < m) {
-      double s0 = (r == lane) ? 1.0 : 0.0, s1 = 0.0;
-#pragma unroll
-      for (int kx = 0; kx + 1 < r; kx += 2) {
-        const double2 l = *reinterpret_cast<const double2*>(R + r * rs + kx);
-        s0 = fma(-l.x, x[kx], s0);
-        s1 = fma(-l.y, x[kx + 1], s1);
-      }
-      if (r & 1) s0 = fma(-R[r * rs + r - 1], x[r - 1], s0);
-      x[r] = (s0 + s1) * dv[r];
+  for (int r = 0; r < m; r++) {
+    const double* Lr = R + r * rs;
+    double s0 = (r == lane) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int kx = 0;
+    for (; kx + 3 < r; kx += 4) {  // rows kx < r already hold L^-1; column `lane` of them is zero above the diagonal
+      s0 = fma(-Lr[kx], R[kx * rs + lane], s0);
+      s1 = fma(-Lr[kx + 1], R[(kx + 1) * rs + lane], s1);
+      s2 = fma(-Lr[kx + 2], R[(kx + 2) * rs + lane], s2);
+      s3 = fma(-Lr[kx + 3], R[(kx + 3) * rs + lane], s3);
     }
+    for (; kx < r; kx++) s0 = fma(-Lr[kx], R[kx * rs + lane], s0);
+    const double xr = ((s0 + s1) + (s2 + s3)) * dv[r];
+    __syncwarp();
+    if (lane < m) R[r * rs + lane] = (lane <= r) ? xr : 0.0;
+    __syncwarp();
   }
-  __syncwarp();
-#pragma unroll
-  for (int r = 0; r < 32; r++)
-    if (r < m && lane < m) R[r * rs + lane] = x[r];  // x[r] = 0 for lane > r
-  __syncwarp();
   return ok;
 }
 }  // namespace
@@ -137,7 +130,7 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
   }
   __syncthreads();
   const int ncols = s_nc0[nn];
-  const BuildPlan pl = build_plan(P, ncols, s_sumRb, s_maxmd, ns, (MODE == 0) ? min(nn, kBuildMaxThreads / 32) : 0);
+  const BuildPlan pl = build_plan(P, ncols, s_sumRb, s_maxmd, ns, (MODE == 0) ? min(nn, kBuildMaxThreads / 32) : 0, nwarps);
   const int Ppad = pl.Ppad, NCp = pl.NCp, NT = pl.NT, LD = pl.LD, SA = pl.SA, slotsz = pl.slot;
   double* base = reinterpret_cast<double*>(smem_raw);
   double* panel = base + pl.o_panel;
@@ -155,8 +148,8 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
   long long* rowsrc = reinterpret_cast<long long*>(base + pl.o_rowsrc);
   long long* colbase = reinterpret_cast<long long*>(base + pl.o_colbase);
   double* vtmp = base + pl.o_vtmp;
-  double* s_cb = base + pl.o_cb;
-  int* pq = reinterpret_cast<int*>(base + pl.o_pq);
+  double* s_cb = base + pl.o_scr;
+  int* pq = reinterpret_cast<int*>(base + pl.o_scr + 2 * (size_t)Ppad);
   int* rowlen = reinterpret_cast<int*>(base + pl.o_rowlen);
   int* cq = reinterpret_cast<int*>(base + pl.o_cq);
   int* colnode = reinterpret_cast<int*>(base + pl.o_colnode);
@@ -215,6 +208,14 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
   mark(1);
 
   const int nstg = Ppad / RS;
+  // warp roles in the sweeps: warp < nfull owns column tile `warp`; the other tiles are shared by two warps that split
+  // the reduction range (the FP64 pipe is per SM sub-partition: this evens out the load of the four of them)
+  const int npair = pl.npair, nfull = NT - npair;
+  const int my_nt = (warp < NT) ? warp : ((warp < NT + npair) ? warp - npair : -1);
+  const bool paired = my_nt >= nfull, second = warp >= NT;
+  double* red = base + pl.o_scr + (size_t)(paired ? my_nt - nfull : 0) * 128;
+  const int bar_id = 1 + (paired ? my_nt - nfull : 0);
+  auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); };
   // stage of the forward sweep: rows [r0, r0 + 16) of the chain's factor, columns [0, r0 + 16)
   auto issue_fwd = [&](int st, double* slot) {
     const int r0 = st * RS, nch = (r0 + RS) >> 1;  // 16-byte chunks per row
@@ -248,27 +249,40 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
     __pipeline_wait_prior(0);
     __syncthreads();
     if (ns == 2 && i + 1 < nstg) issue_fwd(st - 1, ring + ((i + 1) & 1) * slotsz);
-    if (warp < NT) {
+    if (my_nt >= 0) {
       const int r0 = st * RS;
       const double* ap = slot + (lane >> 2) * SA + (lane & 3);
-      const double* bp = panel + (size_t)(lane & 3) * LD + 8 * warp + (lane >> 2);
+      const double* bp = panel + (size_t)(lane & 3) * LD + 8 * my_nt + (lane >> 2);
       double c0[2] = {0, 0}, c1[2] = {0, 0}, d0[2] = {0, 0}, d1[2] = {0, 0};
-      const int K0 = r0 + 8;  // the upper m-tile (rows r0 .. r0+7) has no entries past column r0 + 7
+      const int K0 = r0 + 8, K1 = r0 + 16;  // the upper m-tile (rows r0 .. r0+7) has no entries past column r0 + 7
+      const int Kmid = ((K1 >> 1) + 7) & ~7;
+      const int kbeg = (paired && second) ? Kmid : 0, kend = (paired && !second) ? Kmid : K1;
 #pragma unroll 2
-      for (int kk = 0; kk < K0; kk += 8) {
-        const double a0 = ap[kk], a1 = ap[8 * SA + kk], b0 = bp[(size_t)kk * LD];
-        const double a2 = ap[kk + 4], a3 = ap[8 * SA + kk + 4], b1 = bp[(size_t)(kk + 4) * LD];
-        dmma(c0, a0, b0); dmma(c1, a1, b0); dmma(d0, a2, b1); dmma(d1, a3, b1);
-      }
-      {
-        const double a1 = ap[8 * SA + K0], b0 = bp[(size_t)K0 * LD];
-        const double a3 = ap[8 * SA + K0 + 4], b1 = bp[(size_t)(K0 + 4) * LD];
+      for (int kk = kbeg; kk < kend; kk += 8) {
+        const double b0 = bp[(size_t)kk * LD], b1 = bp[(size_t)(kk + 4) * LD];
+        const double a1 = ap[8 * SA + kk], a3 = ap[8 * SA + kk + 4];
         dmma(c1, a1, b0); dmma(d1, a3, b1);
+        if (kk < K0) {
+          const double a0 = ap[kk], a2 = ap[kk + 4];
+          dmma(c0, a0, b0); dmma(d0, a2, b1);
+        }
       }
-      // the staged rows are [G | -Ri] = -L^-1
-      double* o = panel + (size_t)(r0 + (lane >> 2)) * LD + 8 * warp + 2 * (lane & 3);
-      *reinterpret_cast<double2*>(o) = make_double2(-(c0[0] + d0[0]), -(c0[1] + d0[1]));
-      *reinterpret_cast<double2*>(o + (size_t)8 * LD) = make_double2(-(c1[0] + d1[0]), -(c1[1] + d1[1]));
+      double2 z0 = make_double2(c0[0] + d0[0], c0[1] + d0[1]), z1 = make_double2(c1[0] + d1[0], c1[1] + d1[1]);
+      if (paired && second) {
+        *reinterpret_cast<double2*>(red + lane * 4) = z0;
+        *reinterpret_cast<double2*>(red + lane * 4 + 2) = z1;
+        pair_sync();
+      } else {
+        if (paired) {
+          pair_sync();
+          const double2 p0 = *reinterpret_cast<const double2*>(red + lane * 4), p1 = *reinterpret_cast<const double2*>(red + lane * 4 + 2);
+          z0.x += p0.x; z0.y += p0.y; z1.x += p1.x; z1.y += p1.y;
+        }
+        // the staged rows are [G | -Ri] = -L^-1
+        double* o = panel + (size_t)(r0 + (lane >> 2)) * LD + 8 * my_nt + 2 * (lane & 3);
+        *reinterpret_cast<double2*>(o) = make_double2(-z0.x, -z0.y);
+        *reinterpret_cast<double2*>(o + (size_t)8 * LD) = make_double2(-z1.x, -z1.y);
+      }
     }
     if (ns == 1) __syncthreads();
   }
@@ -322,7 +336,7 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
       long long tc0 = 0, tc1 = 0;
       if (prof && tid == 0) tc0 = clock64();
       if (md <= 32) {
-        okc = warp_chol_inv32(R, md, rs, s_cb + warp * 96, s_cb + warp * 96 + 64, lane, (prof && tid == 0) ? &tc1 : nullptr);
+        okc = warp_chol_inv32(R, md, rs, s_cb + warp * 160, s_cb + warp * 160 + 128, lane, (prof && tid == 0) ? &tc1 : nullptr);
         if (prof && tid == 0) { atomicAdd(prof + 8, (unsigned long long)(tc1 - tc0)); atomicAdd(prof + 9, (unsigned long long)(clock64() - tc1)); }
       } else {
         okc = warp_chol(R, md, rs, lane);
@@ -411,46 +425,61 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
       __pipeline_wait_prior(0);
       __syncthreads();
       if (ns == 2 && i + 1 < nstg) issue_bwd(i + 1, ring + ((i + 1) & 1) * slotsz);
-      if (warp < NT) {
+      if (my_nt >= 0) {
         const int r0 = i * RS, nk = Ppad - r0;
         const double* ap = slot + (lane & 3) * ST + (lane >> 2);  // A[m][k] = stage[k][m] (transposed use)
-        const double* bp = panel + (size_t)(r0 + (lane & 3)) * LD + 8 * warp + (lane >> 2);
+        const double* bp = panel + (size_t)(r0 + (lane & 3)) * LD + 8 * my_nt + (lane >> 2);
         double c0[2] = {0, 0}, c1[2] = {0, 0}, d0[2] = {0, 0}, d1[2] = {0, 0};
-        // rows r0 .. r0+7 of the stage have no entries in columns r0+8 .. r0+15 (lower-triangular factor)
-        dmma(c0, ap[0], bp[0]);
-        dmma(d0, ap[4 * ST], bp[(size_t)4 * LD]);
+        const int Kmid = ((nk >> 1) + 7) & ~7;
+        const int kbeg = (paired && second) ? Kmid : 0, kend = (paired && !second) ? Kmid : nk;
 #pragma unroll 2
-        for (int kk = 8; kk < nk; kk += 8) {
-          const double a0 = ap[kk * ST], a1 = ap[kk * ST + 8], b0 = bp[(size_t)kk * LD];
-          const double a2 = ap[(kk + 4) * ST], a3 = ap[(kk + 4) * ST + 8], b1 = bp[(size_t)(kk + 4) * LD];
-          dmma(c0, a0, b0); dmma(c1, a1, b0); dmma(d0, a2, b1); dmma(d1, a3, b1);
+        for (int kk = kbeg; kk < kend; kk += 8) {
+          const double b0 = bp[(size_t)kk * LD], b1 = bp[(size_t)(kk + 4) * LD];
+          const double a0 = ap[kk * ST], a2 = ap[(kk + 4) * ST];
+          dmma(c0, a0, b0); dmma(d0, a2, b1);
+          if (kk >= 8) {  // rows r0 .. r0+7 of the stage have no entries in columns r0+8 .. r0+15 (lower-triangular factor)
+            const double a1 = ap[kk * ST + 8], a3 = ap[(kk + 4) * ST + 8];
+            dmma(c1, a1, b0); dmma(d1, a3, b1);
+          }
         }
-        const int r = r0 + (lane >> 2), c = 8 * warp + 2 * (lane & 3);
-        const long long cb0 = colbase[c], cb1 = colbase[c + 1];
-        const double v00 = -(c0[0] + d0[0]), v01 = -(c0[1] + d0[1]), v10 = -(c1[0] + d1[0]), v11 = -(c1[1] + d1[1]);
-        if (r < P) {
-          if (cb0 >= 0) out[cb0 + r] = v00;
-          if (cb1 >= 0) out[cb1 + r] = v01;
-        }
-        if (r + 8 < P) {
-          if (cb0 >= 0) out[cb0 + r + 8] = v10;
-          if (cb1 >= 0) out[cb1 + r + 8] = v11;
-        }
-        if (do_gw) {
-          const double w0 = wpa[r], w1 = wpa[r + 8];  // zero past P
-          gacc[0] = fma(v00, w0, fma(v10, w1, gacc[0]));
-          gacc[1] = fma(v01, w0, fma(v11, w1, gacc[1]));
+        double2 z0 = make_double2(c0[0] + d0[0], c0[1] + d0[1]), z1 = make_double2(c1[0] + d1[0], c1[1] + d1[1]);
+        if (paired && second) {
+          *reinterpret_cast<double2*>(red + lane * 4) = z0;
+          *reinterpret_cast<double2*>(red + lane * 4 + 2) = z1;
+          pair_sync();
+        } else {
+          if (paired) {
+            pair_sync();
+            const double2 p0 = *reinterpret_cast<const double2*>(red + lane * 4), p1 = *reinterpret_cast<const double2*>(red + lane * 4 + 2);
+            z0.x += p0.x; z0.y += p0.y; z1.x += p1.x; z1.y += p1.y;
+          }
+          const int r = r0 + (lane >> 2), c = 8 * my_nt + 2 * (lane & 3);
+          const long long cb0 = colbase[c], cb1 = colbase[c + 1];
+          const double v00 = -z0.x, v01 = -z0.y, v10 = -z1.x, v11 = -z1.y;
+          if (r < P) {
+            if (cb0 >= 0) out[cb0 + r] = v00;
+            if (cb1 >= 0) out[cb1 + r] = v01;
+          }
+          if (r + 8 < P) {
+            if (cb0 >= 0) out[cb0 + r + 8] = v10;
+            if (cb1 >= 0) out[cb1 + r + 8] = v11;
+          }
+          if (do_gw) {
+            const double w0 = wpa[r], w1 = wpa[r + 8];  // zero past P
+            gacc[0] = fma(v00, w0, fma(v10, w1, gacc[0]));
+            gacc[1] = fma(v01, w0, fma(v11, w1, gacc[1]));
+          }
         }
       }
       if (ns == 1) __syncthreads();
     }
-    if (do_gw && warp < NT) {  // G w_pa per column: fixed-order reduction over the lanes that share the column
+    if (do_gw && warp < NT) {  // (warps >= NT are second halves) G w_pa per column: fixed-order reduction over the lanes that share the column
 #pragma unroll
       for (int o = 4; o < 32; o <<= 1) {
         gacc[0] += __shfl_xor_sync(0xffffffffu, gacc[0], o);
         gacc[1] += __shfl_xor_sync(0xffffffffu, gacc[1], o);
       }
-      if ((lane >> 2) == 0) { gw[8 * warp + 2 * lane] = gacc[0]; gw[8 * warp + 2 * lane + 1] = gacc[1]; }
+      if ((lane >> 2) == 0) { gw[8 * my_nt + 2 * lane] = gacc[0]; gw[8 * my_nt + 2 * lane + 1] = gacc[1]; }
     }
     __syncthreads();
   };

@@ -42,12 +42,15 @@ __host__ __device__ inline int rb_doubles(int m) { return ((m + 7) & ~7) * rb_st
 // ---- shared-memory plan of build_level_kernel (one work group = a run of sibling blocks)
 struct BuildPlan {
   int Ppad, NCp, NT, LD, SA, slot, ring;
-  size_t o_panel, o_ring, o_pxs, o_pys, o_wpa, o_cxs, o_cys, o_wcol, o_tvec, o_gw, o_rdiag, o_rowsrc, o_colbase, o_vtmp, o_cb,
-      o_pq, o_rowlen, o_cq, o_colnode, total;
+  size_t o_panel, o_ring, o_pxs, o_pys, o_wpa, o_cxs, o_cys, o_wcol, o_tvec, o_gw, o_rdiag, o_rowsrc, o_colbase, o_vtmp, o_scr,
+      o_rowlen, o_cq, o_colnode, total;
+  int npair;
 };
 // P parent rows, ncols rows in the group's blocks, sumRb = sum of rb_doubles over its blocks (reference levels),
-// maxmd = largest block, ns = ring depth (1 or 2), nchol = warps factorising at once (reference levels: min(blocks, 16))
-__host__ __device__ inline BuildPlan build_plan(int P, int ncols, int sumRb, int maxmd, int ns, int nchol) {
+// maxmd = largest block, ns = ring depth (1 or 2), nchol = warps factorising at once (reference levels: min(blocks, 16)),
+// nwarps = warps of the CTA
+__host__ __device__ inline int build_npair(int NT, int nwarps) { const int x = nwarps - NT; return x < 0 ? 0 : (x < NT ? x : NT); }
+__host__ __device__ inline BuildPlan build_plan(int P, int ncols, int sumRb, int maxmd, int ns, int nchol, int nwarps) {
   BuildPlan p;
   p.Ppad = (P + 15) & ~15;
   p.NCp = (ncols + 7) & ~7;
@@ -61,13 +64,21 @@ __host__ __device__ inline BuildPlan build_plan(int P, int ncols, int sumRb, int
   auto take = [&](size_t n_doubles) { size_t r = o; o += ((n_doubles + 1) & ~(size_t)1); return r; };
   p.o_panel = take((size_t)p.Ppad * p.LD);
   p.o_ring = take((size_t)p.ring);
-  p.o_pxs = take(p.Ppad); p.o_pys = take(p.Ppad); p.o_wpa = take(p.Ppad);
+  p.npair = build_npair(p.NT, nwarps);  // column tiles whose reduction range is shared by two warps
+  {
+    // one scratch region, three lives: parent coordinates (covariance phase: x, y, outcome), partial sums of the paired
+    // warps (sweeps: 128 doubles per pair), pivot columns and 1/diag of the factorising warps (2 x 64 + 32 doubles each)
+    size_t a = 2 * (size_t)p.Ppad + (p.Ppad + 1) / 2, b = (size_t)p.npair * 128, c = (size_t)nchol * 160;
+    if (b > a) a = b;
+    if (c > a) a = c;
+    p.o_scr = take(a);
+  }
+  p.o_pxs = p.o_scr; p.o_pys = p.o_scr + p.Ppad; p.o_wpa = take(p.Ppad);
   p.o_cxs = take(p.LD); p.o_cys = take(p.LD); p.o_wcol = take(p.LD); p.o_tvec = take(p.LD); p.o_gw = take(p.LD);
   p.o_rdiag = take(p.LD);
   p.o_rowsrc = take(p.Ppad); p.o_colbase = take(p.LD);
   p.o_vtmp = take(maxmd > 32 ? (size_t)(kBuildMaxThreads / 32) * (maxmd + 2) : 0);
-  p.o_cb = take((size_t)nchol * 96);  // per factorising warp: pivot columns (2 x 32) and 1 / diag (32)
-  p.o_pq = take((p.Ppad + 1) / 2); p.o_rowlen = take((p.Ppad + 1) / 2);
+  p.o_rowlen = take((p.Ppad + 1) / 2);
   p.o_cq = take((p.LD + 1) / 2); p.o_colnode = take((p.LD + 1) / 2);
   p.total = o * 8 + 16;
   return p;

@@ -344,14 +344,14 @@ int Model::build_layout(std::string& e) {
   // BUILD work groups: runs of sibling blocks (they share their ancestor chain), at most max_group_cols columns
   // (one warp per 8 columns) and sized to the shared-memory budget
   h_grp_slot0.clear(); h_grp_nn.clear();
-  auto group_plan = [&](int s, int nn, int mode, int ns) {
+  auto group_plan = [&](int s, int nn, int mode, int ns, int nwarps) {
     int ncols = 0, sumRb = 0, maxmd = 1;
     for (int d = 0; d < nn; d++) {
       ncols += h_m[s + d];
       if (mode == 0) sumRb += rb_doubles(h_m[s + d]);
       maxmd = std::max(maxmd, h_m[s + d]);
     }
-    return build_plan(h_P[s], ncols, sumRb, maxmd, ns, mode == 0 ? std::min(nn, kBuildMaxThreads / 32) : 0);
+    return build_plan(h_P[s], ncols, sumRb, maxmd, ns, mode == 0 ? std::min(nn, kBuildMaxThreads / 32) : 0, nwarps);
   };
   auto make_groups = [&](LevelInfo& L, int mode) -> int {
     L.grp0 = (int)h_grp_slot0.size();
@@ -359,7 +359,9 @@ int Model::build_layout(std::string& e) {
     L.build_launches.clear();
     const int end = L.slot0 + L.nslots;
     const int col_cap = std::min(max_group_cols, kMaxGroupCols);
-    struct Grp { int s, nn, NT; size_t need1, need2; };
+    struct Grp { int s, nn, NT; };
+    const int wmax = kBuildMaxThreads / 32;
+    auto warps_for = [&](int NT) { return std::min(wmax, std::max(4, (2 * NT) & ~3)); };
     std::vector<Grp> gs;
     int s = L.slot0;
     while (s < end) {
@@ -368,7 +370,7 @@ int Model::build_layout(std::string& e) {
       while (s + nn < end && nn < kMaxGroupNodes) {
         const int t = s + nn;
         if (nn > 0 && (h_lastpar[s] < 0 || h_lastpar[t] != h_lastpar[s])) break;  // roots never share a chain
-        const BuildPlan pl = group_plan(s, nn + 1, mode, 1);
+        const BuildPlan pl = group_plan(s, nn + 1, mode, 1, wmax);
         if (pl.total > smem_budget || pl.NCp > kMaxGroupCols || (nn > 0 && pl.NCp > col_cap)) break;
         best = pl;
         nn++;
@@ -377,7 +379,7 @@ int Model::build_layout(std::string& e) {
         e = "a block is too large for one BUILD work group (m=" + std::to_string(h_m[s]) + ", P=" + std::to_string(h_P[s]) + ")";
         return 4;
       }
-      gs.push_back({s, nn, best.NT, best.total, group_plan(s, nn, mode, 2).total});
+      gs.push_back({s, nn, best.NT});
       L.maxNC = std::max(L.maxNC, best.NCp);
       s += nn;
     }
@@ -390,9 +392,13 @@ int Model::build_layout(std::string& e) {
       size_t need1 = 0, need2 = 0;
       int maxNT = 1;
       for (const Grp& g : gs)
+        if (g.NT > lo && g.NT <= hi) maxNT = std::max(maxNT, g.NT);
+      const int nw = warps_for(maxNT);
+      for (const Grp& g : gs)
         if (g.NT > lo && g.NT <= hi) {
           h_grp_slot0.push_back(g.s); h_grp_nn.push_back(g.nn);
-          need1 = std::max(need1, g.need1); need2 = std::max(need2, g.need2); maxNT = std::max(maxNT, g.NT);
+          need1 = std::max(need1, group_plan(g.s, g.nn, mode, 1, nw).total);
+          need2 = std::max(need2, group_plan(g.s, g.nn, mode, 2, nw).total);
         }
       bl.ngrp = (int)h_grp_slot0.size() - bl.grp0;
       if (bl.ngrp == 0) continue;
@@ -402,7 +408,7 @@ int Model::build_layout(std::string& e) {
       else if (need1 <= half_sm) bl.ns = 1;
       else bl.ns = (need2 <= smem_budget) ? 2 : 1;
       bl.smem = (bl.ns == 2) ? need2 : need1;
-      bl.threads = 32 * std::min(kBuildMaxThreads / 32, std::max(4, maxNT));
+      bl.threads = 32 * nw;
       L.build_launches.push_back(bl);
     }
     L.ngrp = (int)h_grp_slot0.size() - L.grp0;
