@@ -216,26 +216,32 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
   double* red = base + pl.o_scr + (size_t)(paired ? my_nt - nfull : 0) * 128;
   const int bar_id = 1 + (paired ? my_nt - nfull : 0);
   auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); };
+  // 16-byte cp.async with zero fill of the bytes past `valid_bytes` (0, 8 or 16)
+  auto cp16 = [](double* dst, const double* src, int valid_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(valid_bytes) : "memory");
+  };
+  // threads per staged row: a power of two, so that the (row, chunk) split of a stage needs no division
+  int tpr_log = 0;
+  while ((RS << (tpr_log + 1)) <= nth) tpr_log++;
   // stage of the forward sweep: rows [r0, r0 + 16) of the chain's factor, columns [0, r0 + 16)
   auto issue_fwd = [&](int st, double* slot) {
-    const int r0 = st * RS, nch = (r0 + RS) >> 1;  // 16-byte chunks per row
-    for (int idx = tid; idx < RS * nch; idx += nth) {
-      const int rr = idx / nch, c2 = (idx - rr * nch) * 2;
-      const int r = r0 + rr;
-      const int valid = min(max(rowlen[r] - c2, 0), 2);
-      const double* src = S.G + rowsrc[r] + (valid ? c2 : 0);
-      __pipeline_memcpy_async(slot + rr * SA + c2, src, 16, 16 - 8 * valid);
+    const int r0 = st * RS, kext = r0 + RS;
+    const int rr = tid >> tpr_log;
+    if (rr >= RS) return;
+    const int r = r0 + rr, len = rowlen[r];
+    const double* src = S.G + rowsrc[r];
+    double* dst = slot + rr * SA;
+    for (int c2 = (tid & ((1 << tpr_log) - 1)) * 2; c2 < kext; c2 += 2 << tpr_log) {
+      const int valid = min(max(len - c2, 0), 2);
+      cp16(dst + c2, src + (valid ? c2 : 0), 8 * valid);
     }
   };
   // stage of the backward sweep: columns [r0, r0 + 16) of rows [r0, Ppad)
   auto issue_bwd = [&](int st, double* slot) {
-    const int r0 = st * RS, nrow = Ppad - r0;
-    for (int idx = tid; idx < nrow * 8; idx += nth) {
-      const int rr = idx >> 3, c2 = (idx & 7) * 2;
-      const int r = r0 + rr;
+    const int r0 = st * RS, c2 = (tid & 7) * 2;
+    for (int r = r0 + (tid >> 3); r < Ppad; r += nth >> 3) {
       const int valid = min(max(rowlen[r] - (r0 + c2), 0), 2);
-      const double* src = S.G + rowsrc[r] + (valid ? r0 + c2 : 0);
-      __pipeline_memcpy_async(slot + rr * ST + c2, src, 16, 16 - 8 * valid);
+      cp16(slot + (r - r0) * ST + c2, S.G + rowsrc[r] + (valid ? r0 + c2 : 0), 8 * valid);
     }
   };
 

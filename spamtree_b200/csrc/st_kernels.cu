@@ -43,7 +43,7 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
   double* smu = gwj + (size_t)(k + 1) * m;
   double* wn = smu + m;
   double* rr = wn + m;
-  const double* G = S.G + T.goff[sd];
+  const double* G = S.G + T.goff[sd];  // the block's rows of the chain factor, [G | -Ri | 0], one contiguous run
   const double* Rig = S.Ri + T.rioff[sd];
   const int nch = T.child_ptr[sd + 1] - T.child_ptr[sd];
   const int* ch = T.child_idx + T.child_ptr[sd];
@@ -57,21 +57,22 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
   if (tid >= 32 && tid < 32 + min(nch, 16)) c_voff[tid - 32] = T.voff[ch[tid - 32]];
   for (int e = tid; e < msq; e += nth) RiS[e] = Rig[e];
   __syncthreads();
-  for (int j = 0; j < k; j++) {
-    const int po = c_po[j], r0 = c_r0[j], ma = c_m[j];
-    for (int t = tid; t < ma; t += nth) wpa[po + t] = w[r0 + t];
+  for (int e = tid; e < P; e += nth) {
+    int j = 0;
+    while (j + 1 < k && e >= c_po[j + 1]) j++;
+    wpa[e] = w[c_r0[j] + (e - c_po[j])];
   }
   __syncthreads();
-  // gwj[j][r] = G_j(r,:) w_{a_j}   (pieces of H w_pa scaled by Ri; :1063 / :1103)
+  // gwj[j][r] = G_j(r,:) w_{a_j}   (pieces of H w_pa scaled by Ri; :1063 / :1103); ancestor fastest: a warp reads adjacent row segments
   for (int e = tid; e < k * m; e += nth) {
-    const int j = e / m, r = e - j * m;
+    const int r = e / k, j = e - r * k;
     const int mj = c_m[j], po = c_po[j];
     const double* g = G + (size_t)r * gs + po;
     double s0 = 0, s1 = 0;
     int pp = 0;
     for (; pp + 1 < mj; pp += 2) { s0 = fma(g[pp], wpa[po + pp], s0); s1 = fma(g[pp + 1], wpa[po + pp + 1], s1); }
     if (pp < mj) s0 = fma(g[pp], wpa[po + pp], s0);
-    gwj[e] = s0 + s1;
+    gwj[j * m + r] = s0 + s1;
   }
   __syncthreads();
   for (int r = tid; r < m; r += nth) {
@@ -105,7 +106,41 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
     __syncthreads();
     if (warp == 0) {
       // w = Sc'(Sc Smu + z), Sc = chol(Sigi_tot)^-1 (:1054, :1086), done as two triangular solves
-      if (warp_chol(Sig, m, m, lane)) {
+      bool okc = true;
+      if (m <= 32) {
+        // lane i keeps row i of Sigi_tot in registers, rotated so that the pivot column is a[0] (the pivot column is
+        // broadcast by shuffles); the forward solve
+        // L x = Smu rides along as an extra column; L overwrites Sig for the backward solve L' w = x + z
+        double a[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) a[j] = (lane < m && j <= lane) ? Sig[lane * m + j] : 0.0;
+        double b = (lane < m) ? smu[lane] : 0.0, myinv = 0.0;
+        __syncwarp();
+        for (int j = 0; j < m; j++) {
+          double d = __shfl_sync(0xffffffffu, a[0], j);
+          if (!(d > 0.0) || !isfinite(d)) { okc = false; d = 1.0; }
+          const double inv = rsqrt(d), sd = d * inv;
+          const double l = (lane == j) ? sd : ((lane > j) ? a[0] * inv : 0.0);
+          const double xj = __shfl_sync(0xffffffffu, b, j) * inv;
+          if (lane == j) { b = xj; myinv = inv; } else if (lane > j) b = fma(-l, xj, b);
+          if (lane >= j && lane < m) Sig[lane * m + j] = l;
+#pragma unroll
+          for (int i = 0; i < 31; i++) {
+            const double lc = __shfl_sync(0xffffffffu, l, min(j + 1 + i, 31));
+            a[i] = fma(-l, lc, a[i + 1]);
+          }
+          a[31] = 0.0;
+        }
+        __syncwarp();
+        if (okc) {
+          double y = (lane < m) ? b + z[row0 + lane] : 0.0;
+          for (int j = m - 1; j >= 0; j--) {
+            const double wj = __shfl_sync(0xffffffffu, y * myinv, j);
+            if (lane == j) y = wj; else if (lane < j) y = fma(-Sig[j * m + lane], wj, y);
+          }
+          if (lane < m) { wn[lane] = y; w[row0 + lane] = y; }
+        }
+      } else if (warp_chol(Sig, m, m, lane)) {
         for (int c = 0; c < m; c++) {  // forward: L x = smu
           __syncwarp();
           const double xc = smu[c] / Sig[c * m + c];
@@ -125,6 +160,9 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
         __syncwarp();
         for (int r = lane; r < m; r += 32) { wn[r] = smu[r]; w[row0 + r] = smu[r]; }
       } else {
+        okc = false;
+      }
+      if (!okc) {
         if (lane == 0) atomicAdd(fail, 1);
         for (int r = lane; r < m; r += 32) wn[r] = w[row0 + r];
       }
@@ -245,18 +283,20 @@ cudaError_t launch_gram(const DevTree& T, const DevSlot& S, int slot0, int nslot
 }
 
 // ------------------------------------------------------------------------------------------------ LLW
-// llcomp[s] = m*hl2pi - 0.5*|Ri w_u - G w_pa|^2  (get_loglik_w_std, :791-813); one warp per node
+// llcomp[s] = m*hl2pi - 0.5*|Ri w_u - G w_pa|^2  (get_loglik_w_std, :791-813); one warp per node.
+// A reference block's rows of the chain factor are [G | -Ri | 0], so its contribution is one streaming product
+// |[G | -Ri] [w_pa ; w_u]|^2 over contiguous rows; the warp stages [w_pa ; w_u] in shared memory once.
 __global__ void __launch_bounds__(kLlwThreads)
-llw_kernel(DevTree T, DevSlot S, int nslots, const double* __restrict__ w) {
-  const int lane = threadIdx.x & 31;
-  const int sd = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+llw_kernel(DevTree T, DevSlot S, int nslots, const double* __restrict__ w, int maxlen) {
+  extern __shared__ __align__(16) double llw_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int sd = blockIdx.x * (blockDim.x >> 5) + wib;
   if (sd >= nslots) return;
-  const int m = T.m[sd], k = T.k[sd], coff = T.chain_off[sd], row0 = T.row0[sd];
+  double* wx = llw_smem + (size_t)wib * maxlen;
+  const int m = T.m[sd], k = T.k[sd], P = T.P[sd], coff = T.chain_off[sd], row0 = T.row0[sd], gs = T.gs[sd];
   const bool ref = T.isref[sd] != 0;
   const double* G = S.G + T.goff[sd];
-  const double* Ri = S.Ri + T.rioff[sd];
-  const int rsm = tile_rs(m), gs = T.gs[sd];
-  // lane j keeps the metadata of ancestor j (k <= 32): no dependent global loads inside the row loop
+  // lane j keeps the metadata of ancestor j (k <= 32)
   int a_m = 0, a_po = 0, a_r0 = 0;
   if (lane < k) {
     const int a = T.chain[coff + lane];
@@ -264,28 +304,57 @@ llw_kernel(DevTree T, DevSlot S, int nslots, const double* __restrict__ w) {
     a_po = T.chain_poff[coff + lane];
     a_r0 = T.row0[a];
   }
+  for (int j = 0; j < k; j++) {
+    const int mj = __shfl_sync(0xffffffffu, a_m, j), po = __shfl_sync(0xffffffffu, a_po, j), ar0 = __shfl_sync(0xffffffffu, a_r0, j);
+    for (int t = lane; t < mj; t += 32) wx[po + t] = w[ar0 + t];
+  }
+  const int len = ref ? P + m : P;
+  if (ref)
+    for (int t = lane; t < m; t += 32) wx[P + t] = w[row0 + t];
+  __syncwarp();
   double wc = 0;
-  for (int r = 0; r < m; r++) {
-    double s = 0;
-    if (ref) {
-      for (int r2 = lane; r2 <= r; r2 += 32) s = fma(Ri[r * rsm + r2], w[row0 + r2], s);
-    } else if (lane == 0) {
-      s = Ri[r] * w[row0 + r];
+  int r = 0;
+  for (; r + 1 < m; r += 2) {  // two rows at a time: independent load streams
+    const double* g0 = G + (size_t)r * gs;
+    const double* g1 = g0 + gs;
+    double s0 = 0, s1 = 0;
+    for (int c = lane; c < len; c += 32) {
+      const double x = wx[c];
+      s0 = fma(__ldg(g0 + c), x, s0);
+      s1 = fma(__ldg(g1 + c), x, s1);
     }
-    for (int j = 0; j < k; j++) {
-      const int mj = __shfl_sync(0xffffffffu, a_m, j), po = __shfl_sync(0xffffffffu, a_po, j), ar0 = __shfl_sync(0xffffffffu, a_r0, j);
-      const double* g = G + (size_t)r * gs + po;
-      for (int pp = lane; pp < mj; pp += 32) s = fma(-g[pp], w[ar0 + pp], s);
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    if (!ref) {
+      const double* Ri = S.Ri + T.rioff[sd];
+      s0 -= Ri[r] * w[row0 + r];
+      s1 -= Ri[r + 1] * w[row0 + r + 1];
     }
-    s = warp_sum(s);
-    wc = fma(s, s, wc);
+    wc = fma(s0, s0, wc);
+    wc = fma(s1, s1, wc);
+  }
+  if (r < m) {
+    const double* g0 = G + (size_t)r * gs;
+    double s0 = 0;
+    for (int c = lane; c < len; c += 32) s0 = fma(__ldg(g0 + c), wx[c], s0);
+    s0 = warp_sum(s0);
+    if (!ref) s0 -= S.Ri[T.rioff[sd] + r] * w[row0 + r];
+    wc = fma(s0, s0, wc);
   }
   if (lane == 0) S.llcomp[sd] = (double)m * kHl2pi - 0.5 * wc;
 }
-cudaError_t launch_llw(const DevTree& T, const DevSlot& S, int nslots, const double* w, cudaStream_t st) {
+cudaError_t launch_llw(const DevTree& T, const DevSlot& S, int nslots, const double* w, int maxlen, cudaStream_t st) {
   if (nslots <= 0) return cudaSuccess;
   const int wpb = kLlwThreads / 32;
-  llw_kernel<<<(nslots + wpb - 1) / wpb, kLlwThreads, 0, st>>>(T, S, nslots, w);
+  maxlen = (maxlen + 1) & ~1;
+  const size_t smem = (size_t)wpb * maxlen * sizeof(double);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(llw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  llw_kernel<<<(nslots + wpb - 1) / wpb, kLlwThreads, smem, st>>>(T, S, nslots, w, maxlen);
   return cudaGetLastError();
 }
 

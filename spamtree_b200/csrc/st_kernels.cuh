@@ -96,7 +96,7 @@ cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlot& S, int slo
                          double* probe_sig, double* probe_smu, int* fail, size_t smem, cudaStream_t st);
 cudaError_t launch_gram(const DevTree& T, const DevSlot& S, int slot0, int nslots, double* U, double* SigS,
                         cudaStream_t st);
-cudaError_t launch_llw(const DevTree& T, const DevSlot& S, int nslots, const double* w, cudaStream_t st);
+cudaError_t launch_llw(const DevTree& T, const DevSlot& S, int nslots, const double* w, int maxlen, cudaStream_t st);
 cudaError_t launch_loglik_reduce(const double* logdet, const double* llcomp, int first, int n, const int* fail,
                                  int fail_as_count, double* out, cudaStream_t st);
 cudaError_t launch_frontier_sum(const DevTree& T, int n, const int* pseudo, const int* c0, const int* c1, const int* vlen,

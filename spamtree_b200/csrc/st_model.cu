@@ -339,6 +339,8 @@ int Model::build_layout(std::string& e) {
   for (int s = 0; s < n_obs_nodes; s++)
     if (h_child_ptr[s + 1] > h_child_ptr[s]) { h_soff[s] = s_total; s_total += pad2((long long)h_m[s] * h_m[s]); }
   isref_host_ = isref;
+  llw_maxlen_ = 2;
+  for (int s = 0; s < n_obs_nodes; s++) llw_maxlen_ = std::max(llw_maxlen_, h_P[s] + h_m[s]);
   sd_total_ = sd_total;
 
   // BUILD work groups: runs of sibling blocks (they share their ancestor chain), at most max_group_cols columns
@@ -747,10 +749,22 @@ int Model::gibbs_launch_only() {
       int rc = allreduce_dev(d_V + v_front0, v_front_len);
       if (rc) return rc;
     }
+    static const bool profile = getenv("ST_PROFILE_GIBBS") != nullptr;  // development aid: per-level event timing
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, stream); }
     ST_CUDA(launch_gibbs(L.is_ref, dt, ds[cur], L.slot0, L.nslots, d_w, d_xb, d_z, d_tausq_inv, d_S, d_V,
                          probes ? d_probe_sig : nullptr, probes ? d_probe_smu : nullptr, d_fail, L.smem_gibbs, stream),
             "gibbs_level_kernel");
     n_launches++;
+    if (profile) {
+      cudaEventRecord(pe1, stream);
+      cudaStreamSynchronize(stream);
+      float pms = 0;
+      cudaEventElapsedTime(&pms, pe0, pe1);
+      cudaEventDestroy(pe0); cudaEventDestroy(pe1);
+      fprintf(stderr, "[gibbs profile] level slot0=%d nodes=%d ref=%d smem=%zu maxm=%d maxP=%d  %.3f ms\n", L.slot0, L.nslots, L.is_ref,
+              L.smem_gibbs, L.maxm, L.maxP, pms);
+    }
   }
   return 0;
 }
@@ -781,7 +795,7 @@ int Model::deal_with_w(const double* z, uint64_t seed) {
 int Model::get_loglik_w(int slot, double* out2) {
   if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   const int ps = phys(slot);
-  ST_CUDA(launch_llw(dt, ds[ps], n_obs_nodes, d_w, stream), "llw_kernel");
+  ST_CUDA(launch_llw(dt, ds[ps], n_obs_nodes, d_w, llw_maxlen_, stream), "llw_kernel");
   n_launches++;
   double r3[3];
   int rc = reduce_loglik(ps, nullptr, r3);
@@ -1063,7 +1077,7 @@ int Model::bench_iteration(const double* theta_prop, int do_swap, uint64_t seed,
   if (rc) return rc;
   ST_CUDA(cudaMemcpyAsync(h_scalars + 40, d_fail, sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H fail");
   ST_CUDA(cudaEventRecord(ev[1], stream), "event");
-  ST_CUDA(launch_llw(dt, ds[cur], n_obs_nodes, d_w, stream), "llw_kernel");
+  ST_CUDA(launch_llw(dt, ds[cur], n_obs_nodes, d_w, llw_maxlen_, stream), "llw_kernel");
   n_launches++;
   double rl[3], rb[3];
   rc = reduce_loglik(cur, nullptr, rl);

@@ -191,6 +191,7 @@ class Model {
   int rowstats(bool faithful_index);
   std::vector<int> isref_host_;
   long long sd_total_ = 0;
+  int llw_maxlen_ = 2;  // longest [w_pa ; w_u] any block stages in the LLW kernel
   int rowstat_blocks_ = 1;
   int draw_normals(uint64_t seed);
   int upload_rows(const double* boundary_order, double* dev);
