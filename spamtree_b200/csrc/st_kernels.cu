@@ -242,43 +242,164 @@ cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlot& S, int slo
 
 // ------------------------------------------------------------------------------------------------ message Grams
 // U_d[j] = G_j'G_j + sum_children U_c[j]  (= sum over the subtree of AK_uP_u_all[J_j, J_j], :1190-1192) and
-// SigS_d = sum_children U_c[tile of d]  (= arma::sum(Sigi_children(d), 2), :1049).  One block per node.
+// SigS_d = sum_children U_c[tile of d]  (= arma::sum(Sigi_children(d), 2), :1049).  One CTA per node.
+// Childless children ("fused": the bulk of the tree) never store their own tiles: the parent forms their G_c'G_c
+// from their row blocks directly.  The rows (own + fused children) are staged in shared memory in chunks and every
+// thread accumulates one 5 x 5 sub-block of the lower triangle of one tile in registers.
 __global__ void __launch_bounds__(kGramThreads)
-gram_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ U, double* __restrict__ SigS) {
+gram_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ U, double* __restrict__ SigS, int rch, int ldx,
+                  int tile_doubles) {
+  extern __shared__ __align__(16) double gram_smem[];
+  __shared__ int t_po[kMaxChain + 1], t_m[kMaxChain + 1], t_item0[kMaxChain + 2], t_uo[kMaxChain + 1], t_to[kMaxChain + 2];
+  __shared__ int s_rows;
+  __shared__ long long s_rowoff[kGramMaxRows];  // per staged row: offset of the row in S.G and its valid columns
+  __shared__ int s_rowncol[kGramMaxRows];
+  __shared__ long long s_cu[kGramChildTab];     // per (child, tile): offset of the child's stored tile, -1 when the child is fused
   const int tid = threadIdx.x, nth = blockDim.x;
   const int sd = slot0 + blockIdx.x;
-  const int m = T.m[sd], k = T.k[sd], coff = T.chain_off[sd];
+  if (T.ufused[sd]) return;
+  double* tiles = gram_smem;                 // the assembled tiles (both triangles), tile j at t_to[j]
+  double* stage = gram_smem + tile_doubles;  // rch staged rows of ldx doubles
+  const int m = T.m[sd], k = T.k[sd], P = T.P[sd], coff = T.chain_off[sd];
   const int nch = T.child_ptr[sd + 1] - T.child_ptr[sd];
   const int* ch = T.child_idx + T.child_ptr[sd];
-  const double* G = S.G + T.goff[sd];
-  const int gs = T.gs[sd];
+  const long long so = T.soff[sd];
+  const int ntile = k + (so >= 0 ? 1 : 0);  // the block's own tile exists only through its children
+  if (tid <= k) {
+    t_po[tid] = (tid < k) ? T.chain_poff[coff + tid] : P;
+    t_m[tid] = (tid < k) ? T.m[T.chain[coff + tid]] : m;
+    t_uo[tid] = (tid < k) ? T.chain_uoff[coff + tid] : 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int it = 0, to = 0;
+    for (int j = 0; j < ntile; j++) {
+      t_item0[j] = it; t_to[j] = to;
+      const int nb = (t_m[j] + 4) / 5;
+      it += nb * (nb + 1) / 2;
+      to += t_m[j] * t_m[j];
+    }
+    t_item0[ntile] = it; t_to[ntile] = to;
+    int rows = m;
+    for (int c = 0; c < nch; c++) if (T.ufused[ch[c]]) rows += T.m[ch[c]];
+    s_rows = rows;
+  }
+  const bool ctab = nch * ntile <= kGramChildTab;
+  if (ctab)
+    for (int e = tid; e < nch * ntile; e += nth) {
+      const int c = e / ntile, jj = e - c * ntile, cc = ch[c];
+      s_cu[e] = T.ufused[cc] ? -1 : T.uoff[cc] + T.chain_uoff[T.chain_off[cc] + jj];
+    }
+  __syncthreads();
+  const int nitems = t_item0[ntile], nrows = s_rows;
   double* Ud = U + T.uoff[sd];
-  for (int j = 0; j < k; j++) {
-    const int mj = T.m[T.chain[coff + j]];
-    const double* g = G + T.chain_poff[coff + j];
-    const int uo = T.chain_uoff[coff + j];
-    const int rsj = gs;
-    for (int e = tid; e < mj * mj; e += nth) {
-      const int a = e / mj, b = e - a * mj;
-      double s = 0;
-      for (int r = 0; r < m; r++) s = fma(__ldg(g + (size_t)r * rsj + a), __ldg(g + (size_t)r * rsj + b), s);
-      for (int c = 0; c < nch; c++) s += U[T.uoff[ch[c]] + T.chain_uoff[T.chain_off[ch[c]] + j] + e];
-      Ud[uo + e] = s;
+  for (int item0 = 0; item0 < nitems; item0 += nth) {  // (one round unless the chain is very long)
+    const int item = item0 + tid;
+    const bool act = item < nitems;
+    int j = 0, bi = 0, bj = 0;
+    if (act) {
+      while (item >= t_item0[j + 1]) j++;
+      const int rem = item - t_item0[j];
+      while ((bi + 1) * (bi + 2) / 2 <= rem) bi++;
+      bj = rem - bi * (bi + 1) / 2;
+    }
+    const int mj = act ? t_m[j] : 1, po = act ? t_po[j] : 0;
+    int ca[5], cb[5];
+#pragma unroll
+    for (int t = 0; t < 5; t++) { ca[t] = po + min(5 * bi + t, mj - 1); cb[t] = po + min(5 * bj + t, mj - 1); }
+    double acc[5][5];
+#pragma unroll
+    for (int x = 0; x < 5; x++)
+#pragma unroll
+      for (int y = 0; y < 5; y++) acc[x][y] = 0.0;
+    // stream the rows through shared memory: row ids 0..m-1 are the block's own (tiles j < k only), then the fused children's
+    for (int rbase = 0; rbase < nrows; rbase += rch) {
+      const int nr = min(rch, nrows - rbase);
+      __syncthreads();
+      for (int rr = tid; rr < nr; rr += nth) {  // where does staged row rr live?
+        int r = rbase + rr;
+        if (r < m) { s_rowoff[rr] = T.goff[sd] + (long long)r * T.gs[sd]; s_rowncol[rr] = P; }
+        else {
+          r -= m;
+          for (int c = 0; c < nch; c++) {
+            const int cc = ch[c];
+            if (!T.ufused[cc]) continue;
+            const int mc = T.m[cc];
+            if (r < mc) { s_rowoff[rr] = T.goff[cc] + (long long)r * T.gs[cc]; s_rowncol[rr] = P + m; break; }
+            r -= mc;
+          }
+        }
+      }
+      __syncthreads();
+      {
+        const int hl = ldx >> 1;  // 16-byte chunks per staged row; columns past the row's end are zero-filled
+        for (int idx = tid; idx < nr * hl; idx += nth) {
+          const int rr = idx / hl, x = (idx - rr * hl) * 2;
+          const int valid = min(max(s_rowncol[rr] - x, 0), 2);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(stage + (size_t)rr * ldx + x)),
+                       "l"(S.G + s_rowoff[rr] + (valid ? x : 0)), "r"(8 * valid) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+      if (act) {
+        const int rb = (j == k) ? max(0, m - rbase) : 0;  // the block's own rows carry no entries of its own tile
+        for (int rr = rb; rr < nr; rr++) {
+          const double* x = stage + (size_t)rr * ldx;
+          double av[5], bv[5];
+#pragma unroll
+          for (int t = 0; t < 5; t++) { av[t] = x[ca[t]]; bv[t] = x[cb[t]]; }
+#pragma unroll
+          for (int xx = 0; xx < 5; xx++)
+#pragma unroll
+            for (int yy = 0; yy < 5; yy++) acc[xx][yy] = fma(av[xx], bv[yy], acc[xx][yy]);
+        }
+      }
+    }
+    if (act) {  // both triangles of the tile
+      double* tj = tiles + t_to[j];
+#pragma unroll
+      for (int xx = 0; xx < 5; xx++)
+#pragma unroll
+        for (int yy = 0; yy < 5; yy++) {
+          const int a = 5 * bi + xx, b = 5 * bj + yy;
+          if (a < mj && b < mj) { tj[a * mj + b] = acc[xx][yy]; tj[b * mj + a] = acc[xx][yy]; }
+        }
     }
   }
-  const long long so = T.soff[sd];
-  if (so >= 0) {
-    for (int e = tid; e < m * m; e += nth) {
-      double s = 0;
-      for (int c = 0; c < nch; c++) s += U[T.uoff[ch[c]] + T.chain_uoff[T.chain_off[ch[c]] + k] + e];
-      SigS[so + e] = s;
+  __syncthreads();
+  // add the stored tiles of the children that keep theirs, write out (coalesced)
+  for (int eg = tid; eg < t_to[ntile]; eg += nth) {
+    int j = 0;
+    while (eg >= t_to[j + 1]) j++;
+    const int e = eg - t_to[j];
+    double v = tiles[eg];
+    if (ctab) {
+      for (int c = 0; c < nch; c++) {
+        const long long cu = s_cu[c * ntile + j];
+        if (cu >= 0) v += U[cu + e];
+      }
+    } else {
+      for (int c = 0; c < nch; c++) {
+        const int cc = ch[c];
+        if (!T.ufused[cc]) v += U[T.uoff[cc] + T.chain_uoff[T.chain_off[cc] + j] + e];
+      }
     }
+    if (j < k) Ud[t_uo[j] + e] = v; else SigS[so + e] = v;
   }
 }
-cudaError_t launch_gram(const DevTree& T, const DevSlot& S, int slot0, int nslots, double* U, double* SigS,
-                        cudaStream_t st) {
+cudaError_t launch_gram(const DevTree& T, const DevSlot& S, int slot0, int nslots, double* U, double* SigS, int rch,
+                        int ldx, int tile_doubles, cudaStream_t st) {
   if (nslots <= 0) return cudaSuccess;
-  gram_level_kernel<<<nslots, kGramThreads, 0, st>>>(T, S, slot0, U, SigS);
+  const size_t smem = ((size_t)tile_doubles + (size_t)rch * ldx) * sizeof(double);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(gram_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  gram_level_kernel<<<nslots, kGramThreads, smem, st>>>(T, S, slot0, U, SigS, rch, ldx, tile_doubles);
   return cudaGetLastError();
 }
 

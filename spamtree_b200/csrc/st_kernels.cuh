@@ -16,7 +16,9 @@ constexpr int kMaxGroupCols = 128;
 constexpr int kMaxGroupNodes = 32;
 constexpr int kMaxChain = 32;
 constexpr int kGibbsThreads = 128;
-constexpr int kGramThreads = 128;
+constexpr int kGramThreads = 256;
+constexpr int kGramMaxRows = 256;   // rows gram_level_kernel stages per chunk
+constexpr int kGramChildTab = 256;  // (child, tile) offsets it tabulates
 constexpr int kLlwThreads = 128;
 constexpr int kLlwMaxP = 1024;  // parent-set rows the LLW kernel stages per warp (checked at st_create)
 constexpr int kMaxStats = 40;  // q * (p + 1)
@@ -94,8 +96,8 @@ cudaError_t launch_build(int mode, const DevTree& T, const DevSlot& S, double* o
 cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlot& S, int slot0, int nslots, double* w,
                          const double* xb, const double* z, const double* tausq_inv, const double* SigS, double* V,
                          double* probe_sig, double* probe_smu, int* fail, size_t smem, cudaStream_t st);
-cudaError_t launch_gram(const DevTree& T, const DevSlot& S, int slot0, int nslots, double* U, double* SigS,
-                        cudaStream_t st);
+cudaError_t launch_gram(const DevTree& T, const DevSlot& S, int slot0, int nslots, double* U, double* SigS, int rch,
+                        int ldx, int tile_doubles, cudaStream_t st);
 cudaError_t launch_llw(const DevTree& T, const DevSlot& S, int nslots, const double* w, int maxlen, cudaStream_t st);
 cudaError_t launch_loglik_reduce(const double* logdet, const double* llcomp, int first, int n, const int* fail,
                                  int fail_as_count, double* out, cudaStream_t st);

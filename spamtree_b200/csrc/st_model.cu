@@ -237,6 +237,7 @@ int Model::build_layout(std::string& e) {
   h_gs.assign(n_nodes, 0);
   h_goff.assign(n_nodes, 0); h_rioff.assign(n_nodes, 0); h_voff.assign(n_nodes, 0); h_uoff.assign(n_nodes, 0); h_soff.assign(n_nodes, -1);
   g_total = ri_total = v_total = u_total = s_total = gpred_total = 0;
+  std::vector<long long> h_usize(n_nodes, 0);
   long long sd_total = 0;
   std::vector<int> isref(n_nodes, 0);
   auto poff_check = [&](int u) {
@@ -272,7 +273,7 @@ int Model::build_layout(std::string& e) {
       h_goff[s] = g_total; g_total += boff;
       h_rioff[s] = ri_total; ri_total += isref[s] ? (long long)h_m[s] * tile_rs(h_m[s]) : pad2(h_m[s]);
       h_voff[s] = v_total; v_total += pad2(poff);
-      h_uoff[s] = u_total; u_total += uo;
+      h_usize[s] = uo;
     } else {
       h_goff[s] = gpred_total; gpred_total += boff;
       h_rioff[s] = sd_total; sd_total += pad2(h_m[s]);
@@ -284,7 +285,7 @@ int Model::build_layout(std::string& e) {
   n_top_slots = 0;
   std::vector<char> is_front(n_nodes, 0);
   h_front_pseudo.clear(); h_front_c0.clear(); h_front_c1.clear(); h_front_vlen.clear(); h_front_ulen.clear();
-  v_front0 = v_total; u_front0 = u_total;
+  v_front0 = v_total;
   if (part) {
     if (n_top_levels < 0 || n_top_levels >= (int)levels.size()) { e = "partition: n_top_levels out of range"; return 1; }
     for (int g = 0; g < n_top_levels; g++) n_top_slots += levels[g].nslots;
@@ -314,14 +315,13 @@ int Model::build_layout(std::string& e) {
         h_P.push_back(poff);
         h_goff.push_back(0); h_rioff.push_back(0); h_soff.push_back(-1); h_gs.push_back(0);
         h_voff.push_back(v_total); v_total += pad2(poff);
-        h_uoff.push_back(u_total); u_total += uo;
+        h_uoff.push_back(0); h_usize.push_back(uo);
         h_front_pseudo.push_back(ps); h_front_c0.push_back(c0); h_front_c1.push_back(c);
         h_front_vlen.push_back(poff); h_front_ulen.push_back((int)uo);
       }
       if (c != CL.slot0 + CL.nslots) { e = "partition: a block of the cut level has no replicated parent"; return 1; }
     }
     v_front_len = v_total - v_front0;
-    u_front_len = u_total - u_front0;
   }
   // direct children among observed nodes (contiguous by construction of the slot order)
   h_child_ptr.assign(n_slots_total + 1, 0);
@@ -338,6 +338,18 @@ int Model::build_layout(std::string& e) {
   }
   for (int s = 0; s < n_obs_nodes; s++)
     if (h_child_ptr[s + 1] > h_child_ptr[s]) { h_soff[s] = s_total; s_total += pad2((long long)h_m[s] * h_m[s]); }
+  // message Grams: a childless block that is pulled by an ordinary parent is "fused" — the parent forms its tiles from
+  // the block's rows on the fly (gram_level_kernel) and they are never stored.  Blocks under a replicated frontier block
+  // keep theirs (frontier_sum_kernel adds them up for the all-reduce).
+  h_ufused.assign(n_slots_total, 0);
+  for (int s = 0; s < n_obs_nodes; s++)
+    h_ufused[s] = (h_child_ptr[s + 1] == h_child_ptr[s] && h_lastpar[s] >= 0 && !is_front[h_lastpar[s]]) ? 1 : 0;
+  u_total = 0;
+  for (int s = 0; s < n_obs_nodes; s++)
+    if (!h_ufused[s]) { h_uoff[s] = u_total; u_total += h_usize[s]; }
+  u_front0 = u_total;
+  for (int s = n_nodes; s < n_slots_total; s++) { h_uoff[s] = u_total; u_total += h_usize[s]; }
+  u_front_len = u_total - u_front0;
   isref_host_ = isref;
   llw_maxlen_ = 2;
   for (int s = 0; s < n_obs_nodes; s++) llw_maxlen_ = std::max(llw_maxlen_, h_P[s] + h_m[s]);
@@ -419,6 +431,27 @@ int Model::build_layout(std::string& e) {
       L.smem_gibbs = std::max(L.smem_gibbs, gibbs_smem_bytes(L.is_ref, h_m[t], h_P[t], h_k[t]));
     }
     if (mode != 2 && L.smem_gibbs > 227 * 1024) { e = "a block is too large for the Gibbs kernel's shared memory"; return 4; }
+    if (mode != 2) {  // gram_level_kernel: rows staged per chunk (own rows + the rows of the fused children)
+      int ldx = 2, maxrows = 1;
+      long long tiles = 2;
+      L.gram_skip = true;
+      for (int t = L.slot0; t < end; t++) {
+        if (h_ufused[t]) continue;
+        L.gram_skip = false;
+        int rows = h_m[t];
+        for (int c = h_child_ptr[t]; c < h_child_ptr[t + 1]; c++) if (h_ufused[h_child_idx[c]]) rows += h_m[h_child_idx[c]];
+        maxrows = std::max(maxrows, rows);
+        ldx = std::max(ldx, (h_P[t] + h_m[t] + 1) & ~1);
+        long long td = (long long)h_m[t] * h_m[t];
+        for (int j = 0; j < h_k[t]; j++) { const long long mj = h_m[h_chain[h_chain_off[t] + j]]; td += mj * mj; }
+        tiles = std::max(tiles, (td + 1) & ~1LL);
+      }
+      if (tiles * 8 > 160 * 1024) { e = "a block's message Gram tiles do not fit the Gram kernel's shared memory"; return 4; }
+      L.gram_ldx = ldx;
+      L.gram_tiles = (int)tiles;
+      const size_t room = (size_t)100 * 1024 > (size_t)tiles * 8 + (size_t)ldx * 8 ? (size_t)100 * 1024 - (size_t)tiles * 8 : (size_t)ldx * 8;
+      L.gram_rch = (int)std::max<size_t>(1, std::min<size_t>(std::min(maxrows, kGramMaxRows), room / ((size_t)ldx * 8)));
+    }
     return 0;
   };
   for (auto& L : levels) { int rc = make_groups(L, L.is_ref ? 0 : 1); if (rc) return rc; }
@@ -504,6 +537,8 @@ int Model::upload(std::string& e) {
   ST_CUDA(dev_upload(h_soff, d_soff, owned), "upload soff");
   ST_CUDA(dev_upload(h_child_ptr, d_cptr, owned), "upload child_ptr");
   ST_CUDA(dev_upload(h_child_idx, d_cidx, owned), "upload child_idx");
+  int* d_ufused;
+  ST_CUDA(dev_upload(h_ufused, d_ufused, owned), "upload ufused");
   ST_CUDA(dev_upload(h_chain, d_chain, owned), "upload chain");
   ST_CUDA(dev_upload(h_chain_poff, d_cpoff, owned), "upload chain_poff");
   ST_CUDA(dev_upload(h_chain_uoff, d_cuoff, owned), "upload chain_uoff");
@@ -517,7 +552,7 @@ int Model::upload(std::string& e) {
   dt.cx = d_cx; dt.cy = d_cy; dt.mvq = d_mvq; dt.y = d_y; dt.X = d_X;
   dt.m = d_m; dt.row0 = d_row0; dt.isref = d_isref; dt.k = d_k; dt.P = d_P; dt.lastpar = d_lastpar; dt.chain_off = d_choff;
   dt.goff = d_goff; dt.gs = d_gs; dt.rioff = d_rioff; dt.voff = d_voff; dt.uoff = d_uoff; dt.soff = d_soff;
-  dt.child_ptr = d_cptr; dt.child_idx = d_cidx;
+  dt.child_ptr = d_cptr; dt.child_idx = d_cidx; dt.ufused = d_ufused;
   dt.chain = d_chain; dt.chain_poff = d_cpoff; dt.chain_uoff = d_cuoff;
   for (int s = 0; s < 2; s++) {
     ST_CUDA(dev_zeros(ds[s].G, g_total, owned), "alloc G");
@@ -731,8 +766,22 @@ int Model::refresh_grams() {
       int rc = allreduce_dev(d_U + u_front0, u_front_len);
       if (rc) return rc;
     }
-    ST_CUDA(launch_gram(dt, ds[cur], levels[g].slot0, levels[g].nslots, d_U, d_S, stream), "gram_level_kernel");
+    if (levels[g].gram_skip) continue;  // all blocks of the level are fused into their parents
+    static const bool profile = getenv("ST_PROFILE_GIBBS") != nullptr;
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, stream); }
+    ST_CUDA(launch_gram(dt, ds[cur], levels[g].slot0, levels[g].nslots, d_U, d_S, levels[g].gram_rch, levels[g].gram_ldx, levels[g].gram_tiles, stream),
+            "gram_level_kernel");
     n_launches++;
+    if (profile) {
+      cudaEventRecord(pe1, stream);
+      cudaStreamSynchronize(stream);
+      float pms = 0;
+      cudaEventElapsedTime(&pms, pe0, pe1);
+      cudaEventDestroy(pe0); cudaEventDestroy(pe1);
+      fprintf(stderr, "[gram profile] level slot0=%d nodes=%d rch=%d ldx=%d  %.3f ms\n", levels[g].slot0, levels[g].nslots,
+              levels[g].gram_rch, levels[g].gram_ldx, pms);
+    }
   }
   gram_stale = false;
   return 0;

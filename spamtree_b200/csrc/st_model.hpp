@@ -46,7 +46,8 @@ struct DevTree {
   const int* gs;         // row stride of that row block: [ G (P) | -Ri (m, reference blocks) | 0 ], g_stride()
   const long long* rioff;// Ri storage offset (doubles)
   const long long* voff; // message vector offset (P doubles)
-  const long long* uoff; // message Gram offset (tiles m_a x m_a per ancestor)
+  const long long* uoff; // message Gram offset (tiles m_a x m_a per ancestor); unused when ufused
+  const int* ufused;     // 1: childless block whose Gram tiles are formed by its parent on the fly (never stored)
   const long long* soff; // child-sum Gram (m x m) offset, -1 when the node has no children
   const int* child_ptr;
   const int* child_idx;  // direct observed children (slots)
@@ -79,6 +80,8 @@ struct LevelInfo {
   std::vector<BuildLaunch> build_launches;
   int maxP = 0, maxm = 0, maxNC = 0, maxk = 0;
   size_t smem_gibbs = 0;
+  int gram_rch = 1, gram_ldx = 2, gram_tiles = 2;  // gram_level_kernel: staged rows per chunk, their leading dimension, doubles of the assembled tiles
+  bool gram_skip = false;          // every block of the level is fused into its parent
 };
 
 class Model {
@@ -111,7 +114,7 @@ class Model {
   std::vector<int> slot_of_block, block_of_slot;
   std::vector<int> h_m, h_row0, h_k, h_P, h_chain_off, h_chain, h_chain_poff, h_chain_uoff, h_lastpar, h_gs;
   std::vector<long long> h_goff, h_rioff, h_voff, h_uoff, h_soff;
-  std::vector<int> h_child_ptr, h_child_idx;
+  std::vector<int> h_child_ptr, h_child_idx, h_ufused;
   ivec perm;   // node-major row -> boundary row
   ivec iperm;  // boundary row -> node-major row
   std::vector<LevelInfo> levels;  // observed levels, root first
