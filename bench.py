@@ -24,6 +24,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "mcmc_iterations_per_sec"
 UNIT = "it/s"
+# DRAM traffic (bytes) of all build_level_kernel launches of ONE BUILD, from an ncu pass on a B200 of this pool
+# (profiles/r1_launches_v4.txt); None until measured for a workload
+NCU_BUILD_DRAM_BYTES = {"C4": 2.392e9}
 
 
 def load_peaks():
@@ -235,9 +238,14 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = e2e_steps / float(te[0])
     cnt = gm.counters()
-    tw = torch.tensor([cnt["f_alg"], cnt["f_exec"], c1["launches"] - c0["launches"]], dtype=torch.float64, device=dev)
+    tw = torch.tensor([cnt["f_alg"], cnt["f_exec"], c1["launches"] - c0["launches"], cnt["f_alg_build"], cnt["f_exec_build"],
+                       cnt["b_alg_build"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tw)  # work and launches of the whole job (replicated top levels counted on every rank)
+    # BUILD time of the job: max over ranks of the per-rank mean
+    tb = torch.tensor([float(phase[2]) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
     n_all, q, p = int(d["y"].size), int(d["q"]), 3
     n_local = n_all if sp is None else int(sp["y"].size)
     h2d = 8 * (npar + q + p * q)
@@ -245,11 +253,10 @@ def main():
 
     if rank == 0:
         hbm_peak, peak_src = load_peaks()
-        build_ms = float(phase[2]) / args.steps
-        # BUILD share of the SURVEY §8d flop count: F_alg minus the Gibbs/LLW terms is not separable from counters alone,
-        # so the roofline of the dominant kernel is quoted on the executed-formulation flops of BUILD
-        f_alg, f_exec = float(tw[0]), float(tw[1])
+        build_ms = float(tb[0])
+        f_alg, f_exec, f_alg_build, f_exec_build, b_alg_build = (float(tw[i]) for i in (0, 1, 3, 4, 5))
         fp64_peak_job = fp64_peak * world
+        traffic = NCU_BUILD_DRAM_BYTES.get(args.workload) if world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * elapsed_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -266,20 +273,29 @@ def main():
             "gpu_launches": int(tw[2]),
             "device_ms_per_step": {"gibbs": float(phase[0]) / args.steps, "llw": float(phase[1]) / args.steps,
                                    "build": build_ms, "beta_tausq": float(phase[3]) / args.steps, "max_over_ranks_total": 1e3 * dev_s_max / args.steps},
-            "roofline": {"bound": "tensor", "pipe": "FP64 DFMA (sm_100a has no tcgen05 FP64 kind)", "kernel": "build_level_kernel (all levels of one BUILD)",
-                         "achieved": None,
-                         "peak": fp64_peak_job, "unit": "TFLOP/s",
-                         "frac": None, "traffic": None,
-                         "achieved_executed": None,
+            # dominant kernel: build_level_kernel (all level launches of one BUILD, ~80 % of the step).  achieved = F_build
+            # (SURVEY §8d formula summed over the actual tree) / the BUILD time measured here with CUDA events on the
+            # launching stream; peak = cuBLAS DGEMM measured in this run (MEASURED_PEAKS.json has no FP64 figure)
+            "roofline": {"bound": "tensor", "pipe": "FP64 tensor-core MMA (mma.sync m8n8k4 f64; tcgen05 has no FP64 kind) + FP64 FMA pipe for the covariance kernels",
+                         "kernel": "build_level_kernel (all level launches of one BUILD)",
+                         "achieved": f_alg_build / (build_ms * 1e-3) / 1e12 if build_ms > 0 else None,
+                         "peak": fp64_peak_job, "unit": "TFLOP/s", "frac": None,
+                         "traffic": traffic,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum over the build_level_kernel launches of one BUILD (profiles/r1_launches_v4.txt)",
+                         "achieved_executed": f_exec_build / (build_ms * 1e-3) / 1e12 if build_ms > 0 else None,
+                         "algorithmic_output_bytes": b_alg_build,
+                         "whole_step": {"achieved": None, "achieved_executed": None, "frac": None},
                          "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure); HBM peak " + peak_src,
-                         "f_alg_per_iteration": f_alg, "f_executed_per_iteration": f_exec, "hbm_peak_gbs": hbm_peak},
+                         "f_alg_per_iteration": f_alg, "f_executed_per_iteration": f_exec,
+                         "f_alg_build": f_alg_build, "f_executed_build": f_exec_build, "hbm_peak_gbs": hbm_peak},
         }
-        # achieved = algorithmic flops of one step / step time (whole step: the BUILD kernel is >90 % of it)
         step_s = elapsed_max / args.steps
-        line["roofline"]["achieved"] = f_alg / step_s / 1e12
-        line["roofline"]["achieved_executed"] = f_exec / step_s / 1e12
-        line["roofline"]["frac"] = line["roofline"]["achieved"] / fp64_peak_job if fp64_peak else None
-        line["roofline"]["frac_executed"] = line["roofline"]["achieved_executed"] / fp64_peak_job if fp64_peak else None
+        rf = line["roofline"]
+        if fp64_peak and rf["achieved"] is not None:
+            rf["frac"] = rf["achieved"] / fp64_peak_job
+            rf["frac_executed"] = rf["achieved_executed"] / fp64_peak_job
+        rf["whole_step"] = {"achieved": f_alg / step_s / 1e12, "achieved_executed": f_exec / step_s / 1e12,
+                            "frac": (f_alg / step_s / 1e12) / fp64_peak_job if fp64_peak else None}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cb, _ = cpu_baseline_sample(args.workload, d, t, csr, theta, iters=1)

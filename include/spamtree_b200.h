@@ -166,9 +166,10 @@ int st_mcmc_run(st_handle* h, const st_mcmc_opts* opts, st_mcmc_out* out);
  * + optional swap + tausq + beta (spamtree_fit.cpp:167-330 minus predict/save).  ms_out[0..3] receive the
  * CUDA-event times of {gibbs, llw, build, rest} when non-NULL. */
 int st_bench_iteration(st_handle* h, const double* theta_prop, int do_swap, uint64_t seed, double* out3, float* ms_out);
-/* counts of kernel launches and algorithmic work since creation: out = {kernel launches, F_alg flops of the last
- * iteration (SURVEY §8d formula on the actual tree), executed-flop estimate of the lean formulation, covariance evals} */
-int st_get_counters(st_handle* h, double* out4);
+/* counts of kernel launches and algorithmic work: out[8] = {kernel launches since creation, F_alg flops of one iteration
+ * (SURVEY §8d formula on the actual tree), executed-flop estimate of the lean formulation, covariance evaluations,
+ * F_alg of BUILD alone (F_build), executed-flop estimate of BUILD alone, compulsory output bytes of one BUILD, 0} */
+int st_get_counters(st_handle* h, double* out8);
 int st_sync(st_handle* h);
 
 /* ---- DAG construction: tree_dep.cpp ---- */

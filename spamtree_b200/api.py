@@ -335,9 +335,10 @@ class SpamTreeMV:
         return o, ms
 
     def counters(self):
-        o = np.zeros(4)
+        o = np.zeros(8)
         self._chk(lib.st_get_counters(self._h, _dp(o)))
-        return {"launches": o[0], "f_alg": o[1], "f_exec": o[2], "n_cov": o[3]}
+        return {"launches": o[0], "f_alg": o[1], "f_exec": o[2], "n_cov": o[3], "f_alg_build": o[4], "f_exec_build": o[5],
+                "b_alg_build": o[6]}
 
     def sync(self):
         self._chk(lib.st_sync(self._h))

@@ -199,9 +199,10 @@ int st_bench_iteration(st_handle* h, const double* theta_prop, int do_swap, uint
   ST_GUARD_BEGIN return h->model.bench_iteration(theta_prop, do_swap, seed, out3, ms_out);
   ST_GUARD_END(h)
 }
-int st_get_counters(st_handle* h, double* out4) {
-  if (!h || !out4) return ST_ERR_INVALID;
-  out4[0] = h->model.n_launches; out4[1] = h->model.f_alg; out4[2] = h->model.f_exec; out4[3] = h->model.n_cov;
+int st_get_counters(st_handle* h, double* out8) {
+  if (!h || !out8) return ST_ERR_INVALID;
+  out8[0] = h->model.n_launches; out8[1] = h->model.f_alg; out8[2] = h->model.f_exec; out8[3] = h->model.n_cov;
+  out8[4] = h->model.f_alg_build; out8[5] = h->model.f_exec_build; out8[6] = h->model.b_alg_build; out8[7] = 0.0;
   return ST_OK;
 }
 int st_sync(st_handle* h) {

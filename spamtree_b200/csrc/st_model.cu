@@ -458,7 +458,7 @@ int Model::build_layout(std::string& e) {
   { int rc = make_groups(pred_level, 2); if (rc) return rc; }
 
   // work counters per iteration (SURVEY §8d formulas on the actual tree)
-  f_alg = f_exec = n_cov = 0;
+  f_alg = f_exec = n_cov = f_alg_build = f_exec_build = b_alg_build = 0;
   for (int s = 0; s < n_obs_nodes; s++) {
     const double m = h_m[s], P = h_P[s], rho = isref[s], chi = (h_child_ptr[s + 1] > h_child_ptr[s]) ? 1.0 : 0.0;
     const double C = (double)children.len(block_of_slot[s]);
@@ -467,6 +467,9 @@ int Model::build_layout(std::string& e) {
                       (1 - rho) * (3 * m * P + 2 * P * P * m + 2 * P * P + 2 * P * m + 10 * m);
     const double fl = 2 * m * P + rho * 2 * m * m + (1 - rho) * 2 * m;
     f_alg += fb + fg + fl;
+    f_alg_build += fb;
+    f_exec_build += 2 * m * P * P + rho * (2 * m * m * P + m * m * P + 2 * m * m * m / 3) + (1 - rho) * 3 * m * P + 2 * m * P;
+    b_alg_build += 8 * (m * P + rho * m * m + (1 - rho) * m);  // compulsory output of BUILD: G and Ri of the slot
     // lean formulation actually executed: Z (mP^2) + H' (mP^2) + Z'Z (rho m^2 P, else mP) + G (rho m^2 P/ else mP) + chol/inv + Gibbs/LLW matvecs
     f_exec += 2 * m * P * P + rho * (2 * m * m * P + m * m * P + 2 * m * m * m / 3) + (1 - rho) * 3 * m * P + 2 * m * P +
               (4 * m * P + rho * (2 * m * m * m / 3 + 4 * m * m)) + (2 * m * P + rho * m * m);

@@ -160,7 +160,7 @@ class Model {
   cudaEvent_t ev[8]{};
   std::vector<void*> owned;  // device allocations to free
   // counters
-  double n_launches = 0, f_alg = 0, f_exec = 0, n_cov = 0;
+  double n_launches = 0, f_alg = 0, f_exec = 0, n_cov = 0, f_alg_build = 0, f_exec_build = 0, b_alg_build = 0;
   std::string err;
 
   // ---- life cycle

@@ -21,23 +21,30 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
 
 
 def launches(path):
+    """long-format csv of `ncu --metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum] --csv`"""
     rows = list(csv.reader(open(path)))
     h = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     H, data = rows[h], rows[h + 1:]
-    ki, vi, gi = H.index("Kernel Name"), H.index("Metric Value"), H.index("Grid Size")
-    tot = sum(float(r[vi].replace(",", "")) for r in data if len(r) > vi)
-    agg = {}
-    print(f"{'id':>4} {'kernel':<44} {'grid':>12} {'us':>10} {'share':>7}")
+    ki, vi, gi, bi, mi = H.index("Kernel Name"), H.index("Metric Value"), H.index("Grid Size"), H.index("Block Size"), H.index("Metric Name")
+    per = {}
     for r in data:
         if len(r) <= vi:
             continue
-        us = float(r[vi].replace(",", "")) / 1e3
-        name = r[ki].split("(")[0][:44]
-        agg[name] = agg.get(name, 0) + us
-        print(f"{r[0]:>4} {name:<44} {r[gi]:>12} {us:10.1f} {100 * us * 1e3 / tot:6.1f}%")
-    print("\nper kernel:")
-    for k, v in sorted(agg.items(), key=lambda kv: -kv[1]):
-        print(f"  {k:<44} {v:10.1f} us {100 * v * 1e3 / tot:6.1f}%")
+        d = per.setdefault(int(r[0]), {"name": r[ki].split("(")[0].replace("void ", "").replace("st::", "")[:40], "grid": r[gi], "block": r[bi]})
+        d[r[mi]] = float(r[vi].replace(",", ""))
+    tot = sum(d.get("gpu__time_duration.sum", 0.0) for d in per.values())
+    agg = {}
+    print(f"{'id':>4} {'kernel':<40} {'grid':>14} {'block':>12} {'us':>10} {'share':>7} {'dram rd MB':>11} {'dram wr MB':>11}")
+    for i in sorted(per):
+        d = per[i]
+        us = d.get("gpu__time_duration.sum", 0.0) / 1e3
+        rd, wr = d.get("dram__bytes_read.sum", float("nan")) / 1e6, d.get("dram__bytes_write.sum", float("nan")) / 1e6
+        a = agg.setdefault(d["name"], [0.0, 0.0, 0.0, 0])
+        a[0] += us; a[1] += rd; a[2] += wr; a[3] += 1
+        print(f"{i:>4} {d['name']:<40} {d['grid']:>14} {d['block']:>12} {us:10.1f} {100 * us * 1e3 / max(tot, 1):6.1f}% {rd:11.1f} {wr:11.1f}")
+    print("\nper kernel (all captured launches):")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        print(f"  {k:<40} {v[3]:4d} launches {v[0]:10.1f} us {100 * v[0] * 1e3 / max(tot, 1):6.1f}%   dram read {v[1]:9.1f} MB  write {v[2]:9.1f} MB")
 
 
 def report(path):
