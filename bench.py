@@ -122,7 +122,7 @@ def cpu_baseline_sample(workload, d, t, csr, theta, iters=1):
                       f"1 untimed BUILD + 1 untimed iteration, then {iters} timed iteration(s) of {float(np.mean(ts)):.2f} s"}, ts
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     if rank != 0:
         return
     d, t, csr, theta = build_problem(args.workload, 2021)
@@ -146,7 +146,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": int(cores), "kind": "port",
                              "sample": f"{steps} timed iteration(s) after {warm} warm-up on the full {args.workload} tree, lean-state oracle"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -160,11 +160,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="iterations of the end-to-end leg (default: --steps)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner ...) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -302,7 +309,7 @@ def main():
                 line["cpu_baseline"] = cb
             except Exception as ex:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {ex}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     gm.close()
     if world > 1:
         dist.destroy_process_group()

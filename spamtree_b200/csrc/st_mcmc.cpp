@@ -81,6 +81,11 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
   if (o.rng_mode == 0) zbuf.resize(M.n_all);
   const bool pglob = M.part && !M.global_rows.empty();  // partitioned: draw for every row of the problem, keep ours
   if (pglob) zglob.resize(M.n_global_rows);
+  // w of a saved iteration goes to the caller's buffer asynchronously (overlapping the next iteration) unless yhat, which
+  // is formed on the host from w, is requested too
+  const bool async_save = out.w_mcmc && !out.yhat_mcmc;
+  if (async_save) { rc = M.save_begin(out.w_mcmc, (size_t)o.keep * M.n_all * sizeof(double)); if (rc) return rc; }
+  struct SaveGuard { Model& M; bool on; ~SaveGuard() { if (on) M.save_end(); } } guard{M, async_save};
   const auto t0 = std::chrono::steady_clock::now();
   for (int m = 0; m < mcmc; m++) {
     bool predicting = false;
@@ -161,7 +166,8 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
             out.beta_mcmc[a + (size_t)msaved * M.p + (size_t)j * M.p * o.keep] = M.Bcoeff[a + (size_t)j * M.p];
       if (out.theta_mcmc)
         for (int j = 0; j < npar; j++) out.theta_mcmc[j + (size_t)msaved * npar] = M.theta[M.cur][j];
-      const bool want_rows = out.w_mcmc || out.yhat_mcmc;
+      const bool want_rows = (out.w_mcmc || out.yhat_mcmc) && !async_save;
+      if (async_save) { rc = M.save_w_async(out.w_mcmc + (size_t)msaved * M.n_all); if (rc) return rc; }
       if (want_rows) {
         wbuf.resize(M.n_all);
         rc = M.get_w(wbuf.data());
@@ -184,6 +190,7 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
       msaved++;
     }
   }
+  if (async_save) { guard.on = false; rc = M.save_end(); if (rc) return rc; }  // the timed region ends when every saved w is on the host
   out.mcmc_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (out.paramsd) std::copy(ad.paramsd.a.begin(), ad.paramsd.a.end(), out.paramsd);
   return 0;

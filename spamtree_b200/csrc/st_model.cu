@@ -70,6 +70,10 @@ Model::~Model() {
   if (h_scalars) cudaFreeHost(h_scalars);
   if (h_stage) cudaFreeHost(h_stage);
   for (auto& e : ev) if (e) cudaEventDestroy(e);
+  if (save_registered) cudaHostUnregister(save_registered);
+  if (ev_wready) cudaEventDestroy(ev_wready);
+  if (ev_wcopied) cudaEventDestroy(ev_wcopied);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -964,6 +968,48 @@ int Model::get_w(double* out) {
   return 0;
 }
 int Model::set_w(const double* in) { return upload_rows(in, d_w); }
+
+int Model::save_begin(double* host_base, size_t bytes) {
+  if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
+  save_registered = nullptr;
+  save_pending = false;
+  if (!host_base || bytes == 0) return 0;
+  if (!copy_stream) {
+    ST_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    ST_CUDA(cudaEventCreateWithFlags(&ev_wready, cudaEventDisableTiming), "cudaEventCreate");
+    ST_CUDA(cudaEventCreateWithFlags(&ev_wcopied, cudaEventDisableTiming), "cudaEventCreate");
+    ST_CUDA(dev_zeros(d_wsave, n_all, owned), "alloc wsave");
+    std::vector<long long> ip(iperm.begin(), iperm.end());
+    ST_CUDA(dev_upload(ip, d_iperm, owned), "upload iperm");
+  }
+  // page-lock the caller's output range for the duration of the run; if that is refused the save stays synchronous
+  if (cudaHostRegister(host_base, bytes, cudaHostRegisterPortable) == cudaSuccess) save_registered = host_base;
+  else (void)cudaGetLastError();
+  return 0;
+}
+
+int Model::save_w_async(double* host_dst) {
+  if (!save_registered) return get_w(host_dst);
+  if (save_pending) ST_CUDA(cudaStreamWaitEvent(stream, ev_wcopied, 0), "wait for the previous save");  // d_wsave is reused
+  ST_CUDA(launch_permute(d_w, d_wsave, d_iperm, n_all, stream), "permute_kernel");
+  n_launches++;
+  ST_CUDA(cudaEventRecord(ev_wready, stream), "event");
+  ST_CUDA(cudaStreamWaitEvent(copy_stream, ev_wready, 0), "wait");
+  ST_CUDA(cudaMemcpyAsync(host_dst, d_wsave, n_all * sizeof(double), cudaMemcpyDeviceToHost, copy_stream), "D2H w (async)");
+  ST_CUDA(cudaEventRecord(ev_wcopied, copy_stream), "event");
+  save_pending = true;
+  return 0;
+}
+
+int Model::save_end() {
+  int rc = 0;
+  if (copy_stream && save_pending) {
+    if (cudaStreamSynchronize(copy_stream) != cudaSuccess) { err = "asynchronous save of w failed"; rc = 2; }
+    save_pending = false;
+  }
+  if (save_registered) { cudaHostUnregister(save_registered); save_registered = nullptr; }
+  return rc;
+}
 int Model::get_xb(double* out) {
   if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   ST_CUDA(cudaMemcpyAsync(h_stage, d_xb, n_all * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H xb");

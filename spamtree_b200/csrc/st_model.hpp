@@ -156,7 +156,12 @@ class Model {
   int* d_fail = nullptr;
   int *d_grp_slot0 = nullptr, *d_grp_nn = nullptr;
   double* h_stage = nullptr;  // pinned n_all staging buffer
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_wready = nullptr, ev_wcopied = nullptr;
+  double* d_wsave = nullptr;        // w in boundary order (staging of the asynchronous save)
+  long long* d_iperm = nullptr;     // boundary row -> node-major row
+  void* save_registered = nullptr;  // host range page-locked by save_begin
+  bool save_pending = false;
   cudaEvent_t ev[8]{};
   std::vector<void*> owned;  // device allocations to free
   // counters
@@ -175,6 +180,11 @@ class Model {
   int gibbs_sample_beta(const double* zb, bool faithful_index);  // :1364-1391
   int gibbs_sample_tausq(const double* fixed);         // :1393-1417
   int get_w(double* out);
+  // saved iterations: un-permute w on the device and copy it to `host_dst` (page-locked by save_begin) on a second
+  // stream, so that the copy overlaps the next iteration; save_end waits for the copies in flight
+  int save_begin(double* host_base, size_t bytes);
+  int save_w_async(double* host_dst);
+  int save_end();
   int set_w(const double* in);
   int get_xb(double* out);
   int set_tausq_inv(const double* t);

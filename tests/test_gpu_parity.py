@@ -159,6 +159,23 @@ def test_lockstep_chain_matches_oracle_chain():
         om.close()
 
 
+def test_asynchronous_save_of_w_equals_the_synchronous_one():
+    """saved iterations without yhat copy w to the caller's buffer on a second stream while the next iteration runs
+    (st_model.cu: save_w_async); the saved draws must be the very same numbers as with the synchronous path"""
+    from spamtree_b200 import synth
+    pb = common.make_problem(3, 4000)
+    npar = pb["theta"].size
+    bounds, sd = synth.default_bounds(3), np.eye(npar) * 1e-4
+    res = []
+    for yhat in (True, False):
+        gm = common.product_model(pb)
+        res.append(gm.mcmc(bounds, sd, keep=6, burn=3, thin=2, adapting=True, seed=9, rng_mode=0, save_w=True, save_yhat=yhat))  # mode 0: the host stream is consumed identically with and without yhat
+        gm.close()
+    assert res[0]["w_mcmc"].shape == res[1]["w_mcmc"].shape and np.abs(res[0]["w_mcmc"]).max() > 0
+    assert np.array_equal(res[0]["w_mcmc"], res[1]["w_mcmc"])
+    assert np.array_equal(res[0]["theta_mcmc"], res[1]["theta_mcmc"])
+
+
 def test_cholesky_failure_rejects_without_error():
     """BUILD returns ok = 0 (spamtree_model.cpp:971-982) and the slot recovers; never an exception"""
     pb = common.make_problem(3, 900)
