@@ -81,12 +81,17 @@ __device__ __forceinline__ bool warp_chol_inv32(double* R, int m, int rs, double
 }
 }  // namespace
 
-// MODE 0: reference level, 1: non-reference level, 2: prediction blocks (outG = Hpred receives H, outRi = sd)
+// MODE 0: reference level, 1: non-reference level, 2: prediction blocks (outG = Hpred receives H, outRi = sd).
+// phase (MODE 1, childless blocks only): 0 = everything; 1 = forward half: Z, the diagonal Schur complements and the
+// log-density pieces, with Z parked in G's storage (nobody reads a childless block's G unless its slot becomes the
+// current one); 2 = the deferred half: Z is read back, scaled and pushed through the backward sweep into G.
+// In phases 1 and 2 the panel has one extra column that carries w_pa, so that v = L^-1 w_pa and with it
+// H w_pa = Z'v come out of the forward sweep.
 template <int MODE>
 __global__ void __launch_bounds__(kBuildMaxThreads)
 build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __restrict__ outH, double* __restrict__ outRi,
                    const int* __restrict__ grp_slot0, const int* __restrict__ grp_nn, const double* __restrict__ w,
-                   CovTab tab, int* __restrict__ fail, int ns, unsigned long long* __restrict__ prof) {
+                   CovTab tab, int* __restrict__ fail, int ns, int phase, unsigned long long* __restrict__ prof) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ CovTabS ct;
   __shared__ int s_cm[kMaxChain], s_crow[kMaxChain + 1], s_crow0g[kMaxChain], s_cgs[kMaxChain];
@@ -130,7 +135,8 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
   }
   __syncthreads();
   const int ncols = s_nc0[nn];
-  const BuildPlan pl = build_plan(P, ncols, s_sumRb, s_maxmd, ns, (MODE == 0) ? min(nn, kBuildMaxThreads / 32) : 0, nwarps);
+  const int xcol = (MODE == 1 && phase != 0) ? 1 : 0;
+  const BuildPlan pl = build_plan(P, ncols + xcol, s_sumRb, s_maxmd, ns, (MODE == 0) ? min(nn, kBuildMaxThreads / 32) : 0, nwarps);
   const int Ppad = pl.Ppad, NCp = pl.NCp, NT = pl.NT, LD = pl.LD, SA = pl.SA, slotsz = pl.slot;
   double* base = reinterpret_cast<double*>(smem_raw);
   double* panel = base + pl.o_panel;
@@ -184,7 +190,19 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
   mark(0);
 
   // ---- phase 2: covariance panel K_{pa,u}; rows >= P and columns past the group's are zero
-  for (int c = lane; c < LD; c += 32) {
+  const bool completing = (MODE == 1 && phase == 2);
+  if (completing) {
+    // deferred half: the panel is Z, parked in G's storage by the forward half, scaled by the stored 1 / sqrt(R_ii)
+    for (int e = tid; e < Ppad * LD; e += nth) panel[e] = 0.0;
+    for (int c = tid; c < ncols; c += nth) rdiag[c] = outRi[s_nrioff[colnode[c]] + (c - s_nc0[colnode[c]])];
+    __syncthreads();
+    for (int c = warp; c < ncols; c += nwarps) {
+      const double* src = S.G + colbase[c];
+      const double ri = rdiag[c];
+      for (int i = lane; i < P; i += 32) panel[(size_t)i * LD + c] = ri * src[i];
+    }
+  }
+  for (int c = lane; c < LD && !completing; c += 32) {
     const bool real = colnode[c] >= 0;
     const double xc = cxs[c], yc = cys[c];
     const int qc = cq[c];
@@ -203,6 +221,10 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
     for (; i < P; i += nwarps)
       panel[(size_t)i * LD + c] = real ? cov_eval(ct, pxs[i], pys[i], pq[i], xc, yc, qc) : 0.0;
     for (i = P + warp; i < Ppad; i += nwarps) panel[(size_t)i * LD + c] = 0.0;
+  }
+  if (xcol && !completing) {
+    __syncthreads();  // the loop above zero-filled the columns past the group's
+    for (int i = tid; i < Ppad; i += nth) panel[(size_t)i * LD + ncols] = wpa[i];  // extra column: w_pa (zero past P)
   }
   // (the first __syncthreads of the sweep below publishes the panel)
   mark(1);
@@ -246,15 +268,16 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
   };
 
   // ---- phase 3: Z = L^-1 K in place, bottom rows first (row r of Z needs rows <= r of K)
-  if (ns == 2 && nstg > 0) issue_fwd(nstg - 1, ring);
-  for (int i = 0; i < nstg; i++) {
-    const int st = nstg - 1 - i;
+  const int nfw = completing ? 0 : nstg;
+  if (ns == 2 && nfw > 0) issue_fwd(nfw - 1, ring);
+  for (int i = 0; i < nfw; i++) {
+    const int st = nfw - 1 - i;
     double* slot = ring + ((ns == 2) ? (i & 1) * slotsz : 0);
     if (ns == 1) issue_fwd(st, slot);
     __pipeline_commit();
     __pipeline_wait_prior(0);
     __syncthreads();
-    if (ns == 2 && i + 1 < nstg) issue_fwd(st - 1, ring + ((i + 1) & 1) * slotsz);
+    if (ns == 2 && i + 1 < nfw) issue_fwd(st - 1, ring + ((i + 1) & 1) * slotsz);
     if (my_nt >= 0) {
       const int r0 = st * RS;
       const double* ap = slot + (lane >> 2) * SA + (lane & 3);
@@ -392,15 +415,19 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
       if (lane == 0) s_nlogdet[d] = ld;
     }
     __syncthreads();
-  } else {
+  } else if (!completing) {
     for (int c = tid; c < NCp; c += nth) {
-      const int d = colnode[c];
+      const int d = (c < ncols) ? colnode[c] : -1;
       if (d < 0) continue;
-      double q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+      double q0 = 0, q1 = 0, q2 = 0, q3 = 0, g0 = 0, g1 = 0;
       for (int pp = 0; pp < Ppad; pp += 4) {
         const double z0 = panel[(size_t)pp * LD + c], z1 = panel[(size_t)(pp + 1) * LD + c];
         const double z2 = panel[(size_t)(pp + 2) * LD + c], z3 = panel[(size_t)(pp + 3) * LD + c];
         q0 = fma(z0, z0, q0); q1 = fma(z1, z1, q1); q2 = fma(z2, z2, q2); q3 = fma(z3, z3, q3);
+        if (xcol) {  // H w_pa = Z'v with v = L^-1 w_pa in the extra column
+          const double* v = panel + (size_t)pp * LD + ncols;
+          g0 = fma(z0, v[0], g0); g1 = fma(z1, v[LD], g1); g0 = fma(z2, v[2 * LD], g0); g1 = fma(z3, v[3 * LD], g1);
+        }
       }
       const double R = cov_eval(ct, cxs[c], cys[c], cq[c], cxs[c], cys[c], cq[c]) - ((q0 + q1) + (q2 + q3));
       const bool ok = (R > 0.0) && isfinite(R);
@@ -411,6 +438,7 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
         rdiag[c] = ri;
         outRi[s_nrioff[d] + t] = ri;
         tvec[c] = ri * wcol[c];
+        if (xcol) gw[c] = ri * (g0 + g1);  // G w_pa
       } else {
         outRi[s_nrioff[d] + t] = ok ? sqrt(R) : 0.0;  // predict_std zeroes the sd when the Cholesky fails (:1316-1322)
       }
@@ -490,8 +518,36 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
     __syncthreads();
   };
 
+  // wcore = e' prec e = |Ri w_u - G w_pa|^2 (:913 / :950) ; logdet = sum log diag(Ri) (:966)
+  auto finalize = [&]() {
+    for (int d = warp; d < nn; d += nwarps) {
+      const int md = s_nm[d], c0d = s_nc0[d];
+      double wc = 0, ld = 0;
+      for (int r = lane; r < md; r += 32) {
+        const double t = tvec[c0d + r] - gw[c0d + r];
+        wc = fma(t, t, wc);
+        if (MODE == 1) ld += log(rdiag[c0d + r]);
+      }
+      wc = warp_sum(wc);
+      if (MODE == 1) ld = warp_sum(ld); else ld = s_nlogdet[d];
+      if (lane == 0) {
+        S.logdet[s0 + d] = ld;
+        S.llcomp[s0 + d] = (double)md * kHl2pi - 0.5 * wc;  // :967-968
+      }
+    }
+  };
   if (MODE == 2) {
     bwd_sweep(outG, false);  // H of the prediction blocks
+  } else if (MODE == 1 && phase == 1) {
+    // forward half only: park Z (unscaled) where G will go; the backward sweep runs if and when the slot is taken up
+    for (int c = warp; c < ncols; c += nwarps) {
+      double* dst = outG + colbase[c];
+      for (int i = lane; i < P; i += 32) dst[i] = panel[(size_t)i * LD + c];
+    }
+    finalize();
+  } else if (completing) {
+    __syncthreads();
+    bwd_sweep(outG, false);
   } else {
     if (outH != nullptr) {
       bwd_sweep(outH, false);  // H = K_{u,pa} Kxx_inv (:887), kept only on request
@@ -549,22 +605,7 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
     __syncthreads();
     mark(5);
     bwd_sweep(outG, true);  // G = Ri H (bottom-left block of Kxx_invchol(u), tree_utils.cpp:205)
-    // wcore = e' prec e = |Ri w_u - G w_pa|^2 (:913 / :950) ; logdet = sum log diag(Ri) (:966)
-    for (int d = warp; d < nn; d += nwarps) {
-      const int md = s_nm[d], c0d = s_nc0[d];
-      double wc = 0, ld = 0;
-      for (int r = lane; r < md; r += 32) {
-        const double t = tvec[c0d + r] - gw[c0d + r];
-        wc = fma(t, t, wc);
-        if (MODE == 1) ld += log(rdiag[c0d + r]);
-      }
-      wc = warp_sum(wc);
-      if (MODE == 1) ld = warp_sum(ld); else ld = s_nlogdet[d];
-      if (lane == 0) {
-        S.logdet[s0 + d] = ld;
-        S.llcomp[s0 + d] = (double)md * kHl2pi - 0.5 * wc;  // :967-968
-      }
-    }
+    finalize();
   }
   mark(6);
 }
@@ -572,7 +613,7 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
 template <int MODE>
 static cudaError_t launch_build_t(const DevTree& T, const DevSlot& S, double* outG, double* outH, double* outRi,
                                   const int* grp_slot0, const int* grp_nn, int ngrp, const double* w, const CovTab& tab,
-                                  int* fail, int ns, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof) {
+                                  int* fail, int ns, int phase, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof) {
   auto kern = build_level_kernel<MODE>;
   static size_t configured[3] = {0, 0, 0};
   if (smem > configured[MODE]) {
@@ -580,16 +621,16 @@ static cudaError_t launch_build_t(const DevTree& T, const DevSlot& S, double* ou
     if (e != cudaSuccess) return e;
     configured[MODE] = smem;
   }
-  kern<<<ngrp, nthreads, smem, st>>>(T, S, outG, outH, outRi, grp_slot0, grp_nn, w, tab, fail, ns, prof);
+  kern<<<ngrp, nthreads, smem, st>>>(T, S, outG, outH, outRi, grp_slot0, grp_nn, w, tab, fail, ns, phase, prof);
   return cudaGetLastError();
 }
 cudaError_t launch_build(int mode, const DevTree& T, const DevSlot& S, double* outG, double* outH, double* outRi,
                          const int* grp_slot0, const int* grp_nn, int ngrp, const double* w, const CovTab& tab, int* fail,
-                         int ns, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof) {
+                         int ns, int phase, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof) {
   if (ngrp <= 0) return cudaSuccess;
-  if (mode == 0) return launch_build_t<0>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, smem, st, nthreads, prof);
-  if (mode == 1) return launch_build_t<1>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, smem, st, nthreads, prof);
-  return launch_build_t<2>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, smem, st, nthreads, prof);
+  if (mode == 0) return launch_build_t<0>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, phase, smem, st, nthreads, prof);
+  if (mode == 1) return launch_build_t<1>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, phase, smem, st, nthreads, prof);
+  return launch_build_t<2>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, phase, smem, st, nthreads, prof);
 }
 
 }  // namespace st

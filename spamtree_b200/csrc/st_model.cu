@@ -362,8 +362,8 @@ int Model::build_layout(std::string& e) {
   // BUILD work groups: runs of sibling blocks (they share their ancestor chain), at most max_group_cols columns
   // (one warp per 8 columns) and sized to the shared-memory budget
   h_grp_slot0.clear(); h_grp_nn.clear();
-  auto group_plan = [&](int s, int nn, int mode, int ns, int nwarps) {
-    int ncols = 0, sumRb = 0, maxmd = 1;
+  auto group_plan = [&](int s, int nn, int mode, int ns, int nwarps, int xcol) {
+    int ncols = xcol, sumRb = 0, maxmd = 1;
     for (int d = 0; d < nn; d++) {
       ncols += h_m[s + d];
       if (mode == 0) sumRb += rb_doubles(h_m[s + d]);
@@ -377,6 +377,13 @@ int Model::build_layout(std::string& e) {
     L.build_launches.clear();
     const int end = L.slot0 + L.nslots;
     const int col_cap = std::min(max_group_cols, kMaxGroupCols);
+    L.deferrable = false;
+    if (mode == 1 && !keep_H && defer_leaves) {
+      L.deferrable = L.nslots > 0;
+      for (int t = L.slot0; t < end; t++)
+        if (h_child_ptr[t + 1] > h_child_ptr[t] || h_lastpar[t] < 0) L.deferrable = false;
+    }
+    const int xcol = L.deferrable ? 1 : 0;  // the deferred scheme carries w_pa as one extra panel column
     struct Grp { int s, nn, NT; };
     const int wmax = kBuildMaxThreads / 32;
     auto warps_for = [&](int NT) { return std::min(wmax, std::max(4, (2 * NT) & ~3)); };
@@ -388,7 +395,7 @@ int Model::build_layout(std::string& e) {
       while (s + nn < end && nn < kMaxGroupNodes) {
         const int t = s + nn;
         if (nn > 0 && (h_lastpar[s] < 0 || h_lastpar[t] != h_lastpar[s])) break;  // roots never share a chain
-        const BuildPlan pl = group_plan(s, nn + 1, mode, 1, wmax);
+        const BuildPlan pl = group_plan(s, nn + 1, mode, 1, wmax, xcol);
         if (pl.total > smem_budget || pl.NCp > kMaxGroupCols || (nn > 0 && pl.NCp > col_cap)) break;
         best = pl;
         nn++;
@@ -415,8 +422,8 @@ int Model::build_layout(std::string& e) {
       for (const Grp& g : gs)
         if (g.NT > lo && g.NT <= hi) {
           h_grp_slot0.push_back(g.s); h_grp_nn.push_back(g.nn);
-          need1 = std::max(need1, group_plan(g.s, g.nn, mode, 1, nw).total);
-          need2 = std::max(need2, group_plan(g.s, g.nn, mode, 2, nw).total);
+          need1 = std::max(need1, group_plan(g.s, g.nn, mode, 1, nw, xcol).total);
+          need2 = std::max(need2, group_plan(g.s, g.nn, mode, 2, nw, xcol).total);
         }
       bl.ngrp = (int)h_grp_slot0.size() - bl.grp0;
       if (bl.ngrp == 0) continue;
@@ -609,6 +616,7 @@ int Model::upload(std::string& e) {
 int Model::init(std::string& e) {
   // development overrides of the BUILD tiling
   if (const char* v = getenv("ST_BUILD_NS")) force_build_ns = atoi(v);
+  if (const char* v = getenv("ST_DEFER")) defer_leaves = atoi(v) != 0;
   if (const char* v = getenv("ST_MAX_COLS")) max_group_cols = atoi(v);
   if (const char* v = getenv("ST_SMEM_BUDGET")) smem_budget = (size_t)atol(v);
   int rc = build_bookkeeping(e);
@@ -707,8 +715,10 @@ int Model::launch_build_levels(int pslot, const CovTab& tab) {
         cudaEventRecord(pe0, stream);
       }
       ST_CUDA(launch_build(L.is_ref ? 0 : 1, dt, ds[pslot], ds[pslot].G, keep_H ? ds[pslot].H : nullptr, ds[pslot].Ri,
-                           d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w, tab, d_fail, B.ns, B.smem, stream, B.threads, d_prof),
+                           d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w, tab, d_fail, B.ns, L.deferrable ? 1 : 0, B.smem, stream,
+                           B.threads, d_prof),
               "build_level_kernel");
+      if (L.deferrable) deferred_[pslot] = true;
       n_launches++;
       if (profile) {
         unsigned long long h[16];
@@ -728,6 +738,24 @@ int Model::launch_build_levels(int pslot, const CovTab& tab) {
     }
   }
   if (profile) cudaFree(d_prof);
+  return 0;
+}
+
+// The deferred half of BUILD: childless non-reference blocks of the slot get their G (backward sweep over the parked Z).
+int Model::complete_slot(int pslot) {
+  if (!deferred_[pslot]) return 0;
+  CovTab tab{};  // not evaluated in this phase
+  tab.q = q;
+  for (auto& L : levels) {
+    if (!L.deferrable) continue;
+    for (const auto& B : L.build_launches) {
+      ST_CUDA(launch_build(1, dt, ds[pslot], ds[pslot].G, nullptr, ds[pslot].Ri, d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w,
+                           tab, d_fail, B.ns, 2, B.smem, stream, B.threads, nullptr),
+              "build_level_kernel(deferred half)");
+      n_launches++;
+    }
+  }
+  deferred_[pslot] = false;
   return 0;
 }
 
@@ -765,6 +793,7 @@ int Model::draw_normals(uint64_t seed) {
 }
 
 int Model::refresh_grams() {
+  { int rc = complete_slot(cur); if (rc) return rc; }
   for (int g = (int)levels.size() - 1; g >= 0; g--) {
     if (part && n_top_levels >= 1 && g == n_top_levels - 1) {  // children of this level live on several ranks
       ST_CUDA(launch_frontier_sum(dt, (int)h_front_pseudo.size(), d_front_pseudo, d_front_c0, d_front_c1, d_front_vlen, d_front_ulen,
@@ -795,6 +824,7 @@ int Model::refresh_grams() {
 }
 
 int Model::gibbs_launch_only() {
+  { int rc = complete_slot(cur); if (rc) return rc; }
   if (gram_stale) { int rc = refresh_grams(); if (rc) return rc; }
   for (int g = (int)levels.size() - 1; g >= 0; g--) {
     const LevelInfo& L = levels[g];
@@ -851,6 +881,7 @@ int Model::deal_with_w(const double* z, uint64_t seed) {
 int Model::get_loglik_w(int slot, double* out2) {
   if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   const int ps = phys(slot);
+  { int rc = complete_slot(ps); if (rc) return rc; }
   ST_CUDA(launch_llw(dt, ds[ps], n_obs_nodes, d_w, llw_maxlen_, stream), "llw_kernel");
   n_launches++;
   double r3[3];
@@ -866,6 +897,7 @@ void Model::accept_make_change() {
   cur = 1 - cur;
   gram_stale = true;
   pred_H_valid = false;
+  if (stream && complete_slot(cur) != 0) deferred_[cur] = true;  // (an error here resurfaces at the next consumer)
 }
 
 int Model::predict(bool theta_changed) {
@@ -877,7 +909,7 @@ int Model::predict(bool theta_changed) {
     if (!make_covtab(theta[cur].data(), (int)theta[cur].size(), q, tab, e)) { err = e; return 1; }
     for (const auto& B : pred_level.build_launches) {
       ST_CUDA(launch_build(2, dt, ds[cur], d_Hpred, nullptr, d_sdpred, d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w, tab,
-                           d_fail, B.ns, B.smem, stream, B.threads, nullptr),
+                           d_fail, B.ns, 0, B.smem, stream, B.threads, nullptr),
               "build_level_kernel(predict)");
       n_launches++;
     }
@@ -1033,6 +1065,7 @@ int Model::sync() {
 int Model::get_node_state(int slot, int u, const std::string& which, double* out, int64_t cap, int64_t* count) {
   if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   const int ps = phys(slot);
+  { int rc = complete_slot(ps); if (rc) return rc; }
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
   auto emit = [&](const dvec& v) {
     *count = (int64_t)v.size();
@@ -1189,12 +1222,12 @@ int Model::bench_iteration(const double* theta_prop, int do_swap, uint64_t seed,
   if (rc) return rc;
   rc = reduce_loglik(pa, d_fail, rb);
   if (rc) return rc;
-  ST_CUDA(cudaEventRecord(ev[3], stream), "event");
   loglik_w[cur] = rl[0]; logdetCi[cur] = rl[1];
   const bool ok = rb[2] == 0.0;
   if (ok) { loglik_w[pa] = rb[0]; logdetCi[pa] = rb[1]; }
   out3[0] = loglik_w[pa]; out3[1] = loglik_w[cur]; out3[2] = ok ? 1.0 : 0.0;
-  if (ok && do_swap) accept_make_change();
+  if (ok && do_swap) accept_make_change();  // includes the deferred half of BUILD for the accepted slot
+  ST_CUDA(cudaEventRecord(ev[3], stream), "event");
   rc = gibbs_sample_tausq(nullptr);
   if (rc) return rc;
   rc = gibbs_sample_beta(nullptr, part ? false : (beta_widx_mode != 0));

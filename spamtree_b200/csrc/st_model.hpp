@@ -78,6 +78,9 @@ struct LevelInfo {
     int ns = 2;               // depth of the cp.async ring (1 when that lets two CTAs share an SM, or when 2 does not fit)
   };
   std::vector<BuildLaunch> build_launches;
+  // childless non-reference level: BUILD runs its forward half only (log-density) and parks Z in G's storage; the
+  // backward half runs when the slot is taken up (accepted proposal).  Not when H is kept (parity getters).
+  bool deferrable = false;
   int maxP = 0, maxm = 0, maxNC = 0, maxk = 0;
   size_t smem_gibbs = 0;
   int gram_rch = 1, gram_ldx = 2, gram_tiles = 2;  // gram_level_kernel: staged rows per chunk, their leading dimension, doubles of the assembled tiles
@@ -99,6 +102,7 @@ class Model {
   int device = 0;
   size_t smem_budget = 227 * 1024 - 5 * 1024;  // dynamic; the kernel also holds ~4.5 KB of static shared memory (227 KB per CTA)
   int force_build_ns = 0;    // development override of the ring depth (ST_BUILD_NS)
+  bool defer_leaves = true;  // childless non-reference levels: backward half of BUILD only when the slot is taken up (ST_DEFER=0 disables)
   int max_group_cols = 104;  // upper bound on the columns one BUILD work group handles (one warp per 8 columns)
   bool probes = true;        // record Sigi_tot / Smu_tot of the last Gibbs sweep (st_get_node_state)
   // ---- bookkeeping, same meaning as the reference's members
@@ -199,6 +203,8 @@ class Model {
   int build_layout(std::string& e);
   int upload(std::string& e);
   int launch_build_levels(int pslot, const CovTab& tab);
+  int complete_slot(int pslot);  // the deferred half of BUILD for the slot's childless levels, if pending
+  bool deferred_[2] = {false, false};
   int refresh_grams();
   int gibbs_launch_only();
   int rowstats(bool faithful_index);

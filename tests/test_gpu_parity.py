@@ -159,6 +159,47 @@ def test_lockstep_chain_matches_oracle_chain():
         om.close()
 
 
+def test_deferred_backward_half_of_childless_levels():
+    """with keep_H = 0 the childless non-reference level gets only the forward half of BUILD (log-density); G appears when
+    the slot is taken up.  Everything downstream must equal the eager model (keep_H = 1 never defers)."""
+    pb = common.make_problem(3, 6000)
+    ge, gd = common.product_model(pb, keep_H=True), common.product_model(pb, keep_H=False)
+    rng = np.random.default_rng(4)
+    n = pb["d"]["y"].size
+    w0 = rng.standard_normal(n) * .3
+    th2 = pb["theta"] * (1 + .01 * rng.standard_normal(pb["theta"].size))
+    for g in (ge, gd):
+        g.w = w0
+        g.get_loglik_comps_w(0)
+        g.theta_update(1, th2)
+    a, b = ge.get_loglik_comps_w(1), gd.get_loglik_comps_w(1)
+    assert a[0] and b[0] and abs(a[1] - b[1]) <= 1e-11 * abs(a[1]) and abs(a[2] - b[2]) <= 1e-12 * abs(a[2])
+    for g in (ge, gd):
+        g.accept_make_change()
+    t = pb["tree"]
+    nchi, npar = np.diff(t["children_ptr"]), np.diff(t["parents_ptr"])
+    obs = ge.index("block_ct_obs")
+    leaves = [u for u in range(t["n_blocks"]) if nchi[u] == 0 and npar[u] > 0 and obs[u] > 0][:40]
+    assert leaves
+    for u in leaves:
+        assert np.array_equal(ge.node_state("G", u), gd.node_state("G", u)), u
+        assert np.array_equal(ge.node_state("Ri", u), gd.node_state("Ri", u)), u
+    z = rng.standard_normal(n)
+    for g in (ge, gd):
+        g.deal_with_w(z)
+    assert np.array_equal(ge.w, gd.w)
+    la, lb = ge.get_loglik_w(0), gd.get_loglik_w(0)
+    assert abs(la[0] - lb[0]) <= 1e-12 * abs(la[0])
+    # a rejected proposal leaves the current slot untouched
+    for g in (ge, gd):
+        g.theta_update(1, pb["theta"])
+        g.get_loglik_comps_w(1)
+        g.deal_with_w(z)
+    assert np.array_equal(ge.w, gd.w)
+    ge.close()
+    gd.close()
+
+
 def test_asynchronous_save_of_w_equals_the_synchronous_one():
     """saved iterations without yhat copy w to the caller's buffer on a second stream while the next iteration runs
     (st_model.cu: save_w_async); the saved draws must be the very same numbers as with the synchronous path"""
