@@ -1,0 +1,90 @@
+"""Known-answer vectors produced by THE REFERENCE'S OWN CODE (tests/golden/ref_*.npz, written by
+tests/golden/make_golden_from_reference.py from oracle/_ref = the reference's model layer compiled unmodified against
+the Armadillo stand-in).  The CPU oracle is checked against them on the CPU, the CUDA path on the GPU — the latter is the
+direct statement "same inputs -> the reference's numbers" that does not go through the oracle.
+Tolerances: integer structures bit-exact; floating point 1e-9 relative (north_star), 2e-8 for q = 1 where the
+reference's cexpcov takes the distance from a norm expansion whose rounding noise the product does not reproduce
+(DESIGN.md §2)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import common
+from common import relerr
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FILES = sorted(glob.glob(os.path.join(G, "ref_q*_n*.npz")))
+
+
+def _tol(q):
+    return 2e-8 if q == 1 else 1e-9
+
+
+def _problem(g):
+    pb = common.make_problem(int(g["q"]), int(g["n"]))
+    assert np.array_equal(pb["tree"]["blocking"], g["blocking"]), "the deterministic tree builder changed: regenerate the golden files"
+    return pb
+
+
+def _run(g, pb, m, getH, getRi, geti):
+    """the same call sequence as the generator, on model m; returns nothing, asserts"""
+    q, tol = int(g["q"]), _tol(int(g["q"]))
+    nb = pb["tree"]["n_blocks"]
+    for name in ["blocks_not_empty", "blocks_predicting", "block_is_reference", "block_ct_obs"]:
+        assert np.array_equal(geti(name, None), g["i_" + name]), name
+    for name in ["parents_indexing", "children_indexing", "dim_by_parent", "this_is_jth_child"]:
+        ptr, val = g["i_" + name + "_ptr"], g["i_" + name]
+        for u in range(nb):
+            assert np.array_equal(geti(name, u), val[ptr[u]:ptr[u + 1]]), (name, u)
+    m.w = g["w0"]
+    ok, ll, ld = m.get_loglik_comps_w(0)
+    assert ok and abs(ll - float(g["loglik"])) <= tol * abs(ll) and abs(ld - float(g["logdet"])) <= tol * abs(ld)
+    for key in g.files:
+        if key.startswith("Ri_"):
+            u = int(key[3:])
+            assert relerr(getRi(u), g[key]) <= 10 * tol, key
+            if f"H_{u}" in g.files:
+                assert relerr(getH(u), g[f"H_{u}"]) <= 10 * tol, f"H_{u}"
+    obs = np.isfinite(pb["d"]["y"])
+    m.set_tausq_inv(g["tau"])
+    for z, wk, lk in [("z1", "w_sweep1", "llw_sweep1"), ("z2", "w_sweep2", "llw_sweep2")]:
+        m.deal_with_w(g[z])
+        assert relerr(m.w[obs], g[wk][obs]) <= 100 * tol, wk
+        l = m.get_loglik_w(0)[0]
+        assert abs(l - float(g[lk])) <= 100 * tol * abs(l), lk
+    m.theta_update(1, g["theta2"])
+    ok2, ll2, ld2 = m.get_loglik_comps_w(1)
+    assert ok2 and abs(ll2 - float(g["loglik2"])) <= 100 * tol * abs(ll2) and abs(ld2 - float(g["logdet2"])) <= tol * abs(ld2)
+    m.accept_make_change()
+    m.deal_with_w(g["z3"])
+    assert relerr(m.w[obs], g["w_sweep3"][obs]) <= 100 * tol
+    l = m.get_loglik_w(0)[0]
+    assert abs(l - float(g["llw_sweep3"])) <= 100 * tol * abs(l)
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
+def test_oracle_against_reference_outputs(path):
+    g = np.load(path)
+    pb = _problem(g)
+    om = common.oracle_model(pb)
+    isref = om.geti("block_is_reference")
+    _run(g, pb, om, lambda u: om.get("H", u), lambda u: om.get("Ri", u) if isref[u] else om.get("ccholprecdiag", u),
+         lambda name, u: om.geti(name) if u is None else om.geti(name, u))
+    om.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
+def test_cuda_against_reference_outputs(path):
+    g = np.load(path)
+    pb = _problem(g)
+    gm = common.product_model(pb)
+    _run(g, pb, gm, lambda u: gm.node_state("H", u), lambda u: gm.node_state("Ri", u),
+         lambda name, u: gm.index(name) if u is None else gm.index(name, u))
+    gm.close()
+
+
+def test_fixtures_are_present():
+    assert len(FILES) >= 3
