@@ -161,6 +161,16 @@ typedef struct {                 /* caller-allocated; NULL pointers are skipped 
 } st_mcmc_out;
 int st_mcmc_run(st_handle* h, const st_mcmc_opts* opts, st_mcmc_out* out);
 
+/* ---- multi-GPU: native collectives (no reference counterpart) ---- */
+/* Native collective path of a partitioned handle: the library owns an NCCL communicator and enqueues its all-reduces
+ * on the handle's own stream (no host synchronisation, no callback).  Rank 0 calls st_nccl_unique_id, the 128 bytes
+ * are handed to every rank by whatever means the host has (torch.distributed broadcast in spamtree_b200/dist.py), and
+ * every rank calls st_attach_nccl on its handle — collectively, like ncclCommInitRank.  libnccl.so.2 is resolved at
+ * run time (dlopen), so handles that never attach need no NCCL at all.  Without it the `allreduce` callback is used. */
+#define ST_NCCL_UNIQUE_ID_BYTES 128
+int st_nccl_unique_id(unsigned char* out128);
+int st_attach_nccl(st_handle* h, const unsigned char* id128);
+
 /* ---- bench / profiling hooks (no reference counterpart) ---- */
 /* One hot-path iteration without host random draws: GIBBS (device normals) + LLW + BUILD(alter, theta_prop)
  * + optional swap + tausq + beta (spamtree_fit.cpp:167-330 minus predict/save).  ms_out[0..3] receive the

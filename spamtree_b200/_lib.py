@@ -99,6 +99,8 @@ SIGNATURES = {
     "st_mcmc_run": (C.c_int, [C.c_void_p, C.POINTER(StMcmcOpts), C.POINTER(StMcmcOut)]),
     "st_bench_iteration": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_uint64, c_double_p, c_float_p]),
     "st_get_counters": (C.c_int, [C.c_void_p, c_double_p]),
+    "st_nccl_unique_id": (C.c_int, [C.c_char_p]),
+    "st_attach_nccl": (C.c_int, [C.c_void_p, C.c_char_p]),
     "st_sync": (C.c_int, [C.c_void_p]),
     "st_kthresholds": (C.c_int, [c_double_p, C.c_int64, C.c_int32, c_double_p]),
     "st_part_axis_parallel_lmt": (C.c_int, [c_double_p, C.c_int64, C.c_int32, c_double_p, c_int64_p, c_double_p]),

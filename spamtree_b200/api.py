@@ -334,6 +334,13 @@ class SpamTreeMV:
         self._chk(lib.st_bench_iteration(self._h, _dp(t), int(bool(do_swap)), int(seed), _dp(o), ms.ctypes.data_as(_lib.c_float_p)))
         return o, ms
 
+    def attach_nccl(self, unique_id):
+        """collective over the ranks of the partition: the library creates its own NCCL communicator from the 128-byte id of
+        st_nccl_unique_id and from then on enqueues its all-reduces on its stream (no callback, no host synchronisation)"""
+        b = bytes(unique_id)
+        assert len(b) == 128
+        self._chk(lib.st_attach_nccl(self._h, b))
+
     def counters(self):
         o = np.zeros(8)
         self._chk(lib.st_get_counters(self._h, _dp(o)))

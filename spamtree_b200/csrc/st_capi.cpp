@@ -199,6 +199,17 @@ int st_bench_iteration(st_handle* h, const double* theta_prop, int do_swap, uint
   ST_GUARD_BEGIN return h->model.bench_iteration(theta_prop, do_swap, seed, out3, ms_out);
   ST_GUARD_END(h)
 }
+int st_nccl_unique_id(unsigned char* out128) {
+  if (!out128) return ST_ERR_INVALID;
+  std::string e;
+  const int rc = st::Model::nccl_unique_id(out128, e);
+  if (rc) g_create_error = e;
+  return rc;
+}
+int st_attach_nccl(st_handle* h, const unsigned char* id128) {
+  if (!h || !id128) return ST_ERR_INVALID;
+  return h->model.attach_nccl(id128);
+}
 int st_get_counters(st_handle* h, double* out8) {
   if (!h || !out8) return ST_ERR_INVALID;
   out8[0] = h->model.n_launches; out8[1] = h->model.f_alg; out8[2] = h->model.f_exec; out8[3] = h->model.n_cov;

@@ -10,7 +10,42 @@
 
 #include "st_kernels.cuh"
 
+#include <dlfcn.h>
+
 namespace st {
+
+// ---- NCCL, resolved at run time: in a torch process dlopen returns the copy torch has already loaded
+namespace {
+struct NcclApi {
+  typedef struct { char internal[128]; } UniqueId;
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  std::string why;
+  NcclApi() {
+    void* h = nullptr;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (h) break;
+    }
+    if (!h) { why = "libnccl.so.2 not found"; return; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+    ok = GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+    if (!ok) why = "libnccl lacks a required symbol";
+  }
+};
+NcclApi& nccl() { static NcclApi a; return a; }
+constexpr int kNcclDouble = 8, kNcclSum = 0;  // ncclFloat64, ncclSum (nccl.h)
+}  // namespace
+
+
 
 #define ST_CUDA(call, what)                                   \
   do {                                                        \
@@ -66,6 +101,7 @@ bool make_covtab(const double* theta, int n_theta, int q, CovTab& tab, std::stri
 Model::~Model() {
   if (device < 0) return;
   cudaSetDevice(device);
+  if (nccl_comm) { cudaStreamSynchronize(stream); nccl().CommDestroy(nccl_comm); nccl_comm = nullptr; }
   for (void* p : owned) cudaFree(p);
   if (h_scalars) cudaFreeHost(h_scalars);
   if (h_stage) cudaFreeHost(h_stage);
@@ -661,8 +697,38 @@ int Model::init(std::string& e) {
 }
 
 // ------------------------------------------------------------------------------------------------------ operations
+int Model::nccl_unique_id(unsigned char* out128, std::string& e) {
+  NcclApi& N = nccl();
+  if (!N.ok) { e = N.why; return 4; }
+  NcclApi::UniqueId id;
+  const int rc = N.GetUniqueId(&id);
+  if (rc != 0) { e = std::string("ncclGetUniqueId: ") + (N.GetErrorString ? N.GetErrorString(rc) : "error"); return 2; }
+  std::memcpy(out128, id.internal, 128);
+  return 0;
+}
+
+int Model::attach_nccl(const unsigned char* id128) {
+  if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
+  if (!part || nranks <= 1) return 0;
+  NcclApi& N = nccl();
+  if (!N.ok) { err = N.why; return 4; }
+  ST_CUDA(cudaSetDevice(device), "cudaSetDevice");
+  NcclApi::UniqueId id;
+  std::memcpy(id.internal, id128, 128);
+  void* comm = nullptr;
+  const int rc = N.CommInitRank(&comm, nranks, id, rank);
+  if (rc != 0) { err = std::string("ncclCommInitRank: ") + (N.GetErrorString ? N.GetErrorString(rc) : "error"); return 2; }
+  nccl_comm = comm;
+  return 0;
+}
+
 int Model::allreduce_dev(double* dptr, int64_t n) {
   if (!part || nranks <= 1 || n <= 0) return 0;
+  if (nccl_comm) {  // in order on the handle's stream: no host synchronisation
+    const int rc = nccl().AllReduce(dptr, dptr, (size_t)n, kNcclDouble, kNcclSum, nccl_comm, stream);
+    if (rc != 0) { err = std::string("ncclAllReduce: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error"); return 2; }
+    return 0;
+  }
   ST_CUDA(cudaStreamSynchronize(stream), "sync before allreduce");
   if (!allreduce_fn || allreduce_fn(allreduce_ctx, dptr, n) != 0) { err = "partition: the allreduce callback failed"; return 1; }
   return 0;

@@ -137,6 +137,10 @@ class Model {
   int *d_front_pseudo = nullptr, *d_front_c0 = nullptr, *d_front_c1 = nullptr, *d_front_vlen = nullptr, *d_front_ulen = nullptr;
   long long v_front0 = 0, v_front_len = 0, u_front0 = 0, u_front_len = 0;
   int allreduce_dev(double* dptr, int64_t n);
+  // native path: library-owned NCCL communicator, all-reduces enqueued on `stream` (st_attach_nccl)
+  void* nccl_comm = nullptr;
+  int attach_nccl(const unsigned char* id128);
+  static int nccl_unique_id(unsigned char* out128, std::string& e);
   int reduce_loglik(int ps, const int* fail, double* out3_host);
   // ---- parameters (host copies of the small ones)
   dvec theta[2];

@@ -32,7 +32,7 @@ def make_allreduce(device=None):
     return allreduce
 
 
-def partitioned_model(d, tree, theta, beta, tausq, rank, nranks, device, allreduce, keep_H=False):
+def partitioned_model(d, tree, theta, beta, tausq, rank, nranks, device, allreduce, keep_H=False, native_nccl=True):
     """SpamTreeMV of this rank's share of the problem (d: data dict with y/X/coords/mv_id/q; tree: make_tree output)"""
     pl = part.plan(tree, d["y"], nranks)
     sp = part.subproblem(d, tree, pl, rank, nranks)
@@ -40,4 +40,29 @@ def partitioned_model(d, tree, theta, beta, tausq, rank, nranks, device, allredu
     gm = SpamTreeMV(sp["y"], sp["X"], sp["coords"], sp["mv_id"], sp["res_is_ref"], None, None, False, sp["block_names"],
                     sp["block_groups"], None, beta, theta, tausq, csr=sp["csr"], device=device, keep_H=keep_H,
                     partition=sp if nranks > 1 else None, q=d["q"])
+    if nranks > 1 and native_nccl:
+        attach_native_nccl(gm, rank)
     return gm, sp, pl
+
+
+def nccl_unique_id():
+    import ctypes as C
+    from ._lib import lib
+    buf = C.create_string_buffer(128)
+    rc = lib.st_nccl_unique_id(buf)
+    if rc:
+        raise RuntimeError("st_nccl_unique_id failed: " + lib.st_last_error(None).decode())
+    return buf.raw
+
+
+def attach_native_nccl(gm, rank):
+    """gives the partitioned handle its own NCCL communicator: rank 0 draws the unique id, torch.distributed hands it to
+    the other ranks, every rank attaches (collective).  Only with the nccl backend (a gloo group has no GPUs to talk to)."""
+    import torch
+    import torch.distributed as dist
+    if dist.get_backend() != "nccl":
+        return False
+    box = [nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    gm.attach_nccl(box[0])
+    return True
