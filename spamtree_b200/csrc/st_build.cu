@@ -109,6 +109,9 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
   auto mark = [&](int ph) {
     if (prof && tid == 0) { const long long t = clock64(); atomicAdd(prof + ph, (unsigned long long)(t - tprev)); tprev = t; }
   };
+  // Programmatic dependent launch: the next level's CTAs may be scheduled as soon as SMs free up (they fill the tail of
+  // this launch and run their setup and covariance panel, which depend on nothing this launch writes) ...
+  asm volatile("griddepcontrol.launch_dependents;");
   load_covtab(ct, tab);
   // ---- setup: metadata of the chain and of the group's blocks
   {
@@ -193,6 +196,7 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
   const bool completing = (MODE == 1 && phase == 2);
   if (completing) {
     // deferred half: the panel is Z, parked in G's storage by the forward half, scaled by the stored 1 / sqrt(R_ii)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int e = tid; e < Ppad * LD; e += nth) panel[e] = 0.0;
     for (int c = tid; c < ncols; c += nth) rdiag[c] = outRi[s_nrioff[colnode[c]] + (c - s_nc0[colnode[c]])];
     __syncthreads();
@@ -268,6 +272,9 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
   };
 
   // ---- phase 3: Z = L^-1 K in place, bottom rows first (row r of Z needs rows <= r of K)
+  // ... and wait here, before the first read of the ancestors' row blocks, until the previous launches have completed
+  // and their writes are visible (a no-op for a launch without the programmatic attribute)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int nfw = completing ? 0 : nstg;
   if (ns == 2 && nfw > 0) issue_fwd(nfw - 1, ring);
   for (int i = 0; i < nfw; i++) {
@@ -613,7 +620,7 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
 template <int MODE>
 static cudaError_t launch_build_t(const DevTree& T, const DevSlot& S, double* outG, double* outH, double* outRi,
                                   const int* grp_slot0, const int* grp_nn, int ngrp, const double* w, const CovTab& tab,
-                                  int* fail, int ns, int phase, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof) {
+                                  int* fail, int ns, int phase, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof, bool pdl) {
   auto kern = build_level_kernel<MODE>;
   static size_t configured[3] = {0, 0, 0};
   if (smem > configured[MODE]) {
@@ -621,16 +628,29 @@ static cudaError_t launch_build_t(const DevTree& T, const DevSlot& S, double* ou
     if (e != cudaSuccess) return e;
     configured[MODE] = smem;
   }
-  kern<<<ngrp, nthreads, smem, st>>>(T, S, outG, outH, outRi, grp_slot0, grp_nn, w, tab, fail, ns, phase, prof);
-  return cudaGetLastError();
+  if (!pdl) {
+    kern<<<ngrp, nthreads, smem, st>>>(T, S, outG, outH, outRi, grp_slot0, grp_nn, w, tab, fail, ns, phase, prof);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ngrp);
+  cfg.blockDim = dim3(nthreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, T, S, outG, outH, outRi, grp_slot0, grp_nn, w, tab, fail, ns, phase, prof);
 }
 cudaError_t launch_build(int mode, const DevTree& T, const DevSlot& S, double* outG, double* outH, double* outRi,
                          const int* grp_slot0, const int* grp_nn, int ngrp, const double* w, const CovTab& tab, int* fail,
-                         int ns, int phase, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof) {
+                         int ns, int phase, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof, bool pdl) {
   if (ngrp <= 0) return cudaSuccess;
-  if (mode == 0) return launch_build_t<0>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, phase, smem, st, nthreads, prof);
-  if (mode == 1) return launch_build_t<1>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, phase, smem, st, nthreads, prof);
-  return launch_build_t<2>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, phase, smem, st, nthreads, prof);
+  if (mode == 0) return launch_build_t<0>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, phase, smem, st, nthreads, prof, pdl);
+  if (mode == 1) return launch_build_t<1>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, phase, smem, st, nthreads, prof, pdl);
+  return launch_build_t<2>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, phase, smem, st, nthreads, prof, pdl);
 }
 
 }  // namespace st

@@ -92,7 +92,8 @@ inline size_t gibbs_smem_bytes(int is_ref, int m, int P, int k) {
 
 cudaError_t launch_build(int mode, const DevTree& T, const DevSlot& S, double* outG, double* outH, double* outRi,
                          const int* grp_slot0, const int* grp_nn, int ngrp, const double* w, const CovTab& tab, int* fail,
-                         int ns, int phase, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof = nullptr);
+                         int ns, int phase, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof = nullptr,
+                         bool pdl = false);  // pdl: programmatic dependent launch on the previous kernel of the stream
 cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlot& S, int slot0, int nslots, double* w,
                          const double* xb, const double* z, const double* tausq_inv, const double* SigS, double* V,
                          double* probe_sig, double* probe_smu, int* fail, size_t smem, cudaStream_t st);

@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include "../../include/spamtree_b200.h"
 #include "st_model.hpp"
@@ -86,8 +88,19 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
   const bool async_save = out.w_mcmc && !out.yhat_mcmc;
   if (async_save) { rc = M.save_begin(out.w_mcmc, (size_t)o.keep * M.n_all * sizeof(double)); if (rc) return rc; }
   struct SaveGuard { Model& M; bool on; ~SaveGuard() { if (on) M.save_end(); } } guard{M, async_save};
+  // ST_PROFILE_MCMC=1: host wall-clock per phase of the loop, printed by every rank at the end (development aid)
+  static const bool prof = getenv("ST_PROFILE_MCMC") != nullptr;
+  double tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto tick = [&]() { return std::chrono::steady_clock::now(); };
+  auto lap = [&](int i, std::chrono::steady_clock::time_point& t) {
+    if (!prof) return;
+    const auto n = tick();
+    tph[i] += std::chrono::duration<double>(n - t).count();
+    t = n;
+  };
   const auto t0 = std::chrono::steady_clock::now();
   for (int m = 0; m < mcmc; m++) {
+    auto tl = tick();
     bool predicting = false;
     const int mx = m - o.burn;
     if (mx >= 0 && mx % o.thin == 0) predicting = true;
@@ -104,10 +117,12 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
         rc = M.deal_with_w(nullptr, o.seed);
       }
       if (rc) return rc;
+      lap(0, tl);
       double o2[2];
       rc = M.get_loglik_w(0, o2);
       if (rc) return rc;
       current_loglik = M.loglik_w[M.cur];
+      lap(1, tl);
     }
     if (o.sample_theta) {  // :203-289
       dvec U(npar), new_param(npar);
@@ -124,6 +139,7 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
       M.theta_update(1, new_param.data());
       rc = M.get_loglik_comps_w(1, o3);
       if (rc) return rc;
+      lap(2, tl);
       const bool acceptable = o3[2] != 0.0;
       const double new_loglik = M.loglik_w[1 - M.cur];
       current_loglik = M.loglik_w[M.cur];
@@ -146,6 +162,7 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
         param = new_param;
       }
       if (o.adapting) ad.adapt(U, (acceptable ? 1.0 : 0.0) * std::exp(logaccept), m);  // :285
+      lap(3, tl);
     }
     bool need_update = false;  // :300
     for (int j = 0; j < npar; j++)
@@ -155,8 +172,10 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
       if (rc) return rc;
       predict_param = param;
     }
+    lap(4, tl);
     if (o.sample_tausq) { rc = M.gibbs_sample_tausq(nullptr); if (rc) return rc; }
     if (o.sample_beta) { rc = M.gibbs_sample_beta(nullptr, o.faithful_beta_index != 0); if (rc) return rc; }
+    lap(5, tl);
     if (mx >= 0 && mx % o.thin == 0) {  // save, :376-389
       if (out.tausq_mcmc)
         for (int j = 0; j < M.q; j++) out.tausq_mcmc[j + (size_t)msaved * M.q] = 1.0 / M.tausq_inv[j];
@@ -189,9 +208,14 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
         }
       msaved++;
     }
+    lap(6, tl);
   }
   if (async_save) { guard.on = false; rc = M.save_end(); if (rc) return rc; }  // the timed region ends when every saved w is on the host
   out.mcmc_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (prof)
+    fprintf(stderr, "[mcmc profile] rank %d: %d iterations, %lld accepted; ms/iteration: gibbs %.3f llw %.3f build %.3f accept+adapt %.3f predict %.3f tausq+beta %.3f save %.3f | total %.3f\n",
+            M.rank, mcmc, (long long)out.n_accepted, 1e3 * tph[0] / mcmc, 1e3 * tph[1] / mcmc, 1e3 * tph[2] / mcmc, 1e3 * tph[3] / mcmc,
+            1e3 * tph[4] / mcmc, 1e3 * tph[5] / mcmc, 1e3 * tph[6] / mcmc, 1e3 * out.mcmc_time / mcmc);
   if (out.paramsd) std::copy(ad.paramsd.a.begin(), ad.paramsd.a.end(), out.paramsd);
   return 0;
 }

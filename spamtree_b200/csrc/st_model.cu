@@ -653,6 +653,7 @@ int Model::init(std::string& e) {
   // development overrides of the BUILD tiling
   if (const char* v = getenv("ST_BUILD_NS")) force_build_ns = atoi(v);
   if (const char* v = getenv("ST_DEFER")) defer_leaves = atoi(v) != 0;
+  if (const char* v = getenv("ST_PDL")) use_pdl = atoi(v) != 0;
   if (const char* v = getenv("ST_MAX_COLS")) max_group_cols = atoi(v);
   if (const char* v = getenv("ST_SMEM_BUDGET")) smem_budget = (size_t)atol(v);
   int rc = build_bookkeeping(e);
@@ -772,6 +773,7 @@ int Model::launch_build_levels(int pslot, const CovTab& tab) {
   if (profile) {
     cudaMalloc((void**)&d_prof, 16 * sizeof(unsigned long long));
   }
+  bool first_launch = true;
   for (auto& L : levels) {
     for (const auto& B : L.build_launches) {
       cudaEvent_t pe0 = nullptr, pe1 = nullptr;
@@ -780,10 +782,13 @@ int Model::launch_build_levels(int pslot, const CovTab& tab) {
         cudaEventCreate(&pe0); cudaEventCreate(&pe1);
         cudaEventRecord(pe0, stream);
       }
+      // every launch but the first of a BUILD may start before its predecessor has drained (programmatic dependent
+      // launch): it waits inside the kernel before it reads the ancestors' row blocks
       ST_CUDA(launch_build(L.is_ref ? 0 : 1, dt, ds[pslot], ds[pslot].G, keep_H ? ds[pslot].H : nullptr, ds[pslot].Ri,
                            d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w, tab, d_fail, B.ns, L.deferrable ? 1 : 0, B.smem, stream,
-                           B.threads, d_prof),
+                           B.threads, d_prof, use_pdl && !first_launch && !profile),
               "build_level_kernel");
+      first_launch = false;
       if (L.deferrable) deferred_[pslot] = true;
       n_launches++;
       if (profile) {

@@ -102,6 +102,7 @@ class Model {
   int device = 0;
   size_t smem_budget = 227 * 1024 - 5 * 1024;  // dynamic; the kernel also holds ~4.5 KB of static shared memory (227 KB per CTA)
   int force_build_ns = 0;    // development override of the ring depth (ST_BUILD_NS)
+  bool use_pdl = true;       // level launches of a BUILD use programmatic dependent launch (ST_PDL=0 disables)
   bool defer_leaves = true;  // childless non-reference levels: backward half of BUILD only when the slot is taken up (ST_DEFER=0 disables)
   int max_group_cols = 104;  // upper bound on the columns one BUILD work group handles (one warp per 8 columns)
   bool probes = true;        // record Sigi_tot / Smu_tot of the last Gibbs sweep (st_get_node_state)
