@@ -31,6 +31,9 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
                    const double* __restrict__ z, const double* __restrict__ tausq_inv, const double* __restrict__ SigS,
                    double* __restrict__ V, double* probe_sig, double* probe_smu, int* __restrict__ fail) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // programmatic dependent launch: the next (shallower) level may start early; it waits below before it reads the
+  // messages this level writes (everything before that point depends on ancestors only)
+  asm volatile("griddepcontrol.launch_dependents;");
   const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int sd = slot0 + blockIdx.x;
   const int m = T.m[sd], k = T.k[sd], P = T.P[sd], coff = T.chain_off[sd], row0 = T.row0[sd];
@@ -94,6 +97,7 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
       Sig[e] = s;
       if (probe_sig) probe_sig[T.rioff[sd] + e] = s;
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the children's messages (V) are read from here on
     // Smu_tot = (H'prec)' w_pa + sum_children + tausq_inv (y - XB)  (:1062-1077)
     for (int a = tid; a < m; a += nth) {
       double s = 0;
@@ -174,6 +178,7 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
       rr[r] = s;
     }
   } else {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int a = tid; a < m; a += nth) {
       const double ri = RiS[a], prec = ri * ri;
       const double tsqi = tausq_inv[T.mvq[row0 + a]];
@@ -217,27 +222,26 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
 
 cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlot& S, int slot0, int nslots, double* w,
                          const double* xb, const double* z, const double* tausq_inv, const double* SigS, double* V,
-                         double* probe_sig, double* probe_smu, int* fail, size_t smem, cudaStream_t st) {
+                         double* probe_sig, double* probe_smu, int* fail, size_t smem, cudaStream_t st, bool pdl) {
   if (nslots <= 0) return cudaSuccess;
   static size_t configured[2] = {0, 0};
-  if (is_ref) {
-    auto kern = gibbs_level_kernel<1>;
-    if (smem > configured[1]) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      configured[1] = smem;
-    }
-    kern<<<nslots, kGibbsThreads, smem, st>>>(T, S, slot0, w, xb, z, tausq_inv, SigS, V, probe_sig, probe_smu, fail);
-  } else {
-    auto kern = gibbs_level_kernel<0>;
-    if (smem > configured[0]) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      configured[0] = smem;
-    }
-    kern<<<nslots, kGibbsThreads, smem, st>>>(T, S, slot0, w, xb, z, tausq_inv, SigS, V, probe_sig, probe_smu, fail);
+  auto kern = is_ref ? gibbs_level_kernel<1> : gibbs_level_kernel<0>;
+  if (smem > configured[is_ref ? 1 : 0]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured[is_ref ? 1 : 0] = smem;
   }
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nslots);
+  cfg.blockDim = dim3(kGibbsThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, T, S, slot0, w, xb, z, tausq_inv, SigS, V, probe_sig, probe_smu, fail);
 }
 
 // ------------------------------------------------------------------------------------------------ message Grams

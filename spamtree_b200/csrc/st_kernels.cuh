@@ -96,7 +96,7 @@ cudaError_t launch_build(int mode, const DevTree& T, const DevSlot& S, double* o
                          bool pdl = false);  // pdl: programmatic dependent launch on the previous kernel of the stream
 cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlot& S, int slot0, int nslots, double* w,
                          const double* xb, const double* z, const double* tausq_inv, const double* SigS, double* V,
-                         double* probe_sig, double* probe_smu, int* fail, size_t smem, cudaStream_t st);
+                         double* probe_sig, double* probe_smu, int* fail, size_t smem, cudaStream_t st, bool pdl = false);
 cudaError_t launch_gram(const DevTree& T, const DevSlot& S, int slot0, int nslots, double* U, double* SigS, int rch,
                         int ldx, int tile_doubles, cudaStream_t st);
 cudaError_t launch_llw(const DevTree& T, const DevSlot& S, int nslots, const double* w, int maxlen, cudaStream_t st);

@@ -910,7 +910,8 @@ int Model::gibbs_launch_only() {
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, stream); }
     ST_CUDA(launch_gibbs(L.is_ref, dt, ds[cur], L.slot0, L.nslots, d_w, d_xb, d_z, d_tausq_inv, d_S, d_V,
-                         probes ? d_probe_sig : nullptr, probes ? d_probe_smu : nullptr, d_fail, L.smem_gibbs, stream),
+                         probes ? d_probe_sig : nullptr, probes ? d_probe_smu : nullptr, d_fail, L.smem_gibbs, stream,
+                         use_pdl && !profile && g != (int)levels.size() - 1),
             "gibbs_level_kernel");
     n_launches++;
     if (profile) {
