@@ -26,7 +26,7 @@ METRIC = "mcmc_iterations_per_sec"
 UNIT = "it/s"
 # DRAM traffic (bytes) of all build_level_kernel launches of ONE BUILD, from an ncu pass on a B200 of this pool
 # (profiles/r1_launches_v4.txt); None until measured for a workload
-NCU_BUILD_DRAM_BYTES = {"C4": 2.392e9}
+NCU_BUILD_DRAM_BYTES = {"C4": 2.400e9}
 
 
 def load_peaks():

@@ -649,23 +649,8 @@ int Model::upload(std::string& e) {
   return 0;
 }
 
-int Model::init(std::string& e) {
-  // development overrides of the BUILD tiling
-  if (const char* v = getenv("ST_BUILD_NS")) force_build_ns = atoi(v);
-  if (const char* v = getenv("ST_DEFER")) defer_leaves = atoi(v) != 0;
-  if (const char* v = getenv("ST_PDL")) use_pdl = atoi(v) != 0;
-  if (const char* v = getenv("ST_MAX_COLS")) max_group_cols = atoi(v);
-  if (const char* v = getenv("ST_SMEM_BUDGET")) smem_budget = (size_t)atol(v);
-  int rc = build_bookkeeping(e);
-  if (rc) return rc;
-  if (q * (p + 1) > kMaxStats) { e = "q*(p+1) exceeds 40"; return 4; }
-  rc = build_layout(e);
-  if (rc) return rc;
-  if (n_all >= (1LL << 31)) { e = "n_all must be below 2^31"; return 4; }
-  if (device < 0) return 0;  // host-only handle: bookkeeping and layout, no device state (st_get_index only)
-  rc = upload(e);
-  if (rc) { e = err; return rc; }
-  if (part) {
+int Model::partition_reduce_constants(std::string& e) {
+  int rc = 0;
     // XtX and the per-outcome counts are sums over ALL observed rows of the problem: replicated rows once, then all-reduce
     const int nx = q * p * p + q;
     if (nx > 1024) { e = "partition: q*p*p too large"; return 4; }
@@ -693,6 +678,31 @@ int Model::init(std::string& e) {
       std::copy(hb + (size_t)j * p * p, hb + (size_t)(j + 1) * p * p, XtX[j].a.begin());
       nobs_by_q[j] = (int64_t)std::llround(hb[q * p * p + j]);
     }
+  xtx_pending_ = false;
+  return 0;
+}
+
+int Model::init(std::string& e) {
+  // development overrides of the BUILD tiling
+  if (const char* v = getenv("ST_BUILD_NS")) force_build_ns = atoi(v);
+  if (const char* v = getenv("ST_DEFER")) defer_leaves = atoi(v) != 0;
+  if (const char* v = getenv("ST_PDL")) use_pdl = atoi(v) != 0;
+  if (const char* v = getenv("ST_MAX_COLS")) max_group_cols = atoi(v);
+  if (const char* v = getenv("ST_SMEM_BUDGET")) smem_budget = (size_t)atol(v);
+  int rc = build_bookkeeping(e);
+  if (rc) return rc;
+  if (q * (p + 1) > kMaxStats) { e = "q*(p+1) exceeds 40"; return 4; }
+  rc = build_layout(e);
+  if (rc) return rc;
+  if (n_all >= (1LL << 31)) { e = "n_all must be below 2^31"; return 4; }
+  if (device < 0) return 0;  // host-only handle: bookkeeping and layout, no device state (st_get_index only)
+  rc = upload(e);
+  if (rc) { e = err; return rc; }
+  if (part && allreduce_fn) {
+    rc = partition_reduce_constants(e);
+    if (rc) return rc;
+  } else if (part) {
+    xtx_pending_ = true;  // no callback: summed when the native communicator is attached (st_attach_nccl)
   }
   return 0;
 }
@@ -720,6 +730,11 @@ int Model::attach_nccl(const unsigned char* id128) {
   const int rc = N.CommInitRank(&comm, nranks, id, rank);
   if (rc != 0) { err = std::string("ncclCommInitRank: ") + (N.GetErrorString ? N.GetErrorString(rc) : "error"); return 2; }
   nccl_comm = comm;
+  if (xtx_pending_) {
+    std::string e;
+    const int rc2 = partition_reduce_constants(e);
+    if (rc2) { if (!e.empty()) err = e; return rc2; }
+  }
   return 0;
 }
 
@@ -730,8 +745,9 @@ int Model::allreduce_dev(double* dptr, int64_t n) {
     if (rc != 0) { err = std::string("ncclAllReduce: ") + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "error"); return 2; }
     return 0;
   }
+  if (!allreduce_fn) { err = "partition: no collective path (call st_attach_nccl or supply st_partition.allreduce)"; return 1; }
   ST_CUDA(cudaStreamSynchronize(stream), "sync before allreduce");
-  if (!allreduce_fn || allreduce_fn(allreduce_ctx, dptr, n) != 0) { err = "partition: the allreduce callback failed"; return 1; }
+  if (allreduce_fn(allreduce_ctx, dptr, n) != 0) { err = "partition: the allreduce callback failed"; return 1; }
   return 0;
 }
 

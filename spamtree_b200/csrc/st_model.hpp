@@ -141,6 +141,8 @@ class Model {
   // native path: library-owned NCCL communicator, all-reduces enqueued on `stream` (st_attach_nccl)
   void* nccl_comm = nullptr;
   int attach_nccl(const unsigned char* id128);
+  int partition_reduce_constants(std::string& e);  // XtX and per-outcome counts summed over the ranks
+  bool xtx_pending_ = false;
   static int nccl_unique_id(unsigned char* out128, std::string& e);
   int reduce_loglik(int ps, const int* fail, double* out3_host);
   // ---- parameters (host copies of the small ones)
