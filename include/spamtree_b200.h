@@ -28,7 +28,7 @@ typedef enum {
   ST_ERR_INVALID = 1,   /* bad argument / inconsistent DAG (reference: `throw 1`, spamtree_model.cpp:201-226) */
   ST_ERR_CUDA = 2,      /* CUDA runtime error; st_last_error() has the text */
   ST_ERR_NOT_SPD = 3,   /* Cholesky failed inside the Gibbs step (reference: Rcpp::stop, spamtree_model.cpp:1215-1217) */
-  ST_ERR_UNSUPPORTED = 4, /* shape or option outside what this build handles (e.g. limited_tree) */
+  ST_ERR_UNSUPPORTED = 4, /* shape or option outside what this build handles (e.g. mvbias != 0, q > 8) */
   ST_ERR_NAN = 5        /* NaN log-likelihood at the current theta (reference: `throw 1`, spamtree_fit.cpp:234-237) */
 } st_status;
 
@@ -72,7 +72,8 @@ typedef struct {
   const double* block_groups;  /* n_blocks, tree level of block id i (layer_gibbs_group) */
   const int64_t* res_is_ref;   /* n_res flags per tree level */
   int32_t n_res;
-  int32_t limited_tree;        /* must be 0 in this build (ST_ERR_UNSUPPORTED otherwise) */
+  int32_t limited_tree;        /* 1: every block conditions on its direct parent only (make_edges_limited, tree_dep.cpp:133-186;
+                                  spamtree_model.cpp:901-903, 1275-1278); not combined with a partition */
   const double* theta;         /* n_theta start values (covariance_functions.cpp:34-52 layout) */
   int32_t n_theta;
   const double* beta;          /* p start values */

@@ -165,6 +165,20 @@ def make_tree(coords, y, mv_id, cell_size=25, K=(2, 2), start_level=0, tree_dept
     }
 
 
+def limited_edges_csr(tree, y):
+    """(parents_ptr, parents_idx, children_ptr, children_idx) of make_edges_limited (tree_dep.cpp:133-186) for a tree
+    returned by make_tree; y decides which blocks are non-empty (R/spamtree_fit.R:299-303)"""
+    ne = np.unique(tree["blocking"][np.isfinite(np.asarray(y, dtype=np.float64).reshape(-1))])
+    e = make_edges_limited(tree["parchi_map"], ne, tree["res_is_ref"])
+    out = []
+    for lists in (e["parents"], e["children"]):
+        ptr = np.zeros(len(lists) + 1, dtype=np.int64)
+        ptr[1:] = np.cumsum([len(a) for a in lists])
+        idx = np.concatenate([np.asarray(a, dtype=np.int64) for a in lists]) if ptr[-1] else np.zeros(0, dtype=np.int64)
+        out += [ptr, idx]
+    return tuple(out)
+
+
 def CrossCovarianceAG10(coords1, mv1, coords2, mv2, ai1, ai2, phi_i, thetamv, Dmat, device=0):
     """covariance_functions.cpp:301-355 (R export), evaluated on the GPU"""
     c1, c2 = np.asarray(coords1, dtype=np.float64), np.asarray(coords2, dtype=np.float64)
@@ -458,6 +472,8 @@ def spamtree(y, x, coords, mv_id=None, cell_size=25, K=None, start_level=0, tree
     Z[np.arange(y.size), mvs - 1] = 1
     csr = (tree["indexing_ptr"], tree["indexing_idx"], tree["parents_ptr"], tree["parents_idx"], tree["children_ptr"],
            tree["children_idx"])
+    if limited_tree:  # R/spamtree_fit.R:310-311: make_edges_limited on the same parent-child map
+        csr = csr[:2] + limited_edges_csr(tree, ys)
     results = spamtree_mv_mcmc(
         ys, xs, Z, cs, mvs, tree["blocking"], np.ones(y.size), tree["res_is_ref"], None, None, limited_tree,
         tree["block_names"], tree["block_groups"], None, bounds, np.zeros((y.size, q)), start_theta, start_beta,

@@ -97,7 +97,7 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
   __shared__ int s_cm[kMaxChain], s_crow[kMaxChain + 1], s_crow0g[kMaxChain], s_cgs[kMaxChain];
   __shared__ long long s_cgoff[kMaxChain];
   __shared__ int s_nm[kMaxGroupNodes], s_nc0[kMaxGroupNodes + 1], s_nrow0[kMaxGroupNodes], s_ngs[kMaxGroupNodes], s_nRb[kMaxGroupNodes];
-  __shared__ long long s_ngoff[kMaxGroupNodes], s_nrioff[kMaxGroupNodes];
+  __shared__ long long s_ngoff[kMaxGroupNodes], s_nrioff[kMaxGroupNodes], s_nmoff[kMaxGroupNodes];
   __shared__ double s_nlogdet[kMaxGroupNodes];
   __shared__ int s_sumRb, s_maxmd;
 
@@ -118,11 +118,15 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
     const int coff = T.chain_off[s0];
     for (int j = tid; j < k; j += nth) {
       const int a = T.chain[coff + j];
-      s_cm[j] = T.m[a]; s_crow[j] = T.chain_poff[coff + j]; s_crow0g[j] = T.row0[a]; s_cgoff[j] = T.goff[a]; s_cgs[j] = T.gs[a];
+      s_cm[j] = T.m[a]; s_crow[j] = T.chain_poff[coff + j]; s_crow0g[j] = T.row0[a];
+      // limited trees: the (single) parent contributes its MARGINAL factor rows [-chol(K_pp)^-1 | 0] (:901-903)
+      s_cgoff[j] = T.limited ? T.moff[a] : T.goff[a];
+      s_cgs[j] = T.limited ? ((T.m[a] + 3) & ~3) : T.gs[a];
     }
     for (int d = tid; d < nn; d += nth) {
       s_nm[d] = T.m[s0 + d]; s_nrow0[d] = T.row0[s0 + d]; s_ngoff[d] = T.goff[s0 + d]; s_ngs[d] = T.gs[s0 + d];
       s_nrioff[d] = T.rioff[s0 + d];
+      s_nmoff[d] = (MODE == 0 && T.limited) ? T.moff[s0 + d] : -1;
     }
   }
   __syncthreads();
@@ -134,12 +138,13 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
       if (MODE == 0) rb += rb_doubles(s_nm[d]);
       mx = max(mx, s_nm[d]);
     }
-    s_nc0[nn] = c; s_sumRb = rb; s_maxmd = mx; s_crow[k] = P;
+    s_nc0[nn] = c; s_sumRb = rb; s_maxmd = mx; s_crow[k] = P;  // (limited trees keep a second set of matrices behind the first)
   }
   __syncthreads();
   const int ncols = s_nc0[nn];
   const int xcol = (MODE == 1 && phase != 0) ? 1 : 0;
-  const BuildPlan pl = build_plan(P, ncols + xcol, s_sumRb, s_maxmd, ns, (MODE == 0) ? min(nn, kBuildMaxThreads / 32) : 0, nwarps);
+  const int nmat = (MODE == 0 && T.limited) ? 2 : 1;  // limited trees factorise K_uu (marginal) next to the Schur complement
+  const BuildPlan pl = build_plan(P, ncols + xcol, nmat * s_sumRb, s_maxmd, ns, (MODE == 0) ? min(nmat * nn, kBuildMaxThreads / 32) : 0, nwarps);
   const int Ppad = pl.Ppad, NCp = pl.NCp, NT = pl.NT, LD = pl.LD, SA = pl.SA, slotsz = pl.slot;
   double* base = reinterpret_cast<double*>(smem_raw);
   double* panel = base + pl.o_panel;
@@ -328,7 +333,7 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
   // ---- phase 4/5: Schur complement and its inverse Cholesky factor
   if (MODE == 0) {
     const int sumRb = s_sumRb;
-    for (int e = tid; e < sumRb; e += nth) Rb[e] = 0.0;
+    for (int e = tid; e < nmat * sumRb; e += nth) Rb[e] = 0.0;
     __syncthreads();
     // one 8 x 8 tile of the lower triangle per item; the FP64 pipe is per SM sub-partition, so the items are dealt to a
     // multiple of four warps
@@ -360,14 +365,18 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
       double* R = Rb + s_nRb[d];
 #pragma unroll
       for (int e = 0; e < 2; e++)
-        if (i < md && j + e <= i)
-          R[i * rs + j + e] = cov_eval(ct, cxs[c0d + i], cys[c0d + i], cq[c0d + i], cxs[c0d + j + e], cys[c0d + j + e], cq[c0d + j + e]) - ((c0[e] + d0[e]) + (c1[e] + d1[e]));
+        if (i < md && j + e <= i) {
+          const double kuu = cov_eval(ct, cxs[c0d + i], cys[c0d + i], cq[c0d + i], cxs[c0d + j + e], cys[c0d + j + e], cq[c0d + j + e]);
+          R[i * rs + j + e] = kuu - ((c0[e] + d0[e]) + (c1[e] + d1[e]));
+          if (nmat == 2) R[sumRb + i * rs + j + e] = kuu;  // K_uu itself: its factor is what the children stream
+        }
     }
     __syncthreads();
     mark(3);
-    for (int d = warp; d < nn; d += nwarps) {
+    for (int x = warp; x < nmat * nn; x += nwarps) {
+      const int d = x % nn, which = x / nn;  // which = 1: the marginal K_uu of a limited tree
       const int md = s_nm[d], rs = rb_stride(md);
-      double* R = Rb + s_nRb[d];
+      double* R = Rb + which * sumRb + s_nRb[d];
       bool okc;
       long long tc0 = 0, tc1 = 0;
       if (prof && tid == 0) tc0 = clock64();
@@ -383,7 +392,7 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
         __syncwarp();
         for (int e = lane; e < md * rs; e += 32) R[e] = 0.0;
       }
-      if (lane == 0) s_nlogdet[d] = okc ? 0.0 : -1.0;  // flag, replaced by the log-determinant below
+      if (lane == 0 && which == 0) s_nlogdet[d] = okc ? 0.0 : -1.0;  // flag, replaced by the log-determinant below
     }
     __syncthreads();
     mark(4);
@@ -400,6 +409,14 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
         if (c < md) og[(size_t)r * gsd + c] = -v;
       }
     }
+    if (nmat == 2)  // limited trees: the marginal factor rows [-chol(K_uu)^-1 | 0] for the children's BUILD
+      for (int d = 0; d < nn; d++) {
+        if (s_nmoff[d] < 0) continue;
+        const int md = s_nm[d], rs = rb_stride(md), ms = (md + 3) & ~3;
+        const double* M2 = Rb + sumRb + s_nRb[d];
+        double* om = outG + s_nmoff[d];
+        for (int e = tid; e < md * md; e += nth) { const int r = e / md, c = e - r * md; om[(size_t)r * ms + c] = -M2[r * rs + c]; }
+      }
     // t = Ri w_u (:912-913 via e = w_u - H w_pa: Ri e = Ri w_u - G w_pa) and logdet = sum log diag(Ri) (:966)
     for (int c = tid; c < ncols; c += nth) {
       const int d = colnode[c], c0d = s_nc0[d], r = c - c0d;

@@ -52,7 +52,6 @@ int st_create(const st_problem* pr, st_handle** out) {
   *out = nullptr;
   st_handle* h = nullptr;
   try {
-    if (pr->limited_tree) { g_create_error = "limited_tree = TRUE is not supported by this build"; return ST_ERR_UNSUPPORTED; }
     if (pr->n_all <= 0 || pr->p <= 0 || pr->q <= 0 || pr->n_blocks <= 0) { g_create_error = "empty problem"; return ST_ERR_INVALID; }
     h = new st_handle();
     st::Model& M = h->model;
@@ -68,6 +67,7 @@ int st_create(const st_problem* pr, st_handle** out) {
     M.block_groups.assign(pr->block_groups, pr->block_groups + pr->n_blocks);
     M.res_is_ref.assign(pr->res_is_ref, pr->res_is_ref + pr->n_res);
     M.keep_H = pr->keep_H != 0;
+    M.limited = pr->limited_tree != 0;
     M.device = pr->device;
     if (pr->smem_panel_bytes > 0) M.smem_budget = (size_t)pr->smem_panel_bytes;
     M.theta[0].assign(pr->theta, pr->theta + pr->n_theta);
@@ -80,6 +80,7 @@ int st_create(const st_problem* pr, st_handle** out) {
     if (pr->partition && pr->partition->nranks > 1) {
       const st_partition& pt = *pr->partition;
       if (pt.rank < 0 || pt.rank >= pt.nranks) { g_create_error = "partition: bad rank"; delete h; return ST_ERR_INVALID; }
+      if (M.limited) { g_create_error = "limited_tree = TRUE cannot be combined with a partition"; delete h; return ST_ERR_UNSUPPORTED; }
       M.part = true;
       M.rank = pt.rank; M.nranks = pt.nranks; M.n_top_levels = pt.n_top_levels;
       M.rng_row_offset = pt.rng_row_offset; M.n_global_rows = pt.n_global_rows;

@@ -102,7 +102,9 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
     for (int a = tid; a < m; a += nth) {
       double s = 0;
       for (int r = a; r < m; r++) s = fma(RiS[r * rsm + a], gw[r], s);
-      for (int c = 0; c < nch; c++) s += V[(c < 16 ? c_voff[c] : T.voff[ch[c]]) + P + a];
+      // a child's vector holds its messages by ancestor column; this block's own columns start at P there (its parent set
+      // is this block's chain plus this block) — or at 0 in a limited tree, where the parent set is this block alone
+      for (int c = 0; c < nch; c++) s += V[(c < 16 ? c_voff[c] : T.voff[ch[c]]) + (T.limited ? 0 : P) + a];
       s += tausq_inv[T.mvq[row0 + a]] * (T.y[row0 + a] - xb[row0 + a]);
       smu[a] = s;
       if (probe_smu) probe_smu[row0 + a] = s;
@@ -215,7 +217,8 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
     for (; r + 1 < m; r += 2) { s0 = fma(g[(size_t)r * rsj], vj[r], s0); s1 = fma(g[(size_t)(r + 1) * rsj], vj[r + 1], s1); }
     if (r < m) s0 = fma(g[(size_t)r * rsj], vj[r], s0);
     double s = s0 + s1;
-    for (int c = 0; c < nch; c++) s += V[(c < 16 ? c_voff[c] : T.voff[ch[c]]) + e];
+    if (!T.limited)  // (limited trees: the children's messages stop at this block)
+      for (int c = 0; c < nch; c++) s += V[(c < 16 ? c_voff[c] : T.voff[ch[c]]) + e];
     Vd[e] = s;
   }
 }
@@ -270,7 +273,7 @@ gram_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ U, doubl
   const long long so = T.soff[sd];
   const int ntile = k + (so >= 0 ? 1 : 0);  // the block's own tile exists only through its children
   if (tid <= k) {
-    t_po[tid] = (tid < k) ? T.chain_poff[coff + tid] : P;
+    t_po[tid] = (tid < k) ? T.chain_poff[coff + tid] : (T.limited ? 0 : P);  // where the children's rows hold this block's columns
     t_m[tid] = (tid < k) ? T.m[T.chain[coff + tid]] : m;
     t_uo[tid] = (tid < k) ? T.chain_uoff[coff + tid] : 0;
   }
@@ -292,7 +295,8 @@ gram_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ U, doubl
   if (ctab)
     for (int e = tid; e < nch * ntile; e += nth) {
       const int c = e / ntile, jj = e - c * ntile, cc = ch[c];
-      s_cu[e] = T.ufused[cc] ? -1 : T.uoff[cc] + T.chain_uoff[T.chain_off[cc] + jj];
+      // (limited trees: a child carries one tile, this block's; nothing is passed through to the ancestors)
+      s_cu[e] = (T.ufused[cc] || (T.limited && jj < k)) ? -1 : T.uoff[cc] + T.chain_uoff[T.chain_off[cc] + (T.limited ? 0 : jj)];
     }
   __syncthreads();
   const int nitems = t_item0[ntile], nrows = s_rows;
@@ -329,7 +333,7 @@ gram_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ U, doubl
             const int cc = ch[c];
             if (!T.ufused[cc]) continue;
             const int mc = T.m[cc];
-            if (r < mc) { s_rowoff[rr] = T.goff[cc] + (long long)r * T.gs[cc]; s_rowncol[rr] = P + m; break; }
+            if (r < mc) { s_rowoff[rr] = T.goff[cc] + (long long)r * T.gs[cc]; s_rowncol[rr] = T.limited ? m : P + m; break; }
             r -= mc;
           }
         }
@@ -349,7 +353,8 @@ gram_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ U, doubl
       __syncthreads();
       if (act) {
         const int rb = (j == k) ? max(0, m - rbase) : 0;  // the block's own rows carry no entries of its own tile
-        for (int rr = rb; rr < nr; rr++) {
+        const int re = (T.limited && j < k) ? min(nr, max(0, m - rbase)) : nr;  // limited: the children's rows carry no ancestor tiles
+        for (int rr = rb; rr < re; rr++) {
           const double* x = stage + (size_t)rr * ldx;
           double av[5], bv[5];
 #pragma unroll
@@ -387,7 +392,7 @@ gram_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ U, doubl
     } else {
       for (int c = 0; c < nch; c++) {
         const int cc = ch[c];
-        if (!T.ufused[cc]) v += U[T.uoff[cc] + T.chain_uoff[T.chain_off[cc] + j] + e];
+        if (!T.ufused[cc] && !(T.limited && j < k)) v += U[T.uoff[cc] + T.chain_uoff[T.chain_off[cc] + (T.limited ? 0 : j)] + e];
       }
     }
     if (j < k) Ud[t_uo[j] + e] = v; else SigS[so + e] = v;

@@ -199,6 +199,10 @@ int Model::build_layout(std::string& e) {
     const int lp = (int)parents.back(u);
     if (slot_of_block[lp] < 0 || block_ct_obs[lp] == 0) { why = "a parent is not an observed block of a shallower level"; return false; }
     if (!block_is_reference[lp]) { why = "a parent is not a reference block"; return false; }
+    if (limited) {  // limited trees: the direct parent only (make_edges_limited, tree_dep.cpp:133-186)
+      if (np != 1) { why = "limited_tree = TRUE: a block lists more than one parent (use make_edges_limited)"; return false; }
+      return true;
+    }
     if (parents.len(lp) != np - 1 || !std::equal(parents.row(lp), parents.row(lp) + (np - 1), parents.row(u))) {
       why = "parent set is not the ancestor chain of its last parent";
       return false;
@@ -275,6 +279,7 @@ int Model::build_layout(std::string& e) {
   // chains and storage offsets
   h_chain.clear(); h_chain_poff.clear(); h_chain_uoff.clear();
   h_gs.assign(n_nodes, 0);
+  h_moff.assign(n_nodes, -1);
   h_goff.assign(n_nodes, 0); h_rioff.assign(n_nodes, 0); h_voff.assign(n_nodes, 0); h_uoff.assign(n_nodes, 0); h_soff.assign(n_nodes, -1);
   g_total = ri_total = v_total = u_total = s_total = gpred_total = 0;
   std::vector<long long> h_usize(n_nodes, 0);
@@ -290,6 +295,7 @@ int Model::build_layout(std::string& e) {
     const bool pred = s >= n_obs_nodes;
     const int kk = (int)parents.len(u);
     if (kk > 32) { e = "ancestor chains longer than 32 are not supported"; return 4; }
+    if (limited && kk > 1) { e = "limited_tree = TRUE: a block lists more than one parent (use make_edges_limited)"; return 1; }
     if (!pred && poff_check(u) > kLlwMaxP) { e = "a parent set larger than 1024 rows is not supported"; return 4; }
     h_k[s] = kk;
     h_chain_off[s] = (int)h_chain.size();
@@ -311,6 +317,7 @@ int Model::build_layout(std::string& e) {
     if (!pred) {
       isref[s] = block_is_reference[u] ? 1 : 0;
       h_goff[s] = g_total; g_total += boff;
+      if (limited && isref[s]) { h_moff[s] = g_total; g_total += (long long)h_m[s] * ((h_m[s] + 3) & ~3); }  // marginal factor rows
       h_rioff[s] = ri_total; ri_total += isref[s] ? (long long)h_m[s] * tile_rs(h_m[s]) : pad2(h_m[s]);
       h_voff[s] = v_total; v_total += pad2(poff);
       h_usize[s] = uo;
@@ -353,7 +360,7 @@ int Model::build_layout(std::string& e) {
           uo += pad2((long long)h_m[a] * h_m[a]);
         }
         h_P.push_back(poff);
-        h_goff.push_back(0); h_rioff.push_back(0); h_soff.push_back(-1); h_gs.push_back(0);
+        h_goff.push_back(0); h_rioff.push_back(0); h_soff.push_back(-1); h_gs.push_back(0); h_moff.push_back(-1);
         h_voff.push_back(v_total); v_total += pad2(poff);
         h_uoff.push_back(0); h_usize.push_back(uo);
         h_front_pseudo.push_back(ps); h_front_c0.push_back(c0); h_front_c1.push_back(c);
@@ -402,10 +409,10 @@ int Model::build_layout(std::string& e) {
     int ncols = xcol, sumRb = 0, maxmd = 1;
     for (int d = 0; d < nn; d++) {
       ncols += h_m[s + d];
-      if (mode == 0) sumRb += rb_doubles(h_m[s + d]);
+      if (mode == 0) sumRb += (limited ? 2 : 1) * rb_doubles(h_m[s + d]);  // limited trees factorise K_uu as well
       maxmd = std::max(maxmd, h_m[s + d]);
     }
-    return build_plan(h_P[s], ncols, sumRb, maxmd, ns, mode == 0 ? std::min(nn, kBuildMaxThreads / 32) : 0, nwarps);
+    return build_plan(h_P[s], ncols, sumRb, maxmd, ns, mode == 0 ? std::min((limited ? 2 : 1) * nn, kBuildMaxThreads / 32) : 0, nwarps);
   };
   auto make_groups = [&](LevelInfo& L, int mode) -> int {
     L.grp0 = (int)h_grp_slot0.size();
@@ -581,6 +588,8 @@ int Model::upload(std::string& e) {
   ST_CUDA(dev_upload(h_chain_off, d_choff, owned), "upload chain_off");
   ST_CUDA(dev_upload(h_goff, d_goff, owned), "upload goff");
   ST_CUDA(dev_upload(h_gs, d_gs, owned), "upload gs");
+  long long* d_moff;
+  ST_CUDA(dev_upload(h_moff, d_moff, owned), "upload moff");
   ST_CUDA(dev_upload(h_rioff, d_rioff, owned), "upload rioff");
   ST_CUDA(dev_upload(h_voff, d_voff, owned), "upload voff");
   ST_CUDA(dev_upload(h_uoff, d_uoff, owned), "upload uoff");
@@ -601,7 +610,7 @@ int Model::upload(std::string& e) {
   ST_CUDA(dev_upload(h_front_ulen, d_front_ulen, owned), "upload frontier");
   dt.cx = d_cx; dt.cy = d_cy; dt.mvq = d_mvq; dt.y = d_y; dt.X = d_X;
   dt.m = d_m; dt.row0 = d_row0; dt.isref = d_isref; dt.k = d_k; dt.P = d_P; dt.lastpar = d_lastpar; dt.chain_off = d_choff;
-  dt.goff = d_goff; dt.gs = d_gs; dt.rioff = d_rioff; dt.voff = d_voff; dt.uoff = d_uoff; dt.soff = d_soff;
+  dt.goff = d_goff; dt.gs = d_gs; dt.moff = d_moff; dt.limited = limited ? 1 : 0; dt.rioff = d_rioff; dt.voff = d_voff; dt.uoff = d_uoff; dt.soff = d_soff;
   dt.child_ptr = d_cptr; dt.child_idx = d_cidx; dt.ufused = d_ufused;
   dt.chain = d_chain; dt.chain_poff = d_cpoff; dt.chain_uoff = d_cuoff;
   for (int s = 0; s < 2; s++) {

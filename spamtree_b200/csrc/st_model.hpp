@@ -44,6 +44,8 @@ struct DevTree {
   const int* chain_off;  // into the per-chain-entry arrays
   const long long* goff; // G / H storage offset (doubles) of the block's row block
   const int* gs;         // row stride of that row block: [ G (P) | -Ri (m, reference blocks) | 0 ], g_stride()
+  const long long* moff; // limited trees: offset (in the G array) of the block's MARGINAL factor rows [ -chol(K_uu)^-1 | 0 ], stride (m+3)&~3; -1: none
+  int limited;           // 1: limited tree (children stream the parent's marginal factor, spamtree_model.cpp:901-903)
   const long long* rioff;// Ri storage offset (doubles)
   const long long* voff; // message vector offset (P doubles)
   const long long* uoff; // message Gram offset (tiles m_a x m_a per ancestor); unused when ufused
@@ -99,6 +101,7 @@ class Model {
   dvec block_names, block_groups;
   ivec res_is_ref;
   bool keep_H = true;
+  bool limited = false;  // limited_tree (spamtree_model.cpp:67)
   int device = 0;
   size_t smem_budget = 227 * 1024 - 5 * 1024;  // dynamic; the kernel also holds ~4.5 KB of static shared memory (227 KB per CTA)
   int force_build_ns = 0;    // development override of the ring depth (ST_BUILD_NS)
@@ -118,7 +121,7 @@ class Model {
   int n_obs_nodes = 0, n_nodes = 0;
   std::vector<int> slot_of_block, block_of_slot;
   std::vector<int> h_m, h_row0, h_k, h_P, h_chain_off, h_chain, h_chain_poff, h_chain_uoff, h_lastpar, h_gs;
-  std::vector<long long> h_goff, h_rioff, h_voff, h_uoff, h_soff;
+  std::vector<long long> h_goff, h_rioff, h_voff, h_uoff, h_soff, h_moff;
   std::vector<int> h_child_ptr, h_child_idx, h_ufused;
   ivec perm;   // node-major row -> boundary row
   ivec iperm;  // boundary row -> node-major row

@@ -15,16 +15,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import common  # noqa: E402
 from oracle import ref  # noqa: E402
 
-CASES = [(1, 625), (3, 900), (2, 1200)]   # (q, n): README shape (univariate, n = 625), q = 3 imbalanced, q = 2
+CASES = [(1, 625, False), (3, 900, False), (2, 1200, False), (3, 1100, True)]   # (q, n, limited_tree): README shape, q = 3, q = 2, a limited tree
 
 
-def one(q, n):
-    pb = common.make_problem(q, n)
+def one(q, n, limited):
+    pb = common.make_problem(q, n, limited=limited)
     d, t = pb["d"], pb["tree"]
-    rm = ref.RefModel(d["y"], d["X"], d["coords"], d["mv_id"], t["res_is_ref"], pb["csr"], False, t["block_names"], t["block_groups"],
+    rm = ref.RefModel(d["y"], d["X"], d["coords"], d["mv_id"], t["res_is_ref"], pb["csr"], limited, t["block_names"], t["block_groups"],
                       pb["beta"], pb["theta"], pb["tausq"])
     rng = np.random.default_rng(100 + q)
-    out = {"q": q, "n": n, "blocking": t["blocking"], "theta": pb["theta"]}
+    out = {"q": q, "n": n, "limited": int(limited), "blocking": t["blocking"], "theta": pb["theta"]}
     nb = t["n_blocks"]
     # ---- integer bookkeeping of the constructor (spamtree_model.cpp:194-420)
     for name in ["blocks_not_empty", "blocks_predicting", "block_is_reference", "block_ct_obs"]:
@@ -65,12 +65,13 @@ def one(q, n):
     rm.deal_with_w(z3)
     out.update(theta2=th2, loglik2=ll2, logdet2=ld2, z3=z3, w_sweep3=rm.w, llw_sweep3=rm.get_loglik_w(0)[0])
     rm.close()
-    np.savez_compressed(os.path.join(HERE, f"ref_q{q}_n{n}.npz"), **out)
-    print(f"ref_q{q}_n{n}.npz: {len(out)} arrays, loglik {ll:.12g}")
+    name = f"ref_q{q}_n{n}" + ("_limited" if limited else "") + ".npz"
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(f"{name}: {len(out)} arrays, loglik {ll:.12g}")
 
 
 if __name__ == "__main__":
     if not ref.available():
         raise SystemExit("oracle/_ref/libspamtree_ref.so is missing and /root/reference is not here to build it")
-    for q, n in CASES:
-        one(q, n)
+    for q, n, limited in CASES:
+        one(q, n, limited)

@@ -15,7 +15,7 @@ import common
 from common import relerr
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-FILES = sorted(glob.glob(os.path.join(G, "ref_q*_n*.npz")))
+FILES = sorted(glob.glob(os.path.join(G, "ref_q*_n*.npz")))   # *_limited.npz: limited_tree = TRUE
 
 
 def _tol(q):
@@ -23,7 +23,7 @@ def _tol(q):
 
 
 def _problem(g):
-    pb = common.make_problem(int(g["q"]), int(g["n"]))
+    pb = common.make_problem(int(g["q"]), int(g["n"]), limited=bool(int(g["limited"])) if "limited" in g.files else False)
     assert np.array_equal(pb["tree"]["blocking"], g["blocking"]), "the deterministic tree builder changed: regenerate the golden files"
     return pb
 
@@ -87,4 +87,4 @@ def test_cuda_against_reference_outputs(path):
 
 
 def test_fixtures_are_present():
-    assert len(FILES) >= 3
+    assert len(FILES) >= 4 and any(f.endswith("_limited.npz") for f in FILES)

@@ -11,13 +11,14 @@ from dense_twin import Twin
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
 
-CASES = [(1, 625, .1), (1, 2500, .1), (2, 2000, .1), (3, 3000, .1), (5, 4000, .15), (3, 1200, 0.0), (1, 30, .1), (2, 9, 0.0)]
+CASES = [(1, 625, .1), (1, 2500, .1), (2, 2000, .1), (3, 3000, .1), (5, 4000, .15), (3, 1200, 0.0), (1, 30, .1), (2, 9, 0.0),
+         (3, 3000, .1, True), (1, 625, .1, True)]   # 4th entry: limited_tree = TRUE (make_edges_limited, spamtree_model.cpp:901-903)
 
 
-@pytest.fixture(scope="module", params=CASES, ids=lambda c: f"q{c[0]}_n{c[1]}_miss{c[2]}")
+@pytest.fixture(scope="module", params=CASES, ids=lambda c: f"q{c[0]}_n{c[1]}_miss{c[2]}" + ("_limited" if len(c) > 3 and c[3] else ""))
 def pair(request):
-    q, n, missing = request.param
-    pb = common.make_problem(q, n, missing=missing)
+    q, n, missing = request.param[:3]
+    pb = common.make_problem(q, n, missing=missing, limited=len(request.param) > 3 and request.param[3])
     gm, om = common.product_model(pb), common.oracle_model(pb)
     w0 = np.random.default_rng(7).standard_normal(n) * .5
     gm.w = w0
