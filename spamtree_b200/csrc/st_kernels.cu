@@ -60,6 +60,18 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
   }
   if (tid >= 32 && tid < 32 + min(nch, 16)) c_voff[tid - 32] = T.voff[ch[tid - 32]];
   for (int e = tid; e < msq; e += nth) RiS[e] = Rig[e];
+  // loads that depend on nothing computed here are issued now, so that their latency hides under the phases below:
+  // the children's Gram sum (into Sig), and per row tausq_inv (wn), tausq_inv (y - XB) (smu) and the normal draw (rr)
+  if (REF) {
+    const long long so0 = T.soff[sd];
+    for (int e = tid; e < m * m; e += nth) Sig[e] = (so0 >= 0) ? SigS[so0 + e] : 0.0;
+  }
+  for (int a = tid; a < m; a += nth) {
+    const double tq = tausq_inv[T.mvq[row0 + a]];
+    wn[a] = tq;
+    smu[a] = tq * (T.y[row0 + a] - xb[row0 + a]);
+    rr[a] = z[row0 + a];
+  }
   __syncthreads();
   for (int e = tid; e < P; e += nth) {
     int j = 0;
@@ -88,13 +100,12 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
   const double* gw = gwj + (size_t)k * m;
   if (REF) {
     // Sigi_tot = prec + sum_children + diag(tausq_inv)  (:1044-1051), prec = Ri'Ri (:912)
-    const long long so = T.soff[sd];
     for (int e = tid; e < m * m; e += nth) {
       const int a = e / m, b = e - a * m;
       double s = 0;
       for (int r = max(a, b); r < m; r++) s = fma(RiS[r * rsm + a], RiS[r * rsm + b], s);
-      if (so >= 0) s += SigS[so + e];
-      if (a == b) s += tausq_inv[T.mvq[row0 + a]];
+      s += Sig[e];  // sum over the children, prefetched above
+      if (a == b) s += wn[a];
       Sig[e] = s;
       if (probe_sig) probe_sig[T.rioff[sd] + e] = s;
     }
@@ -106,7 +117,7 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
       // a child's vector holds its messages by ancestor column; this block's own columns start at P there (its parent set
       // is this block's chain plus this block) — or at 0 in a limited tree, where the parent set is this block alone
       for (int c = 0; c < nch; c++) s += V[(c < 16 ? c_voff[c] : T.voff[ch[c]]) + (T.limited ? 0 : P) + a];
-      s += tausq_inv[T.mvq[row0 + a]] * (T.y[row0 + a] - xb[row0 + a]);
+      s += smu[a];  // tausq_inv (y - XB), prefetched above
       smu[a] = s;
       if (probe_smu) probe_smu[row0 + a] = s;
     }
@@ -144,7 +155,7 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
         }
         __syncwarp();
         if (okc) {
-          double y = (lane < m) ? b + z[row0 + lane] : 0.0;
+          double y = (lane < m) ? b + rr[lane] : 0.0;  // z, prefetched above
           for (int j = m - 1; j >= 0; j--) {
             const double wj = __shfl_sync(0xffffffffu, y * myinv, j);
             if (lane == j) y = wj; else if (lane < j) y = fma(-Sig[j * m + lane], wj, y);
@@ -160,7 +171,7 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
           for (int r = c + 1 + lane; r < m; r += 32) smu[r] -= Sig[r * m + c] * xc;
         }
         __syncwarp();
-        for (int r = lane; r < m; r += 32) smu[r] += z[row0 + r];
+        for (int r = lane; r < m; r += 32) smu[r] += rr[r];
         for (int c = m - 1; c >= 0; c--) {  // backward: L' w = x
           __syncwarp();
           const double xc = smu[c] / Sig[c * m + c];
@@ -188,15 +199,14 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
     asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int a = tid; a < m; a += nth) {
       const double ri = RiS[a], prec = ri * ri;
-      const double tsqi = tausq_inv[T.mvq[row0 + a]];
-      const double sig = prec + tsqi;                                             // :1123
-      const double sm = ri * gw[a] + tsqi * (T.y[row0 + a] - xb[row0 + a]);       // :1125-1127
+      const double sig = prec + wn[a];                                            // :1123 (tausq_inv prefetched into wn)
+      const double sm = ri * gw[a] + smu[a];                                      // :1125-1127
       if (probe_sig) probe_sig[T.rioff[sd] + a] = sig;
       if (probe_smu) probe_smu[row0 + a] = sm;
       double wa;
       if (sig > 0.0 && isfinite(sig)) {
         const double sc = 1.0 / sqrt(sig);
-        wa = sc * sc * sm + sc * z[row0 + a];                                     // :1139-1140
+        wa = sc * sc * sm + sc * rr[a];                                           // :1139-1140 (z prefetched into rr)
         w[row0 + a] = wa;
       } else {
         atomicAdd(fail, 1);
