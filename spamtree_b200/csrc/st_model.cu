@@ -920,6 +920,7 @@ int Model::refresh_grams() {
 }
 
 int Model::gibbs_launch_only() {
+  stats_valid_mode_ = -1;  // w is about to change
   { int rc = complete_slot(cur); if (rc) return rc; }
   if (gram_stale) { int rc = refresh_grams(); if (rc) return rc; }
   for (int g = (int)levels.size() - 1; g >= 0; g--) {
@@ -1012,6 +1013,7 @@ int Model::predict(bool theta_changed) {
     }
     pred_H_valid = true;
   }
+  stats_valid_mode_ = -1;  // w of the prediction rows changes
   ST_CUDA(launch_predict_sample(dt, pred_level.slot0, pred_level.nslots, d_Hpred, d_sdpred, d_w, d_z, stream), "predict_sample_kernel");
   n_launches++;
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
@@ -1021,6 +1023,8 @@ int Model::predict(bool theta_changed) {
 int Model::rowstats(bool faithful_index) {
   if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   const int mode = faithful_index ? 1 : 0;
+  // the tausq and the beta step of one iteration read the same statistics (neither w nor XB changes in between)
+  if (stats_valid_mode_ == mode) return 0;
   if (beta_widx_mode != mode) {
     const std::vector<int>& src = faithful_index ? beta_widx_faithful : beta_widx_plain;
     ST_CUDA(cudaMemcpyAsync(d_obs_widx, src.data(), n_all * sizeof(int), cudaMemcpyHostToDevice, stream), "H2D widx");
@@ -1035,6 +1039,7 @@ int Model::rowstats(bool faithful_index) {
   }
   ST_CUDA(cudaMemcpyAsync(h_scalars + 8, d_scalars + 8, q * (p + 1) * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H stats");
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  stats_valid_mode_ = mode;
   return 0;
 }
 
@@ -1083,6 +1088,7 @@ int Model::gibbs_sample_beta(const double* zb, bool faithful_index) {
     for (int a = 0; a < p; a++) Bcoeff[a + (size_t)j * p] = bmu[a] + sz[a];
   }
   ST_CUDA(cudaMemcpyAsync(d_bcoeff, Bcoeff.data(), (size_t)p * q * sizeof(double), cudaMemcpyHostToDevice, stream), "H2D beta");
+  stats_valid_mode_ = -1;  // XB changes
   ST_CUDA(launch_xb(dt, n_all, p, d_bcoeff, d_xb, stream), "xb_kernel");
   n_launches++;
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
@@ -1096,7 +1102,7 @@ int Model::get_w(double* out) {
   for (int64_t i = 0; i < n_all; i++) out[perm[i]] = h_stage[i];
   return 0;
 }
-int Model::set_w(const double* in) { return upload_rows(in, d_w); }
+int Model::set_w(const double* in) { stats_valid_mode_ = -1; return upload_rows(in, d_w); }
 
 int Model::save_begin(double* host_base, size_t bytes) {
   if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }

@@ -227,6 +227,7 @@ class Model {
   int cuda_fail(cudaError_t e, const char* what);
   std::vector<int> beta_widx_faithful, beta_widx_plain;
   int beta_widx_mode = -1;
+  int stats_valid_mode_ = -1;  // row-index mode for which h_scalars holds the current beta / tausq statistics (-1: stale)
   int* d_obs_widx = nullptr;
 };
 
