@@ -123,6 +123,68 @@ __device__ __forceinline__ bool chol_var(double* R, int m, int rs, double* cb, d
   return ok;
 }
 
+// inverse of the lower-triangular L (in R, stride rs, rows padded to 32 with zeros) in place; dv = 1 / diag
+// I0: as in st_build.cu (row r of L^-1 by forward substitution, lane = column)
+// I1: right-looking with rotating accumulators: lane c keeps the not-yet-final entries of column c of L^-1 in registers,
+//     acc[0] is row k; once x_k = acc[0] / L_kk is final, rows k+1.. receive -L[r][k] x_k (column k of L by broadcast loads)
+template <int IV>
+__device__ __forceinline__ void inv_var(double* R, int m, int rs, const double* dv, int lane) {
+  if (IV == 0) {
+    for (int r = 0; r < m; r++) {
+      const double* Lr = R + r * rs;
+      double s0 = (r == lane) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int kx = 0;
+      for (; kx + 3 < r; kx += 4) {
+        s0 = fma(-Lr[kx], R[kx * rs + lane], s0);
+        s1 = fma(-Lr[kx + 1], R[(kx + 1) * rs + lane], s1);
+        s2 = fma(-Lr[kx + 2], R[(kx + 2) * rs + lane], s2);
+        s3 = fma(-Lr[kx + 3], R[(kx + 3) * rs + lane], s3);
+      }
+      for (; kx < r; kx++) s0 = fma(-Lr[kx], R[kx * rs + lane], s0);
+      const double xr = ((s0 + s1) + (s2 + s3)) * dv[r];
+      __syncwarp();
+      if (lane < m) R[r * rs + lane] = (lane <= r) ? xr : 0.0;
+      __syncwarp();
+    }
+  } else {
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) acc[i] = (i == lane) ? 1.0 : 0.0;
+    const int rmax = ((m + 7) & ~7) - 1;  // last row that exists in R
+    for (int k = 0; k < m; k++) {
+      const double x = acc[0] * dv[k];
+      const double* col = R + k;  // column k of L: L[r][k] at col[r * rs]
+#pragma unroll
+      for (int i = 0; i < 31; i++) acc[i] = fma(-col[min(k + 1 + i, rmax) * rs], x, acc[i + 1]);
+      acc[31] = 0.0;
+      __syncwarp();  // every lane has read column k of L (row k of L is dead: its later columns are never read again)
+      if (lane < m) R[k * rs + lane] = x;  // zero above the diagonal (lanes > k never received a contribution)
+    }
+    __syncwarp();
+  }
+}
+
+template <int IV>
+__global__ void bench_inv(const double* A, double* out, long long* cyc, int m, int rs, int reps) {
+  __shared__ double R[32 * 36], cb[128], dv[32];
+  const int lane = threadIdx.x;
+  long long tot = 0;
+  for (int r = 0; r < reps; r++) {
+    for (int e = lane; e < 32 * rs; e += 32) R[e] = 0.0;
+    __syncwarp();
+    for (int e = lane; e < m * m; e += 32) { const int i = e / m, j = e % m; R[i * rs + j] = A[e]; }
+    __syncwarp();
+    chol_var<0>(R, m, rs, cb, dv, lane);
+    __syncwarp();
+    const long long t0 = clock64();
+    inv_var<IV>(R, m, rs, dv, lane);
+    __syncwarp();
+    tot += clock64() - t0;
+  }
+  if (lane == 0) cyc[blockIdx.x] = tot;
+  if (blockIdx.x == 0) for (int e = lane; e < m * m; e += 32) { const int i = e / m, j = e % m; out[e] = (j <= i) ? R[i * rs + j] : 0.0; }
+}
+
 template <int VAR>
 __global__ void bench(const double* A, double* out, long long* cyc, int m, int rs, int reps) {
   __shared__ double R[32 * 36], cb[128], dv[32];
@@ -194,5 +256,28 @@ int main() {
   run(4, "V4 look-ahead pivot, smem broadcast");
   run(5, "V5 look-ahead pivot, shuffle broadcast");
   run(6, "V6 smem broadcast, remaining columns by 8");
+  // inverse variants: compare with the host inverse of L
+  std::vector<double> X(m * m, 0.0);
+  for (int c = 0; c < m; c++)
+    for (int r = c; r < m; r++) {
+      double sacc = (r == c) ? 1.0 : 0.0;
+      for (int k = c; k < r; k++) sacc -= L[r * m + k] * X[k * m + c];
+      X[r * m + c] = sacc / L[r * m + r];
+    }
+  auto run_inv = [&](int iv, const char* name) {
+    for (int it = 0; it < 2; it++) {
+      if (iv == 0) bench_inv<0><<<nblk, 32>>>(dA, dO, dC, m, rs, reps); else bench_inv<1><<<nblk, 32>>>(dA, dO, dC, m, rs, reps);
+      cudaDeviceSynchronize();
+    }
+    cudaMemcpy(O.data(), dO, m * m * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(C.data(), dC, nblk * 8, cudaMemcpyDeviceToHost);
+    double err = 0, cyc = 0;
+    for (int e = 0; e < m * m; e++) err = fmax(err, fabs(O[e] - X[e]));
+    for (auto c : C) cyc += (double)c;
+    printf("%-46s %8.0f cycles / inverse        %6.1f / row     max |X - X_ref| = %.2e  (%s)\n", name, cyc / nblk / reps, cyc / nblk / reps / m, err,
+           cudaGetErrorString(cudaGetLastError()));
+  };
+  run_inv(0, "I0 row-wise forward substitution (current)");
+  run_inv(1, "I1 right-looking, rotating accumulators");
   return 0;
 }
