@@ -88,7 +88,7 @@ __device__ __forceinline__ bool warp_chol_inv32(double* R, int m, int rs, double
 // In phases 1 and 2 the panel has one extra column that carries w_pa, so that v = L^-1 w_pa and with it
 // H w_pa = Z'v come out of the forward sweep.
 template <int MODE>
-__global__ void __launch_bounds__(kBuildMaxThreads)
+__global__ void __launch_bounds__(kBuildMaxThreads, 1)
 build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __restrict__ outH, double* __restrict__ outRi,
                    const int* __restrict__ grp_slot0, const int* __restrict__ grp_nn, const double* __restrict__ w,
                    CovTab tab, int* __restrict__ fail, int ns, int phase, unsigned long long* __restrict__ prof) {
