@@ -639,11 +639,10 @@ static cudaError_t launch_build_t(const DevTree& T, const DevSlot& S, double* ou
                                   const int* grp_slot0, const int* grp_nn, int ngrp, const double* w, const CovTab& tab,
                                   int* fail, int ns, int phase, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof, bool pdl) {
   auto kern = build_level_kernel<MODE>;
-  static size_t configured[3] = {0, 0, 0};
-  if (smem > configured[MODE]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemOptIn optin;
+  {
+    cudaError_t e = ensure_dynamic_smem(kern, smem, optin);
     if (e != cudaSuccess) return e;
-    configured[MODE] = smem;
   }
   if (!pdl) {
     kern<<<ngrp, nthreads, smem, st>>>(T, S, outG, outH, outRi, grp_slot0, grp_nn, w, tab, fail, ns, phase, prof);

@@ -6,6 +6,8 @@
 
 #include "../../include/spamtree_b200.h"
 #include "st_kernels.cuh"
+#include <cuda_runtime.h>
+
 #include "st_model.hpp"
 #include "st_tree.hpp"
 
@@ -41,6 +43,12 @@ static thread_local std::string g_create_error;
 static void csr_assign(st::CSR& c, const int64_t* ptr, const int64_t* idx, int64_t n) {
   c.ptr.assign(ptr, ptr + n + 1);
   c.idx.assign(idx, idx + ptr[n]);
+}
+
+// every entry point that touches device state makes the handle's GPU the calling thread's current device first (a host may
+// hold handles on several GPUs; streams, launches and the shared-memory opt-in are all per device)
+static inline void activate(st_handle* h) {
+  if (h && h->model.device >= 0) cudaSetDevice(h->model.device);
 }
 
 extern "C" {
@@ -106,7 +114,10 @@ int st_create(const st_problem* pr, st_handle** out) {
   return ST_ERR_INVALID;
 }
 
-void st_destroy(st_handle* h) { delete h; }
+void st_destroy(st_handle* h) {
+  activate(h);
+  delete h;
+}
 
 const char* st_last_error(const st_handle* h) { return h ? h->model.err.c_str() : g_create_error.c_str(); }
 
@@ -117,36 +128,43 @@ int st_theta_update(st_handle* h, int slot, const double* theta) {
 }
 int st_get_loglik_comps_w(st_handle* h, int slot, double* out3) {
   if (!h || !out3) return ST_ERR_INVALID;
+  activate(h);
   ST_GUARD_BEGIN return h->model.get_loglik_comps_w(slot, out3);
   ST_GUARD_END(h)
 }
 int st_deal_with_w(st_handle* h, const double* z, uint64_t seed) {
   if (!h) return ST_ERR_INVALID;
+  activate(h);
   ST_GUARD_BEGIN return h->model.deal_with_w(z, seed);
   ST_GUARD_END(h)
 }
 int st_get_loglik_w(st_handle* h, int slot, double* out2) {
   if (!h || !out2) return ST_ERR_INVALID;
+  activate(h);
   ST_GUARD_BEGIN return h->model.get_loglik_w(slot, out2);
   ST_GUARD_END(h)
 }
 int st_accept_make_change(st_handle* h) {
   if (!h) return ST_ERR_INVALID;
+  activate(h);
   h->model.accept_make_change();
   return ST_OK;
 }
 int st_predict(st_handle* h, int theta_changed) {
   if (!h) return ST_ERR_INVALID;
+  activate(h);
   ST_GUARD_BEGIN return h->model.predict(theta_changed != 0);
   ST_GUARD_END(h)
 }
 int st_gibbs_sample_beta(st_handle* h, const double* zb, int faithful_index) {
   if (!h) return ST_ERR_INVALID;
+  activate(h);
   ST_GUARD_BEGIN return h->model.gibbs_sample_beta(zb, faithful_index != 0);
   ST_GUARD_END(h)
 }
 int st_gibbs_sample_tausq(st_handle* h, const double* fixed) {
   if (!h) return ST_ERR_INVALID;
+  activate(h);
   ST_GUARD_BEGIN return h->model.gibbs_sample_tausq(fixed);
   ST_GUARD_END(h)
 }
@@ -157,16 +175,19 @@ int st_seed(st_handle* h, uint64_t seed) {
 }
 int st_get_w(st_handle* h, double* w_out) {
   if (!h || !w_out) return ST_ERR_INVALID;
+  activate(h);
   ST_GUARD_BEGIN return h->model.get_w(w_out);
   ST_GUARD_END(h)
 }
 int st_set_w(st_handle* h, const double* w_in) {
   if (!h || !w_in) return ST_ERR_INVALID;
+  activate(h);
   ST_GUARD_BEGIN return h->model.set_w(w_in);
   ST_GUARD_END(h)
 }
 int st_get_params(st_handle* h, double* Bcoeff, double* tausq_inv, double* XB) {
   if (!h) return ST_ERR_INVALID;
+  activate(h);
   ST_GUARD_BEGIN
   st::Model& M = h->model;
   if (Bcoeff) std::copy(M.Bcoeff.begin(), M.Bcoeff.end(), Bcoeff);
@@ -177,11 +198,13 @@ int st_get_params(st_handle* h, double* Bcoeff, double* tausq_inv, double* XB) {
 }
 int st_set_tausq_inv(st_handle* h, const double* t) {
   if (!h || !t) return ST_ERR_INVALID;
+  activate(h);
   ST_GUARD_BEGIN return h->model.set_tausq_inv(t);
   ST_GUARD_END(h)
 }
 int st_get_node_state(st_handle* h, int slot, int u, const char* which, double* out, int64_t cap, int64_t* count) {
   if (!h || !which || !count) return ST_ERR_INVALID;
+  activate(h);
   ST_GUARD_BEGIN return h->model.get_node_state(slot, u, which, out, cap, count);
   ST_GUARD_END(h)
 }
@@ -192,11 +215,13 @@ int st_get_index(st_handle* h, const char* which, int u, int c, int64_t* out, in
 }
 int st_mcmc_run(st_handle* h, const st_mcmc_opts* opts, st_mcmc_out* out) {
   if (!h || !opts || !out || !opts->set_unif_bounds || !opts->mcmcsd || opts->keep < 0 || opts->thin < 1) return ST_ERR_INVALID;
+  activate(h);
   ST_GUARD_BEGIN return st::mcmc_run(h->model, *opts, *out);
   ST_GUARD_END(h)
 }
 int st_bench_iteration(st_handle* h, const double* theta_prop, int do_swap, uint64_t seed, double* out3, float* ms_out) {
   if (!h || !theta_prop || !out3) return ST_ERR_INVALID;
+  activate(h);
   ST_GUARD_BEGIN return h->model.bench_iteration(theta_prop, do_swap, seed, out3, ms_out);
   ST_GUARD_END(h)
 }
@@ -209,6 +234,7 @@ int st_nccl_unique_id(unsigned char* out128) {
 }
 int st_attach_nccl(st_handle* h, const unsigned char* id128) {
   if (!h || !id128) return ST_ERR_INVALID;
+  activate(h);
   return h->model.attach_nccl(id128);
 }
 int st_get_counters(st_handle* h, double* out8) {
@@ -219,6 +245,7 @@ int st_get_counters(st_handle* h, double* out8) {
 }
 int st_sync(st_handle* h) {
   if (!h) return ST_ERR_INVALID;
+  activate(h);
   return h->model.sync();
 }
 

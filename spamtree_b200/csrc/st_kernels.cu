@@ -242,12 +242,11 @@ cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlot& S, int slo
                          const double* xb, const double* z, const double* tausq_inv, const double* SigS, double* V,
                          double* probe_sig, double* probe_smu, int* fail, size_t smem, cudaStream_t st, bool pdl) {
   if (nslots <= 0) return cudaSuccess;
-  static size_t configured[2] = {0, 0};
+  static SmemOptIn optin[2];
   auto kern = is_ref ? gibbs_level_kernel<1> : gibbs_level_kernel<0>;
-  if (smem > configured[is_ref ? 1 : 0]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = ensure_dynamic_smem(kern, smem, optin[is_ref ? 1 : 0]);
     if (e != cudaSuccess) return e;
-    configured[is_ref ? 1 : 0] = smem;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nslots);
@@ -417,11 +416,10 @@ cudaError_t launch_gram(const DevTree& T, const DevSlot& S, int slot0, int nslot
                         int ldx, int tile_doubles, cudaStream_t st) {
   if (nslots <= 0) return cudaSuccess;
   const size_t smem = ((size_t)tile_doubles + (size_t)rch * ldx) * sizeof(double);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(gram_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemOptIn optin;
+  {
+    cudaError_t e = ensure_dynamic_smem(gram_level_kernel, smem, optin);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   gram_level_kernel<<<nslots, kGramThreads, smem, st>>>(T, S, slot0, U, SigS, rch, ldx, tile_doubles);
   return cudaGetLastError();
@@ -493,11 +491,10 @@ cudaError_t launch_llw(const DevTree& T, const DevSlot& S, int nslots, const dou
   const int wpb = kLlwThreads / 32;
   maxlen = (maxlen + 1) & ~1;
   const size_t smem = (size_t)wpb * maxlen * sizeof(double);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(llw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemOptIn optin;
+  {
+    cudaError_t e = ensure_dynamic_smem(llw_kernel, smem, optin);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   llw_kernel<<<(nslots + wpb - 1) / wpb, kLlwThreads, smem, st>>>(T, S, nslots, w, maxlen);
   return cudaGetLastError();

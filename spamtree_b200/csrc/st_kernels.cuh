@@ -90,6 +90,22 @@ inline size_t gibbs_smem_bytes(int is_ref, int m, int P, int k) {
   return 8 * (msq + (size_t)P + (size_t)(k + 1) * m + 3 * (size_t)m) + 16;
 }
 
+// Opts a kernel in to `smem` bytes of dynamic shared memory on the CURRENT device if it has not been opted in to at
+// least that much there yet (the attribute is per device; static + dynamic together exceed the default 48 KB long before
+// the dynamic part alone does, so the opt-in is unconditional).  `table` is the caller's per-kernel cache.
+struct SmemOptIn { size_t configured[64] = {}; };
+template <class K>
+inline cudaError_t ensure_dynamic_smem(K kern, size_t smem, SmemOptIn& table) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem <= table.configured[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) table.configured[dev] = smem;
+  return e;
+}
+
 cudaError_t launch_build(int mode, const DevTree& T, const DevSlot& S, double* outG, double* outH, double* outRi,
                          const int* grp_slot0, const int* grp_nn, int ngrp, const double* w, const CovTab& tab, int* fail,
                          int ns, int phase, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof = nullptr,
