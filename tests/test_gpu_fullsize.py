@@ -72,3 +72,37 @@ def test_fullsize_properties(name, n):
     gm.predict(True)
     assert np.all(np.isfinite(gm.w))
     gm.close()
+
+
+@pytest.mark.parametrize("name", ["C3", "C4"])
+def test_fullsize_deferred_half_is_consistent(name):
+    """keep_H = 0 (the bench configuration): the childless level gets the forward half of BUILD only and the backward half
+    when the proposal is accepted.  Size-independent checks: the log-density of the forward half equals what LLW computes
+    from the completed G after the swap; a rejected proposal does not disturb the current slot; run-to-run determinism."""
+    d, t, th, gm = _model(name, keep_H=False)
+    N = d["y"].size
+    rng = np.random.default_rng(1)
+    z = rng.standard_normal(N)
+    ok, ll0, _ = gm.get_loglik_comps_w(0)
+    assert ok
+    gm.deal_with_w(z)                                    # completes slot 0 (deferred half) before the sweep
+    w1 = gm.w
+    l_llw = gm.get_loglik_w(0)[0]
+    okb, l_build, _ = gm.get_loglik_comps_w(0)           # forward half again, at the new w
+    assert okb and abs(l_llw - l_build) <= 1e-10 * abs(l_build)
+    th2 = th * (1 + 1e-3 * rng.standard_normal(th.size))
+    gm.theta_update(1, th2)
+    ok2, ll2, _ = gm.get_loglik_comps_w(1)               # proposal: forward half only at the leaves
+    assert ok2
+    # rejected: the current slot still gives the same LLW
+    assert gm.get_loglik_w(0)[0] == l_llw
+    gm.accept_make_change()                              # accepted: backward half runs now
+    assert abs(gm.get_loglik_w(0)[0] - ll2) <= 1e-10 * abs(ll2)
+    gm.deal_with_w(z)
+    w2 = gm.w
+    # determinism: replay from the same state
+    gm.w = w1
+    gm.get_loglik_comps_w(0)
+    gm.deal_with_w(z)
+    assert np.array_equal(gm.w, w2)
+    gm.close()
