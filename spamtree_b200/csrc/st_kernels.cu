@@ -58,7 +58,7 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
     const int a = T.chain[coff + tid];
     c_m[tid] = T.m[a]; c_po[tid] = T.chain_poff[coff + tid]; c_r0[tid] = T.row0[a];
   }
-  if (tid >= 32 && tid < 32 + min(nch, 16)) c_voff[tid - 32] = T.voff[ch[tid - 32]];
+  for (int c = tid; c < min(nch, 16); c += nth) c_voff[c] = T.voff[ch[c]];
   for (int e = tid; e < msq; e += nth) RiS[e] = Rig[e];
   // loads that depend on nothing computed here are issued now, so that their latency hides under the phases below:
   // the children's Gram sum (into Sig), and per row tausq_inv (wn), tausq_inv (y - XB) (smu) and the normal draw (rr)
