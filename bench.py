@@ -105,12 +105,21 @@ def measure_fp64_peak(torch, dev):
     return best
 
 
+def host_threads():
+    """the cores this process may run on (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline_sample(workload, d, t, csr, theta, iters=1):
     """the oracle (restated reference algorithm, OpenMP over the blocks of a level like spamtree_model.cpp:850) timed on
     the host cores on the SAME workload: one untimed BUILD to initialise, then `iters` timed iterations"""
     from oracle import oracle as orc
     om = orc.OracleModel(d["y"], d["X"], d["coords"], d["mv_id"], t["res_is_ref"], csr, False, t["block_names"], t["block_groups"],
                          np.zeros(3), theta, 0.1, flags=orc.FLAG_LEAN)
+    orc.lib().or_set_threads(host_threads())
     cores = orc.lib().or_max_threads()
     om.get_loglik_comps_w(0)
     props = proposals(theta, iters + 1, 99)
@@ -131,6 +140,7 @@ def run_reference(args, rank, world, emit):
     from oracle import oracle as orc
     om = orc.OracleModel(d["y"], d["X"], d["coords"], d["mv_id"], t["res_is_ref"], csr, False, t["block_names"], t["block_groups"],
                          np.zeros(3), theta, 0.1, flags=orc.FLAG_LEAN)
+    orc.lib().or_set_threads(host_threads())  # every host thread, also under torchrun (which exports OMP_NUM_THREADS=1)
     cores = orc.lib().or_max_threads()
     om.get_loglik_comps_w(0)
     props = proposals(theta, warm + steps, 99)
