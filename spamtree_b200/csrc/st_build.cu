@@ -35,7 +35,7 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 // Factorisation: lane i keeps row i in registers, rotated so that the pivot column is always a[0] (the loop stays
 // rolled: the trailing update writes a[i] <- a[i+1] - l_i * l_(j+1+i)); the pivot column is broadcast through cb
 // (2 x 64 doubles).  Inverse: row r of L^-1 overwrites row r of L (lane c solves for column c).  dv: 32 doubles (1/diag).
-__device__ __forceinline__ bool warp_chol_inv32(double* R, int m, int rs, double* cb, double* dv, int lane, long long* tmid) {
+__device__ __noinline__ bool warp_chol_inv32(double* R, int m, int rs, double* cb, double* dv, int lane, long long* tmid) {
   bool ok = true;
   {
     double a[32];
@@ -88,10 +88,10 @@ __device__ __forceinline__ bool warp_chol_inv32(double* R, int m, int rs, double
 // In phases 1 and 2 the panel has one extra column that carries w_pa, so that v = L^-1 w_pa and with it
 // H w_pa = Z'v come out of the forward sweep.
 template <int MODE>
-__global__ void __launch_bounds__(kBuildMaxThreads, 1)
-build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __restrict__ outH, double* __restrict__ outRi,
-                   const int* __restrict__ grp_slot0, const int* __restrict__ grp_nn, const double* __restrict__ w,
-                   CovTab tab, int* __restrict__ fail, int ns, int phase, unsigned long long* __restrict__ prof) {
+__device__ __forceinline__ void
+build_level_body(const DevTree& T, const DevSlot& S, double* __restrict__ outG, double* __restrict__ outH, double* __restrict__ outRi,
+                 const int* __restrict__ grp_slot0, const int* __restrict__ grp_nn, const double* __restrict__ w,
+                 const CovTab& tab, int* __restrict__ fail, int ns, int phase, unsigned long long* __restrict__ prof) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ CovTabS ct;
   __shared__ int s_cm[kMaxChain], s_crow[kMaxChain + 1], s_crow0g[kMaxChain], s_cgs[kMaxChain];
@@ -634,11 +634,29 @@ build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __re
   mark(6);
 }
 
+// Two entry points over the same body, because the register hint that suits one hurts the other (measured on C4): the
+// non-reference / prediction instantiations run 11 % faster when ptxas is told that one CTA per SM is enough (it
+// otherwise squeezes them into 64 registers with spills), the reference instantiation's register-resident Cholesky runs
+// 30 % slower with that hint.
+__global__ void __launch_bounds__(kBuildMaxThreads)
+build_level_kernel_ref(DevTree T, DevSlot S, double* __restrict__ outG, double* __restrict__ outH, double* __restrict__ outRi,
+                       const int* __restrict__ grp_slot0, const int* __restrict__ grp_nn, const double* __restrict__ w,
+                       CovTab tab, int* __restrict__ fail, int ns, int phase, unsigned long long* __restrict__ prof) {
+  build_level_body<0>(T, S, outG, outH, outRi, grp_slot0, grp_nn, w, tab, fail, ns, phase, prof);
+}
+template <int MODE>
+__global__ void __launch_bounds__(kBuildMaxThreads, 1)
+build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __restrict__ outH, double* __restrict__ outRi,
+                   const int* __restrict__ grp_slot0, const int* __restrict__ grp_nn, const double* __restrict__ w,
+                   CovTab tab, int* __restrict__ fail, int ns, int phase, unsigned long long* __restrict__ prof) {
+  build_level_body<MODE>(T, S, outG, outH, outRi, grp_slot0, grp_nn, w, tab, fail, ns, phase, prof);
+}
+
 template <int MODE>
 static cudaError_t launch_build_t(const DevTree& T, const DevSlot& S, double* outG, double* outH, double* outRi,
                                   const int* grp_slot0, const int* grp_nn, int ngrp, const double* w, const CovTab& tab,
                                   int* fail, int ns, int phase, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof, bool pdl) {
-  auto kern = build_level_kernel<MODE>;
+  auto kern = (MODE == 0) ? build_level_kernel_ref : build_level_kernel<MODE == 0 ? 1 : MODE>;
   static SmemOptIn optin;
   {
     cudaError_t e = ensure_dynamic_smem(kern, smem, optin);
