@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspamtree_b200.so")
+LIB_PATH = os.environ.get("SPAMTREE_B200_LIB") or os.path.join(_HERE, "libspamtree_b200.so")  # (override: kernel-variant experiments)
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -25,19 +25,28 @@ namespace st {
 
 namespace {
 constexpr int RS = kBuildRS, ST = kBuildST;
+#ifndef ST_COV_ILP
+#define ST_COV_ILP 4
+#endif
+constexpr int kCovIlp = ST_COV_ILP;  // covariance evaluations in flight per thread
 
 // D(8x8) += A(8x4, row) * B(4x8, col); lane l holds A[l>>2][l&3], B[l&3][l>>2], D[l>>2][2*(l&3) + {0,1}]
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// R (row-major, stride rs, lower triangle valid, m <= 32) <- chol(R)^-1 (lower; strict upper zeroed) by one warp.
-// Factorisation: lane i keeps row i in registers, rotated so that the pivot column is always a[0] (the loop stays
-// rolled: the trailing update writes a[i] <- a[i+1] - l_i * l_(j+1+i)); the pivot column is broadcast through cb
-// (2 x 64 doubles).  Inverse: row r of L^-1 overwrites row r of L (lane c solves for column c).  dv: 32 doubles (1/diag).
-__device__ __noinline__ bool warp_chol_inv32(double* R, int m, int rs, double* cb, double* dv, int lane, long long* tmid) {
+// R (row-major, stride rs, lower triangle valid, m <= 32) <- chol(R)^-1 (lower; strict upper zeroed) by a PAIR of warps
+// that work one pivot apart: role 0 factorises, role 1 inverts.  Both are right-looking and keep their operand in
+// registers, one row (factor) / one column (inverse) per lane, rotated so that the active entry is always element 0 and
+// the loops stay rolled.  Step j of the factorisation publishes column j of L (cb: 2 x 64 doubles, double-buffered, zero
+// past row 31) and 1 / L_jj (dv: 32 doubles); the pair meets at the 64-thread named barrier `bar`; then the factorising
+// warp applies its trailing update a[i] <- a[i+1] - l_i l_(j+1+i) while the inverting warp finalises x_j = acc[0] / L_jj,
+// row j of L^-1, and pushes -L[r][j] x_j into the rows below.  The two latency chains (tools/microbench/chol_bench.cu:
+// ~360 and ~340 cycles per pivot) overlap instead of adding up.  Returns false on a non-positive pivot (dpotrf info > 0);
+// the result is meaningful in the factorising warp only.
+__device__ __noinline__ bool pair_chol_inv32(double* R, int m, int rs, double* cb, double* dv, int lane, int role, int bar) {
   bool ok = true;
-  {
+  if (role == 0) {
     double a[32];
 #pragma unroll
     for (int j = 0; j < 32; j++) a[j] = (lane < m && j <= lane) ? R[lane * rs + j] : 0.0;
@@ -45,42 +54,33 @@ __device__ __noinline__ bool warp_chol_inv32(double* R, int m, int rs, double* c
     cb[96 + lane] = 0.0;
     for (int j = 0; j < m; j++) {
       double d = __shfl_sync(0xffffffffu, a[0], j);
-      if (!(d > 0.0) || !isfinite(d)) { ok = false; d = 1.0; }  // dpotrf info > 0
+      if (!(d > 0.0) || !isfinite(d)) { ok = false; d = 1.0; }
       const double inv = rsqrt(d), sd = d * inv;
       const double l = (lane == j) ? sd : ((lane > j) ? a[0] * inv : 0.0);
       double* c = cb + (j & 1) * 64;
       c[lane] = l;
-      if (lane >= j && lane < m) R[lane * rs + j] = l;
       if (lane == 0) dv[j] = inv;
-      __syncwarp();
-      const double* cj = c + j + 1;  // l of rows j+1 ..; entries past row 31 are never used by a valid element
+      asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");
+      const double* cj = c + j + 1;  // l of rows j+1 ..; entries past row 31 are zero
 #pragma unroll
       for (int i = 0; i < 31; i++) a[i] = fma(-l, cj[i], a[i + 1]);
       a[31] = 0.0;
     }
-  }
-  __syncwarp();
-  if (tmid) *tmid = clock64();
-  // Inverse, right-looking like the factorisation: lane c keeps the not-yet-final entries of column c of L^-1 in
-  // registers, rotated so that acc[0] is row k.  Once x_k = acc[0] / L_kk is final, rows k+1.. receive -L[r][k] x_k
-  // (column k of L by broadcast loads); x_k then overwrites row k of L, whose later columns are never read again.
-  // (tools/microbench/chol_bench.cu: 8.6k cycles against 15.1k for a row-by-row forward substitution.)
-  {
+  } else {
     double acc[32];
 #pragma unroll
     for (int i = 0; i < 32; i++) acc[i] = (i == lane) ? 1.0 : 0.0;
-    const int rmax = ((m + 7) & ~7) - 1;  // last row that exists in R (rows m.. are zero padding)
     for (int k = 0; k < m; k++) {
+      asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");
       const double x = acc[0] * dv[k];
-      const double* col = R + k;
+      const double* cj = cb + (k & 1) * 64 + k + 1;
 #pragma unroll
-      for (int i = 0; i < 31; i++) acc[i] = fma(-col[min(k + 1 + i, rmax) * rs], x, acc[i + 1]);
+      for (int i = 0; i < 31; i++) acc[i] = fma(-cj[i], x, acc[i + 1]);
       acc[31] = 0.0;
-      __syncwarp();
       if (lane < m) R[k * rs + lane] = x;  // zero above the diagonal: lanes > k never received a contribution
     }
-    __syncwarp();
   }
+  asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");  // R holds L^-1 for both warps
   return ok;
 }
 }  // namespace
@@ -215,28 +215,40 @@ build_level_body(const DevTree& T, const DevSlot& S, double* __restrict__ outG, 
       for (int i = lane; i < P; i += 32) panel[(size_t)i * LD + c] = ri * src[i];
     }
   }
-  for (int c = lane; c < LD && !completing; c += 32) {
-    const bool real = colnode[c] >= 0;
-    const double xc = cxs[c], yc = cys[c];
-    const int qc = cq[c];
-    int i = warp;
-    for (; i + 3 * nwarps < P; i += 4 * nwarps) {  // four independent evaluations in flight per thread
-      const int i1 = i + nwarps, i2 = i + 2 * nwarps, i3 = i + 3 * nwarps;
-      const double v0 = cov_eval(ct, pxs[i], pys[i], pq[i], xc, yc, qc);
-      const double v1 = cov_eval(ct, pxs[i1], pys[i1], pq[i1], xc, yc, qc);
-      const double v2 = cov_eval(ct, pxs[i2], pys[i2], pq[i2], xc, yc, qc);
-      const double v3 = cov_eval(ct, pxs[i3], pys[i3], pq[i3], xc, yc, qc);
-      panel[(size_t)i * LD + c] = real ? v0 : 0.0;
-      panel[(size_t)i1 * LD + c] = real ? v1 : 0.0;
-      panel[(size_t)i2 * LD + c] = real ? v2 : 0.0;
-      panel[(size_t)i3 * LD + c] = real ? v3 : 0.0;
+  if (!completing) {
+    // zero fill: the columns past the group's (all rows) and the rows past P
+    const int npadc = LD - ncols;
+    for (int e = tid; e < Ppad * npadc; e += nth) { const int i = e / npadc; panel[(size_t)i * LD + ncols + (e - i * npadc)] = 0.0; }
+    for (int e = tid; e < (Ppad - P) * ncols; e += nth) { const int i = e / ncols; panel[(size_t)(P + i) * LD + (e - i * ncols)] = 0.0; }
+    // lanes over columns, warps over rows, kCovIlp independent evaluations in flight per thread.  The last, partial run of
+    // 32 columns is packed: with w = the power of two that holds them, a warp covers 32 / w rows at once.
+    auto cov_cols = [&](int c, bool act, int ifirst, int istep) {
+      const double xc = cxs[c], yc = cys[c];
+      const int qc = cq[c];
+      int i = ifirst;
+      for (; i + (kCovIlp - 1) * istep < P; i += kCovIlp * istep) {
+        double v[kCovIlp];
+#pragma unroll
+        for (int u = 0; u < kCovIlp; u++) v[u] = cov_eval(ct, pxs[i + u * istep], pys[i + u * istep], pq[i + u * istep], xc, yc, qc);
+#pragma unroll
+        for (int u = 0; u < kCovIlp; u++) if (act) panel[(size_t)(i + u * istep) * LD + c] = v[u];
+      }
+      for (; i < P; i += istep) {
+        const double v = cov_eval(ct, pxs[i], pys[i], pq[i], xc, yc, qc);
+        if (act) panel[(size_t)i * LD + c] = v;
+      }
+    };
+    const int cfull = ncols & ~31, nrem = ncols - cfull;
+    for (int c = lane; c < cfull; c += 32) cov_cols(c, true, warp, nwarps);
+    if (nrem > 0) {
+      int wl = 0;
+      while ((1 << wl) < nrem) wl++;
+      const int cl = lane & ((1 << wl) - 1), rp = 32 >> wl;
+      cov_cols(cfull + min(cl, nrem - 1), cl < nrem, warp * rp + (lane >> wl), nwarps * rp);
     }
-    for (; i < P; i += nwarps)
-      panel[(size_t)i * LD + c] = real ? cov_eval(ct, pxs[i], pys[i], pq[i], xc, yc, qc) : 0.0;
-    for (i = P + warp; i < Ppad; i += nwarps) panel[(size_t)i * LD + c] = 0.0;
   }
   if (xcol && !completing) {
-    __syncthreads();  // the loop above zero-filled the columns past the group's
+    __syncthreads();  // the zero fill above covered the columns past the group's
     for (int i = tid; i < Ppad; i += nth) panel[(size_t)i * LD + ncols] = wpa[i];  // extra column: w_pa (zero past P)
   }
   // (the first __syncthreads of the sweep below publishes the panel)
@@ -377,26 +389,31 @@ build_level_body(const DevTree& T, const DevSlot& S, double* __restrict__ outG, 
     }
     __syncthreads();
     mark(3);
-    for (int x = warp; x < nmat * nn; x += nwarps) {
+    // one warp pair per matrix (warps 2i and 2i+1 sit on different SM sub-partitions); named barriers 1.. are free here,
+    // the sweeps that use them are over
+    for (int x = warp >> 1; x < nmat * nn; x += nwarps >> 1) {
       const int d = x % nn, which = x / nn;  // which = 1: the marginal K_uu of a limited tree
-      const int md = s_nm[d], rs = rb_stride(md);
+      const int md = s_nm[d], rs = rb_stride(md), role = warp & 1;
       double* R = Rb + which * sumRb + s_nRb[d];
-      bool okc;
-      long long tc0 = 0, tc1 = 0;
+      bool okc = true;
+      long long tc0 = 0;
       if (prof && tid == 0) tc0 = clock64();
       if (md <= 32) {
-        okc = warp_chol_inv32(R, md, rs, s_cb + warp * 160, s_cb + warp * 160 + 128, lane, (prof && tid == 0) ? &tc1 : nullptr);
-        if (prof && tid == 0) { atomicAdd(prof + 8, (unsigned long long)(tc1 - tc0)); atomicAdd(prof + 9, (unsigned long long)(clock64() - tc1)); }
-      } else {
+        double* scr = s_cb + (warp >> 1) * 160;
+        okc = pair_chol_inv32(R, md, rs, scr, scr + 128, lane, role, 1 + (warp >> 1));
+        if (prof && tid == 0) atomicAdd(prof + 8, (unsigned long long)(clock64() - tc0));
+      } else if (role == 0) {
         okc = warp_chol(R, md, rs, lane);
-        if (okc) warp_inv_lower_inplace(R, md, rs, vtmp + warp * (s_maxmd + 2), lane);
+        if (okc) warp_inv_lower_inplace(R, md, rs, vtmp + (warp >> 1) * (s_maxmd + 2), lane);
       }
-      if (!okc) {
-        if (lane == 0) atomicAdd(fail, 1);
-        __syncwarp();
-        for (int e = lane; e < md * rs; e += 32) R[e] = 0.0;
+      if (role == 0) {
+        if (!okc) {
+          if (lane == 0) atomicAdd(fail, 1);
+          __syncwarp();
+          for (int e = lane; e < md * rs; e += 32) R[e] = 0.0;
+        }
+        if (lane == 0 && which == 0) s_nlogdet[d] = okc ? 0.0 : -1.0;  // flag, replaced by the log-determinant below
       }
-      if (lane == 0 && which == 0) s_nlogdet[d] = okc ? 0.0 : -1.0;  // flag, replaced by the log-determinant below
     }
     __syncthreads();
     mark(4);
@@ -444,11 +461,16 @@ build_level_body(const DevTree& T, const DevSlot& S, double* __restrict__ outG, 
     }
     __syncthreads();
   } else if (!completing) {
-    for (int c = tid; c < NCp; c += nth) {
-      const int d = (c < ncols) ? colnode[c] : -1;
-      if (d < 0) continue;
+    // diag(Z'Z) and Z'v per column: the rows are split into parts of 32 so that every thread has work (a narrow group has
+    // far fewer columns than the CTA has threads); partial sums in the idle ring, summed in a fixed order that depends
+    // on P alone (the eager and the deferred scheme, whose panels differ by the w_pa column, stay bit-identical)
+    const int rpp = 32, np = (Ppad + rpp - 1) / rpp;  // np * 2 * NCp <= Ppad * NCp / 8 doubles: inside one backward stage
+    double* part = ring;
+    for (int item = tid; item < np * NCp; item += nth) {
+      const int pt = item / NCp, c = item - pt * NCp;
+      const int pend = min(Ppad, (pt + 1) * rpp);
       double q0 = 0, q1 = 0, q2 = 0, q3 = 0, g0 = 0, g1 = 0;
-      for (int pp = 0; pp < Ppad; pp += 4) {
+      for (int pp = pt * rpp; pp < pend; pp += 4) {
         const double z0 = panel[(size_t)pp * LD + c], z1 = panel[(size_t)(pp + 1) * LD + c];
         const double z2 = panel[(size_t)(pp + 2) * LD + c], z3 = panel[(size_t)(pp + 3) * LD + c];
         q0 = fma(z0, z0, q0); q1 = fma(z1, z1, q1); q2 = fma(z2, z2, q2); q3 = fma(z3, z3, q3);
@@ -457,7 +479,16 @@ build_level_body(const DevTree& T, const DevSlot& S, double* __restrict__ outG, 
           g0 = fma(z0, v[0], g0); g1 = fma(z1, v[LD], g1); g0 = fma(z2, v[2 * LD], g0); g1 = fma(z3, v[3 * LD], g1);
         }
       }
-      const double R = cov_eval(ct, cxs[c], cys[c], cq[c], cxs[c], cys[c], cq[c]) - ((q0 + q1) + (q2 + q3));
+      part[(size_t)(2 * pt) * NCp + c] = (q0 + q1) + (q2 + q3);
+      part[(size_t)(2 * pt + 1) * NCp + c] = g0 + g1;
+    }
+    __syncthreads();
+    for (int c = tid; c < NCp; c += nth) {
+      const int d = (c < ncols) ? colnode[c] : -1;
+      if (d < 0) continue;
+      double qs = 0, gsum = 0;
+      for (int pt = 0; pt < np; pt++) { qs += part[(size_t)(2 * pt) * NCp + c]; gsum += part[(size_t)(2 * pt + 1) * NCp + c]; }
+      const double R = cov_eval(ct, cxs[c], cys[c], cq[c], cxs[c], cys[c], cq[c]) - qs;
       const bool ok = (R > 0.0) && isfinite(R);
       const int t = c - s_nc0[d];
       if (MODE == 1) {
@@ -466,7 +497,7 @@ build_level_body(const DevTree& T, const DevSlot& S, double* __restrict__ outG, 
         rdiag[c] = ri;
         outRi[s_nrioff[d] + t] = ri;
         tvec[c] = ri * wcol[c];
-        if (xcol) gw[c] = ri * (g0 + g1);  // G w_pa
+        if (xcol) gw[c] = ri * gsum;  // G w_pa
       } else {
         outRi[s_nrioff[d] + t] = ok ? sqrt(R) : 0.0;  // predict_std zeroes the sd when the Cholesky fails (:1316-1322)
       }

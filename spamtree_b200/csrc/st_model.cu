@@ -420,6 +420,9 @@ int Model::build_layout(std::string& e) {
     L.build_launches.clear();
     const int end = L.slot0 + L.nslots;
     const int col_cap = std::min(max_group_cols, kMaxGroupCols);
+    // A level with fewer blocks than the GPU has SMs is a latency chain, not a throughput problem: smaller groups (down to
+    // one block per CTA) shorten every phase of the chain and cost nothing, the other SMs are idle anyway.
+    const int nn_cap = (spread_ctas > 0) ? std::max(1, std::min(kMaxGroupNodes, (L.nslots + spread_ctas - 1) / spread_ctas)) : kMaxGroupNodes;
     L.deferrable = false;
     if (mode == 1 && !keep_H && defer_leaves) {
       L.deferrable = L.nslots > 0;
@@ -435,7 +438,7 @@ int Model::build_layout(std::string& e) {
     while (s < end) {
       int nn = 0;
       BuildPlan best{};
-      while (s + nn < end && nn < kMaxGroupNodes) {
+      while (s + nn < end && nn < nn_cap) {
         const int t = s + nn;
         if (nn > 0 && (h_lastpar[s] < 0 || h_lastpar[t] != h_lastpar[s])) break;  // roots never share a chain
         const BuildPlan pl = group_plan(s, nn + 1, mode, 1, wmax, xcol);
@@ -698,6 +701,7 @@ int Model::init(std::string& e) {
   if (const char* v = getenv("ST_PDL")) use_pdl = atoi(v) != 0;
   if (const char* v = getenv("ST_MAX_COLS")) max_group_cols = atoi(v);
   if (const char* v = getenv("ST_SMEM_BUDGET")) smem_budget = (size_t)atol(v);
+  if (const char* v = getenv("ST_SPREAD")) spread_ctas = atoi(v);
   int rc = build_bookkeeping(e);
   if (rc) return rc;
   if (q * (p + 1) > kMaxStats) { e = "q*(p+1) exceeds 40"; return 4; }
@@ -829,7 +833,7 @@ int Model::launch_build_levels(int pslot, const CovTab& tab) {
         fprintf(stderr, "[build profile] level slot0=%d groups=%d ref=%d threads=%d ns=%d smem=%zu  %.3f ms  cycles/group=%.0f : setup %.1f%% cov %.1f%% fwd %.1f%% ZtZ %.1f%% chol %.1f%% Y %.1f%% bwd+out %.1f%%\n",
                 L.slot0, B.ngrp, L.is_ref, B.threads, B.ns, B.smem, pms, tot / std::max(1, B.ngrp), 100 * h[0] / tot, 100 * h[1] / tot,
                 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, 100 * h[5] / tot, 100 * h[6] / tot);
-        if (L.is_ref) fprintf(stderr, "      chol (warp 0): factorise %.1f%% invert %.1f%% of kernel\n", 100 * h[8] / tot, 100 * h[9] / tot);
+        if (L.is_ref) fprintf(stderr, "      chol (warp pair 0: factorise + invert, one pivot apart): %.1f%% of kernel\n", 100 * h[8] / tot);
       }
     }
   }
