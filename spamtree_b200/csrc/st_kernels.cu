@@ -15,6 +15,7 @@
 // FP64 throughout; B200 has no tcgen05 FP64 kind, the dense contractions are register-tiled DFMA.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "st_device.cuh"
@@ -269,18 +270,20 @@ cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlot& S, int slo
 // thread accumulates one 5 x 5 sub-block of the lower triangle of one tile in registers.
 __global__ void __launch_bounds__(kGramThreads)
 gram_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ U, double* __restrict__ SigS, int rch, int ldx,
-                  int tile_doubles) {
+                  int stage_off) {
   extern __shared__ __align__(16) double gram_smem[];
   __shared__ int t_po[kMaxChain + 1], t_m[kMaxChain + 1], t_item0[kMaxChain + 2], t_uo[kMaxChain + 1], t_to[kMaxChain + 2];
   __shared__ int s_rows;
   __shared__ long long s_rowoff[kGramMaxRows];  // per staged row: offset of the row in S.G and its valid columns
   __shared__ int s_rowncol[kGramMaxRows];
   __shared__ long long s_cu[kGramChildTab];     // per (child, tile): offset of the child's stored tile, -1 when the child is fused
+  __shared__ int f_m[kGramFusedTab], f_gs[kGramFusedTab], f_r0[kGramFusedTab + 1];  // fused children: rows, row stride, first staged row
+  __shared__ long long f_goff[kGramFusedTab];
   const int tid = threadIdx.x, nth = blockDim.x;
   const int sd = slot0 + blockIdx.x;
   if (T.ufused[sd]) return;
   double* tiles = gram_smem;                 // the assembled tiles (both triangles), tile j at t_to[j]
-  double* stage = gram_smem + tile_doubles;  // rch staged rows of ldx doubles
+  double* stage = gram_smem + stage_off;      // rch staged rows of ldx doubles; stage_off = 0: they share the tiles' storage
   const int m = T.m[sd], k = T.k[sd], P = T.P[sd], coff = T.chain_off[sd];
   const int nch = T.child_ptr[sd + 1] - T.child_ptr[sd];
   const int* ch = T.child_idx + T.child_ptr[sd];
@@ -290,6 +293,14 @@ gram_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ U, doubl
     t_po[tid] = (tid < k) ? T.chain_poff[coff + tid] : (T.limited ? 0 : P);  // where the children's rows hold this block's columns
     t_m[tid] = (tid < k) ? T.m[T.chain[coff + tid]] : m;
     t_uo[tid] = (tid < k) ? T.chain_uoff[coff + tid] : 0;
+  }
+  // the fused children's row blocks, tabulated once (one thread per child: independent loads)
+  const bool ftab = nch <= kGramFusedTab;
+  if (ftab && tid < nch) {
+    const int cc = ch[tid];
+    f_m[tid] = T.ufused[cc] ? T.m[cc] : 0;
+    f_goff[tid] = T.goff[cc];
+    f_gs[tid] = T.gs[cc];
   }
   __syncthreads();
   if (tid == 0) {
@@ -302,7 +313,11 @@ gram_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ U, doubl
     }
     t_item0[ntile] = it; t_to[ntile] = to;
     int rows = m;
-    for (int c = 0; c < nch; c++) if (T.ufused[ch[c]]) rows += T.m[ch[c]];
+    for (int c = 0; c < nch; c++) {
+      if (ftab) { f_r0[c] = rows; rows += f_m[c]; }
+      else if (T.ufused[ch[c]]) rows += T.m[ch[c]];
+    }
+    if (ftab) f_r0[nch] = rows;
     s_rows = rows;
   }
   const bool ctab = nch * ntile <= kGramChildTab;
@@ -341,7 +356,12 @@ gram_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ U, doubl
       for (int rr = tid; rr < nr; rr += nth) {  // where does staged row rr live?
         int r = rbase + rr;
         if (r < m) { s_rowoff[rr] = T.goff[sd] + (long long)r * T.gs[sd]; s_rowncol[rr] = P; }
-        else {
+        else if (ftab) {
+          int c = 0;
+          while (r >= f_r0[c + 1]) c++;  // (children that keep their own tiles have no rows here)
+          s_rowoff[rr] = f_goff[c] + (long long)(r - f_r0[c]) * f_gs[c];
+          s_rowncol[rr] = T.limited ? m : P + m;
+        } else {
           r -= m;
           for (int c = 0; c < nch; c++) {
             const int cc = ch[c];
@@ -380,6 +400,7 @@ gram_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ U, doubl
         }
       }
     }
+    __syncthreads();  // (the tiles may take the place of the staged rows)
     if (act) {  // both triangles of the tile
       double* tj = tiles + t_to[j];
 #pragma unroll
@@ -413,15 +434,15 @@ gram_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ U, doubl
   }
 }
 cudaError_t launch_gram(const DevTree& T, const DevSlot& S, int slot0, int nslots, double* U, double* SigS, int rch,
-                        int ldx, int tile_doubles, cudaStream_t st) {
+                        int ldx, int tile_doubles, int stage_off, int threads, cudaStream_t st) {
   if (nslots <= 0) return cudaSuccess;
-  const size_t smem = ((size_t)tile_doubles + (size_t)rch * ldx) * sizeof(double);
+  const size_t smem = std::max((size_t)tile_doubles, (size_t)stage_off + (size_t)rch * ldx) * sizeof(double);
   static SmemOptIn optin;
   {
     cudaError_t e = ensure_dynamic_smem(gram_level_kernel, smem, optin);
     if (e != cudaSuccess) return e;
   }
-  gram_level_kernel<<<nslots, kGramThreads, smem, st>>>(T, S, slot0, U, SigS, rch, ldx, tile_doubles);
+  gram_level_kernel<<<nslots, threads, smem, st>>>(T, S, slot0, U, SigS, rch, ldx, stage_off);
   return cudaGetLastError();
 }
 

@@ -19,6 +19,7 @@ constexpr int kGibbsThreads = 64;   // two warps per block (measured on C4: 128 
 constexpr int kGramThreads = 256;
 constexpr int kGramMaxRows = 256;   // rows gram_level_kernel stages per chunk
 constexpr int kGramChildTab = 256;  // (child, tile) offsets it tabulates
+constexpr int kGramFusedTab = 64;   // children whose row blocks it tabulates
 constexpr int kLlwThreads = 128;
 constexpr int kLlwMaxP = 1024;  // parent-set rows the LLW kernel stages per warp (checked at st_create)
 constexpr int kMaxStats = 40;  // q * (p + 1)
@@ -114,7 +115,7 @@ cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlot& S, int slo
                          const double* xb, const double* z, const double* tausq_inv, const double* SigS, double* V,
                          double* probe_sig, double* probe_smu, int* fail, size_t smem, cudaStream_t st, bool pdl = false);
 cudaError_t launch_gram(const DevTree& T, const DevSlot& S, int slot0, int nslots, double* U, double* SigS, int rch,
-                        int ldx, int tile_doubles, cudaStream_t st);
+                        int ldx, int tile_doubles, int stage_off, int threads, cudaStream_t st);
 cudaError_t launch_llw(const DevTree& T, const DevSlot& S, int nslots, const double* w, int maxlen, cudaStream_t st);
 cudaError_t launch_loglik_reduce(const double* logdet, const double* llcomp, int first, int n, const int* fail,
                                  int fail_as_count, double* out, cudaStream_t st);

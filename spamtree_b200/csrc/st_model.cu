@@ -489,7 +489,7 @@ int Model::build_layout(std::string& e) {
     }
     if (mode != 2 && L.smem_gibbs > 227 * 1024) { e = "a block is too large for the Gibbs kernel's shared memory"; return 4; }
     if (mode != 2) {  // gram_level_kernel: rows staged per chunk (own rows + the rows of the fused children)
-      int ldx = 2, maxrows = 1;
+      int ldx = 2, maxrows = 1, maxitems = 1;
       long long tiles = 2;
       L.gram_skip = true;
       for (int t = L.slot0; t < end; t++) {
@@ -500,13 +500,32 @@ int Model::build_layout(std::string& e) {
         maxrows = std::max(maxrows, rows);
         ldx = std::max(ldx, (h_P[t] + h_m[t] + 1) & ~1);
         long long td = (long long)h_m[t] * h_m[t];
-        for (int j = 0; j < h_k[t]; j++) { const long long mj = h_m[h_chain[h_chain_off[t] + j]]; td += mj * mj; }
+        int items = ((h_m[t] + 4) / 5) * ((h_m[t] + 4) / 5 + 1) / 2;
+        for (int j = 0; j < h_k[t]; j++) {
+          const long long mj = h_m[h_chain[h_chain_off[t] + j]];
+          td += mj * mj;
+          items += (int)(((mj + 4) / 5) * ((mj + 4) / 5 + 1) / 2);
+        }
         tiles = std::max(tiles, (td + 1) & ~1LL);
+        maxitems = std::max(maxitems, items);
       }
       if (tiles * 8 > 160 * 1024) { e = "a block's message Gram tiles do not fit the Gram kernel's shared memory"; return 4; }
       L.gram_ldx = ldx;
       L.gram_tiles = (int)tiles;
-      const size_t room = (size_t)100 * 1024 > (size_t)tiles * 8 + (size_t)ldx * 8 ? (size_t)100 * 1024 - (size_t)tiles * 8 : (size_t)ldx * 8;
+      // the assembled tiles take the place of the staged rows when every (tile, sub-block) item has its own thread: the
+      // accumulators live in registers until the last row has been consumed
+      // One thread per item, in whole warps.  The kernel needs ~128 registers per thread, so a 128-thread CTA can have
+      // four co-resident CTAs per SM where a 256-thread CTA has two: the staged chunk is sized for that many (the kernel is
+      // latency-bound: load, compute and store phases of different CTAs overlap).
+      L.gram_threads = std::min(kGramThreads, std::max(64, (maxitems + 31) & ~31));
+      if (L.nslots <= 2 * 148) L.gram_threads = kGramThreads;  // a level that does not fill the GPU is a latency chain: widest CTA
+      L.gram_stage_off = (maxitems <= L.gram_threads) ? 0 : (int)tiles;
+      const size_t fixed = (size_t)L.gram_stage_off * 8;
+      const int ctas = std::max(1, std::min(8, 65536 / (128 * L.gram_threads)));
+      size_t room = (size_t)(228 - ctas) * 1024 / ctas - 9 * 1024;  // per CTA: its share of the SM minus the static part
+      if (const char* v = getenv("ST_GRAM_ROOM")) room = (size_t)atol(v);
+      room = std::max(room, std::max((size_t)tiles * 8, fixed + (size_t)ldx * 8));
+      room -= fixed;
       L.gram_rch = (int)std::max<size_t>(1, std::min<size_t>(std::min(maxrows, kGramMaxRows), room / ((size_t)ldx * 8)));
     }
     return 0;
@@ -906,7 +925,7 @@ int Model::refresh_grams() {
     static const bool profile = getenv("ST_PROFILE_GIBBS") != nullptr;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, stream); }
-    ST_CUDA(launch_gram(dt, ds[cur], levels[g].slot0, levels[g].nslots, d_U, d_S, levels[g].gram_rch, levels[g].gram_ldx, levels[g].gram_tiles, stream),
+    ST_CUDA(launch_gram(dt, ds[cur], levels[g].slot0, levels[g].nslots, d_U, d_S, levels[g].gram_rch, levels[g].gram_ldx, levels[g].gram_tiles, levels[g].gram_stage_off, levels[g].gram_threads, stream),
             "gram_level_kernel");
     n_launches++;
     if (profile) {

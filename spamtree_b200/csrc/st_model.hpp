@@ -85,7 +85,7 @@ struct LevelInfo {
   bool deferrable = false;
   int maxP = 0, maxm = 0, maxNC = 0, maxk = 0;
   size_t smem_gibbs = 0;
-  int gram_rch = 1, gram_ldx = 2, gram_tiles = 2;  // gram_level_kernel: staged rows per chunk, their leading dimension, doubles of the assembled tiles
+  int gram_rch = 1, gram_ldx = 2, gram_tiles = 2, gram_stage_off = 2, gram_threads = 256;  // gram_level_kernel: staged rows per chunk, their leading dimension, doubles of the assembled tiles
   bool gram_skip = false;          // every block of the level is fused into its parent
 };
 
