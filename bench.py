@@ -169,6 +169,9 @@ def main():
     ap.add_argument("--ref-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="iterations of the end-to-end leg (default: --steps)")
+    ap.add_argument("--e2e-sd", type=float, default=1e-8,
+                    help="diagonal of mcmcsd in the end-to-end leg (the proposal covariance in logit space, spamtree_fit.cpp:95): small "
+                         "enough that a share of the proposals is accepted at n = 1M, as in a tuned chain; the accepted count is reported")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner ...) goes to stderr
     real_stdout = os.dup(1)
@@ -248,7 +251,7 @@ def main():
     bounds = synth.default_bounds(d["q"])
     npar = theta.size
     barrier()
-    res = gm.mcmc(bounds, np.eye(npar) * 1e-4, keep=e2e_steps, burn=0, thin=1, adapting=True, rng_mode=1, seed=5,
+    res = gm.mcmc(bounds, np.eye(npar) * args.e2e_sd, keep=e2e_steps, burn=0, thin=1, adapting=True, rng_mode=1, seed=5,
                   sample_predicts=False, save_w=True, save_yhat=False, faithful_beta_index=(world == 1))
     te = torch.tensor([res["mcmc_time"]], dtype=torch.float64, device=dev)
     if world > 1:
@@ -285,7 +288,7 @@ def main():
                                        f"{world} ranks, subtree partition below tree level {pl['gc']} (levels above replicated); NCCL all-reduce of "
                                        "3 log-density scalars (x2), cut-level messages and beta/tausq statistics per iteration")},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "accepted": int(res["n_accepted"]), "chol_fail": int(res["n_chol_fail"]), "mcmcsd_diag": args.e2e_sd,
                     "path": "SpamTreeMV.mcmc -> st_mcmc_run (spamtree_mv_mcmc loop), every iteration saved (w copied to the host)"},
             "gpu_launches": int(tw[2]),
             "device_ms_per_step": {"gibbs": float(phase[0]) / args.steps, "llw": float(phase[1]) / args.steps,

@@ -203,23 +203,25 @@ build_level_body(const DevTree& T, const DevSlot& S, double* __restrict__ outG, 
 
   // ---- phase 2: covariance panel K_{pa,u}; rows >= P and columns past the group's are zero
   const bool completing = (MODE == 1 && phase == 2);
-  if (completing) {
-    // deferred half: the panel is Z, parked in G's storage by the forward half, scaled by the stored 1 / sqrt(R_ii)
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    for (int e = tid; e < Ppad * LD; e += nth) panel[e] = 0.0;
-    for (int c = tid; c < ncols; c += nth) rdiag[c] = outRi[s_nrioff[colnode[c]] + (c - s_nc0[colnode[c]])];
-    __syncthreads();
-    for (int c = warp; c < ncols; c += nwarps) {
-      const double* src = S.G + colbase[c];
-      const double ri = rdiag[c];
-      for (int i = lane; i < P; i += 32) panel[(size_t)i * LD + c] = ri * src[i];
-    }
-  }
-  if (!completing) {
+  {
     // zero fill: the columns past the group's (all rows) and the rows past P
     const int npadc = LD - ncols;
     for (int e = tid; e < Ppad * npadc; e += nth) { const int i = e / npadc; panel[(size_t)i * LD + ncols + (e - i * npadc)] = 0.0; }
     for (int e = tid; e < (Ppad - P) * ncols; e += nth) { const int i = e / ncols; panel[(size_t)(P + i) * LD + (e - i * ncols)] = 0.0; }
+  }
+  if (completing) {
+    // deferred half: the panel is Z, parked (unscaled) in G's storage by the forward half.  It goes straight into the
+    // panel with 8-byte cp.async (the transposition rules out wider copies) and lands together with the first stage of
+    // the sweep; the 1 / sqrt(R_ii) scaling is applied to the sweep's outputs.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int c = tid; c < ncols; c += nth) rdiag[c] = outRi[s_nrioff[colnode[c]] + (c - s_nc0[colnode[c]])];
+    for (int e = tid; e < ncols * P; e += nth) {
+      const int c = e / P, i = e - c * P;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(panel + (size_t)i * LD + c)),
+                   "l"(S.G + colbase[c] + i) : "memory");
+    }
+  }
+  if (!completing) {
     // lanes over columns, warps over rows, kCovIlp independent evaluations in flight per thread.  The last, partial run of
     // 32 columns is packed: with w = the power of two that holds them, a warp covers 32 / w rows at once.
     auto cov_cols = [&](int c, bool act, int ifirst, int istep) {
@@ -508,7 +510,8 @@ build_level_body(const DevTree& T, const DevSlot& S, double* __restrict__ outG, 
   }
 
   // ---- backward sweep: out' = L^-T panel, written straight to global memory (row block layout of the group's blocks)
-  auto bwd_sweep = [&](double* __restrict__ out, bool do_gw) {
+  // scale: column c of the result is multiplied by rdiag[c] (non-reference rows: G_i = H_i / sqrt(R_ii), :945-948)
+  auto bwd_sweep = [&](double* __restrict__ out, bool do_gw, bool scale) {
     double gacc[2] = {0, 0};
     if (ns == 2 && nstg > 0) issue_bwd(0, ring);
     for (int i = 0; i < nstg; i++) {
@@ -548,7 +551,8 @@ build_level_body(const DevTree& T, const DevSlot& S, double* __restrict__ outG, 
           }
           const int r = r0 + (lane >> 2), c = 8 * my_nt + 2 * (lane & 3);
           const long long cb0 = colbase[c], cb1 = colbase[c + 1];
-          const double v00 = -z0.x, v01 = -z0.y, v10 = -z1.x, v11 = -z1.y;
+          const double sc0 = scale ? -rdiag[c] : -1.0, sc1 = scale ? -rdiag[c + 1] : -1.0;
+          const double v00 = sc0 * z0.x, v01 = sc1 * z0.y, v10 = sc0 * z1.x, v11 = sc1 * z1.y;
           if (r < P) {
             if (cb0 >= 0) out[cb0 + r] = v00;
             if (cb1 >= 0) out[cb1 + r] = v01;
@@ -596,20 +600,28 @@ build_level_body(const DevTree& T, const DevSlot& S, double* __restrict__ outG, 
     }
   };
   if (MODE == 2) {
-    bwd_sweep(outG, false);  // H of the prediction blocks
+    bwd_sweep(outG, false, false);  // H of the prediction blocks
   } else if (MODE == 1 && phase == 1) {
     // forward half only: park Z (unscaled) where G will go; the backward sweep runs if and when the slot is taken up
-    for (int c = warp; c < ncols; c += nwarps) {
-      double* dst = outG + colbase[c];
-      for (int i = lane; i < P; i += 32) dst[i] = panel[(size_t)i * LD + c];
+    // (a warp moves 4 rows x 8 columns at a time: with LD = 4 mod 8 the 16 reads of a half-warp fall into 16 different
+    // banks, and every four lanes fill one 32-byte sector of a column of Z)
+    {
+      const int ntile = (ncols + 7) >> 3, Ph = ((P + 7) >> 3) << 2;
+      for (int item = warp; item < 2 * ntile; item += nwarps) {
+        const int c = 8 * (item >> 1) + (lane >> 2);
+        if (c >= ncols) continue;
+        double* dst = outG + colbase[c];
+        const int ibeg = (item & 1) * Ph, iend = (item & 1) ? P : min(P, Ph);
+        for (int i = ibeg + (lane & 3); i < iend; i += 4) dst[i] = panel[(size_t)i * LD + c];
+      }
     }
     finalize();
   } else if (completing) {
     __syncthreads();
-    bwd_sweep(outG, false);
+    bwd_sweep(outG, false, true);
   } else {
     if (outH != nullptr) {
-      bwd_sweep(outH, false);  // H = K_{u,pa} Kxx_inv (:887), kept only on request
+      bwd_sweep(outH, false, false);  // H = K_{u,pa} Kxx_inv (:887), kept only on request
       if (MODE == 0) {  // the sweep used the ring: reload Ri
         const int sumRb = s_sumRb;
         for (int e = tid; e < sumRb; e += nth) Rb[e] = 0.0;
@@ -655,15 +667,11 @@ build_level_body(const DevTree& T, const DevSlot& S, double* __restrict__ outG, 
           }
         }
       }
-    } else {
-      for (int e = tid; e < Ppad * NCp; e += nth) {
-        const int pp = e / NCp, c = e - pp * NCp;
-        panel[(size_t)pp * LD + c] *= rdiag[c];  // non-reference rows: G_i = H_i / sqrt(R_ii)
-      }
     }
     __syncthreads();
     mark(5);
-    bwd_sweep(outG, true);  // G = Ri H (bottom-left block of Kxx_invchol(u), tree_utils.cpp:205)
+    // G = Ri H (bottom-left block of Kxx_invchol(u), tree_utils.cpp:205); non-reference rows: the sweep scales its outputs
+    bwd_sweep(outG, true, MODE != 0);
     finalize();
   }
   mark(6);

@@ -210,8 +210,8 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
     }
     lap(6, tl);
   }
-  if (async_save) { guard.on = false; rc = M.save_end(); if (rc) return rc; }  // the timed region ends when every saved w is on the host
-  out.mcmc_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (async_save) { rc = M.save_sync(); if (rc) return rc; }  // the timed region ends when every saved w is on the host
+  out.mcmc_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();  // (the guard releases the page lock)
   if (prof)
     fprintf(stderr, "[mcmc profile] rank %d: %d iterations, %lld accepted; ms/iteration: gibbs %.3f llw %.3f build %.3f accept+adapt %.3f predict %.3f tausq+beta %.3f save %.3f | total %.3f\n",
             M.rank, mcmc, (long long)out.n_accepted, 1e3 * tph[0] / mcmc, 1e3 * tph[1] / mcmc, 1e3 * tph[2] / mcmc, 1e3 * tph[3] / mcmc,

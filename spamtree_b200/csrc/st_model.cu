@@ -1159,12 +1159,17 @@ int Model::save_w_async(double* host_dst) {
   return 0;
 }
 
-int Model::save_end() {
+int Model::save_sync() {
   int rc = 0;
   if (copy_stream && save_pending) {
     if (cudaStreamSynchronize(copy_stream) != cudaSuccess) { err = "asynchronous save of w failed"; rc = 2; }
     save_pending = false;
   }
+  return rc;
+}
+
+int Model::save_end() {
+  const int rc = save_sync();
   if (save_registered) { cudaHostUnregister(save_registered); save_registered = nullptr; }
   return rc;
 }

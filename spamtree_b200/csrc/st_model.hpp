@@ -198,6 +198,7 @@ class Model {
   // saved iterations: un-permute w on the device and copy it to `host_dst` (page-locked by save_begin) on a second
   // stream, so that the copy overlaps the next iteration; save_end waits for the copies in flight
   int save_begin(double* host_base, size_t bytes);
+  int save_sync();  // waits for the copies in flight (every saved w is on the host); save_end also releases the page lock
   int save_w_async(double* host_dst);
   int save_end();
   int set_w(const double* in);
