@@ -85,11 +85,26 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
     const int r = e / k, j = e - r * k;
     const int mj = c_m[j], po = c_po[j];
     const double* g = G + (size_t)r * gs + po;
-    double s0 = 0, s1 = 0;
+    const double* wv = wpa + po;
+    double s[4] = {0, 0, 0, 0};
     int pp = 0;
-    for (; pp + 1 < mj; pp += 2) { s0 = fma(g[pp], wpa[po + pp], s0); s1 = fma(g[pp + 1], wpa[po + pp + 1], s1); }
-    if (pp < mj) s0 = fma(g[pp], wpa[po + pp], s0);
-    gwj[j * m + r] = s0 + s1;
+    for (; pp + 8 <= mj; pp += 8) {  // eight independent global loads in flight per thread (this is the first touch of G: HBM latency)
+      double x[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) x[u] = g[pp + u];
+#pragma unroll
+      for (int u = 0; u < 8; u++) s[u & 3] = fma(x[u], wv[pp + u], s[u & 3]);
+    }
+    if (pp + 4 <= mj) {
+      double x[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) x[u] = g[pp + u];
+#pragma unroll
+      for (int u = 0; u < 4; u++) s[u] = fma(x[u], wv[pp + u], s[u]);
+      pp += 4;
+    }
+    for (; pp < mj; pp++) s[0] = fma(g[pp], wv[pp], s[0]);
+    gwj[j * m + r] = (s[0] + s[1]) + (s[2] + s[3]);
   }
   __syncthreads();
   for (int r = tid; r < m; r += nth) {
@@ -228,11 +243,25 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
     const int rsj = gs;
     const double* g = G + e;
     const double* vj = gwj + (size_t)j * m;
-    double s0 = 0, s1 = 0;
+    double sa[4] = {0, 0, 0, 0};
     int r = 0;
-    for (; r + 1 < m; r += 2) { s0 = fma(g[(size_t)r * rsj], vj[r], s0); s1 = fma(g[(size_t)(r + 1) * rsj], vj[r + 1], s1); }
-    if (r < m) s0 = fma(g[(size_t)r * rsj], vj[r], s0);
-    double s = s0 + s1;
+    for (; r + 8 <= m; r += 8) {  // eight independent loads in flight per thread
+      double x[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) x[u] = g[(size_t)(r + u) * rsj];
+#pragma unroll
+      for (int u = 0; u < 8; u++) sa[u & 3] = fma(x[u], vj[r + u], sa[u & 3]);
+    }
+    if (r + 4 <= m) {
+      double x[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) x[u] = g[(size_t)(r + u) * rsj];
+#pragma unroll
+      for (int u = 0; u < 4; u++) sa[u] = fma(x[u], vj[r + u], sa[u]);
+      r += 4;
+    }
+    for (; r < m; r++) sa[0] = fma(g[(size_t)r * rsj], vj[r], sa[0]);
+    double s = (sa[0] + sa[1]) + (sa[2] + sa[3]);
     if (!T.limited)  // (limited trees: the children's messages stop at this block)
       for (int c = 0; c < nch; c++) s += V[(c < 16 ? c_voff[c] : T.voff[ch[c]]) + e];
     Vd[e] = s;
