@@ -25,8 +25,8 @@ sys.path.insert(0, ROOT)
 METRIC = "mcmc_iterations_per_sec"
 UNIT = "it/s"
 # DRAM traffic (bytes) of all build_level_kernel launches of ONE BUILD, from an ncu pass on a B200 of this pool
-# (profiles/r1_launches_v4.txt); None until measured for a workload
-NCU_BUILD_DRAM_BYTES = {"C4": 2.400e9}
+# (profiles/r1_launches_v5.txt); None until measured for a workload
+NCU_BUILD_DRAM_BYTES = {"C4": 2.4025e9}
 
 
 def load_peaks():
@@ -301,7 +301,7 @@ def main():
                          "achieved": f_alg_build / (build_ms * 1e-3) / 1e12 if build_ms > 0 else None,
                          "peak": fp64_peak_job, "unit": "TFLOP/s", "frac": None,
                          "traffic": traffic,
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum over the build_level_kernel launches of one BUILD (profiles/r1_launches_v4.txt)",
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum over the build_level_kernel launches of one BUILD (profiles/r1_launches_v5.txt)",
                          "achieved_executed": f_exec_build / (build_ms * 1e-3) / 1e12 if build_ms > 0 else None,
                          "algorithmic_output_bytes": b_alg_build,
                          "whole_step": {"achieved": None, "achieved_executed": None, "frac": None},

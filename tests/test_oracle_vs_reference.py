@@ -12,18 +12,21 @@ from oracle import ref
 pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libspamtree_ref.so not built (needs /root/reference)")
 
 
-def _pair(q, n, missing=.1, limited=False):
-    pb = common.make_problem(q, n, missing=missing, limited=limited)
+def _pair(q, n, missing=.1, limited=False, cell_size=25):
+    pb = common.make_problem(q, n, missing=missing, limited=limited, cell_size=cell_size)
     d, t = pb["d"], pb["tree"]
     rm = ref.RefModel(d["y"], d["X"], d["coords"], d["mv_id"], t["res_is_ref"], pb["csr"], limited, t["block_names"], t["block_groups"],
                       pb["beta"], pb["theta"], pb["tausq"])
     return pb, rm, common.oracle_model(pb)
 
 
-@pytest.mark.parametrize("q,n,tol,limited", [(1, 625, 2e-9, False), (2, 1500, 1e-10, False), (3, 3000, 1e-10, False), (5, 2500, 1e-10, False),
-                                             (3, 900, 1e-10, False), (3, 1500, 1e-10, True), (1, 625, 2e-9, True)])
-def test_oracle_matches_reference_model_layer(q, n, tol, limited):
-    pb, rm, om = _pair(q, n, limited=limited)
+@pytest.mark.parametrize("q,n,tol,limited,cell", [(1, 625, 2e-9, False, 25), (2, 1500, 1e-10, False, 25), (3, 3000, 1e-10, False, 25),
+                                                  (5, 2500, 1e-10, False, 25), (3, 900, 1e-10, False, 25), (3, 1500, 1e-10, True, 25),
+                                                  (1, 625, 2e-9, True, 25),
+                                                  # other cell sizes (rows per reference block), incl. blocks of more than 32 rows
+                                                  (2, 1500, 1e-10, False, 9), (2, 2000, 1e-10, False, 36), (3, 3000, 1e-10, False, 49)])
+def test_oracle_matches_reference_model_layer(q, n, tol, limited, cell):
+    pb, rm, om = _pair(q, n, limited=limited, cell_size=cell)
     t = pb["tree"]
     nb = t["n_blocks"]
     # integer bookkeeping of the constructor: bit-exact (spamtree_model.cpp:194-420)
