@@ -518,7 +518,7 @@ int Model::build_layout(std::string& e) {
       // four co-resident CTAs per SM where a 256-thread CTA has two: the staged chunk is sized for that many (the kernel is
       // latency-bound: load, compute and store phases of different CTAs overlap).
       L.gram_threads = std::min(kGramThreads, std::max(64, (maxitems + 31) & ~31));
-      if (L.nslots <= 2 * 148) L.gram_threads = kGramThreads;  // a level that does not fill the GPU is a latency chain: widest CTA
+      if (L.nslots <= 2 * n_sm) L.gram_threads = kGramThreads;  // a level that does not fill the GPU is a latency chain: widest CTA
       L.gram_stage_off = (maxitems <= L.gram_threads) ? 0 : (int)tiles;
       const size_t fixed = (size_t)L.gram_stage_off * 8;
       const int ctas = std::max(1, std::min(8, 65536 / (128 * L.gram_threads)));
@@ -720,6 +720,12 @@ int Model::init(std::string& e) {
   if (const char* v = getenv("ST_PDL")) use_pdl = atoi(v) != 0;
   if (const char* v = getenv("ST_MAX_COLS")) max_group_cols = atoi(v);
   if (const char* v = getenv("ST_SMEM_BUDGET")) smem_budget = (size_t)atol(v);
+  if (device >= 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) n_sm = v;
+    else (void)cudaGetLastError();
+  }
+  if (spread_ctas < 0) spread_ctas = n_sm;
   if (const char* v = getenv("ST_SPREAD")) spread_ctas = atoi(v);
   int rc = build_bookkeeping(e);
   if (rc) return rc;

@@ -108,7 +108,8 @@ class Model {
   bool use_pdl = true;       // level launches of a BUILD use programmatic dependent launch (ST_PDL=0 disables)
   bool defer_leaves = true;  // childless non-reference levels: backward half of BUILD only when the slot is taken up (ST_DEFER=0 disables)
   int max_group_cols = 104;  // upper bound on the columns one BUILD work group handles (one warp per 8 columns)
-  int spread_ctas = 148;     // levels with few blocks use smaller groups, as long as the groups stay within this many CTAs (ST_SPREAD; 0 disables)
+  int n_sm = 148;            // SMs of the device (B200: 148; queried at init when the handle has a device)
+  int spread_ctas = -1;      // levels with few blocks use smaller groups, as long as the groups stay within this many CTAs (default: the SM count; ST_SPREAD; 0 disables)
   bool probes = true;        // record Sigi_tot / Smu_tot of the last Gibbs sweep (st_get_node_state)
   // ---- bookkeeping, same meaning as the reference's members
   int64_t n_obs = 0;
