@@ -135,24 +135,24 @@ def run_reference(args, rank, world, emit):
     if rank != 0:
         return
     d, t, csr, theta = build_problem(args.workload, 2021)
-    steps = max(1, min(args.steps, args.ref_steps))
-    warm = min(args.warmup, 1)
+    warm = max(1, min(args.warmup, 1))
     from oracle import oracle as orc
     om = orc.OracleModel(d["y"], d["X"], d["coords"], d["mv_id"], t["res_is_ref"], csr, False, t["block_names"], t["block_groups"],
                          np.zeros(3), theta, 0.1, flags=orc.FLAG_LEAN)
     orc.lib().or_set_threads(host_threads())  # every host thread, also under torchrun (which exports OMP_NUM_THREADS=1)
     cores = orc.lib().or_max_threads()
     om.get_loglik_comps_w(0)
-    props = proposals(theta, warm + steps, 99)
-    for i in range(warm):
-        om.timed_iteration(props[i], False)
+    props = proposals(theta, warm + args.steps, 99)
+    t_warm = max(om.timed_iteration(props[i], False) for i in range(warm))
+    # exactly --steps iterations unless that would take more than ~2.5 minutes of CPU time (or --ref-steps says otherwise)
+    steps = max(1, min(args.steps, args.ref_steps if args.ref_steps > 0 else max(2, int(150.0 / max(t_warm, 1e-6)))))
     ts = [om.timed_iteration(props[warm + i], do_swap=(i % 4 == 3)) for i in range(steps)]
     v = steps / float(np.sum(ts))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "n": int(d["y"].size), "q": int(d["q"]), "blocks": int(t["n_blocks"]),
                        "note": "reference algorithm (CPU oracle port, OpenMP over the blocks of a level) on the host cores; "
-                               "steps clamped to --ref-steps so that the run ends within minutes"},
+                               "--steps iterations, fewer only if they would not fit ~2.5 minutes"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": int(cores), "kind": "port",
                              "sample": f"{steps} timed iteration(s) after {warm} warm-up on the full {args.workload} tree, lean-state oracle"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -166,7 +166,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C4", choices=["C1", "C2", "C3", "C4", "C5"])
-    ap.add_argument("--ref-steps", type=int, default=2)
+    ap.add_argument("--ref-steps", type=int, default=0, help="cap on the timed iterations of --impl reference (0: as many of --steps as fit ~2.5 min)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="iterations of the end-to-end leg (default: --steps)")
     ap.add_argument("--e2e-sd", type=float, default=1e-8,
