@@ -168,6 +168,45 @@ def test_lockstep_chain_matches_oracle_chain():
         om.close()
 
 
+def _batch_means_se(x, nb=20):
+    x = np.asarray(x, dtype=np.float64)
+    L = x.size // nb
+    return float(x[:L * nb].reshape(nb, L).mean(axis=1).std(ddof=1) / np.sqrt(nb))
+
+
+def test_posterior_summaries_are_statistically_equivalent_with_device_rng():
+    """north_star: 'posterior summaries must be statistically equivalent at a fixed seed'.  With rng_mode = 1 the product
+    draws the n-long normal vectors on the device (Philox), so its chain cannot be compared with the oracle's draw by draw
+    (test_lockstep_chain_matches_oracle_chain does that for rng_mode = 0): the two chains are two MCMC estimates of the same
+    posterior and must agree within Monte-Carlo error (batch-means standard errors).  C1 shape (README example: q = 1,
+    n = 625, 10 % missing), 500 burn-in + 1500 kept iterations, RAM adaptation on.  Thresholds calibrated on two oracle
+    chains with different seeds (z <= 1.8 there); theta[1], theta[2] do not enter the q = 1 covariance (cexpcov,
+    covariance_functions.cpp:95-111 uses ai1[0] and thetamv[0] only) and wander over their prior: not compared."""
+    from spamtree_b200 import synth
+    pb = common.make_problem(1, 625)
+    gm, om = common.product_model(pb), common.oracle_model(pb)
+    npar = pb["theta"].size
+    bounds, sd = synth.default_bounds(1), np.eye(npar) * .01
+    kw = dict(keep=1500, burn=500, thin=1, adapting=True, sample_predicts=False)
+    rg = gm.mcmc(bounds, sd, rng_mode=1, seed=11, save_w=True, save_yhat=False, **kw)
+    ro = om.mcmc(bounds, sd, seed=12, **kw)
+    gm.close()
+    om.close()
+    assert rg["n_accepted"] > 150 and ro["n_accepted"] > 150  # both chains move (RAM adaptation targets 23 %)
+    assert abs(rg["n_accepted"] - ro["n_accepted"]) < 0.35 * ro["n_accepted"]
+    pairs = [(f"beta[{a}]", rg["beta_mcmc"][a, :, 0], ro["beta_mcmc"][a, :, 0]) for a in range(3)]
+    pairs += [("tausq", rg["tausq_mcmc"][0], ro["tausq_mcmc"][0]), ("sigmasq = theta[0]", rg["theta_mcmc"][0], ro["theta_mcmc"][0]),
+              ("phi = theta[3]", rg["theta_mcmc"][3], ro["theta_mcmc"][3])]
+    for name, a, b in pairs:
+        se = np.hypot(_batch_means_se(a), _batch_means_se(b))
+        assert abs(a.mean() - b.mean()) <= 4.5 * se, (name, a.mean(), b.mean(), se)
+        if name.startswith(("beta", "tausq")):  # same posterior spread (the Gibbs-sampled, well-mixing parameters)
+            assert 0.5 <= (a.std() + 1e-300) / (b.std() + 1e-300) <= 2.0, (name, a.std(), b.std())
+    mg, mo = rg["w_mcmc"].mean(axis=1), ro["w_mcmc"].mean(axis=1)  # posterior mean of the latent field, all 625 rows
+    assert np.corrcoef(mg, mo)[0, 1] >= 0.995
+    assert np.sqrt(np.mean((mg - mo) ** 2)) <= 0.1 * mo.std()
+
+
 def test_deferred_backward_half_of_childless_levels():
     """with keep_H = 0 the childless non-reference level gets only the forward half of BUILD (log-density); G appears when
     the slot is taken up.  Everything downstream must equal the eager model (keep_H = 1 never defers)."""
