@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--workload", default="C4", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--ref-steps", type=int, default=0, help="cap on the timed iterations of --impl reference (0: as many of --steps as fit ~2.5 min)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-predict-leg", action="store_true", help="skip the extra end-to-end leg with prediction on a thin schedule")
     ap.add_argument("--e2e-steps", type=int, default=0, help="iterations of the end-to-end leg (default: --steps)")
     ap.add_argument("--e2e-sd", type=float, default=1e-8,
                     help="diagonal of mcmcsd in the end-to-end leg (the proposal covariance in logit space, spamtree_fit.cpp:95): small "
@@ -257,6 +258,19 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = e2e_steps / float(te[0])
+    # the same driver with prediction at the missing rows (predict_std, spamtree_model.cpp:1234-1358) on a thin schedule,
+    # as SURVEY §8d asks: every 5th iteration is a saved one (predict + w to the host).  Single GPU only, reported beside e2e.
+    e2e_pred = None
+    if world == 1 and not args.no_predict_leg:
+        try:
+            thin, kp = 5, max(2, e2e_steps // 5)
+            rp = gm.mcmc(bounds, np.eye(npar) * args.e2e_sd, keep=kp, burn=0, thin=thin, adapting=True, rng_mode=1, seed=6,
+                         sample_predicts=True, save_w=True, save_yhat=False, faithful_beta_index=True)
+            e2e_pred = {"value": kp * thin / float(rp["mcmc_time"]), "unit": UNIT, "iterations": kp * thin, "thin": thin,
+                        "accepted": int(rp["n_accepted"]),
+                        "note": "sample_predicts = TRUE: prediction blocks rebuilt and sampled, w saved, on every 5th iteration"}
+        except Exception as ex:  # a reported extra, never allowed to take the bench line down
+            e2e_pred = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
     cnt = gm.counters()
     tw = torch.tensor([cnt["f_alg"], cnt["f_exec"], c1["launches"] - c0["launches"], cnt["f_alg_build"], cnt["f_exec_build"],
                        cnt["b_alg_build"]], dtype=torch.float64, device=dev)
@@ -290,6 +304,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "accepted": int(res["n_accepted"]), "chol_fail": int(res["n_chol_fail"]), "mcmcsd_diag": args.e2e_sd,
                     "path": "SpamTreeMV.mcmc -> st_mcmc_run (spamtree_mv_mcmc loop), every iteration saved (w copied to the host)"},
+            "e2e_with_predict": e2e_pred,
             "gpu_launches": int(tw[2]),
             "device_ms_per_step": {"gibbs": float(phase[0]) / args.steps, "llw": float(phase[1]) / args.steps,
                                    "build": build_ms, "beta_tausq": float(phase[3]) / args.steps, "max_over_ranks_total": 1e3 * dev_s_max / args.steps},
