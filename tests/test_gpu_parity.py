@@ -15,18 +15,22 @@ CASES = [(1, 625, .1), (1, 2500, .1), (2, 2000, .1), (3, 3000, .1), (5, 4000, .1
          (3, 3000, .1, True), (1, 625, .1, True),   # 4th entry: limited_tree = TRUE (make_edges_limited, spamtree_model.cpp:901-903)
          # 5th entry: cell_size of spamtree() (R/spamtree_fit.R:229-233) = rows per reference block: blocks smaller than the
          # default 25, and blocks of more than 32 rows, which take the kernels' general (not register-resident) Cholesky paths
-         (2, 1500, .1, False, 9), (1, 1200, .1, False, 16), (2, 2500, .1, False, 36), (3, 4000, .1, False, 49)]
+         (2, 1500, .1, False, 9), (1, 1200, .1, False, 16), (2, 2500, .1, False, 36), (3, 4000, .1, False, 49),
+         # half of the rows missing; 6th entry: strongly imbalanced outcome proportions (those of C4 / C5)
+         (3, 2400, .5), (3, 3000, .1, False, 25, (.6, .3, .1)), (5, 4000, .1, False, 25, (.55, .25, .10, .07, .03))]
 
 
 def _case_id(c):
-    return f"q{c[0]}_n{c[1]}_miss{c[2]}" + ("_limited" if len(c) > 3 and c[3] else "") + (f"_cell{c[4]}" if len(c) > 4 else "")
+    return (f"q{c[0]}_n{c[1]}_miss{c[2]}" + ("_limited" if len(c) > 3 and c[3] else "") + (f"_cell{c[4]}" if len(c) > 4 and c[4] != 25 else "") +
+            ("_imbalanced" if len(c) > 5 else ""))
 
 
 @pytest.fixture(scope="module", params=CASES, ids=_case_id)
 def pair(request):
     q, n, missing = request.param[:3]
     pb = common.make_problem(q, n, missing=missing, limited=len(request.param) > 3 and request.param[3],
-                             cell_size=request.param[4] if len(request.param) > 4 else 25)
+                             cell_size=request.param[4] if len(request.param) > 4 else 25,
+                             proportions=request.param[5] if len(request.param) > 5 else None)
     gm, om = common.product_model(pb), common.oracle_model(pb)
     w0 = np.random.default_rng(7).standard_normal(n) * .5
     gm.w = w0

@@ -12,21 +12,25 @@ from oracle import ref
 pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libspamtree_ref.so not built (needs /root/reference)")
 
 
-def _pair(q, n, missing=.1, limited=False, cell_size=25):
-    pb = common.make_problem(q, n, missing=missing, limited=limited, cell_size=cell_size)
+def _pair(q, n, missing=.1, limited=False, cell_size=25, proportions=None):
+    pb = common.make_problem(q, n, missing=missing, limited=limited, cell_size=cell_size, proportions=proportions)
     d, t = pb["d"], pb["tree"]
     rm = ref.RefModel(d["y"], d["X"], d["coords"], d["mv_id"], t["res_is_ref"], pb["csr"], limited, t["block_names"], t["block_groups"],
                       pb["beta"], pb["theta"], pb["tausq"])
     return pb, rm, common.oracle_model(pb)
 
 
-@pytest.mark.parametrize("q,n,tol,limited,cell", [(1, 625, 2e-9, False, 25), (2, 1500, 1e-10, False, 25), (3, 3000, 1e-10, False, 25),
-                                                  (5, 2500, 1e-10, False, 25), (3, 900, 1e-10, False, 25), (3, 1500, 1e-10, True, 25),
-                                                  (1, 625, 2e-9, True, 25),
-                                                  # other cell sizes (rows per reference block), incl. blocks of more than 32 rows
-                                                  (2, 1500, 1e-10, False, 9), (2, 2000, 1e-10, False, 36), (3, 3000, 1e-10, False, 49)])
-def test_oracle_matches_reference_model_layer(q, n, tol, limited, cell):
-    pb, rm, om = _pair(q, n, limited=limited, cell_size=cell)
+@pytest.mark.parametrize("q,n,tol,limited,cell,missing,prop", [
+    (1, 625, 2e-9, False, 25, .1, None), (2, 1500, 1e-10, False, 25, .1, None), (3, 3000, 1e-10, False, 25, .1, None),
+    (5, 2500, 1e-10, False, 25, .1, None), (3, 900, 1e-10, False, 25, .1, None), (3, 1500, 1e-10, True, 25, .1, None),
+    (1, 625, 2e-9, True, 25, .1, None),
+    # other cell sizes (rows per reference block), incl. blocks of more than 32 rows
+    (2, 1500, 1e-10, False, 9, .1, None), (2, 2000, 1e-10, False, 36, .1, None), (3, 3000, 1e-10, False, 49, .1, None),
+    # nothing missing (no prediction blocks), half of the rows missing, strongly imbalanced outcomes (the C4 / C5 proportions)
+    (2, 1200, 1e-10, False, 25, 0.0, None), (3, 2400, 1e-10, False, 25, .5, None), (3, 3000, 1e-10, False, 25, .1, (.6, .3, .1)),
+    (5, 4000, 1e-10, False, 25, .1, (.55, .25, .10, .07, .03))])
+def test_oracle_matches_reference_model_layer(q, n, tol, limited, cell, missing, prop):
+    pb, rm, om = _pair(q, n, missing=missing, limited=limited, cell_size=cell, proportions=prop)
     t = pb["tree"]
     nb = t["n_blocks"]
     # integer bookkeeping of the constructor: bit-exact (spamtree_model.cpp:194-420)
