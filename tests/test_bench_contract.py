@@ -1,0 +1,37 @@
+"""bench.py's CPU-runnable arm (--impl reference: the reference algorithm's CPU port on the host cores) prints ONE JSON line
+with the keys the measurement contract names; the CUDA arm needs a GPU and is exercised by the driver."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*extra, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C1", "--steps", "3",
+                        "--warmup", "1", *extra], capture_output=True, text=True, cwd=ROOT, env=e, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return [l for l in r.stdout.splitlines() if l.strip()]
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    lines = _run()
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "mcmc_iterations_per_sec" and d["unit"] == "it/s"
+    assert d["steps"] == 3 and d["warmup"] == 1 and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1e3) < 1e-6 * 1e3
+    assert d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert d["config"]["workload"] == "C1" and d["config"]["n"] == 625
+    cb, e2e = d["cpu_baseline"], d["e2e"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert e2e == {"value": d["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_runs_on_rank_0_only():
+    # under torchrun the other ranks exit 0 without work (and without output)
+    lines = _run("--gpus", "2", env={"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert lines == []
