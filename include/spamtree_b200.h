@@ -162,6 +162,23 @@ typedef struct {                 /* caller-allocated; NULL pointers are skipped 
 } st_mcmc_out;
 int st_mcmc_run(st_handle* h, const st_mcmc_opts* opts, st_mcmc_out* out);
 
+/* ---- the Metropolis-Hastings glue (mh_adapt.h / mh_adapt.cpp), as st_mcmc_run uses it; host-only, no handle ---- */
+/* par_huvtransf_fwd / par_huvtransf_back (Rcpp exports), mh_adapt.cpp:3-15: logit / logistic on (bounds[j], bounds[j + npar]).
+ * bounds: npar x 2. */
+int st_par_huvtransf_fwd(const double* par, int32_t npar, const double* bounds, double* out);
+int st_par_huvtransf_back(const double* par, int32_t npar, const double* bounds, double* out);
+/* One proposal as spamtree_fit.cpp:211-215 forms it: new_param = back(fwd(param) + paramsd U), clipped by unif_bounds
+ * (mh_adapt.h:188-202).  out: new_param (npar), calc_jacobian(new_param, param) (mh_adapt.h:230-239), out_unif_bounds (0/1). */
+int st_mh_propose(int32_t npar, const double* param, const double* bounds, const double* paramsd, const double* U,
+                  double* out /* npar + 2 */);
+/* do_I_accept, mh_adapt.h:20-36, with the caller's uniform draw u: returns 1 (accept) or 0 */
+int st_do_i_accept(double logaccept, double u);
+/* class RAMAdapt, mh_adapt.h:40-135, over a recorded sequence: U npar x steps, alpha[steps], iteration numbers 0..steps-1.
+ * paramsd_out npar x npar after the last step; paramsd_trace (or NULL) npar*npar per step.  ST_ERR_INVALID when
+ * metropolis_sd is not positive definite (arma::chol throws in the reference, :86). */
+int st_ram_adapt(int32_t npar, const double* metropolis_sd, int32_t steps, const double* U, const double* alpha,
+                 double* paramsd_out, double* paramsd_trace);
+
 /* ---- multi-GPU: native collectives (no reference counterpart) ---- */
 /* Native collective path of a partitioned handle: the library owns an NCCL communicator and enqueues its all-reduces
  * on the handle's own stream (no host synchronisation, no callback).  Rank 0 calls st_nccl_unique_id, the 128 bytes

@@ -87,7 +87,7 @@ def _cm(a):
     return _f(a.T).reshape(-1) if a.ndim == 2 else _f(a).reshape(-1)
 
 
-FLAG_LEAN, FLAG_Q1_NORM_EXPANSION, FLAG_CORRECT_BETA_INDEX, FLAG_PROBES = 1, 2, 4, 8
+FLAG_LEAN, FLAG_Q1_NORM_EXPANSION, FLAG_CORRECT_BETA_INDEX, FLAG_PROBES, FLAG_CORRECT_PREDICT_CACHE = 1, 2, 4, 8, 16
 
 
 class OracleModel:

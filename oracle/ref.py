@@ -51,6 +51,19 @@ def lib():
         L.ref_kthresholds.argtypes = [_dp, C.c_int64, C.c_int, _dp]
         L.ref_cross_covariance_ag10.argtypes = [_dp, _ip, C.c_int64, _dp, _ip, C.c_int64, _dp, _dp, _dp, _dp, C.c_int, _dp, C.c_int, _dp]
         L.ref_number_revalue.argtypes = [_ip, C.c_int64, C.c_int, _ip, _ip, C.c_int64, _ip]
+        L.ref_make_edges.restype = C.c_int
+        L.ref_make_edges.argtypes = [_dp, C.c_int64, C.c_int, _ip, C.c_int64, _ip, C.c_int, _ip, _ip, _ip, _ip, _ip]
+        L.ref_part_axis_parallel_lmt.argtypes = [_dp, C.c_int64, C.c_int, _dp, _ip, _dp]
+        L.ref_ram_adapt.restype = C.c_int
+        L.ref_ram_adapt.argtypes = [C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp]
+        L.ref_propose.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp]
+        L.ref_do_i_accept.restype = C.c_int
+        L.ref_do_i_accept.argtypes = [C.c_double, C.c_double]
+        L.ref_spamtree_mv_mcmc.restype = C.c_int
+        L.ref_spamtree_mv_mcmc.argtypes = [C.c_int64, C.c_int, C.c_int, _dp, _dp, _dp, _ip, C.c_int, _ip, _ip, _ip, _ip, _ip, _ip, _dp, _dp,
+                                           _ip, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_double, _dp, _dp, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, _dp, _dp, _dp, _dp, _dp,
+                                           _dp, _ip, _ip]
         _lib = L
     return _lib
 
@@ -197,3 +210,86 @@ def number_revalue(original_mat, from_val, to_val):
     out = np.zeros(nr * nc, dtype=np.int64)
     lib().ref_number_revalue(_pi(flat), nr, nc, _pi(fv), _pi(tv), fv.size, _pi(out))
     return out.reshape(nc, nr).T.copy()
+
+
+def make_edges(parchimat, non_empty_blocks, res_is_ref, limited=False):
+    """the reference's make_edges / make_edges_limited (tree_dep.cpp:75-186): lists of 0-based ids per block"""
+    pm = np.asarray(parchimat, dtype=np.float64)
+    nr, L = pm.shape
+    flat, ne, rr = _cm(pm), _i(non_empty_blocks), _i(res_is_ref)
+    counts = np.zeros(3, dtype=np.int64)
+    if lib().ref_make_edges(_pd(flat), nr, L, _pi(ne), ne.size, _pi(rr), int(limited), None, None, None, None, _pi(counts)):
+        raise RuntimeError("reference make_edges threw")
+    nb = int(counts[0])
+    pp, pi = np.zeros(nb + 1, np.int64), np.zeros(max(int(counts[1]), 1), np.int64)
+    cp, ci = np.zeros(nb + 1, np.int64), np.zeros(max(int(counts[2]), 1), np.int64)
+    lib().ref_make_edges(_pd(flat), nr, L, _pi(ne), ne.size, _pi(rr), int(limited), _pi(pp), _pi(pi), _pi(cp), _pi(ci), _pi(counts))
+    return {"parents": [pi[pp[i]:pp[i + 1]].copy() for i in range(nb)], "children": [ci[cp[i]:cp[i + 1]].copy() for i in range(nb)]}
+
+
+def part_axis_parallel_lmt(coords, thresholds):
+    """tree_dep.cpp:58-67"""
+    coords = np.asarray(coords, dtype=np.float64)
+    n, d = coords.shape
+    ptr = np.zeros(d + 1, dtype=np.int64)
+    for j in range(d):
+        ptr[j + 1] = ptr[j] + len(thresholds[j])
+    thr = _f(np.concatenate([np.asarray(t, dtype=np.float64) for t in thresholds]) if ptr[-1] else np.zeros(1))
+    cm, out = _cm(coords), np.zeros(n * d)
+    lib().ref_part_axis_parallel_lmt(_pd(cm), n, d, _pd(thr), _pi(ptr), _pd(out))
+    return out.reshape(d, n).T.copy()
+
+
+def ram_adapt(metropolis_sd, U, alpha):
+    """the reference's RAMAdapt (mh_adapt.h:40-135) over a recorded sequence: U (steps x npar), alpha (steps);
+    returns (final paramsd, trace steps x npar x npar)"""
+    U = np.asarray(U, dtype=np.float64)
+    steps, npar = U.shape
+    sd, uu, al = _cm(metropolis_sd), _f(U.reshape(-1)), _f(alpha)
+    out, tr = np.zeros(npar * npar), np.zeros(steps * npar * npar)
+    if lib().ref_ram_adapt(npar, _pd(sd), steps, _pd(uu), _pd(al), _pd(out), _pd(tr)):
+        raise RuntimeError("reference RAMAdapt threw (chol failed)")
+    return out.reshape(npar, npar).T.copy(), tr.reshape(steps, npar, npar).transpose(0, 2, 1).copy()
+
+
+def propose(param, bounds, paramsd, U):
+    """spamtree_fit.cpp:211-215 + calc_jacobian (mh_adapt.h:230-239): (new_param, jacobian, out_of_bounds)"""
+    par, B, sd, u = _f(param), _cm(bounds), _cm(paramsd), _f(U)
+    out = np.zeros(par.size + 2)
+    lib().ref_propose(par.size, _pd(par), _pd(B), _pd(sd), _pd(u), _pd(out))
+    return out[:par.size].copy(), float(out[par.size]), bool(out[par.size + 1])
+
+
+def do_i_accept(logaccept, u):
+    return bool(lib().ref_do_i_accept(float(logaccept), float(u)))
+
+
+def spamtree_mv_mcmc(y, X, coords, mv_id, res_is_ref, csr, limited_tree, block_names, block_groups, beta, theta, tausq, bounds, mcmcsd,
+                     keep, burn, thin, adapting=True, sample_beta=True, sample_tausq=True, sample_theta=True, sample_w=True,
+                     sample_predicts=True, seed=1):
+    """the reference's OWN driver spamtree_mv_mcmc (spamtree_fit.cpp:5-430), its R-side random numbers replaced by the host
+    stream the oracle and the product use (seeded with `seed`)"""
+    y = _f(y).reshape(-1)
+    n = y.size
+    Xa = np.asarray(X, dtype=np.float64).reshape(n, -1)
+    p, mv = Xa.shape[1], _i(mv_id)
+    q = int(np.unique(mv).size)
+    Xc, cc = _cm(Xa), _cm(coords)
+    ip, ii, pp, pi, cp, ci = [_i(a) for a in csr]
+    bn, bg, rr, th, be = _f(block_names), _f(block_groups), _i(res_is_ref), _f(theta), _f(beta)
+    nb, npar = ip.size - 1, th.size
+    B, sd = _cm(bounds), _cm(mcmcsd)
+    bm, tm, thm = np.zeros(p * keep * q), np.zeros(q * keep), np.zeros(npar * keep)
+    w, yh, psd = np.zeros(n * keep), np.zeros(n * keep), np.zeros(npar * npar)
+    bco, pil = np.zeros(nb, dtype=np.int64), np.zeros(nb, dtype=np.int64)
+    rc = lib().ref_spamtree_mv_mcmc(n, p, q, _pd(y), _pd(Xc), _pd(cc), _pi(mv), nb, _pi(ip), _pi(ii), _pi(pp), _pi(pi), _pi(cp), _pi(ci),
+                                    _pd(bn), _pd(bg), _pi(rr), rr.size, int(bool(limited_tree)), _pd(th), npar, _pd(be), float(tausq),
+                                    _pd(B), _pd(sd), keep, burn, thin, int(adapting), int(sample_beta), int(sample_tausq),
+                                    int(sample_theta), int(sample_w), int(sample_predicts), int(seed), _pd(bm), _pd(tm), _pd(thm), _pd(w),
+                                    _pd(yh), _pd(psd), _pi(bco), _pi(pil))
+    if rc:
+        raise RuntimeError("the reference's spamtree_mv_mcmc threw")
+    return {"w_mcmc": w.reshape(keep, n).T.copy(), "yhat_mcmc": yh.reshape(keep, n).T.copy(),
+            "beta_mcmc": bm.reshape(q, keep, p).transpose(2, 1, 0).copy(), "tausq_mcmc": tm.reshape(keep, q).T.copy(),
+            "theta_mcmc": thm.reshape(keep, npar).T.copy(), "paramsd": psd.reshape(npar, npar).T.copy(),
+            "block_ct_obs": bco, "parents_indexing_len": pil}

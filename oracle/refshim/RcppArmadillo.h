@@ -8,6 +8,8 @@
 // dtrtri-like).  Nothing in the product includes this file.
 #pragma once
 #include <algorithm>
+#include <any>
+#include <map>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -76,7 +78,8 @@ struct Mat : arma_tag {
   subview_elem<T> operator()(const Mat<uword>& r, const Mat<uword>& c);
   void fill(T v) { std::fill(mem.begin(), mem.end(), v); }
   Mat<T>& zeros() { fill(T(0)); return *this; }
-  T max() const { T m = mem.at(0); for (auto v : mem) if (v > m) m = v; return m; }
+  // as Armadillo's op_max::direct_max: starts from the most negative value, so NaN entries never win a comparison
+  T max() const { (void)mem.at(0); T m = std::numeric_limits<T>::has_infinity ? -std::numeric_limits<T>::infinity() : std::numeric_limits<T>::lowest(); for (auto v : mem) if (v > m) m = v; return m; }
   T min() const { T m = mem.at(0); for (auto v : mem) if (v < m) m = v; return m; }
   bool is_empty() const { return n_elem == 0; }
   Mat<T> t() const {
@@ -316,6 +319,16 @@ struct Cube : arma_tag {
     template <class V> subcube_view& operator=(const V& v) { const Mat<T> b = v.eval(); for (uword j = 0; j < c->n_cols; j++) c->sl[s](r, j) = b.mem[j]; return *this; }
   };
   subcube_view subcube(uword r1, uword, uword s1, uword, uword, uword) { return subcube_view{this, r1, s1}; }
+  struct col_view {  // cube.col(j): an n_rows x n_slices matrix view (as arma)
+    Cube<T>* c; uword j;
+    template <class V> col_view& operator=(const V& v) {
+      const Mat<T> b = v.eval();
+      if (b.n_rows != c->n_rows || b.n_cols != c->n_slices) throw std::logic_error("cube.col(): size mismatch");
+      for (uword s = 0; s < c->n_slices; s++) for (uword i = 0; i < c->n_rows; i++) c->sl[s](i, j) = b(i, s);
+      return *this;
+    }
+  };
+  col_view col(uword j) { return col_view{this, j}; }
   T& operator()(uword i, uword j, uword s) { return sl[s](i, j); }
 };
 typedef Cube<double> cube;
@@ -680,11 +693,15 @@ struct StringMatrix {
 struct RObject {};
 struct NamedValue {
   std::string name;
-  template <class T> NamedValue& operator=(const T&) { return *this; }
+  std::any value;  // a copy of what was assigned (arma::field<...>, arma::mat, double ...)
+  template <class T> NamedValue& operator=(const T& v) { value = v; return *this; }
 };
-inline NamedValue Named(const std::string& n) { return NamedValue{n}; }
-struct List {
-  template <class... A> static List create(const A&...) { return List(); }
+inline NamedValue Named(const std::string& n) { return NamedValue{n, std::any()}; }
+struct List {  // retains its fields so that the driver can read what the reference returned
+  std::map<std::string, std::any> fields;
+  template <class... A> static List create(const A&... a) { List l; (l.fields.emplace(a.name, a.value), ...); return l; }
+  template <class T> const T& get(const std::string& n) const { return std::any_cast<const T&>(fields.at(n)); }
+  bool has(const std::string& n) const { return fields.count(n) != 0; }
 };
 }  // namespace Rcpp
 namespace R {
@@ -692,3 +709,9 @@ inline double runif(double a, double b) { auto& h = arma::rng_hooks(); return a 
 inline double rgamma(double shape, double scale) { auto& h = arma::rng_hooks(); return h.gamma ? h.gamma(shape, scale) : shape * scale; }
 }  // namespace R
 inline void Rprintf(const char*, ...) {}
+// interrupt_handler.h: never interrupted
+#ifndef FALSE
+#define FALSE 0
+#endif
+inline void R_CheckUserInterrupt() {}
+inline int R_ToplevelExec(void (*fn)(void*), void* d) { fn(d); return 1; }

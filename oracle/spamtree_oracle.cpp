@@ -295,6 +295,10 @@ struct Model {
   bool q1_norm_expansion = false;  // App. D #1: cexpcov's |x|^2+|y|^2-2xy distance instead of direct difference
   bool faithful_beta_index = true; // App. D #12
   bool probes = false;
+  // App. D #13: predict(theta_update = false) on a slot whose prediction weights were never computed uses the zeros they
+  // were allocated as (spamtree_model.cpp:472-473, :1256-1296): H = 0, Kxc = 0 -> a draw from the marginal N(0, K_ii).
+  // The state is per theta-slot and survives accept_make_change's swap.  false = recompute instead (what the product does)
+  bool faithful_predict_cache = true;
   // derived
   int64_t n = 0;
   ivec na_ix_all;
@@ -841,7 +845,10 @@ static void predict(Model& M, bool theta_update) {
     const ivec& ix = M.indexing[u];
     const ivec& pix = M.parents_indexing[u];
     const int m = (int)ix.size(), P = (int)pix.size();
-    if (theta_update || d.H[u].empty()) {
+    if (!theta_update && d.H[u].empty() && M.faithful_predict_cache) {  // never computed in this slot: the allocated zeros (:472-473)
+      d.Kxc[u] = Mat(P, m);
+      d.H[u] = Mat(m, P);
+    } else if (theta_update || d.H[u].empty()) {
       covariancef(d.Kxc[u], M, pix.data(), P, ix.data(), m, M.covpars, false);  // :1258
       const int u_par = (int)M.parents[u].back();
       d.H[u] = mtm(d.Kxc[u], Kxx_inv[u_par]);  // :1296
@@ -988,6 +995,7 @@ void* or_create(int64_t n_all, int p, int q, const double* y, const double* X, c
   M->q1_norm_expansion = (flags & 2) != 0;
   M->faithful_beta_index = (flags & 4) == 0;
   M->probes = (flags & 8) != 0;
+  M->faithful_predict_cache = (flags & 16) == 0;
   dvec th(theta, theta + n_theta), be(beta, beta + p);
   if (!model_init(*M, th, be, 1.0 / tausq)) {
     fprintf(stderr, "oracle: %s\n", M->err.c_str());

@@ -99,6 +99,11 @@ SIGNATURES = {
     "st_mcmc_run": (C.c_int, [C.c_void_p, C.POINTER(StMcmcOpts), C.POINTER(StMcmcOut)]),
     "st_bench_iteration": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_uint64, c_double_p, c_float_p]),
     "st_get_counters": (C.c_int, [C.c_void_p, c_double_p]),
+    "st_par_huvtransf_fwd": (C.c_int, [c_double_p, C.c_int32, c_double_p, c_double_p]),
+    "st_par_huvtransf_back": (C.c_int, [c_double_p, C.c_int32, c_double_p, c_double_p]),
+    "st_mh_propose": (C.c_int, [C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "st_do_i_accept": (C.c_int, [C.c_double, C.c_double]),
+    "st_ram_adapt": (C.c_int, [C.c_int32, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p]),
     "st_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "st_attach_nccl": (C.c_int, [C.c_void_p, C.c_char_p]),
     "st_sync": (C.c_int, [C.c_void_p]),

@@ -195,6 +195,55 @@ def CrossCovarianceAG10(coords1, mv1, coords2, mv2, ai1, ai2, phi_i, thetamv, Dm
     return out.reshape(n2, n1).T.copy()
 
 
+# --------------------------------------------------------------------------------------------- mh_adapt.h / mh_adapt.cpp
+def par_huvtransf_fwd(par, set_unif_bounds):
+    """mh_adapt.cpp:3-8"""
+    a, b = _f64(par), _colmajor(np.asarray(set_unif_bounds, dtype=np.float64))
+    out = np.zeros(a.size)
+    rc = lib.st_par_huvtransf_fwd(_dp(a), a.size, _dp(b), _dp(out))
+    if rc:
+        raise SpamTreeError(rc, "st_par_huvtransf_fwd")
+    return out
+
+
+def par_huvtransf_back(par, set_unif_bounds):
+    """mh_adapt.cpp:10-15"""
+    a, b = _f64(par), _colmajor(np.asarray(set_unif_bounds, dtype=np.float64))
+    out = np.zeros(a.size)
+    rc = lib.st_par_huvtransf_back(_dp(a), a.size, _dp(b), _dp(out))
+    if rc:
+        raise SpamTreeError(rc, "st_par_huvtransf_back")
+    return out
+
+
+def mh_propose(param, set_unif_bounds, paramsd, U):
+    """spamtree_fit.cpp:211-215 + calc_jacobian (mh_adapt.h:230-239): (new_param, jacobian, out_unif_bounds)"""
+    a, b, sd, u = _f64(param), _colmajor(np.asarray(set_unif_bounds, dtype=np.float64)), _colmajor(np.asarray(paramsd, dtype=np.float64)), _f64(U)
+    out = np.zeros(a.size + 2)
+    rc = lib.st_mh_propose(a.size, _dp(a), _dp(b), _dp(sd), _dp(u), _dp(out))
+    if rc:
+        raise SpamTreeError(rc, "st_mh_propose")
+    return out[:a.size].copy(), float(out[a.size]), bool(out[a.size + 1])
+
+
+def do_I_accept(logaccept, u):
+    """mh_adapt.h:20-36 with the caller's uniform draw"""
+    return bool(lib.st_do_i_accept(float(logaccept), float(u)))
+
+
+def ram_adapt(metropolis_sd, U, alpha):
+    """class RAMAdapt (mh_adapt.h:40-135) over a recorded sequence: U steps x npar, alpha (steps).
+    Returns (paramsd after the last step, trace steps x npar x npar)."""
+    U = np.asarray(U, dtype=np.float64)
+    steps, npar = U.shape
+    sd, uu, al = _colmajor(np.asarray(metropolis_sd, dtype=np.float64)), _f64(U.reshape(-1)), _f64(alpha)
+    out, tr = np.zeros(npar * npar), np.zeros(max(steps, 1) * npar * npar)
+    rc = lib.st_ram_adapt(npar, _dp(sd), steps, _dp(uu), _dp(al), _dp(out), _dp(tr))
+    if rc:
+        raise SpamTreeError(rc, "st_ram_adapt: metropolis_sd is not positive definite")
+    return out.reshape(npar, npar).T.copy(), tr[:steps * npar * npar].reshape(steps, npar, npar).transpose(0, 2, 1).copy()
+
+
 # --------------------------------------------------------------------------------------------- the model layer
 class SpamTreeMV:
     """src/spamtree_model.h:22-212.  Constructor arguments follow spamtree_model.cpp:8-37 (lists are 0-based id lists)."""

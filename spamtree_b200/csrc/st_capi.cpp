@@ -8,6 +8,7 @@
 #include "st_kernels.cuh"
 #include <cuda_runtime.h>
 
+#include "st_mh.hpp"
 #include "st_model.hpp"
 #include "st_tree.hpp"
 
@@ -224,6 +225,42 @@ int st_bench_iteration(st_handle* h, const double* theta_prop, int do_swap, uint
   activate(h);
   ST_GUARD_BEGIN return h->model.bench_iteration(theta_prop, do_swap, seed, out3, ms_out);
   ST_GUARD_END(h)
+}
+int st_par_huvtransf_fwd(const double* par, int32_t npar, const double* bounds, double* out) {
+  if (!par || !bounds || !out || npar < 0) return ST_ERR_INVALID;
+  for (int j = 0; j < npar; j++) out[j] = st::mh_logit(par[j], bounds[j], bounds[j + npar]);
+  return ST_OK;
+}
+int st_par_huvtransf_back(const double* par, int32_t npar, const double* bounds, double* out) {
+  if (!par || !bounds || !out || npar < 0) return ST_ERR_INVALID;
+  for (int j = 0; j < npar; j++) out[j] = st::mh_logistic(par[j], bounds[j], bounds[j + npar]);
+  return ST_OK;
+}
+int st_mh_propose(int32_t npar, const double* param, const double* bounds, const double* paramsd, const double* U, double* out) {
+  if (!param || !bounds || !paramsd || !U || !out || npar < 1 || npar > st::kMaxPar) return ST_ERR_INVALID;
+  const bool oob = st::mh_propose(npar, param, bounds, paramsd, U, out);
+  out[npar] = st::mh_jacobian(npar, out, param, bounds);
+  out[npar + 1] = oob ? 1.0 : 0.0;
+  return ST_OK;
+}
+int st_do_i_accept(double logaccept, double u) { return u < st::mh_accept_prob(logaccept) ? 1 : 0; }
+int st_ram_adapt(int32_t npar, const double* metropolis_sd, int32_t steps, const double* U, const double* alpha, double* paramsd_out,
+                 double* paramsd_trace) {
+  if (!metropolis_sd || !paramsd_out || npar < 1 || npar > st::kMaxPar || steps < 0 || (steps > 0 && (!U || !alpha))) return ST_ERR_INVALID;
+  try {
+    const size_t pp = (size_t)npar * npar;
+    std::vector<double> sd(pp), prod(pp), scratch(2 * pp);
+    int started = 0;
+    if (!st::ram_init(npar, metropolis_sd, sd.data(), prod.data())) return ST_ERR_INVALID;
+    for (int m = 0; m < steps; m++) {
+      st::ram_adapt(npar, sd.data(), prod.data(), &started, U + (size_t)m * npar, alpha[m], m, scratch.data());
+      if (paramsd_trace) std::copy(sd.begin(), sd.end(), paramsd_trace + (size_t)m * pp);
+    }
+    std::copy(sd.begin(), sd.end(), paramsd_out);
+    return ST_OK;
+  } catch (...) {
+    return ST_ERR_INVALID;
+  }
 }
 int st_nccl_unique_id(unsigned char* out128) {
   if (!out128) return ST_ERR_INVALID;

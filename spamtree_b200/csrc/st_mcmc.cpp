@@ -7,59 +7,21 @@
 #include <cstdlib>
 
 #include "../../include/spamtree_b200.h"
+#include "st_mh.hpp"
 #include "st_model.hpp"
 
 namespace st {
 
-// mh_adapt.h:150-156
-static inline double logistic(double x, double l, double u) { return l + (u - l) / (1.0 + std::exp(-x)); }
-static inline double logit(double x, double l, double u) { return -std::log((u - l) / (x - l) - 1.0); }
-
-// Robust adaptive Metropolis (Vihola 2012) as the reference runs it: mh_adapt.h:40-135
-class RAMAdapt {
- public:
-  int p = 0, g0 = 50;
-  double alpha_star = .234, gamma = 0.5 + 1e-6;
-  SmallMat paramsd, prodparam;
-  bool started = false;
-  void init(int npars, const double* metropolis_sd) {
+// Robust adaptive Metropolis (Vihola 2012) as the reference runs it, mh_adapt.h:40-135: state of st_mh.hpp's functions
+struct RAMAdapt {
+  int p = 0, started = 0;
+  dvec paramsd, prodparam, scratch;
+  bool init(int npars, const double* metropolis_sd) {
     p = npars;
-    paramsd = SmallMat(p);
-    std::copy(metropolis_sd, metropolis_sd + (size_t)p * p, paramsd.a.begin());
-    small_chol(paramsd);  // :86
-    prodparam = paramsd;
-    for (auto& v : prodparam.a) v /= (g0 + 1.0);  // :87
+    paramsd.assign((size_t)p * p, 0.0); prodparam.assign((size_t)p * p, 0.0); scratch.assign(2 * (size_t)p * p, 0.0);
+    return ram_init(p, metropolis_sd, paramsd.data(), prodparam.data());
   }
-  void adapt(const dvec& U, double alpha, int mc) {  // :117-135
-    if (mc < g0) {
-      for (int j = 0; j < p; j++)
-        for (int i = 0; i < p; i++) prodparam(i, j) += U[i] * U[j] / (mc + 1.0);
-      return;
-    }
-    if (!started) { paramsd = prodparam; started = true; }
-    const int i0 = mc - g0;
-    const double eta = std::min(1.0, (p + .0) * std::pow(i0 + 1.0, -gamma));
-    alpha = std::min(1.0, alpha);
-    double uu = 0;
-    for (int i = 0; i < p; i++) uu += U[i] * U[i];
-    SmallMat Sigma(p), T(p), S(p);
-    for (int j = 0; j < p; j++)
-      for (int i = 0; i < p; i++) Sigma(i, j) = (i == j ? 1.0 : 0.0) + eta * (alpha - alpha_star) * U[i] * U[j] / uu;
-    // mm(paramsd, Sigma) in the same accumulation order as a column-major axpy product
-    for (int j = 0; j < p; j++)
-      for (int k = 0; k < p; k++) {
-        const double b = Sigma(k, j);
-        for (int i = 0; i < p; i++) T(i, j) += paramsd(i, k) * b;
-      }
-    for (int j = 0; j < p; j++)
-      for (int i = 0; i < p; i++) {
-        double s = 0;
-        for (int k = 0; k < p; k++) s += T(i, k) * paramsd(j, k);
-        S(i, j) = s;
-      }
-    SmallMat L = S;
-    if (small_chol(L)) paramsd = L;
-  }
+  bool adapt(const dvec& U, double alpha, int mc) { return ram_adapt(p, paramsd.data(), prodparam.data(), &started, U.data(), alpha, mc, scratch.data()); }
 };
 
 int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
@@ -73,12 +35,14 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
   dvec param = M.theta[M.cur], predict_param = param;
   double current_loglik = M.loglik_w[M.cur];
   const int mcmc = o.thin * o.keep + o.burn;
+  if (npar > kMaxPar) { M.err = "more than 64 covariance parameters"; return ST_ERR_UNSUPPORTED; }
   RAMAdapt ad;
-  ad.init(npar, o.mcmcsd);
+  if (!ad.init(npar, o.mcmcsd)) {  // arma::chol(S, "lower") throws in the reference (mh_adapt.h:86)
+    M.err = "mcmcsd is not positive definite";
+    return ST_ERR_INVALID;
+  }
   int msaved = 0;
   out.n_accepted = out.n_chol_fail = 0;
-  auto lo = [&](int j) { return o.set_unif_bounds[j]; };
-  auto hi = [&](int j) { return o.set_unif_bounds[j + npar]; };
   dvec zbuf, wbuf, xbbuf, zglob;
   if (o.rng_mode == 0) zbuf.resize(M.n_all);
   const bool pglob = M.part && !M.global_rows.empty();  // partitioned: draw for every row of the problem, keep ours
@@ -127,15 +91,7 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
     if (o.sample_theta) {  // :203-289
       dvec U(npar), new_param(npar);
       for (int j = 0; j < npar; j++) U[j] = M.rng.norm();
-      for (int j = 0; j < npar; j++) {
-        double s = logit(param[j], lo(j), hi(j));
-        for (int k = 0; k < npar; k++) s += ad.paramsd(j, k) * U[k];
-        new_param[j] = logistic(s, lo(j), hi(j));
-      }
-      for (int j = 0; j < npar; j++) {  // unif_bounds, mh_adapt.h:188-202
-        if (new_param[j] < lo(j)) new_param[j] = lo(j) + 1e-10;
-        if (new_param[j] > hi(j)) new_param[j] = hi(j) - 1e-10;
-      }
+      mh_propose(npar, param.data(), o.set_unif_bounds, ad.paramsd.data(), U.data(), new_param.data());  // :211-215
       M.theta_update(1, new_param.data());
       rc = M.get_loglik_comps_w(1, o3);
       if (rc) return rc;
@@ -144,14 +100,9 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
       const double new_loglik = M.loglik_w[1 - M.cur];
       current_loglik = M.loglik_w[M.cur];
       if (std::isnan(current_loglik)) { M.err = "At nan loglik: error."; return ST_ERR_NAN; }
-      double jac = 0;  // calc_jacobian, mh_adapt.h:230-239
-      for (int j = 0; j < npar; j++)
-        jac += (-std::log(hi(j) - param[j]) - std::log(param[j] - lo(j))) -
-               (-std::log(hi(j) - new_param[j]) - std::log(new_param[j] - lo(j)));
+      const double jac = mh_jacobian(npar, new_param.data(), param.data(), o.set_unif_bounds);  // mh_adapt.h:230-239
       const double logaccept = new_loglik - current_loglik + jac;
-      double acceptj = 1.0;  // do_I_accept, mh_adapt.h:20-36
-      if (!std::isfinite(logaccept)) acceptj = 0.0;
-      else if (logaccept < 0) acceptj = std::exp(logaccept);
+      const double acceptj = mh_accept_prob(logaccept);  // do_I_accept, mh_adapt.h:20-36
       const double u = M.rng.unif();
       const bool accepted = (u < acceptj) && acceptable;
       if (!acceptable) out.n_chol_fail++;
@@ -161,6 +112,7 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
         M.accept_make_change();
         param = new_param;
       }
+      // (a failed chol(S) keeps the previous factor; the reference's arma::chol would throw and end the run, mh_adapt.h:133)
       if (o.adapting) ad.adapt(U, (acceptable ? 1.0 : 0.0) * std::exp(logaccept), m);  // :285
       lap(3, tl);
     }
@@ -216,7 +168,7 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
     fprintf(stderr, "[mcmc profile] rank %d: %d iterations, %lld accepted; ms/iteration: gibbs %.3f llw %.3f build %.3f accept+adapt %.3f predict %.3f tausq+beta %.3f save %.3f | total %.3f\n",
             M.rank, mcmc, (long long)out.n_accepted, 1e3 * tph[0] / mcmc, 1e3 * tph[1] / mcmc, 1e3 * tph[2] / mcmc, 1e3 * tph[3] / mcmc,
             1e3 * tph[4] / mcmc, 1e3 * tph[5] / mcmc, 1e3 * tph[6] / mcmc, 1e3 * out.mcmc_time / mcmc);
-  if (out.paramsd) std::copy(ad.paramsd.a.begin(), ad.paramsd.a.end(), out.paramsd);
+  if (out.paramsd) std::copy(ad.paramsd.begin(), ad.paramsd.end(), out.paramsd);
   return 0;
 }
 

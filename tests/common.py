@@ -33,7 +33,9 @@ def product_model(pb, **kw):
                          t["block_groups"], None, pb["beta"], pb["theta"], pb["tausq"], csr=pb["csr"], **kw)
 
 
-def oracle_model(pb, flags=orc.FLAG_PROBES):
+def oracle_model(pb, flags=orc.FLAG_PROBES | orc.FLAG_CORRECT_PREDICT_CACHE):
+    """the oracle as the product's checker: the product never predicts from never-computed weights (a
+    reference quirk the oracle reproduces by default and tests/test_reference_driver.py pins), hence the flag"""
     d, t = pb["d"], pb["tree"]
     return orc.OracleModel(d["y"], d["X"], d["coords"], d["mv_id"], t["res_is_ref"], pb["csr"], pb.get("limited", False), t["block_names"],
                            t["block_groups"], pb["beta"], pb["theta"], pb["tausq"], flags=flags)

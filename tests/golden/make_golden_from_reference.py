@@ -2,7 +2,8 @@
 model layer (spamtree_model.cpp, covariance_functions.cpp, tree_utils.cpp, tree_dep.cpp, mh_adapt.cpp) compiled
 unmodified from /root/reference/src against the Armadillo/Rcpp stand-in of oracle/refshim/ (`make -C oracle ref`).
 The reference exists only in the build container, so its outputs are committed here as fixtures; the CPU oracle and the
-CUDA path are both checked against them (tests/test_golden_reference.py).
+CUDA path are both checked against them (tests/test_golden_reference.py).  The ref_chain_*.npz files are whole chains of the reference's own MCMC driver
+(spamtree_fit.cpp, compiled unmodified as well).
 Run (where /root/reference exists):  python tests/golden/make_golden_from_reference.py"""
 import os
 import sys
@@ -70,8 +71,39 @@ def one(q, n, limited):
     print(f"{name}: {len(out)} arrays, loglik {ll:.12g}")
 
 
+# (q, n, limited, diag of mcmcsd, keep, burn, thin, adapting, sample_predicts): whole chains of the reference's OWN DRIVER,
+# spamtree_mv_mcmc (spamtree_fit.cpp:5-430), on the host random stream shared with the oracle and the product (rng_mode 0)
+CHAIN_CASES = [(2, 1200, False, 1e-7, 30, 40, 1, True, False), (3, 900, False, 1e-7, 24, 36, 2, True, True),
+               (3, 1100, True, 1e-7, 20, 0, 1, False, False)]
+
+
+def chain(q, n, limited, sd, keep, burn, thin, adapting, predicts, seed=31):
+    from spamtree_b200 import synth
+    pb = common.make_problem(q, n, limited=limited)
+    d, t = pb["d"], pb["tree"]
+    bounds, npar = synth.default_bounds(q), pb["theta"].size
+    r = ref.spamtree_mv_mcmc(d["y"], d["X"], d["coords"], d["mv_id"], t["res_is_ref"], pb["csr"], limited, t["block_names"],
+                             t["block_groups"], pb["beta"], pb["theta"], pb["tausq"], bounds, np.eye(npar) * sd, keep, burn, thin,
+                             adapting=adapting, sample_predicts=predicts, seed=seed)
+    th = r["theta_mcmc"]
+    nmoves = int(np.sum(np.any(np.diff(th, axis=1) != 0, axis=0)))
+    out = {"q": q, "n": n, "limited": int(limited), "blocking": t["blocking"], "sd": sd, "keep": keep, "burn": burn, "thin": thin,
+           "adapting": int(adapting), "predicts": int(predicts), "seed": seed, "theta_mcmc": th, "beta_mcmc": r["beta_mcmc"],
+           "tausq_mcmc": r["tausq_mcmc"], "paramsd": r["paramsd"], "w_saved": r["w_mcmc"][:, [0, keep // 2, keep - 1]],
+           "yhat_saved": r["yhat_mcmc"][:, [0, keep // 2, keep - 1]], "block_ct_obs": r["block_ct_obs"],
+           "parents_indexing_len": r["parents_indexing_len"]}
+    name = f"ref_chain_q{q}_n{n}" + ("_limited" if limited else "") + ".npz"
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(f"{name}: {keep} saved iterations, theta moved between {nmoves} of them")
+
+
 if __name__ == "__main__":
     if not ref.available():
         raise SystemExit("oracle/_ref/libspamtree_ref.so is missing and /root/reference is not here to build it")
-    for q, n, limited in CASES:
-        one(q, n, limited)
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "model"):
+        for q, n, limited in CASES:
+            one(q, n, limited)
+    if which in ("all", "chain"):
+        for c in CHAIN_CASES:
+            chain(*c)

@@ -88,3 +88,60 @@ def test_cuda_against_reference_outputs(path):
 
 def test_fixtures_are_present():
     assert len(FILES) >= 4 and any(f.endswith("_limited.npz") for f in FILES)
+    assert len(CHAIN_FILES) >= 3
+
+
+# ---- whole chains of the reference's OWN DRIVER (spamtree_mv_mcmc, spamtree_fit.cpp:5-430, compiled unmodified) on the
+# host random stream every implementation shares (rng_mode 0): proposals, Jacobian, accept decisions, RAM adaptation,
+# beta / tausq draws, prediction and the saved w / yhat of a whole run
+CHAIN_FILES = sorted(glob.glob(os.path.join(G, "ref_chain_q*_n*.npz")))
+
+
+def _chain_check(g, r, tol_theta, tol_par, tol_rows):
+    keep = int(g["keep"])
+    sel = [0, keep // 2, keep - 1]
+    errs = {"theta_mcmc": relerr(r["theta_mcmc"], g["theta_mcmc"]), "beta_mcmc": relerr(r["beta_mcmc"], g["beta_mcmc"]),
+            "tausq_mcmc": relerr(r["tausq_mcmc"], g["tausq_mcmc"]), "paramsd": relerr(r["paramsd"], g["paramsd"]),
+            "w": relerr(r["w_mcmc"][:, sel], g["w_saved"]), "yhat": relerr(r["yhat_mcmc"][:, sel], g["yhat_saved"])}
+    print("chain vs the reference's driver:", {k: f"{v:.2e}" for k, v in errs.items()})
+    # identical accept / reject decisions: theta changes between exactly the same saved iterations
+    assert np.array_equal(np.any(np.diff(r["theta_mcmc"], axis=1) != 0, axis=0), np.any(np.diff(g["theta_mcmc"], axis=1) != 0, axis=0))
+    assert errs["theta_mcmc"] <= tol_theta and errs["paramsd"] <= tol_par
+    assert errs["beta_mcmc"] <= tol_par and errs["tausq_mcmc"] <= tol_par
+    assert errs["w"] <= tol_rows and errs["yhat"] <= tol_rows
+
+
+def _chain_args(g):
+    from spamtree_b200 import synth
+    q = int(g["q"])
+    pb = common.make_problem(q, int(g["n"]), limited=bool(int(g["limited"])))
+    assert np.array_equal(pb["tree"]["blocking"], g["blocking"]), "the deterministic tree builder changed: regenerate the golden files"
+    kw = dict(keep=int(g["keep"]), burn=int(g["burn"]), thin=int(g["thin"]), adapting=bool(int(g["adapting"])),
+              sample_predicts=bool(int(g["predicts"])), seed=int(g["seed"]))
+    return pb, synth.default_bounds(q), np.eye(pb["theta"].size) * float(g["sd"]), kw
+
+
+@pytest.mark.parametrize("path", CHAIN_FILES, ids=[os.path.basename(f) for f in CHAIN_FILES])
+def test_oracle_chain_against_reference_driver_outputs(path):
+    g = np.load(path)
+    pb, bounds, sd, kw = _chain_args(g)
+    om = common.oracle_model(pb, flags=0)
+    assert np.array_equal(om.geti("block_ct_obs"), g["block_ct_obs"])
+    _chain_check(g, om.mcmc(bounds, sd, **kw), 5e-9, 5e-9, 5e-9)
+    om.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", CHAIN_FILES, ids=[os.path.basename(f) for f in CHAIN_FILES])
+def test_cuda_chain_against_reference_driver_outputs(path):
+    """st_mcmc_run in lock-step mode vs the reference driver's chain.  Per-step differences (<= 1e-9, tested above) are
+    amplified along a chain of up to 84 iterations (w feeds the log-density that decides the next proposal, beta and
+    tausq feed the next sweep), hence the looser bounds on the late draws; the accept decisions must be identical."""
+    g = np.load(path)
+    pb, bounds, sd, kw = _chain_args(g)
+    gm = common.product_model(pb)
+    assert np.array_equal(gm.index("block_ct_obs"), g["block_ct_obs"])
+    plen = np.array([gm.index("parents_indexing", u).size for u in range(pb["tree"]["n_blocks"])])
+    assert np.array_equal(plen, g["parents_indexing_len"])
+    _chain_check(g, gm.mcmc(bounds, sd, rng_mode=0, **kw), 1e-8, 1e-7, 1e-6)
+    gm.close()
