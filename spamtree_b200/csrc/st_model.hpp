@@ -12,18 +12,14 @@
 
 #include <string>
 
+#include "st_chain.hpp"
 #include "st_common.hpp"
+
+struct st_mcmc_opts;
+struct st_mcmc_out;
 
 namespace st {
 
-constexpr int kMaxQ = 8;
-
-// theta -> per outcome-pair coefficients: K(h; i, j) = c1*exp(-r1*h) + c2*exp(-r2*h)
-// (covariance_functions.cpp:113-135, :213-286; q == 1 -> cexpcov :95-111 with direct-difference distance)
-struct CovTab {
-  int q;
-  double c1[kMaxQ * kMaxQ], r1[kMaxQ * kMaxQ], c2[kMaxQ * kMaxQ], r2[kMaxQ * kMaxQ];
-};
 bool make_covtab(const double* theta, int n_theta, int q, CovTab& tab, std::string& err);
 
 // device pointers describing the tree (read-only after st_create)
@@ -65,6 +61,13 @@ struct DevSlot {  // everything that depends on theta (tree_utils.h:63-102, lean
   double* Ri;
   double* logdet;  // per node
   double* llcomp;  // per node
+};
+
+// both theta-slots plus the chain state that says which one is param_data: kernels pick their slot on the device, so an
+// accepted proposal (accept_make_change) needs no host involvement
+struct DevSlots {
+  DevSlot s[2];
+  const ChainDev* chain;
 };
 
 struct LevelInfo {

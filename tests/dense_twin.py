@@ -8,7 +8,7 @@ def theta_unpack(theta, q):
     n_cbase = 3 if q > 2 else 1
     ai1, ai2, phi = theta[:q], theta[q:2 * q], theta[2 * q:3 * q]
     tm = theta[3 * q:3 * q + n_cbase]
-    D = np.zeros((q, q))
+    D = np.zeros((q, q), dtype=theta.dtype)
     rest = theta[3 * q + n_cbase:]
     ix = 0
     for j in range(q):
@@ -18,9 +18,11 @@ def theta_unpack(theta, q):
     return ai1, ai2, phi, tm, D
 
 
-def cov(coordsA, mvA, coordsB, mvB, theta, q):
-    """man/CrossCovarianceAG10.Rd:44-52 / covariance_functions.cpp:113-135,213-286 (mv 1-based)"""
-    ai1, ai2, phi, tm, D = theta_unpack(np.asarray(theta, dtype=np.float64), q)
+def cov(coordsA, mvA, coordsB, mvB, theta, q, dtype=np.float64):
+    """man/CrossCovarianceAG10.Rd:44-52 / covariance_functions.cpp:113-135,213-286 (mv 1-based).
+    dtype = np.longdouble evaluates the same formulas in extended precision (ground truth for the deep blocks)."""
+    ai1, ai2, phi, tm, D = theta_unpack(np.asarray(theta, dtype=dtype), q)
+    coordsA, coordsB = np.asarray(coordsA, dtype=dtype), np.asarray(coordsB, dtype=dtype)
     h = np.sqrt(((coordsA[:, None, :] - coordsB[None, :, :]) ** 2).sum(-1))
     if q == 1:
         return ai1[0] * np.exp(-tm[0] * h)
@@ -139,3 +141,48 @@ class Twin:
                     msgM[a] = msgM[a] + Ha.T @ prec @ (w[ru] - H[:, others] @ w[rp][others])
                     off += ma
         return w, probes
+
+
+# ---- extended-precision (x87 80-bit long double, eps ~ 1e-19) dense algebra for a block and its ancestor chain
+def chol_ld(A):
+    A = np.array(A, dtype=np.longdouble)
+    n = A.shape[0]
+    for j in range(n):
+        A[j, j] = np.sqrt(A[j, j] - A[j, :j] @ A[j, :j])
+        if j + 1 < n:
+            A[j + 1:, j] = (A[j + 1:, j] - A[j + 1:, :j] @ A[j, :j]) / A[j, j]
+    return np.tril(A)
+
+
+def solve_lower_ld(L, B):
+    """L^-1 B"""
+    X = np.array(B, dtype=np.longdouble)
+    for i in range(L.shape[0]):
+        X[i] = (X[i] - L[i, :i] @ X[:i]) / L[i, i]
+    return X
+
+
+def solve_upper_ld(U, B):
+    """U^-1 B"""
+    X = np.array(B, dtype=np.longdouble)
+    for i in range(U.shape[0] - 1, -1, -1):
+        X[i] = (X[i] - U[i, i + 1:] @ X[i + 1:]) / U[i, i]
+    return X
+
+
+def block_truth_ld(coords, mv, ru, rp, theta, q, isref):
+    """H = K_{u,pa} K_pa^-1 (m x P) and Ri = chol(K_uu - H K_{pa,u})^-1 (or 1/sqrt(diag) for a non-reference block) in
+    extended precision: App. A of the survey, spamtree_model.cpp:885-897, :931-948"""
+    ld = np.longdouble
+    Kpp = cov(coords[rp], mv[rp], coords[rp], mv[rp], theta, q, ld)
+    Kpu = cov(coords[rp], mv[rp], coords[ru], mv[ru], theta, q, ld)
+    Kuu = cov(coords[ru], mv[ru], coords[ru], mv[ru], theta, q, ld)
+    L = chol_ld(Kpp)
+    Y = solve_lower_ld(L, Kpu)
+    H = solve_upper_ld(L.T, Y).T
+    R = Kuu - Y.T @ Y
+    if isref:
+        Ri = solve_lower_ld(chol_ld(R), np.eye(ru.size, dtype=ld))
+    else:
+        Ri = 1 / np.sqrt(np.diag(R))
+    return H, Ri

@@ -12,7 +12,9 @@ from common import ROOT
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("nranks,q,n", [(2, 3, 20000), (2, 1, 6000)])
+# 4 ranks cut the tree below level 1 (4 subtrees), 8 ranks below level 2 (16 subtrees, two per rank): the frontier shapes of
+# the 4- and 8-GPU bench runs
+@pytest.mark.parametrize("nranks,q,n", [(2, 3, 20000), (2, 1, 6000), (4, 3, 40000), (8, 3, 60000)])
 def test_partitioned_model_matches_single_gpu(nranks, q, n):
     import torch
     if torch.cuda.device_count() < nranks:
