@@ -146,8 +146,11 @@ typedef struct {
   int32_t keep, burn, thin;
   int32_t adapting, sample_beta, sample_tausq, sample_theta, sample_w, sample_predicts;
   int32_t faithful_beta_index;   /* see st_gibbs_sample_beta */
-  int32_t rng_mode;              /* 0: every draw from the host stream (bit-reproducible against the oracle chain);
-                                    1: the n_all-long normal vectors are drawn on the device */
+  int32_t rng_mode;              /* 0: host-driven chain, every draw from one host stream in the reference's order (lock-step with
+                                    the oracle and with the reference's own driver; one host round trip per step);
+                                    1: device-resident chain: proposal, accept decision, slot swap, RAM adaptation, tausq / beta
+                                    draws and yhat on the device from Philox streams keyed by (seed, row or parameter,
+                                    iteration); the host only enqueues and synchronises once, at the end of the run */
   uint64_t seed;
 } st_mcmc_opts;
 typedef struct {                 /* caller-allocated; NULL pointers are skipped */
@@ -196,7 +199,8 @@ int st_attach_nccl(st_handle* h, const unsigned char* id128);
 int st_bench_iteration(st_handle* h, const double* theta_prop, int do_swap, uint64_t seed, double* out3, float* ms_out);
 /* counts of kernel launches and algorithmic work: out[8] = {kernel launches since creation, F_alg flops of one iteration
  * (SURVEY §8d formula on the actual tree), executed-flop estimate of the lean formulation, covariance evaluations,
- * F_alg of BUILD alone (F_build), executed-flop estimate of BUILD alone, compulsory output bytes of one BUILD, 0} */
+ * F_alg of BUILD alone (F_build), executed-flop estimate of BUILD alone, compulsory output bytes of one BUILD,
+ * bytes of the chain state that a device-resident run sends up / brings back once} */
 int st_get_counters(st_handle* h, double* out8);
 int st_sync(st_handle* h);
 

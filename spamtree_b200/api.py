@@ -408,7 +408,7 @@ class SpamTreeMV:
         o = np.zeros(8)
         self._chk(lib.st_get_counters(self._h, _dp(o)))
         return {"launches": o[0], "f_alg": o[1], "f_exec": o[2], "n_cov": o[3], "f_alg_build": o[4], "f_exec_build": o[5],
-                "b_alg_build": o[6]}
+                "b_alg_build": o[6], "chain_state_bytes": o[7]}
 
     def sync(self):
         self._chk(lib.st_sync(self._h))

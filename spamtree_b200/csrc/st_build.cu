@@ -93,10 +93,20 @@ __device__ __noinline__ bool pair_chol_inv32(double* R, int m, int rs, double* c
 // H w_pa = Z'v come out of the forward sweep.
 template <int MODE>
 __device__ __forceinline__ void
-build_level_body(const DevTree& T, const DevSlot& S, double* __restrict__ outG, double* __restrict__ outH, double* __restrict__ outRi,
+build_level_body(const DevTree& T, const DevSlots& D, int rel, double* __restrict__ predG, double* __restrict__ predRi, int want_H,
                  const int* __restrict__ grp_slot0, const int* __restrict__ grp_nn, const double* __restrict__ w,
-                 const CovTab& tab, int* __restrict__ fail, int ns, int phase, unsigned long long* __restrict__ prof) {
+                 int* __restrict__ fail, int ns, int phase, unsigned long long* __restrict__ prof, const int* __restrict__ run_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // conditional launches of the device-resident chain (deferred half after an accepted proposal, prediction weights after
+  // theta moved): the flag was written by an earlier kernel of the stream and is the same for every thread
+  if (run_flag != nullptr && *run_flag == 0) return;
+  // which theta-slot: read from the chain state in device memory (accept_make_change flips it there)
+  const int phys = D.chain->cur ^ rel;
+  const DevSlot S = pick_slot(D, phys);
+  double* __restrict__ outG = (MODE == 2) ? predG : S.G;
+  double* __restrict__ outH = (MODE != 2 && want_H) ? S.H : nullptr;
+  double* __restrict__ outRi = (MODE == 2) ? predRi : S.Ri;
+  const CovTab& tab = D.chain->tab[phys];
   __shared__ CovTabS ct;
   __shared__ int s_cm[kMaxChain], s_crow[kMaxChain + 1], s_crow0g[kMaxChain], s_cgs[kMaxChain];
   __shared__ long long s_cgoff[kMaxChain];
@@ -682,23 +692,24 @@ build_level_body(const DevTree& T, const DevSlot& S, double* __restrict__ outG, 
 // otherwise squeezes them into 64 registers with spills), the reference instantiation's register-resident Cholesky runs
 // 30 % slower with that hint.
 __global__ void __launch_bounds__(kBuildMaxThreads)
-build_level_kernel_ref(DevTree T, DevSlot S, double* __restrict__ outG, double* __restrict__ outH, double* __restrict__ outRi,
+build_level_kernel_ref(DevTree T, DevSlots D, int rel, double* __restrict__ predG, double* __restrict__ predRi, int want_H,
                        const int* __restrict__ grp_slot0, const int* __restrict__ grp_nn, const double* __restrict__ w,
-                       CovTab tab, int* __restrict__ fail, int ns, int phase, unsigned long long* __restrict__ prof) {
-  build_level_body<0>(T, S, outG, outH, outRi, grp_slot0, grp_nn, w, tab, fail, ns, phase, prof);
+                       int* __restrict__ fail, int ns, int phase, unsigned long long* __restrict__ prof, const int* __restrict__ run_flag) {
+  build_level_body<0>(T, D, rel, predG, predRi, want_H, grp_slot0, grp_nn, w, fail, ns, phase, prof, run_flag);
 }
 template <int MODE>
 __global__ void __launch_bounds__(kBuildMaxThreads, 1)
-build_level_kernel(DevTree T, DevSlot S, double* __restrict__ outG, double* __restrict__ outH, double* __restrict__ outRi,
+build_level_kernel(DevTree T, DevSlots D, int rel, double* __restrict__ predG, double* __restrict__ predRi, int want_H,
                    const int* __restrict__ grp_slot0, const int* __restrict__ grp_nn, const double* __restrict__ w,
-                   CovTab tab, int* __restrict__ fail, int ns, int phase, unsigned long long* __restrict__ prof) {
-  build_level_body<MODE>(T, S, outG, outH, outRi, grp_slot0, grp_nn, w, tab, fail, ns, phase, prof);
+                   int* __restrict__ fail, int ns, int phase, unsigned long long* __restrict__ prof, const int* __restrict__ run_flag) {
+  build_level_body<MODE>(T, D, rel, predG, predRi, want_H, grp_slot0, grp_nn, w, fail, ns, phase, prof, run_flag);
 }
 
 template <int MODE>
-static cudaError_t launch_build_t(const DevTree& T, const DevSlot& S, double* outG, double* outH, double* outRi,
-                                  const int* grp_slot0, const int* grp_nn, int ngrp, const double* w, const CovTab& tab,
-                                  int* fail, int ns, int phase, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof, bool pdl) {
+static cudaError_t launch_build_t(const DevTree& T, const DevSlots& D, int rel, double* predG, double* predRi, int want_H,
+                                  const int* grp_slot0, const int* grp_nn, int ngrp, const double* w,
+                                  int* fail, int ns, int phase, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof, bool pdl,
+                                  const int* run_flag) {
   auto kern = (MODE == 0) ? build_level_kernel_ref : build_level_kernel<MODE == 0 ? 1 : MODE>;
   static SmemOptIn optin;
   {
@@ -706,7 +717,7 @@ static cudaError_t launch_build_t(const DevTree& T, const DevSlot& S, double* ou
     if (e != cudaSuccess) return e;
   }
   if (!pdl) {
-    kern<<<ngrp, nthreads, smem, st>>>(T, S, outG, outH, outRi, grp_slot0, grp_nn, w, tab, fail, ns, phase, prof);
+    kern<<<ngrp, nthreads, smem, st>>>(T, D, rel, predG, predRi, want_H, grp_slot0, grp_nn, w, fail, ns, phase, prof, run_flag);
     return cudaGetLastError();
   }
   cudaLaunchConfig_t cfg = {};
@@ -719,15 +730,15 @@ static cudaError_t launch_build_t(const DevTree& T, const DevSlot& S, double* ou
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, T, S, outG, outH, outRi, grp_slot0, grp_nn, w, tab, fail, ns, phase, prof);
+  return cudaLaunchKernelEx(&cfg, kern, T, D, rel, predG, predRi, want_H, grp_slot0, grp_nn, w, fail, ns, phase, prof, run_flag);
 }
-cudaError_t launch_build(int mode, const DevTree& T, const DevSlot& S, double* outG, double* outH, double* outRi,
-                         const int* grp_slot0, const int* grp_nn, int ngrp, const double* w, const CovTab& tab, int* fail,
-                         int ns, int phase, size_t smem, cudaStream_t st, int nthreads, unsigned long long* prof, bool pdl) {
+cudaError_t launch_build(int mode, const DevTree& T, const DevSlots& D, int rel, double* predG, double* predRi, int want_H,
+                         const int* grp_slot0, const int* grp_nn, int ngrp, const double* w, int* fail, int ns, int phase, size_t smem,
+                         cudaStream_t st, int nthreads, unsigned long long* prof, bool pdl, const int* run_flag) {
   if (ngrp <= 0) return cudaSuccess;
-  if (mode == 0) return launch_build_t<0>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, phase, smem, st, nthreads, prof, pdl);
-  if (mode == 1) return launch_build_t<1>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, phase, smem, st, nthreads, prof, pdl);
-  return launch_build_t<2>(T, S, outG, outH, outRi, grp_slot0, grp_nn, ngrp, w, tab, fail, ns, phase, smem, st, nthreads, prof, pdl);
+  if (mode == 0) return launch_build_t<0>(T, D, rel, predG, predRi, want_H, grp_slot0, grp_nn, ngrp, w, fail, ns, phase, smem, st, nthreads, prof, pdl, run_flag);
+  if (mode == 1) return launch_build_t<1>(T, D, rel, predG, predRi, want_H, grp_slot0, grp_nn, ngrp, w, fail, ns, phase, smem, st, nthreads, prof, pdl, run_flag);
+  return launch_build_t<2>(T, D, rel, predG, predRi, want_H, grp_slot0, grp_nn, ngrp, w, fail, ns, phase, smem, st, nthreads, prof, pdl, run_flag);
 }
 
 }  // namespace st

@@ -277,7 +277,7 @@ int st_attach_nccl(st_handle* h, const unsigned char* id128) {
 int st_get_counters(st_handle* h, double* out8) {
   if (!h || !out8) return ST_ERR_INVALID;
   out8[0] = h->model.n_launches; out8[1] = h->model.f_alg; out8[2] = h->model.f_exec; out8[3] = h->model.n_cov;
-  out8[4] = h->model.f_alg_build; out8[5] = h->model.f_exec_build; out8[6] = h->model.b_alg_build; out8[7] = 0.0;
+  out8[4] = h->model.f_alg_build; out8[5] = h->model.f_exec_build; out8[6] = h->model.b_alg_build; out8[7] = (double)sizeof(st::ChainDev);
   return ST_OK;
 }
 int st_sync(st_handle* h) {

@@ -6,6 +6,17 @@
 
 namespace st {
 
+// the theta-slot `phys` of D, by selects (dynamic indexing of a kernel parameter would force a local-memory copy)
+__device__ __forceinline__ DevSlot pick_slot(const DevSlots& D, int phys) {
+  DevSlot S;
+  S.G = phys ? D.s[1].G : D.s[0].G;
+  S.H = phys ? D.s[1].H : D.s[0].H;
+  S.Ri = phys ? D.s[1].Ri : D.s[0].Ri;
+  S.logdet = phys ? D.s[1].logdet : D.s[0].logdet;
+  S.llcomp = phys ? D.s[1].llcomp : D.s[0].llcomp;
+  return S;
+}
+
 struct CovTabS {  // shared-memory copy of CovTab, plus the table of exp_neg
   int q;
   double c1[kMaxQ * kMaxQ], r1[kMaxQ * kMaxQ], c2[kMaxQ * kMaxQ], r2[kMaxQ * kMaxQ];

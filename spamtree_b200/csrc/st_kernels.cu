@@ -28,13 +28,14 @@ namespace st {
 // REF = 1: full m x m conditional (:1037-1089); REF = 0: row-wise scalars (:1091-1155)
 template <int REF>
 __global__ void __launch_bounds__(kGibbsThreads)
-gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, const double* __restrict__ xb,
+gibbs_level_kernel(DevTree T, DevSlots D, int slot0, double* __restrict__ w, const double* __restrict__ xb,
                    const double* __restrict__ z, const double* __restrict__ tausq_inv, const double* __restrict__ SigS,
                    double* __restrict__ V, double* probe_sig, double* probe_smu, int* __restrict__ fail) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // programmatic dependent launch: the next (shallower) level may start early; it waits below before it reads the
   // messages this level writes (everything before that point depends on ancestors only)
   asm volatile("griddepcontrol.launch_dependents;");
+  const DevSlot S = pick_slot(D, D.chain->cur);  // param_data
   const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int sd = slot0 + blockIdx.x;
   const int m = T.m[sd], k = T.k[sd], P = T.P[sd], coff = T.chain_off[sd], row0 = T.row0[sd];
@@ -268,7 +269,7 @@ gibbs_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ w, cons
   }
 }
 
-cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlot& S, int slot0, int nslots, double* w,
+cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlots& D, int slot0, int nslots, double* w,
                          const double* xb, const double* z, const double* tausq_inv, const double* SigS, double* V,
                          double* probe_sig, double* probe_smu, int* fail, size_t smem, cudaStream_t st, bool pdl) {
   if (nslots <= 0) return cudaSuccess;
@@ -288,7 +289,7 @@ cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlot& S, int slo
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, T, S, slot0, w, xb, z, tausq_inv, SigS, V, probe_sig, probe_smu, fail);
+  return cudaLaunchKernelEx(&cfg, kern, T, D, slot0, w, xb, z, tausq_inv, SigS, V, probe_sig, probe_smu, fail);
 }
 
 // ------------------------------------------------------------------------------------------------ message Grams
@@ -298,9 +299,11 @@ cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlot& S, int slo
 // from their row blocks directly.  The rows (own + fused children) are staged in shared memory in chunks and every
 // thread accumulates one 5 x 5 sub-block of the lower triangle of one tile in registers.
 __global__ void __launch_bounds__(kGramThreads)
-gram_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ U, double* __restrict__ SigS, int rch, int ldx,
-                  int stage_off) {
+gram_level_kernel(DevTree T, DevSlots D, int slot0, double* __restrict__ U, double* __restrict__ SigS, int rch, int ldx,
+                  int stage_off, const int* __restrict__ run_flag) {
   extern __shared__ __align__(16) double gram_smem[];
+  if (run_flag != nullptr && *run_flag == 0) return;  // device-resident chain: only after an accepted proposal
+  const DevSlot S = pick_slot(D, D.chain->cur);       // param_data
   __shared__ int t_po[kMaxChain + 1], t_m[kMaxChain + 1], t_item0[kMaxChain + 2], t_uo[kMaxChain + 1], t_to[kMaxChain + 2];
   __shared__ int s_rows;
   __shared__ long long s_rowoff[kGramMaxRows];  // per staged row: offset of the row in S.G and its valid columns
@@ -462,8 +465,8 @@ gram_level_kernel(DevTree T, DevSlot S, int slot0, double* __restrict__ U, doubl
     if (j < k) Ud[t_uo[j] + e] = v; else SigS[so + e] = v;
   }
 }
-cudaError_t launch_gram(const DevTree& T, const DevSlot& S, int slot0, int nslots, double* U, double* SigS, int rch,
-                        int ldx, int tile_doubles, int stage_off, int threads, cudaStream_t st) {
+cudaError_t launch_gram(const DevTree& T, const DevSlots& D, int slot0, int nslots, double* U, double* SigS, int rch,
+                        int ldx, int tile_doubles, int stage_off, int threads, cudaStream_t st, const int* run_flag) {
   if (nslots <= 0) return cudaSuccess;
   const size_t smem = std::max((size_t)tile_doubles, (size_t)stage_off + (size_t)rch * ldx) * sizeof(double);
   static SmemOptIn optin;
@@ -471,7 +474,7 @@ cudaError_t launch_gram(const DevTree& T, const DevSlot& S, int slot0, int nslot
     cudaError_t e = ensure_dynamic_smem(gram_level_kernel, smem, optin);
     if (e != cudaSuccess) return e;
   }
-  gram_level_kernel<<<nslots, threads, smem, st>>>(T, S, slot0, U, SigS, rch, ldx, stage_off);
+  gram_level_kernel<<<nslots, threads, smem, st>>>(T, D, slot0, U, SigS, rch, ldx, stage_off, run_flag);
   return cudaGetLastError();
 }
 
@@ -480,8 +483,9 @@ cudaError_t launch_gram(const DevTree& T, const DevSlot& S, int slot0, int nslot
 // A reference block's rows of the chain factor are [G | -Ri | 0], so its contribution is one streaming product
 // |[G | -Ri] [w_pa ; w_u]|^2 over contiguous rows; the warp stages [w_pa ; w_u] in shared memory once.
 __global__ void __launch_bounds__(kLlwThreads)
-llw_kernel(DevTree T, DevSlot S, int nslots, const double* __restrict__ w, int maxlen) {
+llw_kernel(DevTree T, DevSlots D, int rel, int nslots, const double* __restrict__ w, int maxlen) {
   extern __shared__ __align__(16) double llw_smem[];
+  const DevSlot S = pick_slot(D, D.chain->cur ^ rel);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int sd = blockIdx.x * (blockDim.x >> 5) + wib;
   if (sd >= nslots) return;
@@ -536,7 +540,7 @@ llw_kernel(DevTree T, DevSlot S, int nslots, const double* __restrict__ w, int m
   }
   if (lane == 0) S.llcomp[sd] = (double)m * kHl2pi - 0.5 * wc;
 }
-cudaError_t launch_llw(const DevTree& T, const DevSlot& S, int nslots, const double* w, int maxlen, cudaStream_t st) {
+cudaError_t launch_llw(const DevTree& T, const DevSlots& D, int rel, int nslots, const double* w, int maxlen, cudaStream_t st) {
   if (nslots <= 0) return cudaSuccess;
   const int wpb = kLlwThreads / 32;
   maxlen = (maxlen + 1) & ~1;
@@ -546,19 +550,20 @@ cudaError_t launch_llw(const DevTree& T, const DevSlot& S, int nslots, const dou
     cudaError_t e = ensure_dynamic_smem(llw_kernel, smem, optin);
     if (e != cudaSuccess) return e;
   }
-  llw_kernel<<<(nslots + wpb - 1) / wpb, kLlwThreads, smem, st>>>(T, S, nslots, w, maxlen);
+  llw_kernel<<<(nslots + wpb - 1) / wpb, kLlwThreads, smem, st>>>(T, D, rel, nslots, w, maxlen);
   return cudaGetLastError();
 }
 
-// out[0] = sum(logdet) + sum(llcomp), out[1] = sum(logdet), out[2] = (fail == 0)  (:987-988 / :815-816).
-// Fixed summation order: deterministic run to run.
-__global__ void __launch_bounds__(1024) loglik_reduce_kernel(const double* __restrict__ logdet,
-                                                             const double* __restrict__ llcomp, int first, int n,
-                                                             const int* __restrict__ fail, int fail_as_count,
+// Sum of the per-block log-density pieces (:987-988 / :815-816), in two parts so that a partitioned run can count the
+// replicated blocks once and all-reduce the rest: block 0 sums [0, n_top) into out[0..2], block 1 sums [n_top, n) into
+// out[4..6]; out[.] = {sum(logdet) + sum(llcomp), sum(logdet), 0 / *fail}.  Fixed summation order: deterministic.
+__global__ void __launch_bounds__(1024) loglik_reduce_kernel(DevSlots D, int rel, int n_top, int n, const int* __restrict__ fail,
                                                              double* __restrict__ out) {
   __shared__ double sa[1024], sb[1024];
+  const DevSlot S = pick_slot(D, D.chain->cur ^ rel);
+  const int first = blockIdx.x ? n_top : 0, last = blockIdx.x ? n : n_top;
   double a = 0, b = 0;
-  for (int i = first + threadIdx.x; i < first + n; i += 1024) { a += logdet[i]; b += llcomp[i]; }
+  for (int i = first + threadIdx.x; i < last; i += 1024) { a += S.logdet[i]; b += S.llcomp[i]; }
   sa[threadIdx.x] = a;
   sb[threadIdx.x] = b;
   __syncthreads();
@@ -567,15 +572,14 @@ __global__ void __launch_bounds__(1024) loglik_reduce_kernel(const double* __res
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    out[0] = sa[0] + sb[0];
-    out[1] = sa[0];
-    if (fail_as_count) out[2] = fail ? (double)*fail : 0.0;
-    else out[2] = (fail == nullptr || *fail == 0) ? 1.0 : 0.0;
+    double* o = out + 4 * blockIdx.x;
+    o[0] = sa[0] + sb[0];
+    o[1] = sa[0];
+    o[2] = (blockIdx.x && fail) ? (double)*fail : 0.0;
   }
 }
-cudaError_t launch_loglik_reduce(const double* logdet, const double* llcomp, int first, int n, const int* fail,
-                                 int fail_as_count, double* out, cudaStream_t st) {
-  loglik_reduce_kernel<<<1, 1024, 0, st>>>(logdet, llcomp, first, n, fail, fail_as_count, out);
+cudaError_t launch_loglik_reduce(const DevSlots& D, int rel, int n_top, int n, const int* fail, double* out8, cudaStream_t st) {
+  loglik_reduce_kernel<<<2, 1024, 0, st>>>(D, rel, n_top, n, fail, out8);
   return cudaGetLastError();
 }
 
@@ -639,26 +643,40 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
   const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
   c[0] = hi1 ^ c[1] ^ k0; c[1] = lo1; c[2] = hi0 ^ c[3] ^ k1; c[3] = lo0;
 }
-__global__ void normals_kernel(double* __restrict__ z, long long n, uint64_t seed, uint64_t counter, long long n_shared,
-                               long long offset) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  // rows replicated on every rank (i < n_shared) use the same key everywhere; the others are shifted by the rank's offset
-  const unsigned long long key = (unsigned long long)(i < n_shared ? i : i + offset);
-  uint32_t c[4] = {(uint32_t)key, (uint32_t)(key >> 32), (uint32_t)counter, (uint32_t)(counter >> 32)};
+__device__ __forceinline__ void philox4x32(uint32_t (&c)[4], uint64_t seed) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
   for (int r = 0; r < 10; r++) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
-  const double u1 = ((((uint64_t)c[0] << 32 | c[1]) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
-  const double u2 = ((((uint64_t)c[2] << 32 | c[3]) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
-  double sn, cs;
-  sincospi(2.0 * u2, &sn, &cs);
-  z[i] = sqrt(-2.0 * log(u1)) * cs;
 }
-cudaError_t launch_normals(double* z, long long n, uint64_t seed, uint64_t counter, long long n_shared, long long offset,
+__device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) { return ((((uint64_t)hi << 32 | lo) >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+// one standard normal / one uniform for (seed, key, counter): Philox4x32-10 + Box-Muller
+__device__ __forceinline__ double philox_normal(uint64_t seed, unsigned long long key, uint64_t counter) {
+  uint32_t c[4] = {(uint32_t)key, (uint32_t)(key >> 32), (uint32_t)counter, (uint32_t)(counter >> 32)};
+  philox4x32(c, seed);
+  double sn, cs;
+  sincospi(2.0 * u01(c[2], c[3]), &sn, &cs);
+  return sqrt(-2.0 * log(u01(c[0], c[1]))) * cs;
+}
+__device__ __forceinline__ double philox_uniform(uint64_t seed, unsigned long long key, uint64_t counter) {
+  uint32_t c[4] = {(uint32_t)key, (uint32_t)(key >> 32), (uint32_t)counter, (uint32_t)(counter >> 32)};
+  philox4x32(c, seed);
+  return u01(c[0], c[1]);
+}
+// streams of the chain's scalar draws: key = kStream* + index, counter = iteration (row streams use key = row id < 2^40)
+constexpr unsigned long long kStreamU = 1ULL << 48, kStreamAccept = 2ULL << 48, kStreamGamma = 3ULL << 48, kStreamBeta = 4ULL << 48;
+constexpr uint64_t kCounterYhat = 1ULL << 62;  // yhat noise: same row keys as the Gibbs normals, disjoint counters
+
+__global__ void normals_kernel(double* __restrict__ z, long long n, uint64_t seed, uint64_t counter,
+                               const long long* __restrict__ rowkey, const int* __restrict__ iter_ptr) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // keyed by the row's id in the whole problem: the same draw whatever the partition (and on every rank that holds the row)
+  z[i] = philox_normal(seed, (unsigned long long)rowkey[i], counter + (iter_ptr ? (uint64_t)*iter_ptr : 0));
+}
+cudaError_t launch_normals(double* z, long long n, uint64_t seed, uint64_t counter, const long long* rowkey, const int* iter_ptr,
                            cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  normals_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z, n, seed, counter, n_shared, offset);
+  normals_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(z, n, seed, counter, rowkey, iter_ptr);
   return cudaGetLastError();
 }
 
@@ -696,19 +714,26 @@ __global__ void __launch_bounds__(256) rowstats_kernel(DevTree T, const int* __r
     __syncthreads();
   }
 }
-__global__ void rowstats_final_kernel(const double* __restrict__ partial, int nblocks, int nv, double* __restrict__ out) {
-  const int v = threadIdx.x;
-  if (v >= nv) return;
+// one CTA per statistic: the partial sums of the stage-1 blocks in a fixed order (deterministic)
+__global__ void __launch_bounds__(128) rowstats_final_kernel(const double* __restrict__ partial, int nblocks, int nv, double* __restrict__ out) {
+  __shared__ double red[128];
+  const int v = blockIdx.x;
   double s = 0;
-  for (int b = 0; b < nblocks; b++) s += partial[(size_t)b * nv + v];
-  out[v] = s;
+  for (int b = threadIdx.x; b < nblocks; b += 128) s += partial[(size_t)b * nv + v];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[v] = red[0];
 }
 cudaError_t launch_rowstats(const DevTree& T, const int* widx, long long n_all, int p, int q, const double* w,
                             const double* xb, double* partial, int nblocks, double* out, cudaStream_t st) {
   rowstats_kernel<<<nblocks, 256, 0, st>>>(T, widx, n_all, p, q, w, xb, partial);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  rowstats_final_kernel<<<1, 256, 0, st>>>(partial, nblocks, q * (p + 1), out);
+  rowstats_final_kernel<<<q * (p + 1), 128, 0, st>>>(partial, nblocks, q * (p + 1), out);
   return cudaGetLastError();
 }
 
@@ -756,6 +781,198 @@ cudaError_t launch_crosscov(const double* x1, const double* y1, const int* q1, l
   const long long n = n1 * n2;
   if (n <= 0) return cudaSuccess;
   crosscov_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x1, y1, q1, n1, x2, y2, q2, n2, tab, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ device-resident chain
+// The steps of spamtree_fit.cpp:203-289 and :376-389 that the reference runs on the host between the model-layer calls,
+// as one-CTA kernels over the chain state in device memory (st_chain.hpp).  The arithmetic is st_mh.hpp's, the same
+// functions the host path (and, through it, the pin against the reference's mh_adapt.h) uses.
+
+// U ~ N(0, I), theta' = back(fwd(theta) + paramsd U) clipped (spamtree_fit.cpp:211-215) -> theta and covariance table of the
+// alter slot
+__global__ void mh_propose_kernel(ChainDev* C) {
+  const int npar = C->npar, cur = C->cur, alt = cur ^ 1;
+  for (int j = threadIdx.x; j < npar; j += blockDim.x) C->U[j] = philox_normal(C->seed, kStreamU + j, (uint64_t)C->iter);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mh_propose(npar, C->theta[cur], C->bounds, C->paramsd, C->U, C->theta[alt]);
+    make_covtab_hd(C->theta[alt], npar, C->q, C->tab[alt]);
+  }
+}
+cudaError_t launch_mh_propose(ChainDev* C, cudaStream_t st) {
+  mh_propose_kernel<<<1, 64, 0, st>>>(C);
+  return cudaGetLastError();
+}
+
+// spamtree_fit.cpp:223-285: log-densities from the two reductions, Jacobian, accept decision, slot swap, RAM adaptation
+__global__ void mh_accept_kernel(ChainDev* C, int mode, int have_llw) {
+  if (threadIdx.x != 0) return;
+  const int npar = C->npar, cur = C->cur, alt = cur ^ 1, m = C->iter;
+  if (have_llw) { C->loglik[cur] = C->red_llw[0] + C->red_llw[4]; C->logdet[cur] = C->red_llw[1] + C->red_llw[5]; }
+  const bool acceptable = C->red_build[6] == 0.0;
+  if (acceptable) {  // on failure the reference leaves the alter slot's log-density untouched (:971-982)
+    C->loglik[alt] = C->red_build[0] + C->red_build[4];
+    C->logdet[alt] = C->red_build[1] + C->red_build[5];
+  } else {
+    C->n_chol_fail++;
+  }
+  const double new_loglik = C->loglik[alt], current_loglik = C->loglik[cur];
+  if (isnan(current_loglik)) C->nan_loglik = 1;  // spamtree_fit.cpp:234-237
+  bool accepted;
+  double logaccept = 0.0;
+  if (mode == 0) {
+    logaccept = new_loglik - current_loglik + mh_jacobian(npar, C->theta[alt], C->theta[cur], C->bounds);
+    const double u = philox_uniform(C->seed, kStreamAccept, (uint64_t)m);
+    C->last_logaccept = logaccept; C->last_u = u;
+    accepted = (u < mh_accept_prob(logaccept)) && acceptable;
+  } else {
+    accepted = (mode == 1) && acceptable;
+  }
+  if (accepted) {
+    C->n_accepted++;
+    C->cur = alt;  // accept_make_change (:1432-1435): the kernels that follow read the new slot
+    C->pred_valid = 0;
+  }
+  C->accepted_now = accepted ? 1 : 0;
+  if (mode == 0 && C->adapting)  // :285 (a failed chol(S) keeps the previous factor and is counted)
+    if (!ram_adapt(npar, C->paramsd, C->prodparam, &C->ram_started, C->U, (acceptable ? 1.0 : 0.0) * exp(logaccept), m, C->scratch))
+      C->n_ram_fail++;
+}
+cudaError_t launch_mh_accept(ChainDev* C, int mode, int have_llw, cudaStream_t st) {
+  mh_accept_kernel<<<1, 32, 0, st>>>(C, mode, have_llw);
+  return cudaGetLastError();
+}
+
+// need_update = any |param - predict_param| > 1e-05 (spamtree_fit.cpp:300); predict_param <- param (:305)
+__global__ void predict_gate_kernel(ChainDev* C) {
+  if (threadIdx.x != 0) return;
+  const double* th = C->theta[C->cur];
+  bool need = !C->pred_valid;
+  for (int j = 0; j < C->npar; j++) {
+    if (fabs(th[j] - C->predict_param[j]) > 1e-05) need = true;
+    C->predict_param[j] = th[j];
+  }
+  C->predict_build = need ? 1 : 0;
+  C->pred_valid = 1;
+}
+cudaError_t launch_predict_gate(ChainDev* C, cudaStream_t st) {
+  predict_gate_kernel<<<1, 32, 0, st>>>(C);
+  return cudaGetLastError();
+}
+
+// Marsaglia-Tsang gamma(shape >= 1, scale) on a Philox stream (the host path's HostRng::gamma, st_common.hpp)
+__device__ inline double philox_gamma(uint64_t seed, unsigned long long key, uint64_t counter, double shape, double scale) {
+  const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (unsigned long long att = 0;; att++) {
+    const double x = philox_normal(seed, key + (att << 8), counter);
+    double v = 1.0 + c * x;
+    if (v <= 0) continue;
+    v = v * v * v;
+    const double u = philox_uniform(seed, key + (att << 8) + 128, counter);
+    if (u < 1.0 - 0.0331 * x * x * x * x) return d * v * scale;
+    if (log(u) < 0.5 * x * x + d * (1.0 - v + log(v))) return d * v * scale;
+  }
+}
+// gibbs_sample_tausq (spamtree_model.cpp:1393-1417) then gibbs_sample_beta (:1364-1391), one thread per outcome.
+// stats[j*(p+1) + a] = X_j'(y - w)_a, stats[j*(p+1) + p] = |y - XB - w|^2 over the outcome's observed rows (rowstats_kernel)
+__global__ void tausq_beta_kernel(ChainDev* C, const double* __restrict__ stats, const double* __restrict__ xtx,
+                                  double* __restrict__ tausq_inv, double* __restrict__ bcoeff, double* __restrict__ scratch,
+                                  int sample_tausq, int sample_beta) {
+  const int j = threadIdx.x, p = C->p, q = C->q;
+  if (j >= q) return;
+  const uint64_t it = (uint64_t)C->iter;
+  if (sample_tausq) {
+    const double bcore = stats[j * (p + 1) + p];
+    tausq_inv[j] = philox_gamma(C->seed, kStreamGamma + ((unsigned long long)j << 32), it, 2.01 + C->nobs[j] / 2.0, 1.0 / (1.0 + .5 * bcore));
+  }
+  if (sample_beta) {
+    const double tq = tausq_inv[j];
+    double* Si = scratch + (size_t)j * 3 * p * p;  // precision -> its Cholesky factor (column-major)
+    double* Sc = Si + p * p;                       // inverse of the factor
+    double* v = Sc + p * p;                        // xp | t | bmu | sz
+    for (int a = 0; a < p; a++)
+      for (int b = 0; b < p; b++) Si[a + b * p] = tq * xtx[(size_t)j * p * p + (b <= a ? b + a * p : a + b * p)] + (a == b ? .01 : 0.0);  // symmatu; Vi = .01 I (:157)
+    if (!mh_chol_lower(Si, p)) { C->gibbs_fail = 1; return; }
+    for (int c = 0; c < p; c++) {  // Sc = Si^-1 (lower)
+      for (int r = 0; r < c; r++) Sc[r + c * p] = 0.0;
+      Sc[c + c * p] = 1.0 / Si[c + c * p];
+      for (int r = c + 1; r < p; r++) {
+        double s = 0;
+        for (int k = c; k < r; k++) s += Si[r + k * p] * Sc[k + c * p];
+        Sc[r + c * p] = -s / Si[r + r * p];
+      }
+    }
+    double *xp = v, *t = v + p, *bmu = v + 2 * p;
+    for (int a = 0; a < p; a++) xp[a] = tq * stats[j * (p + 1) + a];  // Vim = 0 (:158-159)
+    for (int a = 0; a < p; a++) { double s = 0; for (int b = 0; b <= a; b++) s += Sc[a + b * p] * xp[b]; t[a] = s; }
+    for (int a = 0; a < p; a++) { double s = 0; for (int b = a; b < p; b++) s += Sc[b + a * p] * t[b]; bmu[a] = s; }
+    for (int a = 0; a < p; a++) xp[a] = philox_normal(C->seed, kStreamBeta + ((unsigned long long)j << 32) + a, it);
+    for (int a = 0; a < p; a++) {
+      double s = 0;
+      for (int b = a; b < p; b++) s += Sc[b + a * p] * xp[b];
+      bcoeff[a + j * p] = bmu[a] + s;
+    }
+  }
+}
+cudaError_t launch_tausq_beta(ChainDev* C, const double* stats, const double* xtx, double* tausq_inv, double* bcoeff,
+                              double* scratch, int sample_tausq, int sample_beta, cudaStream_t st) {
+  tausq_beta_kernel<<<1, 32, 0, st>>>(C, stats, xtx, tausq_inv, bcoeff, scratch, sample_tausq, sample_beta);
+  return cudaGetLastError();
+}
+
+// save (spamtree_fit.cpp:376-382): column msaved of theta_mcmc (npar x keep), tausq_mcmc (q x keep), beta_mcmc (p x keep x q)
+__global__ void record_kernel(ChainDev* C, const double* __restrict__ tausq_inv, const double* __restrict__ bcoeff,
+                              double* __restrict__ theta_mcmc, double* __restrict__ beta_mcmc, double* __restrict__ tausq_mcmc, int keep) {
+  const int ms = C->msaved, npar = C->npar, p = C->p, q = C->q;
+  if (ms < keep) {
+    for (int j = threadIdx.x; j < npar; j += blockDim.x) theta_mcmc[j + (size_t)ms * npar] = C->theta[C->cur][j];
+    for (int j = threadIdx.x; j < q; j += blockDim.x) tausq_mcmc[j + (size_t)ms * q] = 1.0 / tausq_inv[j];
+    for (int e = threadIdx.x; e < p * q; e += blockDim.x) { const int a = e % p, j = e / p; beta_mcmc[a + (size_t)ms * p + (size_t)j * p * keep] = bcoeff[e]; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) C->msaved = ms + 1;
+}
+cudaError_t launch_record(ChainDev* C, const double* tausq_inv, const double* bcoeff, double* theta_mcmc, double* beta_mcmc,
+                          double* tausq_mcmc, int keep, cudaStream_t st) {
+  record_kernel<<<1, 64, 0, st>>>(C, tausq_inv, bcoeff, theta_mcmc, beta_mcmc, tausq_mcmc, keep);
+  return cudaGetLastError();
+}
+
+// yhat = XB + w + tausq_inv^(-1/2) N(0,1), boundary order (spamtree_fit.cpp:384); iperm: boundary row -> node-major row
+__global__ void yhat_kernel(DevTree T, const double* __restrict__ w, const double* __restrict__ xb, const double* __restrict__ tausq_inv,
+                            const long long* __restrict__ iperm, const long long* __restrict__ rowkey, long long n, const ChainDev* C,
+                            double* __restrict__ out) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  const long long i = iperm[b];
+  const double e = philox_normal(C->seed, (unsigned long long)rowkey[i], kCounterYhat + (uint64_t)C->iter);
+  out[b] = xb[i] + w[i] + rsqrt(tausq_inv[T.mvq[i]]) * e;
+}
+cudaError_t launch_yhat(const DevTree& T, const double* w, const double* xb, const double* tausq_inv, const long long* iperm,
+                        const long long* rowkey, long long n, const ChainDev* C, double* out, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  yhat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(T, w, xb, tausq_inv, iperm, rowkey, n, C, out);
+  return cudaGetLastError();
+}
+
+__global__ void chain_set_theta_kernel(ChainDev* C, int rel, const __grid_constant__ ThetaPack P) {
+  const int phys = C->cur ^ rel;
+  for (int j = threadIdx.x; j < P.n; j += blockDim.x) C->theta[phys][j] = P.theta[j];
+  if (threadIdx.x == 0) C->tab[phys] = P.tab;
+}
+cudaError_t launch_chain_set_theta(ChainDev* C, int rel, const ThetaPack& pack, cudaStream_t st) {
+  chain_set_theta_kernel<<<1, 64, 0, st>>>(C, rel, pack);
+  return cudaGetLastError();
+}
+__global__ void chain_flip_kernel(ChainDev* C) { C->cur ^= 1; C->pred_valid = 0; }
+cudaError_t launch_chain_flip(ChainDev* C, cudaStream_t st) {
+  chain_flip_kernel<<<1, 1, 0, st>>>(C);
+  return cudaGetLastError();
+}
+__global__ void chain_tick_kernel(ChainDev* C) { C->iter++; }
+cudaError_t launch_chain_tick(ChainDev* C, cudaStream_t st) {
+  chain_tick_kernel<<<1, 1, 0, st>>>(C);
   return cudaGetLastError();
 }
 

@@ -25,6 +25,15 @@ struct RAMAdapt {
 };
 
 int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
+  // rng_mode 1: the device-resident chain — proposal, accept decision, RAM adaptation, tausq / beta draws and yhat on the
+  // device, no host round trip per iteration (st_model.cu: Model::chain_run)
+  if (o.rng_mode == 1) return M.chain_run(o, out);
+  // rng_mode 0: every draw from one host stream, in the reference's order (lock-step with the oracle and with the
+  // reference's own driver); a partitioned run draws for every row of the whole problem on every rank and keeps its own
+  if (M.part && M.global_rows.empty()) {
+    M.err = "partitioned handle without global_rows: the host random stream (rng_mode 0) would differ between the ranks";
+    return ST_ERR_INVALID;
+  }
   M.rng.seed(o.seed);
   double o3[3];
   int rc = M.get_loglik_comps_w(0, o3);  // spamtree_fit.cpp:110-111
@@ -44,7 +53,7 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
   int msaved = 0;
   out.n_accepted = out.n_chol_fail = 0;
   dvec zbuf, wbuf, xbbuf, zglob;
-  if (o.rng_mode == 0) zbuf.resize(M.n_all);
+  zbuf.resize(M.n_all);
   const bool pglob = M.part && !M.global_rows.empty();  // partitioned: draw for every row of the problem, keep ours
   if (pglob) zglob.resize(M.n_global_rows);
   // w of a saved iteration goes to the caller's buffer asynchronously (overlapping the next iteration) unless yhat, which
@@ -69,17 +78,13 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
     const int mx = m - o.burn;
     if (mx >= 0 && mx % o.thin == 0) predicting = true;
     if (o.sample_w) {  // :183-187
-      if (o.rng_mode == 0) {
-        if (pglob) {
-          for (int64_t i = 0; i < M.n_global_rows; i++) zglob[i] = M.rng.norm();
-          for (int64_t i = 0; i < M.n_all; i++) zbuf[i] = zglob[M.global_rows[i]];
-        } else {
-          for (int64_t i = 0; i < M.n_all; i++) zbuf[i] = M.rng.norm();  // bigrnorm (:1018)
-        }
-        rc = M.deal_with_w(zbuf.data(), 0);
+      if (pglob) {
+        for (int64_t i = 0; i < M.n_global_rows; i++) zglob[i] = M.rng.norm();
+        for (int64_t i = 0; i < M.n_all; i++) zbuf[i] = zglob[M.global_rows[i]];
       } else {
-        rc = M.deal_with_w(nullptr, o.seed);
+        for (int64_t i = 0; i < M.n_all; i++) zbuf[i] = M.rng.norm();  // bigrnorm (:1018)
       }
+      rc = M.deal_with_w(zbuf.data(), 0);
       if (rc) return rc;
       lap(0, tl);
       double o2[2];
@@ -150,14 +155,15 @@ int mcmc_run(Model& M, const st_mcmc_opts& o, st_mcmc_out& out) {
         rc = M.get_xb(xbbuf.data());
         if (rc) return rc;
       }
-      if (pglob && o.rng_mode == 0)
+      // arma::randn(n) of :384 — drawn whether or not yhat is kept, and for every row of the whole problem on every rank of
+      // a partition, so that the one host stream stays in step everywhere
+      if (pglob)
         for (int64_t i = 0; i < M.n_global_rows; i++) zglob[i] = M.rng.norm();
-      if (o.rng_mode == 0 || out.yhat_mcmc)
-        for (int64_t i = 0; i < M.n_all; i++) {
-          const double e = (pglob && o.rng_mode == 0) ? zglob[M.global_rows[i]] : M.rng.norm();  // arma::randn(n) of :384
-          if (out.yhat_mcmc)
-            out.yhat_mcmc[i + (size_t)msaved * M.n_all] = xbbuf[i] + wbuf[i] + std::pow(M.tausq_inv[M.mv_id[i] - 1], -.5) * e;
-        }
+      for (int64_t i = 0; i < M.n_all; i++) {
+        const double e = pglob ? zglob[M.global_rows[i]] : M.rng.norm();
+        if (out.yhat_mcmc)
+          out.yhat_mcmc[i + (size_t)msaved * M.n_all] = xbbuf[i] + wbuf[i] + std::pow(M.tausq_inv[M.mv_id[i] - 1], -.5) * e;
+      }
       msaved++;
     }
     lap(6, tl);

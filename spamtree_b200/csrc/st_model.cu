@@ -8,8 +8,10 @@
 #include <cstring>
 #include <numeric>
 
+#include "../../include/spamtree_b200.h"
 #include "st_kernels.cuh"
 
+#include <chrono>
 #include <dlfcn.h>
 
 namespace st {
@@ -58,44 +60,12 @@ int Model::cuda_fail(cudaError_t e, const char* what) {
   return 2;  // ST_ERR_CUDA
 }
 
-// covariance_functions.cpp:34-92 (theta layout) folded with :113-135 (C_base) into per outcome-pair coefficients
+// covariance_functions.cpp:34-92 / :113-135 -> per outcome-pair coefficients (make_covtab_hd, st_chain.hpp)
 bool make_covtab(const double* theta, int n_theta, int q, CovTab& tab, std::string& err) {
-  if (q < 1 || q > kMaxQ) { err = "q outside 1..8"; return false; }
-  const int n_cbase = q > 2 ? 3 : 1, npars = 3 * q + n_cbase, kd = n_theta - npars;
-  if (kd < 0 || (q >= 2 && kd != q * (q - 1) / 2) || (q == 1 && kd != 0)) { err = "theta has the wrong length for q"; return false; }
-  const double *ai1 = theta, *ai2 = theta + q, *phi_i = theta + 2 * q, *thetamv = theta + 3 * q;
-  tab.q = q;
-  if (q == 1) {  // cexpcov(…, sigmasq = ai1(0), phi = thetamv(0)) (:220-221)
-    tab.c1[0] = ai1[0]; tab.r1[0] = thetamv[0]; tab.c2[0] = 0; tab.r2[0] = 0;
-    return true;
-  }
-  double D[kMaxQ * kMaxQ] = {0};  // vec_to_symmat: column-major fill of the strict lower triangle
-  int ix = 0;
-  for (int j = 0; j < q; j++)
-    for (int i = j + 1; i < q; i++) { D[i * q + j] = D[j * q + i] = theta[npars + ix]; ix++; }
-  for (int i = 0; i < q; i++)
-    for (int j = 0; j < q; j++) {
-      const double v = D[i * q + j];
-      const int e = i * q + j;
-      double psi_sqrt, psi2, c;
-      if (q > 2) {
-        psi_sqrt = std::exp(0.5 * thetamv[1] * std::log1p(thetamv[0] * (v == 0 ? 0.0 : v)));  // sqrt_fpsi
-        psi2 = psi_sqrt * psi_sqrt;
-        c = thetamv[2];
-      } else {
-        psi_sqrt = std::sqrt((v == 0 ? 0.0 : v) + 1);
-        psi2 = (v == 0 ? 0.0 : v) + 1.0;
-        c = thetamv[0];
-      }
-      if (v == 0) {  // "same outcome" is detected by Dmat(i,j) == 0 (:250)
-        tab.c1[e] = ai1[i] * ai1[i] / psi2; tab.r1[e] = c / psi_sqrt;
-        tab.c2[e] = ai2[i] * ai2[i];        tab.r2[e] = phi_i[i];
-      } else {
-        tab.c1[e] = ai1[i] * ai1[j] / psi2; tab.r1[e] = c / psi_sqrt;
-        tab.c2[e] = 0;                      tab.r2[e] = 0;
-      }
-    }
-  return true;
+  const int rc = make_covtab_hd(theta, n_theta, q, tab);
+  if (rc == 1) err = "q outside 1..8";
+  if (rc == 2) err = "theta has the wrong length for q";
+  return rc == 0;
 }
 
 Model::~Model() {
@@ -104,6 +74,10 @@ Model::~Model() {
   if (nccl_comm) { cudaStreamSynchronize(stream); nccl().CommDestroy(nccl_comm); nccl_comm = nullptr; }
   for (void* p : owned) cudaFree(p);
   if (h_scalars) cudaFreeHost(h_scalars);
+  if (h_mc) cudaFreeHost(h_mc);
+  for (void* g : graph_exec_) if (g) cudaGraphExecDestroy((cudaGraphExec_t)g);
+  if (save_y_.ready) cudaEventDestroy(save_y_.ready);
+  if (save_y_.copied) cudaEventDestroy(save_y_.copied);
   if (h_stage) cudaFreeHost(h_stage);
   for (auto& e : ev) if (e) cudaEventDestroy(e);
   if (save_registered) cudaHostUnregister(save_registered);
@@ -662,6 +636,35 @@ int Model::upload(std::string& e) {
     ST_CUDA(dev_upload(z1, d_fail, owned), "alloc fail");
   }
   ST_CUDA(cudaMallocHost((void**)&h_scalars, (64 + kMaxStats + 1024) * sizeof(double)), "pinned scalars");
+  // chain state in device memory (st_chain.hpp) and its pinned host mirror
+  {
+    void* dc = nullptr;
+    ST_CUDA(cudaMalloc(&dc, sizeof(ChainDev)), "alloc chain");
+    owned.push_back(dc);
+    d_mc = (ChainDev*)dc;
+    ST_CUDA(cudaMallocHost((void**)&h_mc, sizeof(ChainDev)), "pinned chain");
+    std::memset(h_mc, 0, sizeof(ChainDev));
+    h_mc->cur = cur; h_mc->npar = (int)theta[0].size(); h_mc->p = p; h_mc->q = q;
+    for (int sl = 0; sl < 2; sl++) {
+      std::copy(theta[sl].begin(), theta[sl].end(), h_mc->theta[sl]);
+      std::string e2;
+      if (!make_covtab(theta[sl].data(), (int)theta[sl].size(), q, h_mc->tab[sl], e2)) { err = e2; return 1; }
+    }
+    ST_CUDA(cudaMemcpy(d_mc, h_mc, sizeof(ChainDev), cudaMemcpyHostToDevice), "upload chain");
+    dslots.s[0] = ds[0]; dslots.s[1] = ds[1]; dslots.chain = d_mc;
+  }
+  {  // row keys of the device random streams: the row's id in the whole problem (boundary order), node-major here
+    std::vector<long long> key(n_all);
+    const bool pg = part && !global_rows.empty();
+    for (int64_t i = 0; i < n_all; i++) key[i] = pg ? (long long)global_rows[perm[i]] : (long long)perm[i];
+    ST_CUDA(dev_upload(key, d_rowkey, owned), "upload rowkey");
+  }
+  ST_CUDA(dev_zeros(d_xtx, (long long)q * p * p, owned), "alloc xtx");
+  ST_CUDA(dev_zeros(d_bscratch, (long long)q * 3 * p * p + 8 * p, owned), "alloc beta scratch");
+  if (!part) {  // (partitioned handles: after the sums over the ranks, partition_reduce_constants)
+    const int rcx = upload_xtx();
+    if (rcx) return rcx;
+  }
   ST_CUDA(cudaMallocHost((void**)&h_stage, std::max<int64_t>(n_all, 1) * sizeof(double)), "pinned stage");
   // index used by the beta step
   beta_widx_faithful.assign(n_all, -1);
@@ -710,6 +713,17 @@ int Model::partition_reduce_constants(std::string& e) {
       nobs_by_q[j] = (int64_t)std::llround(hb[q * p * p + j]);
     }
   xtx_pending_ = false;
+  return upload_xtx();
+}
+
+// XtX and the per-outcome counts of the whole problem to the device (the device-resident beta / tausq steps read them)
+int Model::upload_xtx() {
+  dvec flat((size_t)q * p * p);
+  for (int j = 0; j < q; j++) std::copy(XtX[j].a.begin(), XtX[j].a.end(), flat.begin() + (size_t)j * p * p);
+  ST_CUDA(cudaMemcpy(d_xtx, flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice), "upload XtX");
+  double nb[kMaxQ] = {0};
+  for (int j = 0; j < q; j++) nb[j] = (double)nobs_by_q[j];
+  ST_CUDA(cudaMemcpy(d_mc->nobs, nb, sizeof(nb), cudaMemcpyHostToDevice), "upload nobs");
   return 0;
 }
 
@@ -789,25 +803,16 @@ int Model::allreduce_dev(double* dptr, int64_t n) {
   return 0;
 }
 
-// sum of the per-block log-density pieces (:987-988 / :815-816).  Partitioned: replicated blocks once + all-reduced rest.
-// out3_host = {loglik_w, logdetCi, number of failed Cholesky factorisations}
-int Model::reduce_loglik(int ps, const int* fail, double* out3_host) {
-  if (!part) {
-    ST_CUDA(launch_loglik_reduce(ds[ps].logdet, ds[ps].llcomp, 0, n_obs_nodes, fail, 1, d_scalars, stream), "loglik_reduce");
-    n_launches++;
-    ST_CUDA(cudaMemcpyAsync(h_scalars, d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H scalars");
-    ST_CUDA(cudaStreamSynchronize(stream), "sync");
-    out3_host[0] = h_scalars[0]; out3_host[1] = h_scalars[1]; out3_host[2] = h_scalars[2];
-    return 0;
-  }
-  ST_CUDA(launch_loglik_reduce(ds[ps].logdet, ds[ps].llcomp, 0, n_top_slots, nullptr, 1, d_scalars, stream), "loglik_reduce");
-  ST_CUDA(launch_loglik_reduce(ds[ps].logdet, ds[ps].llcomp, n_top_slots, n_obs_nodes - n_top_slots, fail, 1, d_scalars + 4, stream), "loglik_reduce");
-  n_launches += 2;
-  int rc = allreduce_dev(d_scalars + 4, 3);
-  if (rc) return rc;
-  ST_CUDA(cudaMemcpyAsync(h_scalars, d_scalars, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H scalars");
+// sum of the per-block log-density pieces (:987-988 / :815-816) of the slot `rel` into dev_red8 (device): [0..2] the
+// replicated blocks (or nothing), [4..6] the rest, all-reduced over the ranks of a partition; [6] = failed factorisations.
+// out3_host (host-driven path) = {loglik_w, logdetCi, failures}: one D2H + synchronisation.
+int Model::reduce_loglik(int rel, const int* fail, double* dev_red8, double* out3_host) {
+  ST_CUDA(launch_loglik_reduce(dslots, rel, part ? n_top_slots : 0, n_obs_nodes, fail, dev_red8, stream), "loglik_reduce");
+  n_launches++;
+  if (part) { int rc = allreduce_dev(dev_red8 + 4, 3); if (rc) return rc; }
+  if (!out3_host) return 0;
+  ST_CUDA(cudaMemcpyAsync(h_scalars, dev_red8, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H scalars");
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
-  // out[0] of the kernel is logdet + llcomp, out[1] logdet
   out3_host[0] = h_scalars[0] + h_scalars[4];
   out3_host[1] = h_scalars[1] + h_scalars[5];
   out3_host[2] = h_scalars[6];
@@ -820,7 +825,18 @@ int Model::theta_update(int slot, const double* th) {
   return 0;
 }
 
-int Model::launch_build_levels(int pslot, const CovTab& tab) {
+int Model::push_slot_theta(int ps) {
+  ThetaPack pk;
+  std::string e;
+  pk.n = (int)theta[ps].size();
+  if (pk.n > kMaxPar) { err = "more than 64 covariance parameters"; return 4; }
+  std::copy(theta[ps].begin(), theta[ps].end(), pk.theta);
+  if (!make_covtab(theta[ps].data(), pk.n, q, pk.tab, e)) { err = e; return 1; }
+  ST_CUDA(launch_chain_set_theta(d_mc, ps == cur ? 0 : 1, pk, stream), "chain_set_theta_kernel");
+  return 0;
+}
+
+int Model::launch_build_levels(int rel) {
   // ST_PROFILE_BUILD=1: per-phase clock64() totals of build_level_kernel, printed per level (development aid)
   static const bool profile = getenv("ST_PROFILE_BUILD") != nullptr;
   unsigned long long* d_prof = nullptr;
@@ -838,12 +854,11 @@ int Model::launch_build_levels(int pslot, const CovTab& tab) {
       }
       // every launch but the first of a BUILD may start before its predecessor has drained (programmatic dependent
       // launch): it waits inside the kernel before it reads the ancestors' row blocks
-      ST_CUDA(launch_build(L.is_ref ? 0 : 1, dt, ds[pslot], ds[pslot].G, keep_H ? ds[pslot].H : nullptr, ds[pslot].Ri,
-                           d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w, tab, d_fail, B.ns, L.deferrable ? 1 : 0, B.smem, stream,
-                           B.threads, d_prof, use_pdl && !first_launch && !profile),
+      ST_CUDA(launch_build(L.is_ref ? 0 : 1, dt, dslots, rel, nullptr, nullptr, keep_H ? 1 : 0, d_grp_slot0 + B.grp0, d_grp_nn + B.grp0,
+                           B.ngrp, d_w, d_fail, B.ns, L.deferrable ? 1 : 0, B.smem, stream, B.threads, d_prof,
+                           use_pdl && !first_launch && !profile),
               "build_level_kernel");
       first_launch = false;
-      if (L.deferrable) deferred_[pslot] = true;
       n_launches++;
       if (profile) {
         unsigned long long h[16];
@@ -866,20 +881,24 @@ int Model::launch_build_levels(int pslot, const CovTab& tab) {
   return 0;
 }
 
-// The deferred half of BUILD: childless non-reference blocks of the slot get their G (backward sweep over the parked Z).
-int Model::complete_slot(int pslot) {
-  if (!deferred_[pslot]) return 0;
-  CovTab tab{};  // not evaluated in this phase
-  tab.q = q;
+// The deferred half of BUILD: childless non-reference blocks of the slot `rel` get their G (backward sweep over the parked
+// Z).  run_flag (device-resident chain): a device int, the launches are no-ops when it is 0.
+int Model::launch_deferred_half(int rel, const int* run_flag) {
   for (auto& L : levels) {
     if (!L.deferrable) continue;
     for (const auto& B : L.build_launches) {
-      ST_CUDA(launch_build(1, dt, ds[pslot], ds[pslot].G, nullptr, ds[pslot].Ri, d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w,
-                           tab, d_fail, B.ns, 2, B.smem, stream, B.threads, nullptr),
+      ST_CUDA(launch_build(1, dt, dslots, rel, nullptr, nullptr, 0, d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w, d_fail, B.ns, 2,
+                           B.smem, stream, B.threads, nullptr, false, run_flag),
               "build_level_kernel(deferred half)");
       n_launches++;
     }
   }
+  return 0;
+}
+int Model::complete_slot(int pslot) {
+  if (!deferred_[pslot]) return 0;
+  const int rc = launch_deferred_half(pslot == cur ? 0 : 1, nullptr);
+  if (rc) return rc;
   deferred_[pslot] = false;
   return 0;
 }
@@ -887,14 +906,14 @@ int Model::complete_slot(int pslot) {
 int Model::get_loglik_comps_w(int slot, double* out3) {
   if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   const int ps = phys(slot);
-  CovTab tab;
-  std::string e;
-  if (!make_covtab(theta[ps].data(), (int)theta[ps].size(), q, tab, e)) { err = e; return 1; }
-  ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
-  int rc = launch_build_levels(ps, tab);
+  int rc = push_slot_theta(ps);
   if (rc) return rc;
+  ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
+  rc = launch_build_levels(ps == cur ? 0 : 1);
+  if (rc) return rc;
+  for (auto& L : levels) if (L.deferrable) deferred_[ps] = true;
   double r3[3];
-  rc = reduce_loglik(ps, d_fail, r3);
+  rc = reduce_loglik(ps == cur ? 0 : 1, d_fail, d_mc->red_build, r3);
   if (rc) return rc;
   const bool ok = r3[2] == 0.0;
   if (ok) { loglik_w[ps] = r3[0]; logdetCi[ps] = r3[1]; }  // on failure the reference leaves them untouched (:971-982)
@@ -912,15 +931,17 @@ int Model::upload_rows(const double* boundary_order, double* dev) {
 }
 
 int Model::draw_normals(uint64_t seed) {
-  ST_CUDA(launch_normals(d_z, n_all, seed, sweep_counter++, part ? n_top_rows : n_all, part ? rng_row_offset : 0, stream), "normals_kernel");
+  ST_CUDA(launch_normals(d_z, n_all, seed, sweep_counter++, d_rowkey, nullptr, stream), "normals_kernel");
   n_launches++;
   return 0;
 }
 
-int Model::refresh_grams() {
-  { int rc = complete_slot(cur); if (rc) return rc; }
+int Model::refresh_grams(const int* run_flag) {
+  if (!run_flag) { int rc = complete_slot(cur); if (rc) return rc; }
   for (int g = (int)levels.size() - 1; g >= 0; g--) {
     if (part && n_top_levels >= 1 && g == n_top_levels - 1) {  // children of this level live on several ranks
+      // (unconditional also in the device-resident chain: every rank must enter the collective, and summing the unchanged
+      // tiles again gives the same pseudo-child)
       ST_CUDA(launch_frontier_sum(dt, (int)h_front_pseudo.size(), d_front_pseudo, d_front_c0, d_front_c1, d_front_vlen, d_front_ulen,
                                   d_V, d_U, 0, 1, stream), "frontier_sum_kernel");
       n_launches++;
@@ -931,7 +952,8 @@ int Model::refresh_grams() {
     static const bool profile = getenv("ST_PROFILE_GIBBS") != nullptr;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, stream); }
-    ST_CUDA(launch_gram(dt, ds[cur], levels[g].slot0, levels[g].nslots, d_U, d_S, levels[g].gram_rch, levels[g].gram_ldx, levels[g].gram_tiles, levels[g].gram_stage_off, levels[g].gram_threads, stream),
+    ST_CUDA(launch_gram(dt, dslots, levels[g].slot0, levels[g].nslots, d_U, d_S, levels[g].gram_rch, levels[g].gram_ldx, levels[g].gram_tiles,
+                        levels[g].gram_stage_off, levels[g].gram_threads, stream, run_flag),
             "gram_level_kernel");
     n_launches++;
     if (profile) {
@@ -944,14 +966,12 @@ int Model::refresh_grams() {
               levels[g].gram_rch, levels[g].gram_ldx, pms);
     }
   }
-  gram_stale = false;
+  if (!run_flag) gram_stale = false;
   return 0;
 }
 
-int Model::gibbs_launch_only() {
-  stats_valid_mode_ = -1;  // w is about to change
-  { int rc = complete_slot(cur); if (rc) return rc; }
-  if (gram_stale) { int rc = refresh_grams(); if (rc) return rc; }
+// the level launches of one Gibbs sweep, leaves to root; fail_ptr: device int that counts failed factorisations
+int Model::gibbs_launch_only(int* fail_ptr) {
   for (int g = (int)levels.size() - 1; g >= 0; g--) {
     const LevelInfo& L = levels[g];
     if (part && n_top_levels >= 1 && g == n_top_levels - 1) {
@@ -964,8 +984,8 @@ int Model::gibbs_launch_only() {
     static const bool profile = getenv("ST_PROFILE_GIBBS") != nullptr;  // development aid: per-level event timing
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, stream); }
-    ST_CUDA(launch_gibbs(L.is_ref, dt, ds[cur], L.slot0, L.nslots, d_w, d_xb, d_z, d_tausq_inv, d_S, d_V,
-                         probes ? d_probe_sig : nullptr, probes ? d_probe_smu : nullptr, d_fail, L.smem_gibbs, stream,
+    ST_CUDA(launch_gibbs(L.is_ref, dt, dslots, L.slot0, L.nslots, d_w, d_xb, d_z, d_tausq_inv, d_S, d_V,
+                         probes ? d_probe_sig : nullptr, probes ? d_probe_smu : nullptr, fail_ptr, L.smem_gibbs, stream,
                          use_pdl && !profile && g != (int)levels.size() - 1),
             "gibbs_level_kernel");
     n_launches++;
@@ -986,22 +1006,20 @@ int Model::deal_with_w(const double* z, uint64_t seed) {
   if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   if (z) { int rc = upload_rows(z, d_z); if (rc) return rc; }
   else { int rc = draw_normals(seed); if (rc) return rc; }
+  stats_valid_mode_ = -1;  // w is about to change
+  { int rc = complete_slot(cur); if (rc) return rc; }
+  if (gram_stale) { int rc = refresh_grams(); if (rc) return rc; }
   ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
-  int rc = gibbs_launch_only();
+  int rc = gibbs_launch_only(d_fail);
   if (rc) return rc;
-  int nfail = 0;
-  ST_CUDA(cudaMemcpyAsync(&nfail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H fail");
+  // failed factorisations, agreed over the ranks of a partition (every rank must take the same exit): the count rides in an
+  // 8-double reduction slot, all-reduced on the stream
+  double* slot8 = d_scalars + 48;
+  ST_CUDA(launch_loglik_reduce(dslots, 0, 0, 0, d_fail, slot8, stream), "fail count");
+  if (part) { rc = allreduce_dev(slot8 + 4, 3); if (rc) return rc; }
+  ST_CUDA(cudaMemcpyAsync(h_scalars + 48, slot8, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H fail");
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
-  if (part) {  // every rank must take the same exit
-    h_scalars[48] = nfail;
-    ST_CUDA(cudaMemcpyAsync(d_scalars + 48, h_scalars + 48, sizeof(double), cudaMemcpyHostToDevice, stream), "H2D");
-    rc = allreduce_dev(d_scalars + 48, 1);
-    if (rc) return rc;
-    ST_CUDA(cudaMemcpyAsync(h_scalars + 48, d_scalars + 48, sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H");
-    ST_CUDA(cudaStreamSynchronize(stream), "sync");
-    nfail = h_scalars[48] != 0.0;
-  }
-  if (nfail) { err = "Error at gibbs_sample_w: conditional precision not positive definite"; return 3; }
+  if (h_scalars[48 + 6] != 0.0) { err = "Error at gibbs_sample_w: conditional precision not positive definite"; return 3; }
   return 0;
 }
 
@@ -1009,10 +1027,10 @@ int Model::get_loglik_w(int slot, double* out2) {
   if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   const int ps = phys(slot);
   { int rc = complete_slot(ps); if (rc) return rc; }
-  ST_CUDA(launch_llw(dt, ds[ps], n_obs_nodes, d_w, llw_maxlen_, stream), "llw_kernel");
+  ST_CUDA(launch_llw(dt, dslots, ps == cur ? 0 : 1, n_obs_nodes, d_w, llw_maxlen_, stream), "llw_kernel");
   n_launches++;
   double r3[3];
-  int rc = reduce_loglik(ps, nullptr, r3);
+  int rc = reduce_loglik(ps == cur ? 0 : 1, nullptr, d_mc->red_llw, r3);
   if (rc) return rc;
   loglik_w[ps] = r3[0];
   logdetCi[ps] = r3[1];
@@ -1024,19 +1042,20 @@ void Model::accept_make_change() {
   cur = 1 - cur;
   gram_stale = true;
   pred_H_valid = false;
-  if (stream && complete_slot(cur) != 0) deferred_[cur] = true;  // (an error here resurfaces at the next consumer)
+  if (!stream) return;
+  if (launch_chain_flip(d_mc, stream) != cudaSuccess) { err = "chain_flip_kernel failed"; return; }
+  if (complete_slot(cur) != 0) deferred_[cur] = true;  // (an error here resurfaces at the next consumer)
 }
 
 int Model::predict(bool theta_changed) {
   if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   if (pred_level.nslots == 0) return 0;
   if (theta_changed || !pred_H_valid) {
-    CovTab tab;
-    std::string e;
-    if (!make_covtab(theta[cur].data(), (int)theta[cur].size(), q, tab, e)) { err = e; return 1; }
+    int rc = push_slot_theta(cur);
+    if (rc) return rc;
     for (const auto& B : pred_level.build_launches) {
-      ST_CUDA(launch_build(2, dt, ds[cur], d_Hpred, nullptr, d_sdpred, d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w, tab,
-                           d_fail, B.ns, 0, B.smem, stream, B.threads, nullptr),
+      ST_CUDA(launch_build(2, dt, dslots, 0, d_Hpred, d_sdpred, 0, d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w, d_fail, B.ns, 0,
+                           B.smem, stream, B.threads, nullptr),
               "build_level_kernel(predict)");
       n_launches++;
     }
@@ -1047,6 +1066,13 @@ int Model::predict(bool theta_changed) {
   n_launches++;
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
   return 0;
+}
+
+// statistics of the beta / tausq steps into d_scalars + 8 (all-reduced over the ranks); no synchronisation
+int Model::enqueue_stats() {
+  ST_CUDA(launch_rowstats(dt, d_obs_widx, n_all, p, q, d_w, d_xb, d_partial, rowstat_blocks_, d_scalars + 8, stream), "rowstats_kernel");
+  n_launches += 2;
+  return allreduce_dev(d_scalars + 8, q * (p + 1));
 }
 
 int Model::rowstats(bool faithful_index) {
@@ -1060,12 +1086,8 @@ int Model::rowstats(bool faithful_index) {
     ST_CUDA(cudaStreamSynchronize(stream), "sync");
     beta_widx_mode = mode;
   }
-  ST_CUDA(launch_rowstats(dt, d_obs_widx, n_all, p, q, d_w, d_xb, d_partial, rowstat_blocks_, d_scalars + 8, stream), "rowstats_kernel");
-  n_launches += 2;
-  {
-    int rc = allreduce_dev(d_scalars + 8, q * (p + 1));
-    if (rc) return rc;
-  }
+  int rc = enqueue_stats();
+  if (rc) return rc;
   ST_CUDA(cudaMemcpyAsync(h_scalars + 8, d_scalars + 8, q * (p + 1) * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H stats");
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
   stats_valid_mode_ = mode;
@@ -1123,7 +1145,6 @@ int Model::gibbs_sample_beta(const double* zb, bool faithful_index) {
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
   return 0;
 }
-
 int Model::get_w(double* out) {
   if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   ST_CUDA(cudaMemcpyAsync(h_stage, d_w, n_all * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H w");
@@ -1137,7 +1158,6 @@ int Model::save_begin(double* host_base, size_t bytes) {
   if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   save_registered = nullptr;
   save_pending = false;
-  if (!host_base || bytes == 0) return 0;
   if (!copy_stream) {
     ST_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     ST_CUDA(cudaEventCreateWithFlags(&ev_wready, cudaEventDisableTiming), "cudaEventCreate");
@@ -1146,6 +1166,7 @@ int Model::save_begin(double* host_base, size_t bytes) {
     std::vector<long long> ip(iperm.begin(), iperm.end());
     ST_CUDA(dev_upload(ip, d_iperm, owned), "upload iperm");
   }
+  if (!host_base || bytes == 0) return 0;
   // page-lock the caller's output range for the duration of the run; if that is refused the save stays synchronous
   if (cudaHostRegister(host_base, bytes, cudaHostRegisterPortable) == cudaSuccess) save_registered = host_base;
   else (void)cudaGetLastError();
@@ -1329,50 +1350,315 @@ int Model::get_index(const std::string& which, int u, int c, int64_t* out, int64
   return 1;
 }
 
-// one hot-path iteration with device normals and event timing (bench hook)
+
+// ------------------------------------------------------------------------------------------------ device-resident iteration
+// One Gibbs sweep, enqueued only: normals keyed by (seed, row, iteration), Gram refresh and deferred half are the callers'
+int Model::enqueue_gibbs(uint64_t seed, bool device_chain) {
+  ST_CUDA(launch_normals(d_z, n_all, seed, device_chain ? 0 : sweep_counter++, d_rowkey, device_chain ? &d_mc->iter : nullptr, stream),
+          "normals_kernel");
+  n_launches++;
+  return gibbs_launch_only(device_chain ? &d_mc->gibbs_fail : d_fail);
+}
+
+// One iteration of spamtree_fit.cpp:167-330 enqueued on the stream without any host synchronisation; every decision is
+// taken on the device (st_chain.hpp).  accept_mode: 0 Metropolis rule with a proposal drawn on the device; 1 / 2: the
+// proposal is already in the alter slot's theta and is taken / rejected (bench hook).  tev != NULL: CUDA events after the
+// phases {start, gibbs, llw, build + accept + deferred half, Gram refresh, tausq + beta}.
+int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_mode) {
+  cudaEvent_t* tev = timing_events_;
+  int rc = 0;
+  if (tev) ST_CUDA(cudaEventRecord(tev[0], stream), "event");
+  if (o.sample_w) {  // :183-187
+    rc = enqueue_gibbs(o.seed, true);
+    if (rc) return rc;
+    if (tev) ST_CUDA(cudaEventRecord(tev[1], stream), "event");
+    ST_CUDA(launch_llw(dt, dslots, 0, n_obs_nodes, d_w, llw_maxlen_, stream), "llw_kernel");
+    n_launches++;
+    rc = reduce_loglik(0, nullptr, d_mc->red_llw, nullptr);
+    if (rc) return rc;
+  } else if (tev) {
+    ST_CUDA(cudaEventRecord(tev[1], stream), "event");
+  }
+  if (tev) ST_CUDA(cudaEventRecord(tev[2], stream), "event");
+  if (o.sample_theta) {  // :203-289
+    if (accept_mode == 0) { ST_CUDA(launch_mh_propose(d_mc, stream), "mh_propose_kernel"); n_launches++; }
+    ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
+    rc = launch_build_levels(1);
+    if (rc) return rc;
+    rc = reduce_loglik(1, d_fail, d_mc->red_build, nullptr);
+    if (rc) return rc;
+    ST_CUDA(launch_mh_accept(d_mc, accept_mode, o.sample_w ? 1 : 0, stream), "mh_accept_kernel");
+    n_launches++;
+    // an accepted proposal: the new param_data's childless level gets its backward half, the message Grams are refreshed
+    rc = launch_deferred_half(0, &d_mc->accepted_now);
+    if (rc) return rc;
+    if (tev) ST_CUDA(cudaEventRecord(tev[3], stream), "event");
+    rc = refresh_grams(&d_mc->accepted_now);
+    if (rc) return rc;
+  } else if (tev) {
+    ST_CUDA(cudaEventRecord(tev[3], stream), "event");
+  }
+  if (tev) ST_CUDA(cudaEventRecord(tev[4], stream), "event");
+  if (predicting && o.sample_predicts && o.sample_w && pred_level.nslots > 0) {  // :302-306, predict_std :1234-1358
+    ST_CUDA(launch_predict_gate(d_mc, stream), "predict_gate_kernel");
+    for (const auto& B : pred_level.build_launches) {
+      ST_CUDA(launch_build(2, dt, dslots, 0, d_Hpred, d_sdpred, 0, d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w, d_fail, B.ns, 0,
+                           B.smem, stream, B.threads, nullptr, false, &d_mc->predict_build),
+              "build_level_kernel(predict)");
+      n_launches++;
+    }
+    ST_CUDA(launch_predict_sample(dt, pred_level.slot0, pred_level.nslots, d_Hpred, d_sdpred, d_w, d_z, stream), "predict_sample_kernel");
+    n_launches += 2;
+  }
+  if (o.sample_tausq || o.sample_beta) {  // :308-330
+    rc = enqueue_stats();
+    if (rc) return rc;
+    ST_CUDA(launch_tausq_beta(d_mc, d_scalars + 8, d_xtx, d_tausq_inv, d_bcoeff, d_bscratch, o.sample_tausq, o.sample_beta, stream),
+            "tausq_beta_kernel");
+    n_launches++;
+    if (o.sample_beta) { ST_CUDA(launch_xb(dt, n_all, p, d_bcoeff, d_xb, stream), "xb_kernel"); n_launches++; }
+  }
+  ST_CUDA(launch_chain_tick(d_mc, stream), "chain_tick_kernel");
+  n_launches++;
+  if (tev) ST_CUDA(cudaEventRecord(tev[5], stream), "event");
+  return 0;
+}
+
+// brings the host's view of the chain (cur, thetas, log-densities, beta, tausq, the flags of the lazy work) back in step
+// with the device after a device-resident run; one synchronisation
+int Model::pull_chain_state() {
+  ST_CUDA(cudaMemcpyAsync(h_mc, d_mc, sizeof(ChainDev), cudaMemcpyDeviceToHost, stream), "D2H chain");
+  ST_CUDA(cudaMemcpyAsync(h_scalars, d_tausq_inv, q * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H tausq");
+  ST_CUDA(cudaMemcpyAsync(h_scalars + 8, d_bcoeff, (size_t)p * q * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H beta");
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  cur = h_mc->cur;
+  for (int sl = 0; sl < 2; sl++) {
+    std::copy(h_mc->theta[sl], h_mc->theta[sl] + theta[sl].size(), theta[sl].begin());
+    loglik_w[sl] = h_mc->loglik[sl];
+    logdetCi[sl] = h_mc->logdet[sl];
+  }
+  std::copy(h_scalars, h_scalars + q, tausq_inv.begin());
+  std::copy(h_scalars + 8, h_scalars + 8 + (size_t)p * q, Bcoeff.begin());
+  bool any_def = false;
+  for (auto& L : levels) any_def |= L.deferrable;
+  deferred_[cur] = false;            // completed on the device whenever a proposal was accepted
+  deferred_[1 - cur] = any_def;      // the alter slot holds the forward half of the last proposal
+  gram_stale = false;
+  pred_H_valid = h_mc->pred_valid != 0;
+  stats_valid_mode_ = -1;
+  return 0;
+}
+
+// state of the device chain before a run / a bench iteration: everything the host-driven path may have changed
+int Model::push_chain_state(const st_mcmc_opts* o, uint64_t seed) {
+  ChainDev& C = *h_mc;
+  const int npar = (int)theta[0].size();
+  if (npar > kMaxPar) { err = "more than 64 covariance parameters"; return 4; }
+  std::memset(&C, 0, sizeof(ChainDev));
+  for (int j = 0; j < q; j++) C.nobs[j] = (double)nobs_by_q[j];
+  C.cur = cur; C.npar = npar; C.p = p; C.q = q;
+  for (int sl = 0; sl < 2; sl++) {
+    std::copy(theta[sl].begin(), theta[sl].end(), C.theta[sl]);
+    std::string e2;
+    if (!make_covtab(theta[sl].data(), npar, q, C.tab[sl], e2)) { err = e2; return 1; }
+    C.loglik[sl] = loglik_w[sl]; C.logdet[sl] = logdetCi[sl];
+  }
+  std::copy(theta[cur].begin(), theta[cur].end(), C.predict_param);
+  C.pred_valid = pred_H_valid ? 1 : 0;
+  C.seed = seed;
+  if (o) {
+    C.adapting = o->adapting;
+    std::copy(o->set_unif_bounds, o->set_unif_bounds + 2 * npar, C.bounds);
+    if (!ram_init(npar, o->mcmcsd, C.paramsd, C.prodparam)) { err = "mcmcsd is not positive definite"; return 1; }
+  }
+  // (h_chain is pinned and is not touched again before pull_chain_state's synchronisation: no wait needed here)
+  ST_CUDA(cudaMemcpyAsync(d_mc, h_mc, sizeof(ChainDev), cudaMemcpyHostToDevice, stream), "H2D chain");
+  return 0;
+}
+
+// the row-index mode of the beta step on the device; one synchronisation when it changes
+int Model::set_widx_mode(bool faithful_index) {
+  const int mode = faithful_index ? 1 : 0;
+  if (beta_widx_mode == mode) return 0;
+  const std::vector<int>& src = faithful_index ? beta_widx_faithful : beta_widx_plain;
+  ST_CUDA(cudaMemcpyAsync(d_obs_widx, src.data(), n_all * sizeof(int), cudaMemcpyHostToDevice, stream), "H2D widx");
+  ST_CUDA(cudaStreamSynchronize(stream), "sync");
+  beta_widx_mode = mode;
+  return 0;
+}
+
+// one hot-path iteration with event timing (bench hook): the device-resident iteration with a host-supplied proposal and
+// accept decision; the only synchronisation is the one that reads the events and the log-densities back
 int Model::bench_iteration(const double* theta_prop, int do_swap, uint64_t seed, double* out3, float* ms_out) {
   if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
-  const int pa = 1 - cur;
-  CovTab tab;
+  int rc = complete_slot(cur);
+  if (rc) return rc;
+  if (gram_stale) { rc = refresh_grams(); if (rc) return rc; }
+  rc = set_widx_mode(part ? false : (beta_widx_mode != 0));
+  if (rc) return rc;
+  rc = push_chain_state(nullptr, seed);  // the device's chain state takes over from the host's
+  if (rc) return rc;
+  // the proposal into the alter slot (device decides which physical slot that is)
+  ThetaPack pk;
   std::string e;
-  std::copy(theta_prop, theta_prop + theta[pa].size(), theta[pa].begin());
-  if (!make_covtab(theta[pa].data(), (int)theta[pa].size(), q, tab, e)) { err = e; return 1; }
-  ST_CUDA(cudaEventRecord(ev[0], stream), "event");
-  int rc = draw_normals(seed);
+  pk.n = (int)theta[0].size();
+  std::copy(theta_prop, theta_prop + pk.n, pk.theta);
+  if (!make_covtab(theta_prop, pk.n, q, pk.tab, e)) { err = e; return 1; }
+  ST_CUDA(launch_chain_set_theta(d_mc, 1, pk, stream), "chain_set_theta_kernel");
+  st_mcmc_opts o{};
+  o.sample_beta = o.sample_tausq = o.sample_theta = o.sample_w = 1;
+  o.seed = seed;
+  timing_events_ = ev;
+  rc = enqueue_iteration(o, false, do_swap ? 1 : 2);
+  timing_events_ = nullptr;
   if (rc) return rc;
-  ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
-  rc = gibbs_launch_only();
+  rc = pull_chain_state();
   if (rc) return rc;
-  ST_CUDA(cudaMemcpyAsync(h_scalars + 40, d_fail, sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H fail");
-  ST_CUDA(cudaEventRecord(ev[1], stream), "event");
-  ST_CUDA(launch_llw(dt, ds[cur], n_obs_nodes, d_w, llw_maxlen_, stream), "llw_kernel");
-  n_launches++;
-  double rl[3], rb[3];
-  rc = reduce_loglik(cur, nullptr, rl);
+  if (h_mc->gibbs_fail) { err = "Error at gibbs_sample_w: conditional precision not positive definite"; return 3; }
+  const bool ok = h_mc->red_build[6] == 0.0;
+  out3[0] = loglik_w[1 - cur]; out3[1] = loglik_w[cur]; out3[2] = ok ? 1.0 : 0.0;
+  if (h_mc->accepted_now) { out3[0] = loglik_w[cur]; out3[1] = loglik_w[1 - cur]; }  // {proposal, previous current}
+  if (ms_out) {
+    float t[5];
+    for (int i = 0; i < 5; i++) ST_CUDA(cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]), "elapsed");
+    ms_out[0] = t[0] + t[3];  // GIBBS sweep + the Gram refresh an accepted proposal triggers
+    ms_out[1] = t[1];         // LLW
+    ms_out[2] = t[2];         // BUILD + accept + the deferred half of an accepted proposal
+    ms_out[3] = t[4];         // tausq + beta
+  }
+  return 0;
+}
+
+// S.dbuf (n_all doubles, boundary order, written by the kernel just enqueued on `stream`) -> host_dst on the copy stream
+int Model::save_rows_async(AsyncSave& S, double* host_dst) {
+  ST_CUDA(cudaEventRecord(S.ready, stream), "event");
+  ST_CUDA(cudaStreamWaitEvent(copy_stream, S.ready, 0), "wait");
+  ST_CUDA(cudaMemcpyAsync(host_dst, S.dbuf, n_all * sizeof(double), cudaMemcpyDeviceToHost, copy_stream), "D2H rows (async)");
+  ST_CUDA(cudaEventRecord(S.copied, copy_stream), "event");
+  S.pending = true;
+  return 0;
+}
+
+// The loop of spamtree_mv_mcmc (spamtree_fit.cpp:167-391) with the chain state in device memory: the host only enqueues
+// (one CUDA-graph launch per iteration on a single-GPU handle), saved iterations leave through asynchronous copies, and
+// the one synchronisation is at the end of the run.  Random numbers: Philox streams keyed by (seed, row or parameter,
+// iteration) — rows by their id in the whole problem, so that a partitioned run draws what a single-GPU run draws.
+int Model::chain_run(const st_mcmc_opts& o, st_mcmc_out& out) {
+  if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
+  if (part && o.faithful_beta_index) {
+    err = "partitioned runs support only the corrected beta row index (faithful_index = 0): the reference's mis-indexing "
+          "(SURVEY App. D #12) mixes rows that live on different ranks";
+    return 4;
+  }
+  double o3[3];
+  int rc = get_loglik_comps_w(0, o3);  // spamtree_fit.cpp:110-111
   if (rc) return rc;
-  int nfail_gibbs;
-  std::memcpy(&nfail_gibbs, h_scalars + 40, sizeof(int));
-  if (nfail_gibbs) { err = "Error at gibbs_sample_w: conditional precision not positive definite"; return 3; }
-  ST_CUDA(cudaEventRecord(ev[2], stream), "event");
-  ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
-  rc = launch_build_levels(pa, tab);
+  rc = get_loglik_comps_w(1, o3);
   if (rc) return rc;
-  rc = reduce_loglik(pa, d_fail, rb);
+  rc = complete_slot(cur);
   if (rc) return rc;
-  loglik_w[cur] = rl[0]; logdetCi[cur] = rl[1];
-  const bool ok = rb[2] == 0.0;
-  if (ok) { loglik_w[pa] = rb[0]; logdetCi[pa] = rb[1]; }
-  out3[0] = loglik_w[pa]; out3[1] = loglik_w[cur]; out3[2] = ok ? 1.0 : 0.0;
-  if (ok && do_swap) accept_make_change();  // includes the deferred half of BUILD for the accepted slot
-  ST_CUDA(cudaEventRecord(ev[3], stream), "event");
-  rc = gibbs_sample_tausq(nullptr);
+  if (gram_stale) { rc = refresh_grams(); if (rc) return rc; }
+  rc = set_widx_mode(o.faithful_beta_index != 0);
   if (rc) return rc;
-  rc = gibbs_sample_beta(nullptr, part ? false : (beta_widx_mode != 0));
+  const int npar = (int)theta[0].size(), keep = o.keep, mcmc = o.thin * o.keep + o.burn;
+  // sample arrays on the device, copied out once at the end
+  double* dsamp = nullptr;
+  const size_t n_th = (size_t)npar * keep, n_be = (size_t)p * keep * q, n_ta = (size_t)q * keep;
+  ST_CUDA(cudaMalloc((void**)&dsamp, std::max<size_t>(n_th + n_be + n_ta, 1) * sizeof(double)), "alloc samples");
+  struct Free { double* p; ~Free() { if (p) cudaFree(p); } } free_samp{dsamp};
+  d_theta_mcmc = dsamp; d_beta_mcmc = dsamp + n_th; d_tausq_mcmc = dsamp + n_th + n_be;
+  rc = push_chain_state(&o, o.seed);
   if (rc) return rc;
-  ST_CUDA(cudaEventRecord(ev[4], stream), "event");
-  ST_CUDA(cudaStreamSynchronize(stream), "sync");
-  if (ms_out)
-    for (int i = 0; i < 4; i++) ST_CUDA(cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]), "elapsed");
+  // saved rows: w through the existing staging (un-permute kernel), yhat through its own
+  const bool save_w = out.w_mcmc != nullptr, save_y = out.yhat_mcmc != nullptr;
+  if (save_w || save_y) { rc = save_begin(save_w ? out.w_mcmc : nullptr, (size_t)keep * n_all * sizeof(double)); if (rc) return rc; }
+  if (save_y) {
+    if (!save_y_.dbuf) {
+      ST_CUDA(dev_zeros(save_y_.dbuf, n_all, owned), "alloc yhat");
+      ST_CUDA(cudaEventCreateWithFlags(&save_y_.ready, cudaEventDisableTiming), "cudaEventCreate");
+      ST_CUDA(cudaEventCreateWithFlags(&save_y_.copied, cudaEventDisableTiming), "cudaEventCreate");
+    }
+    save_y_.pending = false;
+    save_y_.registered = (cudaHostRegister(out.yhat_mcmc, (size_t)keep * n_all * sizeof(double), cudaHostRegisterPortable) == cudaSuccess) ? out.yhat_mcmc : nullptr;
+    if (!save_y_.registered) (void)cudaGetLastError();
+  }
+  struct SaveGuard {
+    Model& M; bool on;
+    ~SaveGuard() {
+      if (!on) return;
+      M.save_end();
+      if (M.save_y_.registered) { cudaHostUnregister(M.save_y_.registered); M.save_y_.registered = nullptr; }
+    }
+  } guard{*this, save_w || save_y};
+  // one CUDA graph per kind of iteration (with / without prediction); partitioned handles enqueue directly (their
+  // collectives are library calls on the stream)
+  static const bool no_graph = getenv("ST_GRAPH") && atoi(getenv("ST_GRAPH")) == 0;
+  bool use_graph = !part && !no_graph;
+  const int key_base = (o.sample_beta ? 1 : 0) | (o.sample_tausq ? 2 : 0) | (o.sample_theta ? 4 : 0) | (o.sample_w ? 8 : 0) | (o.sample_predicts ? 16 : 0);
+  int msaved = 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int m = 0; m < mcmc; m++) {
+    const int mx = m - o.burn;
+    const bool saved = mx >= 0 && mx % o.thin == 0;
+    const bool predicting = saved;
+    const int which = predicting ? 1 : 0;
+    bool launched = false;
+    if (use_graph && m > 0) {  // (iteration 0 runs directly: it also sets the kernels' shared-memory attributes)
+      if (graph_key_[which] != key_base || !graph_exec_[which]) {
+        if (graph_exec_[which]) { cudaGraphExecDestroy((cudaGraphExec_t)graph_exec_[which]); graph_exec_[which] = nullptr; }
+        cudaGraph_t g = nullptr;
+        const double nl0 = n_launches;
+        bool ok = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+        int rcc = ok ? enqueue_iteration(o, predicting, 0) : 0;
+        if (ok) ok = (cudaStreamEndCapture(stream, &g) == cudaSuccess) && g && rcc == 0;
+        cudaGraphExec_t ge = nullptr;
+        if (ok) ok = cudaGraphInstantiate(&ge, g, 0) == cudaSuccess;
+        if (g) cudaGraphDestroy(g);
+        if (ok) { graph_exec_[which] = ge; graph_key_[which] = key_base; graph_launches_[which] = n_launches - nl0; }
+        else { (void)cudaGetLastError(); use_graph = false; }
+        n_launches = nl0;  // (capturing enqueues nothing)
+      }
+      if (use_graph) {
+        ST_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec_[which], stream), "cudaGraphLaunch");
+        n_launches += graph_launches_[which];
+        launched = true;
+      }
+    }
+    if (!launched) { rc = enqueue_iteration(o, predicting, 0); if (rc) return rc; }
+    if (saved) {  // :376-389
+      ST_CUDA(launch_record(d_mc, d_tausq_inv, d_bcoeff, d_theta_mcmc, d_beta_mcmc, d_tausq_mcmc, keep, stream), "record_kernel");
+      n_launches++;
+      if (save_w) { rc = save_w_async(out.w_mcmc + (size_t)msaved * n_all); if (rc) return rc; }
+      if (save_y) {
+        if (save_y_.pending) ST_CUDA(cudaStreamWaitEvent(stream, save_y_.copied, 0), "wait for the previous save");
+        ST_CUDA(launch_yhat(dt, d_w, d_xb, d_tausq_inv, d_iperm, d_rowkey, n_all, d_mc, save_y_.dbuf, stream), "yhat_kernel");
+        n_launches++;
+        if (save_y_.registered) { rc = save_rows_async(save_y_, out.yhat_mcmc + (size_t)msaved * n_all); if (rc) return rc; }
+        else {
+          ST_CUDA(cudaMemcpyAsync(out.yhat_mcmc + (size_t)msaved * n_all, save_y_.dbuf, n_all * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H yhat");
+          ST_CUDA(cudaStreamSynchronize(stream), "sync");
+        }
+      }
+      msaved++;
+    }
+  }
+  // the one synchronisation of the run: chain state, samples, the saves in flight
+  rc = pull_chain_state();
+  if (rc) return rc;
+  if (copy_stream) ST_CUDA(cudaStreamSynchronize(copy_stream), "sync saves");
+  save_pending = false;
+  save_y_.pending = false;
+  dvec hs(std::max<size_t>(n_th + n_be + n_ta, 1));
+  ST_CUDA(cudaMemcpy(hs.data(), dsamp, (n_th + n_be + n_ta) * sizeof(double), cudaMemcpyDeviceToHost), "D2H samples");
+  out.mcmc_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (out.theta_mcmc) std::copy(hs.begin(), hs.begin() + n_th, out.theta_mcmc);
+  if (out.beta_mcmc) std::copy(hs.begin() + n_th, hs.begin() + n_th + n_be, out.beta_mcmc);
+  if (out.tausq_mcmc) std::copy(hs.begin() + n_th + n_be, hs.end(), out.tausq_mcmc);
+  if (out.paramsd) std::copy(h_mc->paramsd, h_mc->paramsd + (size_t)npar * npar, out.paramsd);
+  out.n_accepted = h_mc->n_accepted;
+  out.n_chol_fail = h_mc->n_chol_fail;
+  if (h_mc->gibbs_fail) { err = "Error at gibbs_sample_w: conditional precision not positive definite"; return 3; }
+  if (h_mc->nan_loglik) { err = "At nan loglik: error."; return 5; }
   return 0;
 }
 

@@ -12,11 +12,9 @@
 
 #include <string>
 
+#include "../../include/spamtree_b200.h"
 #include "st_chain.hpp"
 #include "st_common.hpp"
-
-struct st_mcmc_opts;
-struct st_mcmc_out;
 
 namespace st {
 
@@ -152,7 +150,10 @@ class Model {
   int partition_reduce_constants(std::string& e);  // XtX and per-outcome counts summed over the ranks
   bool xtx_pending_ = false;
   static int nccl_unique_id(unsigned char* out128, std::string& e);
-  int reduce_loglik(int ps, const int* fail, double* out3_host);
+  int upload_xtx();
+  // log-density pieces of the slot `rel` summed into `dev_red8` (+ all-reduce of the rank's own part); out3_host != NULL
+  // also brings {loglik_w, logdetCi, failed factorisations} to the host (one synchronisation)
+  int reduce_loglik(int rel, const int* fail, double* dev_red8, double* out3_host);
   // ---- parameters (host copies of the small ones)
   dvec theta[2];
   double loglik_w[2] = {0, 0}, logdetCi[2] = {0, 0};
@@ -166,6 +167,14 @@ class Model {
   // ---- device
   DevTree dt{};
   DevSlot ds[2]{};
+  DevSlots dslots{};                // both slots + the chain state: what the kernels take
+  ChainDev *d_mc = nullptr, *h_mc = nullptr;  // the chain state (st_chain.hpp) on the device and its pinned host mirror
+  long long* d_rowkey = nullptr;    // node-major row -> row id in the whole problem (key of the device random streams)
+  double *d_xtx = nullptr, *d_bscratch = nullptr;   // XtX per outcome; scratch of the device beta step
+  double *d_theta_mcmc = nullptr, *d_beta_mcmc = nullptr, *d_tausq_mcmc = nullptr, *d_yhat = nullptr;  // sample arrays of a device-resident run
+  void* graph_exec_[2] = {nullptr, nullptr};  // cudaGraphExec_t of one device-resident iteration without / with prediction
+  int graph_key_[2] = {-1, -1};
+  double graph_launches_[2] = {0, 0};
   double *d_w = nullptr, *d_xb = nullptr, *d_z = nullptr, *d_V = nullptr, *d_U = nullptr, *d_S = nullptr;
   double *d_Hpred = nullptr, *d_sdpred = nullptr;
   double *d_probe_sig = nullptr, *d_probe_smu = nullptr;  // Sigi_tot / Smu_tot probes (rioff / row0 indexed)
@@ -212,17 +221,38 @@ class Model {
   int get_index(const std::string& which, int u, int c, int64_t* out, int64_t cap, int64_t* count);
   int bench_iteration(const double* theta_prop, int do_swap, uint64_t seed, double* out3, float* ms_out);
   int sync();
+  // ---- the device-resident chain (rng_mode 1): spamtree_fit.cpp:167-391 without a host round trip per iteration
+  int chain_run(const st_mcmc_opts& o, st_mcmc_out& out);
 
  private:
   int phys(int slot) const { return slot ? 1 - cur : cur; }
   int build_bookkeeping(std::string& e);
   int build_layout(std::string& e);
   int upload(std::string& e);
-  int launch_build_levels(int pslot, const CovTab& tab);
+  int launch_build_levels(int rel);
   int complete_slot(int pslot);  // the deferred half of BUILD for the slot's childless levels, if pending
+  int launch_deferred_half(int rel, const int* run_flag);
+  int push_slot_theta(int ps);   // host-driven path: theta[ps] and its covariance table into the device chain state
+  int enqueue_gibbs(uint64_t seed, bool device_chain);
+  int enqueue_stats();
+  int enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_mode);
+  int push_chain_state(const st_mcmc_opts* o, uint64_t seed);
+  int pull_chain_state();
+  int set_widx_mode(bool faithful_index);
+  cudaEvent_t* timing_events_ = nullptr;
+  // asynchronous saves of a device-resident run: a row vector in boundary order goes from its device staging buffer to
+  // the caller's (page-locked) array on the copy stream while the next iteration runs
+  struct AsyncSave {
+    double* dbuf = nullptr;
+    cudaEvent_t ready = nullptr, copied = nullptr;
+    void* registered = nullptr;
+    bool pending = false;
+  };
+  AsyncSave save_y_;
+  int save_rows_async(AsyncSave& S, double* host_dst);
   bool deferred_[2] = {false, false};
-  int refresh_grams();
-  int gibbs_launch_only();
+  int refresh_grams(const int* run_flag = nullptr);
+  int gibbs_launch_only(int* fail_ptr);
   int rowstats(bool faithful_index);
   std::vector<int> isref_host_;
   long long sd_total_ = 0;

@@ -22,10 +22,12 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "mcmc_iterations_per_sec" and d["unit"] == "it/s"
-    assert d["steps"] == 3 and d["warmup"] == 1 and d["higher_is_better"] is True and d["n_gpus"] == 1
+    # (both arms raise --warmup to at least 3 and report what they ran)
+    assert d["steps"] == 3 and d["warmup"] == 3 and d["higher_is_better"] is True and d["n_gpus"] == 1
     assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1e3) < 1e-6 * 1e3
     assert d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert d["config"]["workload"] == "C1" and d["config"]["n"] == 625
+    assert set(d["config"]) == {"workload", "n", "q", "p", "blocks", "levels", "theta", "l2", "parallelism"}  # = the product arm's keys
     cb, e2e = d["cpu_baseline"], d["e2e"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert e2e == {"value": d["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
