@@ -44,24 +44,24 @@ def _run(g, pb, m, getH, getRi, geti):
     for key in g.files:
         if key.startswith("Ri_"):
             u = int(key[3:])
-            assert relerr(getRi(u), g[key]) <= 10 * tol, key
+            assert relerr(getRi(u), g[key]) <= tol, key
             if f"H_{u}" in g.files:
-                assert relerr(getH(u), g[f"H_{u}"]) <= 10 * tol, f"H_{u}"
+                assert relerr(getH(u), g[f"H_{u}"]) <= tol, f"H_{u}"
     obs = np.isfinite(pb["d"]["y"])
     m.set_tausq_inv(g["tau"])
     for z, wk, lk in [("z1", "w_sweep1", "llw_sweep1"), ("z2", "w_sweep2", "llw_sweep2")]:
         m.deal_with_w(g[z])
-        assert relerr(m.w[obs], g[wk][obs]) <= 100 * tol, wk
+        assert relerr(m.w[obs], g[wk][obs]) <= tol, wk
         l = m.get_loglik_w(0)[0]
-        assert abs(l - float(g[lk])) <= 100 * tol * abs(l), lk
+        assert abs(l - float(g[lk])) <= tol * abs(l), lk
     m.theta_update(1, g["theta2"])
     ok2, ll2, ld2 = m.get_loglik_comps_w(1)
-    assert ok2 and abs(ll2 - float(g["loglik2"])) <= 100 * tol * abs(ll2) and abs(ld2 - float(g["logdet2"])) <= tol * abs(ld2)
+    assert ok2 and abs(ll2 - float(g["loglik2"])) <= tol * abs(ll2) and abs(ld2 - float(g["logdet2"])) <= tol * abs(ld2)
     m.accept_make_change()
     m.deal_with_w(g["z3"])
-    assert relerr(m.w[obs], g["w_sweep3"][obs]) <= 100 * tol
+    assert relerr(m.w[obs], g["w_sweep3"][obs]) <= tol
     l = m.get_loglik_w(0)[0]
-    assert abs(l - float(g["llw_sweep3"])) <= 100 * tol * abs(l)
+    assert abs(l - float(g["llw_sweep3"])) <= tol * abs(l)
 
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
@@ -134,14 +134,13 @@ def test_oracle_chain_against_reference_driver_outputs(path):
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", CHAIN_FILES, ids=[os.path.basename(f) for f in CHAIN_FILES])
 def test_cuda_chain_against_reference_driver_outputs(path):
-    """st_mcmc_run in lock-step mode vs the reference driver's chain.  Per-step differences (<= 1e-9, tested above) are
-    amplified along a chain of up to 84 iterations (w feeds the log-density that decides the next proposal, beta and
-    tausq feed the next sweep), hence the looser bounds on the late draws; the accept decisions must be identical."""
+    """st_mcmc_run in lock-step mode (rng_mode 0) vs the reference driver's chain: identical accept decisions, every saved
+    draw to 1e-9 (measured on the B200: 1e-14 after up to 84 iterations)"""
     g = np.load(path)
     pb, bounds, sd, kw = _chain_args(g)
     gm = common.product_model(pb)
     assert np.array_equal(gm.index("block_ct_obs"), g["block_ct_obs"])
     plen = np.array([gm.index("parents_indexing", u).size for u in range(pb["tree"]["n_blocks"])])
     assert np.array_equal(plen, g["parents_indexing_len"])
-    _chain_check(g, gm.mcmc(bounds, sd, rng_mode=0, **kw), 1e-8, 1e-7, 1e-6)
+    _chain_check(g, gm.mcmc(bounds, sd, rng_mode=0, **kw), 1e-9, 1e-9, 1e-9)
     gm.close()

@@ -68,8 +68,11 @@ def test_gibbs_conditionals_and_draw(pair):
     om.get_loglik_comps_w(0)
     obs, isref = om.geti("block_ct_obs"), om.geti("block_is_reference")
     rng = np.random.default_rng(8)
+    worst_cond = 1.0
     for sweep in range(3):
-        z = rng.standard_normal(n)
+        # the third sweep draws no noise: w is then the conditional MEAN of every block as the sampler realises it
+        # (Sc'(Sc Smu_tot), spamtree_model.cpp:1086) — compared directly, no inverse formed by the test
+        z = rng.standard_normal(n) if sweep < 2 else np.zeros(n)
         gm.deal_with_w(z)
         om.deal_with_w(z)
         assert relerr(gm.w, om.w) <= TOL
@@ -78,16 +81,22 @@ def test_gibbs_conditionals_and_draw(pair):
                 continue
             Sg, So = gm.node_state("Sigi_tot", u), om.get("Sigi_tot", u)
             Mg, Mo = gm.node_state("Smu_tot", u), om.get("Smu_tot", u)
-            assert relerr(Sg, So) <= TOL and relerr(Mg, Mo) <= 10 * TOL
-            if isref[u]:  # conditional covariance Sigi_tot^-1 and mean Sigi_tot^-1 Smu_tot
+            assert relerr(Sg, So) <= TOL and relerr(Mg, Mo) <= TOL
+            if isref[u]:  # conditional covariance Sigi_tot^-1 and mean Sigi_tot^-1 Smu_tot, inverted HERE by numpy: the
+                # inversion amplifies the (<= 1e-9) difference of the two precisions by the condition number of Sigi_tot
                 m = Mo.size
-                Cg, Co = np.linalg.inv(Sg.reshape(m, m)), np.linalg.inv(So.reshape(m, m))
-                assert relerr(Cg, Co) <= 100 * TOL  # conditioning of Sigi_tot enters here
-                assert relerr(Cg @ Mg, Co @ Mo) <= 100 * TOL
+                So2 = So.reshape(m, m)
+                cond = float(np.linalg.cond(So2))
+                worst_cond = max(worst_cond, cond)
+                Cg, Co = np.linalg.inv(Sg.reshape(m, m)), np.linalg.inv(So2)
+                bound = max(TOL, 4 * cond * max(relerr(Sg, So), relerr(Mg, Mo), 1e-16))
+                assert relerr(Cg, Co) <= bound and relerr(Cg @ Mg, Co @ Mo) <= bound, (u, cond)
+                assert relerr(Cg, Co) <= 100 * TOL and relerr(Cg @ Mg, Co @ Mo) <= 100 * TOL
             else:
                 assert relerr(Mg / Sg, Mo / So) <= TOL
         lg, lo = gm.get_loglik_w(0), om.get_loglik_w(0)
         assert abs(lg[0] - lo[0]) <= TOL * abs(lo[0]) and abs(lg[1] - lo[1]) <= TOL * abs(lo[1])
+    print(f"largest condition number of a block's conditional precision: {worst_cond:.2e}")
 
 
 def test_predict_beta_tausq(pair):
@@ -162,12 +171,8 @@ def test_lockstep_chain_matches_oracle_chain():
         rg = gm.mcmc(bounds, sd, rng_mode=0, **kw)
         ro = om.mcmc(bounds, sd, **kw)
         assert rg["n_accepted"] == ro["n_accepted"] and rg["n_accepted"] >= 1
-        assert relerr(rg["theta_mcmc"], ro["theta_mcmc"]) <= 1e-8
-        assert relerr(rg["beta_mcmc"], ro["beta_mcmc"]) <= 1e-7
-        assert relerr(rg["tausq_mcmc"], ro["tausq_mcmc"]) <= 1e-7
-        assert relerr(rg["w_mcmc"], ro["w_mcmc"]) <= 1e-6
-        assert relerr(rg["yhat_mcmc"], ro["yhat_mcmc"]) <= 1e-6
-        assert relerr(rg["paramsd"], ro["paramsd"]) <= 1e-7
+        for k in ("theta_mcmc", "beta_mcmc", "tausq_mcmc", "w_mcmc", "yhat_mcmc", "paramsd"):
+            assert relerr(rg[k], ro[k]) <= TOL, (k, relerr(rg[k], ro[k]))
         gm.close()
         om.close()
 
@@ -314,7 +319,9 @@ def test_cross_covariance_ag10_on_gpu():
 
 
 def test_gpu_matches_dense_math_directly():
-    """independent of the oracle: H, Ri, log-density against scipy-free dense numpy on a small tree"""
+    """independent of the oracle: H, Ri, log-density against scipy-free dense numpy on a small tree (the dense float64
+    solve of numpy is itself only good to ~cond * eps, hence one digit of slack on H and Ri; the full-size tests compare
+    the deepest blocks with extended-precision dense algebra at 1e-9)"""
     pb = common.make_problem(3, 900)
     gm, tw = common.product_model(pb), Twin(pb)
     w = np.random.default_rng(2).standard_normal(900)
