@@ -215,6 +215,7 @@ def main():
         sp, pl = None, None
         gm = sb.SpamTreeMV(d["y"], d["X"], d["coords"], d["mv_id"], t["res_is_ref"], None, None, False, t["block_names"], t["block_groups"],
                            None, np.zeros(3), theta, 0.1, csr=csr, keep_H=False, device=local_rank)
+    gm.set_beta_index(False)  # the corrected row index at every N (a partition supports no other): same chain for every N
     gm.get_loglik_comps_w(0)
     gm.get_loglik_comps_w(1)
     props = proposals(theta, args.warmup + args.steps, 99)

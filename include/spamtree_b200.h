@@ -197,6 +197,9 @@ int st_attach_nccl(st_handle* h, const unsigned char* id128);
  * + optional swap + tausq + beta (spamtree_fit.cpp:167-330 minus predict/save).  ms_out[0..3] receive the
  * CUDA-event times of {gibbs, llw, build, rest} when non-NULL. */
 int st_bench_iteration(st_handle* h, const double* theta_prop, int do_swap, uint64_t seed, double* out3, float* ms_out);
+/* row index of the beta step used by st_bench_iteration: 1 = the reference's (the default on a single-GPU
+ * handle), 0 = the corrected one (the only one a partitioned handle supports) */
+int st_set_beta_index(st_handle* h, int faithful);
 /* counts of kernel launches and algorithmic work: out[8] = {kernel launches since creation, F_alg flops of one iteration
  * (SURVEY §8d formula on the actual tree), executed-flop estimate of the lean formulation, covariance evaluations,
  * F_alg of BUILD alone (F_build), executed-flop estimate of BUILD alone, compulsory output bytes of one BUILD,

@@ -98,6 +98,7 @@ SIGNATURES = {
     "st_get_index": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, c_int64_p, C.c_int64, c_int64_p]),
     "st_mcmc_run": (C.c_int, [C.c_void_p, C.POINTER(StMcmcOpts), C.POINTER(StMcmcOut)]),
     "st_bench_iteration": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_uint64, c_double_p, c_float_p]),
+    "st_set_beta_index": (C.c_int, [C.c_void_p, C.c_int]),
     "st_get_counters": (C.c_int, [C.c_void_p, c_double_p]),
     "st_par_huvtransf_fwd": (C.c_int, [c_double_p, C.c_int32, c_double_p, c_double_p]),
     "st_par_huvtransf_back": (C.c_int, [c_double_p, C.c_int32, c_double_p, c_double_p]),

@@ -397,6 +397,10 @@ class SpamTreeMV:
         self._chk(lib.st_bench_iteration(self._h, _dp(t), int(bool(do_swap)), int(seed), _dp(o), ms.ctypes.data_as(_lib.c_float_p)))
         return o, ms
 
+    def set_beta_index(self, faithful):
+        """row index of the beta step in bench_iteration: the reference's (App. D #12) or the corrected one"""
+        self._chk(lib.st_set_beta_index(self._h, int(bool(faithful))))
+
     def attach_nccl(self, unique_id):
         """collective over the ranks of the partition: the library creates its own NCCL communicator from the 128-byte id of
         st_nccl_unique_id and from then on enqueues its all-reduces on its stream (no callback, no host synchronisation)"""
@@ -449,18 +453,19 @@ def spamtree_mv_mcmc(y, X, Z, coords, mv_id, blocking, gix_block, res_is_ref, pa
                      mcmc_keep=100, mcmc_burn=100, mcmc_thin=1, num_threads=1, use_alg='S', adapting=False,
                      main_verbose=True, verbose=False, debug=False, printall=False, sample_beta=True,
                      sample_tausq=True, sample_theta=True, sample_w=True, sample_predicts=True, *, device=0, seed=1,
-                     rng_mode=0, csr=None, save_w=True, save_yhat=True):
+                     rng_mode=0, csr=None, save_w=True, save_yhat=True, keep_H=False):
     """Mirror of the Rcpp export (src/spamtree_fit.cpp:5-54): same positional arguments, same returned names
     (:403-414).  Z, blocking, gix_block, start_w, num_threads, use_alg and the verbosity flags are accepted and ignored
     exactly as the reference ignores them (SURVEY App. D #6); keyword-only arguments are additions of this build."""
     model = SpamTreeMV(y, X, coords, mv_id, res_is_ref, parents, children, limited_tree, layer_names, layer_gibbs_group,
-                       indexing, beta, theta, tausq, device=device, csr=csr)
+                       indexing, beta, theta, tausq, device=device, csr=csr, keep_H=keep_H)
     try:
         res = model.mcmc(set_unif_bounds_in, mcmcsd, mcmc_keep, mcmc_burn, mcmc_thin, adapting, sample_beta,
                          sample_tausq, sample_theta, sample_w, sample_predicts, True, rng_mode, seed, save_w, save_yhat)
+        # the rest of the reference's returned list (spamtree_fit.cpp:410-412)
         res["block_ct_obs"] = model.index("block_ct_obs")
-        res["indexing"] = indexing
-        res["parents_indexing"] = None  # available per block through SpamTreeMV.index("parents_indexing", u)
+        res["indexing"] = indexing if indexing is not None else csr_to_lists(model._csr[0], model._csr[1])
+        res["parents_indexing"] = [model.index("parents_indexing", u) for u in range(model.n_blocks)]
     finally:
         model.close()
     return res

@@ -262,6 +262,13 @@ int st_ram_adapt(int32_t npar, const double* metropolis_sd, int32_t steps, const
     return ST_ERR_INVALID;
   }
 }
+int st_set_beta_index(st_handle* h, int faithful) {
+  if (!h) return ST_ERR_INVALID;
+  if (h->model.part && faithful) { h->model.err = "partitioned handles support only the corrected beta row index"; return ST_ERR_UNSUPPORTED; }
+  activate(h);
+  ST_GUARD_BEGIN return h->model.set_widx_mode(faithful != 0);
+  ST_GUARD_END(h)
+}
 int st_nccl_unique_id(unsigned char* out128) {
   if (!out128) return ST_ERR_INVALID;
   std::string e;

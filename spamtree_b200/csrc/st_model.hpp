@@ -221,6 +221,7 @@ class Model {
   int get_index(const std::string& which, int u, int c, int64_t* out, int64_t cap, int64_t* count);
   int bench_iteration(const double* theta_prop, int do_swap, uint64_t seed, double* out3, float* ms_out);
   int sync();
+  int set_widx_mode(bool faithful_index);
   // ---- the device-resident chain (rng_mode 1): spamtree_fit.cpp:167-391 without a host round trip per iteration
   int chain_run(const st_mcmc_opts& o, st_mcmc_out& out);
 
@@ -238,7 +239,6 @@ class Model {
   int enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_mode);
   int push_chain_state(const st_mcmc_opts* o, uint64_t seed);
   int pull_chain_state();
-  int set_widx_mode(bool faithful_index);
   cudaEvent_t* timing_events_ = nullptr;
   // asynchronous saves of a device-resident run: a row vector in boundary order goes from its device staging buffer to
   // the caller's (page-locked) array on the copy stream while the next iteration runs
