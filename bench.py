@@ -113,10 +113,20 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_baseline_sample(workload, d, t, csr, theta, iters=1):
+def cpu_backend():
+    """dense kernels of the CPU arm: scipy's bundled OpenBLAS when it is there (the reference reaches BLAS/LAPACK through
+    Armadillo), else the port's own loops.  The parity tests always use the loops."""
+    from oracle import oracle as orc
+    path = orc.use_blas(True)
+    return ("port+blas: dense kernels by " + os.path.basename(path) + " (1 thread per call), OpenMP over the blocks of a level") if path else \
+        "port: plain loops, OpenMP over the blocks of a level"
+
+
+def cpu_baseline_sample(workload, d, t, csr, theta, iters=1, blas=True):
     """the oracle (restated reference algorithm, OpenMP over the blocks of a level like spamtree_model.cpp:850) timed on
     the host cores on the SAME workload: one untimed BUILD to initialise, then `iters` timed iterations"""
     from oracle import oracle as orc
+    backend = cpu_backend() if blas else (orc.use_blas(False) or "port: plain loops, OpenMP over the blocks of a level")
     om = orc.OracleModel(d["y"], d["X"], d["coords"], d["mv_id"], t["res_is_ref"], csr, False, t["block_names"], t["block_groups"],
                          np.zeros(3), theta, 0.1, flags=orc.FLAG_LEAN)
     orc.lib().or_set_threads(host_threads())
@@ -126,7 +136,8 @@ def cpu_baseline_sample(workload, d, t, csr, theta, iters=1):
     om.timed_iteration(props[iters], False)  # warm-up: first touch of the per-block state
     ts = [om.timed_iteration(props[i], do_swap=(i % 4 == 3)) for i in range(iters)]
     om.close()
-    return {"value": 1.0 / float(np.mean(ts)), "unit": UNIT, "cores": int(cores), "kind": "port",
+    orc.use_blas(False)
+    return {"value": 1.0 / float(np.mean(ts)), "unit": UNIT, "cores": int(cores), "kind": "port", "backend": backend,
             "sample": f"{workload} full tree, lean-state oracle (identical arithmetic per block, P x P scratch not kept): "
                       f"1 untimed BUILD + 1 untimed iteration, then {iters} timed iteration(s) of {float(np.mean(ts)):.2f} s"}, ts
 
@@ -145,6 +156,7 @@ def run_reference(args, rank, world, emit):
     d, t, csr, theta = build_problem(args.workload, 2021)
     warm = max(args.warmup, 3)  # the same warm-up policy as the product arm
     from oracle import oracle as orc
+    backend = cpu_backend() if not args.cpu_loops else "port: plain loops, OpenMP over the blocks of a level"
     om = orc.OracleModel(d["y"], d["X"], d["coords"], d["mv_id"], t["res_is_ref"], csr, False, t["block_names"], t["block_groups"],
                          np.zeros(3), theta, 0.1, flags=orc.FLAG_LEAN)
     orc.lib().or_set_threads(host_threads())  # every host thread, also under torchrun (which exports OMP_NUM_THREADS=1)
@@ -160,7 +172,7 @@ def run_reference(args, rank, world, emit):
             "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_of(args.workload, d, t, "host cores: reference algorithm (CPU oracle port, OpenMP over the blocks of a level); "
                                 "--steps iterations, fewer only if they would not fit ~2.5 minutes"),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": int(cores), "kind": "port",
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": int(cores), "kind": "port", "backend": backend,
                              "sample": f"{steps} timed iteration(s) after {warm} warm-up on the full {args.workload} tree, lean-state oracle"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -175,6 +187,7 @@ def main():
     ap.add_argument("--workload", default="C4", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--ref-steps", type=int, default=0, help="cap on the timed iterations of --impl reference (0: as many of --steps as fit ~2.5 min)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-loops", action="store_true", help="CPU arm with the port's own loops instead of the host's OpenBLAS")
     ap.add_argument("--no-predict-leg", action="store_true", help="skip the extra end-to-end leg with prediction on a thin schedule")
     ap.add_argument("--e2e-steps", type=int, default=0, help="iterations of the end-to-end leg (default: --steps)")
     ap.add_argument("--e2e-sd", type=float, default=1e-8,
@@ -350,8 +363,11 @@ def main():
                             "frac": (f_alg / step_s / 1e12) / fp64_peak_job if fp64_peak else None}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cb, _ = cpu_baseline_sample(args.workload, d, t, csr, theta, iters=3)
+                cb, _ = cpu_baseline_sample(args.workload, d, t, csr, theta, iters=3, blas=not args.cpu_loops)
                 line["cpu_baseline"] = cb
+                if not args.cpu_loops:  # ... and the plain-loop port next to it, so that the two can be told apart
+                    cl, _ = cpu_baseline_sample(args.workload, d, t, csr, theta, iters=1, blas=False)
+                    line["cpu_baseline_loops"] = cl
             except Exception as ex:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {ex}"}
         emit(line)

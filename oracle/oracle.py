@@ -35,6 +35,8 @@ def lib():
         L.or_destroy.argtypes = [C.c_void_p]
         L.or_seed.argtypes = [C.c_void_p, C.c_uint64]
         L.or_set_threads.argtypes = [C.c_int]
+        L.or_use_blas.restype = C.c_int
+        L.or_use_blas.argtypes = [C.c_char_p]
         L.or_max_threads.restype = C.c_int
         L.or_theta_update.argtypes = [C.c_void_p, C.c_int, _dp]
         L.or_build.restype = C.c_int
@@ -85,6 +87,24 @@ def _pi(a):
 def _cm(a):
     a = np.asarray(a, dtype=np.float64)
     return _f(a.T).reshape(-1) if a.ndim == 2 else _f(a).reshape(-1)
+
+
+def use_blas(on=True):
+    """route the oracle's dense kernels through scipy's bundled OpenBLAS (the "port+blas" CPU baseline of bench.py); returns
+    the library path, or None when it is not available.  use_blas(False) restores the plain loops (the parity default)."""
+    if not on:
+        lib().or_use_blas(None)
+        return None
+    try:
+        import glob
+        import scipy
+        cands = sorted(glob.glob(os.path.join(os.path.dirname(scipy.__file__), "..", "scipy.libs", "libscipy_openblas*.so")))
+    except Exception:
+        cands = []
+    for c in cands:
+        if lib().or_use_blas(os.path.abspath(c).encode()) == 0:
+            return os.path.abspath(c)
+    return None
 
 
 FLAG_LEAN, FLAG_Q1_NORM_EXPANSION, FLAG_CORRECT_BETA_INDEX, FLAG_PROBES, FLAG_CORRECT_PREDICT_CACHE = 1, 2, 4, 8, 16

@@ -37,6 +37,7 @@
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
+#include <dlfcn.h>
 #endif
 
 namespace {
@@ -57,9 +58,32 @@ struct Mat {
   void clear() { r = c = 0; dvec().swap(a); }
 };
 
+// ---- optional BLAS/LAPACK backend ("port+blas" CPU baseline): the same algorithm with its dense kernels routed through an
+// OpenBLAS the host already has (scipy's bundled libscipy_openblas: scipy_dgemm_, scipy_dsyrk_, scipy_dpotrf_, scipy_dtrtri_,
+// scipy_dgemv_), the way the reference's Armadillo calls reach R's BLAS/LAPACK (SURVEY §8c lists the call sites).
+// Off by default: the parity tests use the plain loops below (bit-reproducible); or_use_blas(path) switches it on.
+struct BlasApi {
+  bool on = false;
+  void (*dgemm)(const char*, const char*, const int*, const int*, const int*, const double*, const double*, const int*, const double*,
+                const int*, const double*, double*, const int*) = nullptr;
+  void (*dsyrk)(const char*, const char*, const int*, const int*, const double*, const double*, const int*, const double*, double*,
+                const int*) = nullptr;
+  void (*dgemv)(const char*, const int*, const int*, const double*, const double*, const int*, const double*, const int*, const double*,
+                double*, const int*) = nullptr;
+  void (*dpotrf)(const char*, const int*, double*, const int*, int*) = nullptr;
+  void (*dtrtri)(const char*, const char*, const int*, double*, const int*, int*) = nullptr;
+  void (*set_threads)(int) = nullptr;
+};
+static BlasApi g_blas;
+
 // C = A * B
 static Mat mm(const Mat& A, const Mat& B) {
   Mat C(A.r, B.c);
+  if (g_blas.on && A.r && A.c && B.c) {
+    const double one = 1.0, zero = 0.0;
+    g_blas.dgemm("N", "N", &A.r, &B.c, &A.c, &one, A.a.data(), &A.r, B.a.data(), &B.r, &zero, C.a.data(), &C.r);
+    return C;
+  }
   for (int j = 0; j < B.c; j++)
     for (int k = 0; k < A.c; k++) {
       const double b = B(k, j);
@@ -73,6 +97,11 @@ static Mat mm(const Mat& A, const Mat& B) {
 // C = A' * B
 static Mat mtm(const Mat& A, const Mat& B) {
   Mat C(A.c, B.c);
+  if (g_blas.on && A.r && A.c && B.c) {
+    const double one = 1.0, zero = 0.0;
+    g_blas.dgemm("T", "N", &A.c, &B.c, &A.r, &one, A.a.data(), &A.r, B.a.data(), &B.r, &zero, C.a.data(), &C.r);
+    return C;
+  }
   for (int j = 0; j < B.c; j++)
     for (int i = 0; i < A.c; i++) {
       const double* ap = &A.a[(size_t)i * A.r];
@@ -89,6 +118,13 @@ static Mat mtm(const Mat& A, const Mat& B) {
 static Mat ltl(const Mat& L) {
   const int n = L.r;
   Mat C(n, n);
+  if (g_blas.on && n) {  // arma: A.t() * A -> dsyrk (spamtree_model.cpp:867,906,912,948)
+    const double one = 1.0, zero = 0.0;
+    g_blas.dsyrk("U", "T", &n, &n, &one, L.a.data(), &n, &zero, C.a.data(), &n);
+    for (int j = 0; j < n; j++)
+      for (int i = j + 1; i < n; i++) C(i, j) = C(j, i);
+    return C;
+  }
   for (int j = 0; j < n; j++)
     for (int i = 0; i <= j; i++) {
       const double* ap = &L.a[(size_t)i * n];
@@ -103,6 +139,12 @@ static Mat ltl(const Mat& L) {
 }
 static dvec mv(const Mat& A, const dvec& x) {
   dvec y(A.r, 0.0);
+  if (g_blas.on && A.r && A.c) {
+    const double one = 1.0, zero = 0.0;
+    const int inc = 1;
+    g_blas.dgemv("N", &A.r, &A.c, &one, A.a.data(), &A.r, x.data(), &inc, &zero, y.data(), &inc);
+    return y;
+  }
   for (int k = 0; k < A.c; k++) {
     const double xk = x[k];
     const double* ap = &A.a[(size_t)k * A.r];
@@ -112,6 +154,12 @@ static dvec mv(const Mat& A, const dvec& x) {
 }
 static dvec mtv(const Mat& A, const dvec& x) {
   dvec y(A.c, 0.0);
+  if (g_blas.on && A.r && A.c) {
+    const double one = 1.0, zero = 0.0;
+    const int inc = 1;
+    g_blas.dgemv("T", &A.r, &A.c, &one, A.a.data(), &A.r, x.data(), &inc, &zero, y.data(), &inc);
+    return y;
+  }
   for (int j = 0; j < A.c; j++) {
     const double* ap = &A.a[(size_t)j * A.r];
     double s = 0;
@@ -128,6 +176,14 @@ static void symmatu(Mat& A) {
 // arma::chol(A, "lower") -> LAPACK dpotrf('L'): false if a pivot is <= 0 or NaN
 static bool chol_lower(Mat& A) {
   const int n = A.r;
+  if (g_blas.on && n) {
+    int info = 0;
+    g_blas.dpotrf("L", &n, A.a.data(), &n, &info);
+    if (info != 0) return false;
+    for (int j = 0; j < n; j++)
+      for (int i = 0; i < j; i++) A(i, j) = 0.0;
+    return true;
+  }
   for (int j = 0; j < n; j++) {
     double ajj = A(j, j);
     for (int k = 0; k < j; k++) ajj -= A(j, k) * A(j, k);
@@ -148,6 +204,12 @@ static bool chol_lower(Mat& A) {
 static Mat inv_lower(const Mat& L) {
   const int n = L.r;
   Mat X(n, n);
+  if (g_blas.on && n) {
+    X = L;
+    int info = 0;
+    g_blas.dtrtri("L", "N", &n, X.a.data(), &n, &info);
+    return X;
+  }
   for (int j = 0; j < n; j++) {
     X(j, j) = 1.0 / L(j, j);
     for (int i = j + 1; i < n; i++) {
@@ -1007,6 +1069,26 @@ void* or_create(int64_t n_all, int p, int q, const double* y, const double* X, c
 }
 void or_destroy(void* h) { delete (Model*)h; }
 void or_seed(void* h, uint64_t s) { ((Model*)h)->rng.seed(s); }
+// switches the dense kernels to the OpenBLAS at `path` (single-threaded per call: the parallelism stays OpenMP over the
+// blocks of a level, like the reference's); returns 0, or 1 when the library or a symbol is missing.  path == NULL: off.
+int or_use_blas(const char* path) {
+  g_blas.on = false;
+  if (!path) return 0;
+  void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) return 1;
+  BlasApi b;
+  b.dgemm = (decltype(b.dgemm))dlsym(h, "scipy_dgemm_");
+  b.dsyrk = (decltype(b.dsyrk))dlsym(h, "scipy_dsyrk_");
+  b.dgemv = (decltype(b.dgemv))dlsym(h, "scipy_dgemv_");
+  b.dpotrf = (decltype(b.dpotrf))dlsym(h, "scipy_dpotrf_");
+  b.dtrtri = (decltype(b.dtrtri))dlsym(h, "scipy_dtrtri_");
+  b.set_threads = (decltype(b.set_threads))dlsym(h, "scipy_openblas_set_num_threads");
+  if (!b.dgemm || !b.dsyrk || !b.dgemv || !b.dpotrf || !b.dtrtri) return 1;
+  if (b.set_threads) b.set_threads(1);
+  b.on = true;
+  g_blas = b;
+  return 0;
+}
 void or_set_threads(int n) {
 #ifdef _OPENMP
   omp_set_num_threads(n);
