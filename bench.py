@@ -24,9 +24,22 @@ sys.path.insert(0, ROOT)
 
 METRIC = "mcmc_iterations_per_sec"
 UNIT = "it/s"
-# DRAM traffic (bytes) of all build_level_kernel launches of ONE BUILD, from an ncu pass on a B200 of this pool
-# (profiles/r1_launches_v5.txt); None until measured for a workload
-NCU_BUILD_DRAM_BYTES = {"C4": 2.4025e9}
+
+
+def build_dram_traffic(workload):
+    """DRAM bytes of the build_level_kernel launches of ONE BUILD from the tracked ncu summary (profiles/*_build_dram.json,
+    written by tools/ncu_build_dram.py) — only while the kernel sources it was measured on are the ones that run now"""
+    import glob
+    import hashlib
+    h = hashlib.sha1()
+    for f in ["spamtree_b200/csrc/st_build.cu", "spamtree_b200/csrc/st_device.cuh", "spamtree_b200/csrc/st_kernels.cuh"]:
+        h.update(open(os.path.join(ROOT, f), "rb").read())
+    sha = h.hexdigest()
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_build_dram.json")), reverse=True):
+        d = json.load(open(path))
+        if d.get("workload") == workload and d.get("sources_sha1") == sha:
+            return d["dram_bytes"], f"{os.path.relpath(path, ROOT)} (ncu dram__bytes_read.sum + dram__bytes_write.sum over the build_level_kernel launches of one BUILD; kernel sources {sha[:10]})"
+    return None, f"no ncu summary under profiles/ matches the kernel sources that ran ({sha[:10]}): not reported"
 
 
 def load_peaks():
@@ -248,7 +261,7 @@ def main():
         sampler.start()
         time.sleep(0.3)
     c0 = gm.counters()
-    phase = np.zeros(4)
+    phase = np.zeros(5)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
@@ -259,8 +272,9 @@ def main():
     elapsed = time.perf_counter() - t0
     c1 = gm.counters()
     clocks = sampler.finish() if sampler else None
-    # device time of the step = sum of the CUDA-event phase times (gibbs, llw, build, rest) on the launching stream
-    dev_ms = float(phase.sum())
+    # device time of the step: CUDA events around the whole iteration on the launching stream (the per-phase times do not
+    # add up to it: the upper levels of BUILD run on a second stream underneath the Gibbs sweep)
+    dev_ms = float(phase[4])
     tt = torch.tensor([elapsed, dev_ms * 1e-3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -319,7 +333,7 @@ def main():
         build_ms = float(tb[0])
         f_alg, f_exec, f_alg_build, f_exec_build, b_alg_build = (float(tw[i]) for i in (0, 1, 3, 4, 5))
         fp64_peak_job = fp64_peak * world
-        traffic = NCU_BUILD_DRAM_BYTES.get(args.workload) if world == 1 else None
+        traffic, traffic_note = build_dram_traffic(args.workload) if world == 1 else (None, "single-GPU figure only")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * elapsed_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -346,7 +360,7 @@ def main():
                          "achieved": f_alg_build / (build_ms * 1e-3) / 1e12 if build_ms > 0 else None,
                          "peak": fp64_peak_job, "unit": "TFLOP/s", "frac": None,
                          "traffic": traffic,
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum over the build_level_kernel launches of one BUILD (profiles/r1_launches_v5.txt)",
+                         "traffic_note": traffic_note,
                          "achieved_executed": f_exec_build / (build_ms * 1e-3) / 1e12 if build_ms > 0 else None,
                          "algorithmic_output_bytes": b_alg_build,
                          "whole_step": {"achieved": None, "achieved_executed": None, "frac": None},

@@ -95,8 +95,13 @@ template <int MODE>
 __device__ __forceinline__ void
 build_level_body(const DevTree& T, const DevSlots& D, int rel, double* __restrict__ predG, double* __restrict__ predRi, int want_H,
                  const int* __restrict__ grp_slot0, const int* __restrict__ grp_nn, const double* __restrict__ w,
-                 int* __restrict__ fail, int ns, int phase, unsigned long long* __restrict__ prof, const int* __restrict__ run_flag) {
+                 int* __restrict__ fail, int ns, int phase_arg, unsigned long long* __restrict__ prof, const int* __restrict__ run_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // bit 2 of the phase argument: the launch runs while the Gibbs sweep is still rewriting w (st_model.cu: the early levels of a
+  // BUILD overlap the sweep on a second stream); its log-density pieces e' prec e are then left to an LLW pass over the
+  // finished slot, everything that depends on theta alone (G, Ri, logdet) is written as usual
+  const int phase = phase_arg & 3;
+  const bool density = (phase_arg & 4) == 0;
   // conditional launches of the device-resident chain (deferred half after an accepted proposal, prediction weights after
   // theta moved): the flag was written by an earlier kernel of the stream and is the same for every thread
   if (run_flag != nullptr && *run_flag == 0) return;
@@ -605,7 +610,7 @@ build_level_body(const DevTree& T, const DevSlots& D, int rel, double* __restric
       if (MODE == 1) ld = warp_sum(ld); else ld = s_nlogdet[d];
       if (lane == 0) {
         S.logdet[s0 + d] = ld;
-        S.llcomp[s0 + d] = (double)md * kHl2pi - 0.5 * wc;  // :967-968
+        if (density) S.llcomp[s0 + d] = (double)md * kHl2pi - 0.5 * wc;  // :967-968
       }
     }
   };

@@ -483,12 +483,12 @@ cudaError_t launch_gram(const DevTree& T, const DevSlots& D, int slot0, int nslo
 // A reference block's rows of the chain factor are [G | -Ri | 0], so its contribution is one streaming product
 // |[G | -Ri] [w_pa ; w_u]|^2 over contiguous rows; the warp stages [w_pa ; w_u] in shared memory once.
 __global__ void __launch_bounds__(kLlwThreads)
-llw_kernel(DevTree T, DevSlots D, int rel, int nslots, const double* __restrict__ w, int maxlen) {
+llw_kernel(DevTree T, DevSlots D, int rel, int slot0, int nslots, const double* __restrict__ w, int maxlen) {
   extern __shared__ __align__(16) double llw_smem[];
   const DevSlot S = pick_slot(D, D.chain->cur ^ rel);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int sd = blockIdx.x * (blockDim.x >> 5) + wib;
-  if (sd >= nslots) return;
+  const int sd = slot0 + blockIdx.x * (blockDim.x >> 5) + wib;
+  if (sd >= slot0 + nslots) return;
   double* wx = llw_smem + (size_t)wib * maxlen;
   const int m = T.m[sd], k = T.k[sd], P = T.P[sd], coff = T.chain_off[sd], row0 = T.row0[sd], gs = T.gs[sd];
   const bool ref = T.isref[sd] != 0;
@@ -540,7 +540,7 @@ llw_kernel(DevTree T, DevSlots D, int rel, int nslots, const double* __restrict_
   }
   if (lane == 0) S.llcomp[sd] = (double)m * kHl2pi - 0.5 * wc;
 }
-cudaError_t launch_llw(const DevTree& T, const DevSlots& D, int rel, int nslots, const double* w, int maxlen, cudaStream_t st) {
+cudaError_t launch_llw(const DevTree& T, const DevSlots& D, int rel, int slot0, int nslots, const double* w, int maxlen, cudaStream_t st) {
   if (nslots <= 0) return cudaSuccess;
   const int wpb = kLlwThreads / 32;
   maxlen = (maxlen + 1) & ~1;
@@ -550,7 +550,7 @@ cudaError_t launch_llw(const DevTree& T, const DevSlots& D, int rel, int nslots,
     cudaError_t e = ensure_dynamic_smem(llw_kernel, smem, optin);
     if (e != cudaSuccess) return e;
   }
-  llw_kernel<<<(nslots + wpb - 1) / wpb, kLlwThreads, smem, st>>>(T, D, rel, nslots, w, maxlen);
+  llw_kernel<<<(nslots + wpb - 1) / wpb, kLlwThreads, smem, st>>>(T, D, rel, slot0, nslots, w, maxlen);
   return cudaGetLastError();
 }
 

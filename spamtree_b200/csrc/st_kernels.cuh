@@ -118,7 +118,8 @@ cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlots& D, int sl
                          double* probe_sig, double* probe_smu, int* fail, size_t smem, cudaStream_t st, bool pdl = false);
 cudaError_t launch_gram(const DevTree& T, const DevSlots& D, int slot0, int nslots, double* U, double* SigS, int rch,
                         int ldx, int tile_doubles, int stage_off, int threads, cudaStream_t st, const int* run_flag = nullptr);
-cudaError_t launch_llw(const DevTree& T, const DevSlots& D, int rel, int nslots, const double* w, int maxlen, cudaStream_t st);
+// blocks [slot0, slot0 + nslots) of the slot
+cudaError_t launch_llw(const DevTree& T, const DevSlots& D, int rel, int slot0, int nslots, const double* w, int maxlen, cudaStream_t st);
 // out8[0..2] = {sum logdet + sum llcomp, sum logdet, 0} over blocks [0, n_top) and out8[4..6] = the same over [n_top, n) with
 // out8[6] = *fail (or 0): the two parts a partitioned run needs (replicated blocks once, the rank's own all-reduced)
 cudaError_t launch_loglik_reduce(const DevSlots& D, int rel, int n_top, int n, const int* fail, double* out8, cudaStream_t st);

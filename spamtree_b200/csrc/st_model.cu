@@ -84,6 +84,9 @@ Model::~Model() {
   if (ev_wready) cudaEventDestroy(ev_wready);
   if (ev_wcopied) cudaEventDestroy(ev_wcopied);
   if (copy_stream) cudaStreamDestroy(copy_stream);
+  if (stream2) cudaStreamDestroy(stream2);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -552,6 +555,9 @@ int Model::upload(std::string& e) {
   (void)e;
   ST_CUDA(cudaSetDevice(device), "cudaSetDevice");
   ST_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  ST_CUDA(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking), "cudaStreamCreate");
+  ST_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming), "cudaEventCreate");
+  ST_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming), "cudaEventCreate");
   for (auto& x : ev) ST_CUDA(cudaEventCreate(&x), "cudaEventCreate");
   // per row
   dvec cx(n_all), cy(n_all), yy(n_all), Xp((size_t)n_all * p), xb(n_all, 0.0);
@@ -732,6 +738,7 @@ int Model::init(std::string& e) {
   if (const char* v = getenv("ST_BUILD_NS")) force_build_ns = atoi(v);
   if (const char* v = getenv("ST_DEFER")) defer_leaves = atoi(v) != 0;
   if (const char* v = getenv("ST_PDL")) use_pdl = atoi(v) != 0;
+  if (const char* v = getenv("ST_OVERLAP")) overlap = atoi(v) != 0;
   if (const char* v = getenv("ST_MAX_COLS")) max_group_cols = atoi(v);
   if (const char* v = getenv("ST_SMEM_BUDGET")) smem_budget = (size_t)atol(v);
   if (device >= 0) {
@@ -836,7 +843,8 @@ int Model::push_slot_theta(int ps) {
   return 0;
 }
 
-int Model::launch_build_levels(int rel) {
+// levels [l0, l1) of a BUILD of the slot `rel` on stream `st`; no_density: their log-density pieces are left to an LLW pass
+int Model::launch_build_levels(int rel, int l0, int l1, bool no_density, cudaStream_t st) {
   // ST_PROFILE_BUILD=1: per-phase clock64() totals of build_level_kernel, printed per level (development aid)
   static const bool profile = getenv("ST_PROFILE_BUILD") != nullptr;
   unsigned long long* d_prof = nullptr;
@@ -844,26 +852,29 @@ int Model::launch_build_levels(int rel) {
     cudaMalloc((void**)&d_prof, 16 * sizeof(unsigned long long));
   }
   bool first_launch = true;
-  for (auto& L : levels) {
+  if (l1 < 0) l1 = (int)levels.size();
+  if (!st) st = stream;
+  for (int li = l0; li < l1; li++) {
+    auto& L = levels[li];
     for (const auto& B : L.build_launches) {
       cudaEvent_t pe0 = nullptr, pe1 = nullptr;
       if (profile) {
-        cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), stream);
+        cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st);
         cudaEventCreate(&pe0); cudaEventCreate(&pe1);
-        cudaEventRecord(pe0, stream);
+        cudaEventRecord(pe0, st);
       }
       // every launch but the first of a BUILD may start before its predecessor has drained (programmatic dependent
       // launch): it waits inside the kernel before it reads the ancestors' row blocks
       ST_CUDA(launch_build(L.is_ref ? 0 : 1, dt, dslots, rel, nullptr, nullptr, keep_H ? 1 : 0, d_grp_slot0 + B.grp0, d_grp_nn + B.grp0,
-                           B.ngrp, d_w, d_fail, B.ns, L.deferrable ? 1 : 0, B.smem, stream, B.threads, d_prof,
+                           B.ngrp, d_w, d_fail, B.ns, (L.deferrable ? 1 : 0) | (no_density ? 4 : 0), B.smem, st, B.threads, d_prof,
                            use_pdl && !first_launch && !profile),
               "build_level_kernel");
       first_launch = false;
       n_launches++;
       if (profile) {
         unsigned long long h[16];
-        cudaEventRecord(pe1, stream);
-        cudaStreamSynchronize(stream);
+        cudaEventRecord(pe1, st);
+        cudaStreamSynchronize(st);
         float pms = 0;
         cudaEventElapsedTime(&pms, pe0, pe1);
         cudaEventDestroy(pe0); cudaEventDestroy(pe1);
@@ -909,7 +920,7 @@ int Model::get_loglik_comps_w(int slot, double* out3) {
   int rc = push_slot_theta(ps);
   if (rc) return rc;
   ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
-  rc = launch_build_levels(ps == cur ? 0 : 1);
+  rc = launch_build_levels(ps == cur ? 0 : 1, 0, -1, false, stream);
   if (rc) return rc;
   for (auto& L : levels) if (L.deferrable) deferred_[ps] = true;
   double r3[3];
@@ -1027,7 +1038,7 @@ int Model::get_loglik_w(int slot, double* out2) {
   if (!stream) { err = "this handle has no device state (created with device < 0)"; return 2; }
   const int ps = phys(slot);
   { int rc = complete_slot(ps); if (rc) return rc; }
-  ST_CUDA(launch_llw(dt, dslots, ps == cur ? 0 : 1, n_obs_nodes, d_w, llw_maxlen_, stream), "llw_kernel");
+  ST_CUDA(launch_llw(dt, dslots, ps == cur ? 0 : 1, 0, n_obs_nodes, d_w, llw_maxlen_, stream), "llw_kernel");
   n_launches++;
   double r3[3];
   int rc = reduce_loglik(ps == cur ? 0 : 1, nullptr, d_mc->red_llw, r3);
@@ -1367,12 +1378,30 @@ int Model::enqueue_gibbs(uint64_t seed, bool device_chain) {
 int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_mode) {
   cudaEvent_t* tev = timing_events_;
   int rc = 0;
+  const int nlev = (int)levels.size();
+  // Overlap (two streams): theta' and everything of its BUILD that depends on theta alone do not need the new w, so the
+  // levels above the deepest one run on `stream2` UNDERNEATH the Gibbs sweep and LLW of the main stream — their many small,
+  // latency-bound launches fill the gaps of the sweep and vice versa.  Only the log-density pieces e' prec e need the new
+  // w: the deepest level (the bulk of the rows) is built after the sweep as usual, the levels built early get theirs from
+  // an LLW pass over the finished slot.  Same arithmetic per block as the sequential order.
+  const bool ovl = overlap && o.sample_w && o.sample_theta && nlev >= 2 && stream2 != nullptr;
   if (tev) ST_CUDA(cudaEventRecord(tev[0], stream), "event");
+  if (ovl) {
+    ST_CUDA(cudaEventRecord(ev_fork, stream), "event");
+    ST_CUDA(cudaStreamWaitEvent(stream2, ev_fork, 0), "fork");
+    if (tev) ST_CUDA(cudaEventRecord(tev[6], stream2), "event");
+    if (accept_mode == 0) { ST_CUDA(launch_mh_propose(d_mc, stream2), "mh_propose_kernel"); n_launches++; }
+    ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream2), "memset");
+    rc = launch_build_levels(1, 0, nlev - 1, true, stream2);
+    if (rc) return rc;
+    if (tev) ST_CUDA(cudaEventRecord(tev[7], stream2), "event");
+    ST_CUDA(cudaEventRecord(ev_join, stream2), "event");
+  }
   if (o.sample_w) {  // :183-187
     rc = enqueue_gibbs(o.seed, true);
     if (rc) return rc;
     if (tev) ST_CUDA(cudaEventRecord(tev[1], stream), "event");
-    ST_CUDA(launch_llw(dt, dslots, 0, n_obs_nodes, d_w, llw_maxlen_, stream), "llw_kernel");
+    ST_CUDA(launch_llw(dt, dslots, 0, 0, n_obs_nodes, d_w, llw_maxlen_, stream), "llw_kernel");
     n_launches++;
     rc = reduce_loglik(0, nullptr, d_mc->red_llw, nullptr);
     if (rc) return rc;
@@ -1381,10 +1410,19 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
   }
   if (tev) ST_CUDA(cudaEventRecord(tev[2], stream), "event");
   if (o.sample_theta) {  // :203-289
-    if (accept_mode == 0) { ST_CUDA(launch_mh_propose(d_mc, stream), "mh_propose_kernel"); n_launches++; }
-    ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
-    rc = launch_build_levels(1);
-    if (rc) return rc;
+    if (ovl) {
+      ST_CUDA(cudaStreamWaitEvent(stream, ev_join, 0), "join");
+      rc = launch_build_levels(1, nlev - 1, nlev, false, stream);
+      if (rc) return rc;
+      const int n_early = levels[nlev - 1].slot0;  // blocks of the levels built underneath the sweep
+      ST_CUDA(launch_llw(dt, dslots, 1, 0, n_early, d_w, llw_maxlen_, stream), "llw_kernel(early levels of the proposal)");
+      n_launches++;
+    } else {
+      if (accept_mode == 0) { ST_CUDA(launch_mh_propose(d_mc, stream), "mh_propose_kernel"); n_launches++; }
+      ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
+      rc = launch_build_levels(1, 0, nlev, false, stream);
+      if (rc) return rc;
+    }
     rc = reduce_loglik(1, d_fail, d_mc->red_build, nullptr);
     if (rc) return rc;
     ST_CUDA(launch_mh_accept(d_mc, accept_mode, o.sample_w ? 1 : 0, stream), "mh_accept_kernel");
@@ -1519,12 +1557,17 @@ int Model::bench_iteration(const double* theta_prop, int do_swap, uint64_t seed,
   out3[0] = loglik_w[1 - cur]; out3[1] = loglik_w[cur]; out3[2] = ok ? 1.0 : 0.0;
   if (h_mc->accepted_now) { out3[0] = loglik_w[cur]; out3[1] = loglik_w[1 - cur]; }  // {proposal, previous current}
   if (ms_out) {
-    float t[5];
+    float t[5], early = 0.f;
     for (int i = 0; i < 5; i++) ST_CUDA(cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]), "elapsed");
+    const bool ovl = overlap && (int)levels.size() >= 2 && stream2 != nullptr;
+    if (ovl) ST_CUDA(cudaEventElapsedTime(&early, ev[6], ev[7]), "elapsed");
     ms_out[0] = t[0] + t[3];  // GIBBS sweep + the Gram refresh an accepted proposal triggers
     ms_out[1] = t[1];         // LLW
-    ms_out[2] = t[2];         // BUILD + accept + the deferred half of an accepted proposal
+    // BUILD + accept + the deferred half of an accepted proposal; with the overlap on, the early levels are timed on their own
+    // stream (they run underneath the sweep and LLW, so the phases no longer add up to the step) and added here
+    ms_out[2] = t[2] + early;
     ms_out[3] = t[4];         // tausq + beta
+    ST_CUDA(cudaEventElapsedTime(&ms_out[4], ev[0], ev[5]), "elapsed");  // the whole iteration on the main stream
   }
   return 0;
 }

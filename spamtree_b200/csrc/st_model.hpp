@@ -185,6 +185,9 @@ class Model {
   int *d_grp_slot0 = nullptr, *d_grp_nn = nullptr;
   double* h_stage = nullptr;  // pinned n_all staging buffer
   cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream2 = nullptr;   // the early levels of a proposal's BUILD run here, underneath the Gibbs sweep
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap = true;              // ST_OVERLAP=0 disables
   cudaEvent_t ev_wready = nullptr, ev_wcopied = nullptr;
   double* d_wsave = nullptr;        // w in boundary order (staging of the asynchronous save)
   long long* d_iperm = nullptr;     // boundary row -> node-major row
@@ -230,7 +233,7 @@ class Model {
   int build_bookkeeping(std::string& e);
   int build_layout(std::string& e);
   int upload(std::string& e);
-  int launch_build_levels(int rel);
+  int launch_build_levels(int rel, int l0, int l1, bool no_density, cudaStream_t st);
   int complete_slot(int pslot);  // the deferred half of BUILD for the slot's childless levels, if pending
   int launch_deferred_half(int rel, const int* run_flag);
   int push_slot_theta(int ps);   // host-driven path: theta[ps] and its covariance table into the device chain state

@@ -38,7 +38,7 @@ def main():
         gm.sync()
         wall = (time.time() - ts) * 1e3
         tot.append(wall)
-        print(f"  it {it}: gibbs {ms[0]:.3f} llw {ms[1]:.3f} build {ms[2]:.3f} rest {ms[3]:.3f} ms | wall {wall:.3f} ms | ok {o[2]} ll {o[0]:.6g}", flush=True)
+        print(f"  it {it}: gibbs {ms[0]:.3f} llw {ms[1]:.3f} build {ms[2]:.3f} rest {ms[3]:.3f} total {ms[4]:.3f} ms | wall {wall:.3f} ms | ok {o[2]} ll {o[0]:.6g}", flush=True)
     c = gm.counters()
     best = min(tot)
     print(f"F_alg {c['f_alg']:.3e} F_exec {c['f_exec']:.3e} n_cov {c['n_cov']:.3e}; best wall {best:.3f} ms -> {1e3 / best:.1f} it/s; "
