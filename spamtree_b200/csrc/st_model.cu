@@ -508,6 +508,14 @@ int Model::build_layout(std::string& e) {
     return 0;
   };
   for (auto& L : levels) { int rc = make_groups(L, L.is_ref ? 0 : 1); if (rc) return rc; }
+  // the leading levels whose BUILD is a chain of small launches (fewer work groups than SMs): built underneath the Gibbs
+  // sweep by the device-resident iteration; never the deepest level.  Measured on C4 / one B200 (ms per iteration): no
+  // overlap 7.18, levels 0-4 (<= 128 groups) 7.17, + level 5 (256 groups) 7.21, + level 6 7.34, everything but the leaves 7.42
+  // — a level that fills the GPU only competes with the sweep; C1 (n = 625): 4 998 -> 6 455 it/s end to end
+  n_early_levels_ = 0;
+  while (n_early_levels_ + 1 < (int)levels.size() && levels[n_early_levels_].ngrp <= n_sm && !levels[n_early_levels_].deferrable)
+    n_early_levels_++;
+  if (const char* v = getenv("ST_EARLY_LEVELS")) n_early_levels_ = std::max(0, std::min(atoi(v), (int)levels.size() - 1));
   { int rc = make_groups(pred_level, 2); if (rc) return rc; }
 
   // work counters per iteration (SURVEY §8d formulas on the actual tree)
@@ -1380,11 +1388,13 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
   int rc = 0;
   const int nlev = (int)levels.size();
   // Overlap (two streams): theta' and everything of its BUILD that depends on theta alone do not need the new w, so the
-  // levels above the deepest one run on `stream2` UNDERNEATH the Gibbs sweep and LLW of the main stream — their many small,
-  // latency-bound launches fill the gaps of the sweep and vice versa.  Only the log-density pieces e' prec e need the new
-  // w: the deepest level (the bulk of the rows) is built after the sweep as usual, the levels built early get theirs from
-  // an LLW pass over the finished slot.  Same arithmetic per block as the sequential order.
-  const bool ovl = overlap && o.sample_w && o.sample_theta && nlev >= 2 && stream2 != nullptr;
+  // upper levels of the tree — few work groups each, a chain of latency-bound launches — are built on `stream2` UNDERNEATH
+  // the Gibbs sweep and LLW of the main stream, where they cost nothing.  Only the log-density pieces e' prec e need the new
+  // w: the levels built early get theirs from an LLW pass over their (few) blocks after the sweep; the big levels are built
+  // after the sweep as before (they would only compete with it for the SMs: measured at C4, overlapping everything but the
+  // deepest level is slower than no overlap).  Same arithmetic per block as the sequential order.
+  const int n_early = n_early_levels_;
+  const bool ovl = overlap && o.sample_w && o.sample_theta && n_early >= 1 && stream2 != nullptr;
   if (tev) ST_CUDA(cudaEventRecord(tev[0], stream), "event");
   if (ovl) {
     ST_CUDA(cudaEventRecord(ev_fork, stream), "event");
@@ -1392,7 +1402,7 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
     if (tev) ST_CUDA(cudaEventRecord(tev[6], stream2), "event");
     if (accept_mode == 0) { ST_CUDA(launch_mh_propose(d_mc, stream2), "mh_propose_kernel"); n_launches++; }
     ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream2), "memset");
-    rc = launch_build_levels(1, 0, nlev - 1, true, stream2);
+    rc = launch_build_levels(1, 0, n_early, true, stream2);
     if (rc) return rc;
     if (tev) ST_CUDA(cudaEventRecord(tev[7], stream2), "event");
     ST_CUDA(cudaEventRecord(ev_join, stream2), "event");
@@ -1412,10 +1422,10 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
   if (o.sample_theta) {  // :203-289
     if (ovl) {
       ST_CUDA(cudaStreamWaitEvent(stream, ev_join, 0), "join");
-      rc = launch_build_levels(1, nlev - 1, nlev, false, stream);
+      rc = launch_build_levels(1, n_early, nlev, false, stream);
       if (rc) return rc;
-      const int n_early = levels[nlev - 1].slot0;  // blocks of the levels built underneath the sweep
-      ST_CUDA(launch_llw(dt, dslots, 1, 0, n_early, d_w, llw_maxlen_, stream), "llw_kernel(early levels of the proposal)");
+      const int nb_early = levels[n_early].slot0;  // blocks of the levels built underneath the sweep
+      ST_CUDA(launch_llw(dt, dslots, 1, 0, nb_early, d_w, llw_maxlen_, stream), "llw_kernel(early levels of the proposal)");
       n_launches++;
     } else {
       if (accept_mode == 0) { ST_CUDA(launch_mh_propose(d_mc, stream), "mh_propose_kernel"); n_launches++; }
@@ -1559,7 +1569,7 @@ int Model::bench_iteration(const double* theta_prop, int do_swap, uint64_t seed,
   if (ms_out) {
     float t[5], early = 0.f;
     for (int i = 0; i < 5; i++) ST_CUDA(cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]), "elapsed");
-    const bool ovl = overlap && (int)levels.size() >= 2 && stream2 != nullptr;
+    const bool ovl = overlap && n_early_levels_ >= 1 && stream2 != nullptr;
     if (ovl) ST_CUDA(cudaEventElapsedTime(&early, ev[6], ev[7]), "elapsed");
     ms_out[0] = t[0] + t[3];  // GIBBS sweep + the Gram refresh an accepted proposal triggers
     ms_out[1] = t[1];         // LLW

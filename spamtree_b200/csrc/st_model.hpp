@@ -188,6 +188,7 @@ class Model {
   cudaStream_t stream2 = nullptr;   // the early levels of a proposal's BUILD run here, underneath the Gibbs sweep
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap = true;              // ST_OVERLAP=0 disables
+  int n_early_levels_ = 0;          // leading tree levels whose BUILD runs underneath the sweep (ST_EARLY_LEVELS overrides)
   cudaEvent_t ev_wready = nullptr, ev_wcopied = nullptr;
   double* d_wsave = nullptr;        // w in boundary order (staging of the asynchronous save)
   long long* d_iperm = nullptr;     // boundary row -> node-major row
