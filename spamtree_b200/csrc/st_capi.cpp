@@ -389,6 +389,8 @@ int st_cross_covariance_ag10(const double* coords1, const int64_t* mv1, int64_t 
     std::vector<int> q1(n1), q2(n2);
     for (int64_t i = 0; i < n1; i++) q1[i] = (int)mv1[i] - 1;
     for (int64_t i = 0; i < n2; i++) q2[i] = (int)mv2[i] - 1;
+    for (int v : q1) if (v < 0 || v >= q) { g_create_error = "mv_id outside 1..q"; return ST_ERR_INVALID; }
+    for (int v : q2) if (v < 0 || v >= q) { g_create_error = "mv_id outside 1..q"; return ST_ERR_INVALID; }
     double *dx1 = nullptr, *dx2 = nullptr, *dout = nullptr;
     int *dq1 = nullptr, *dq2 = nullptr;
     cudaError_t ce = cudaSuccess;

@@ -94,6 +94,11 @@ Model::~Model() {
 int Model::build_bookkeeping(std::string& e) {
   const int nb = n_blocks;
   if ((int64_t)indexing.size() != nb || (int64_t)parents.size() != nb || (int64_t)children.size() != nb) { e = "CSR sizes do not match n_blocks"; return 1; }
+  // the ABI promises status codes, not out-of-bounds reads: block ids of the edge lists must be block ids
+  for (const CSR* c : {&parents, &children})
+    for (int64_t v : c->idx)
+      if (v < 0 || v >= nb) { e = "a parents / children list holds a block id outside 0..n_blocks-1"; return 1; }
+  if ((int64_t)block_names.size() != nb || (int64_t)block_groups.size() != nb) { e = "block_names / block_groups do not match n_blocks"; return 1; }
   // na_ix_all, counts (spamtree_model.cpp:80-96)
   nobs_by_q.assign(q, 0);
   for (int64_t i = 0; i < n_all; i++) {
@@ -562,8 +567,14 @@ static cudaError_t dev_zeros(double*& d, long long n, std::vector<void*>& owned)
 int Model::upload(std::string& e) {
   (void)e;
   ST_CUDA(cudaSetDevice(device), "cudaSetDevice");
-  ST_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
-  ST_CUDA(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking), "cudaStreamCreate");
+  {
+    // the main stream outranks the second one: when both have thread blocks pending, those of the Gibbs sweep (a chain of
+    // short launches) are dispatched before those of the BUILD levels that run underneath it
+    int lo = 0, hi = 0;
+    ST_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi), "cudaDeviceGetStreamPriorityRange");
+    ST_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, hi), "cudaStreamCreate");
+    ST_CUDA(cudaStreamCreateWithPriority(&stream2, cudaStreamNonBlocking, lo), "cudaStreamCreate");
+  }
   ST_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming), "cudaEventCreate");
   ST_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming), "cudaEventCreate");
   for (auto& x : ev) ST_CUDA(cudaEventCreate(&x), "cudaEventCreate");

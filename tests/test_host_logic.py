@@ -163,3 +163,17 @@ def test_colocated_outcomes_are_kept_together():
     assert np.array_equal(b[0::2], b[1::2])  # sorted rows come in co-located pairs
     t2 = sb.make_tree(coords, y, mv, cherrypick_group_locations=False)
     assert not np.array_equal(t2["blocking"][0::2], t2["blocking"][1::2])
+
+
+def test_malformed_edge_lists_are_rejected_with_a_status_code():
+    """the ABI promises status codes: a parents / children list that names a block outside 0..n_blocks-1 must not be indexed"""
+    import spamtree_b200 as sb
+    pb = common.make_problem(2, 600)
+    d, t = pb["d"], pb["tree"]
+    for which in (3, 5):  # parents_idx, children_idx
+        csr = [a.copy() for a in pb["csr"]]
+        csr[which][0] = t["n_blocks"] + 7
+        with pytest.raises(sb.SpamTreeError) as e:
+            sb.SpamTreeMV(d["y"], d["X"], d["coords"], d["mv_id"], t["res_is_ref"], None, None, False, t["block_names"], t["block_groups"],
+                          None, pb["beta"], pb["theta"], pb["tausq"], csr=tuple(csr), device=-1)
+        assert e.value.code == 1 and "block id" in str(e.value)
