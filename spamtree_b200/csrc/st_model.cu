@@ -517,8 +517,12 @@ int Model::build_layout(std::string& e) {
   // sweep by the device-resident iteration; never the deepest level.  Measured on C4 / one B200 (ms per iteration): no
   // overlap 7.18, levels 0-4 (<= 128 groups) 7.17, + level 5 (256 groups) 7.21, + level 6 7.34, everything but the leaves 7.42
   // — a level that fills the GPU only competes with the sweep; C1 (n = 625): 4 998 -> 6 455 it/s end to end
+  // A rank of a partitioned run holds a fraction of the big levels and is latency-dominated: there the threshold is four
+  // waves of work groups (C4 on 8 B200: 577 it/s without overlap, 607 with the one-wave threshold, 639 with levels up to
+  // 512 groups early; on one GPU the wider threshold costs 0.5 %).
+  const int early_thr = (part ? 4 : 1) * n_sm;
   n_early_levels_ = 0;
-  while (n_early_levels_ + 1 < (int)levels.size() && levels[n_early_levels_].ngrp <= n_sm && !levels[n_early_levels_].deferrable)
+  while (n_early_levels_ + 1 < (int)levels.size() && levels[n_early_levels_].ngrp <= early_thr && !levels[n_early_levels_].deferrable)
     n_early_levels_++;
   if (const char* v = getenv("ST_EARLY_LEVELS")) n_early_levels_ = std::max(0, std::min(atoi(v), (int)levels.size() - 1));
   { int rc = make_groups(pred_level, 2); if (rc) return rc; }
