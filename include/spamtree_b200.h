@@ -44,7 +44,8 @@ typedef struct {
   int32_t n_top_levels;         /* replicated levels (0: the ranks hold disjoint trees) */
   int64_t rng_row_offset;       /* rows owned by lower ranks: keeps the device normal streams of the ranks disjoint */
   int64_t n_global_rows;        /* rows of the whole problem */
-  const int64_t* global_rows;   /* n_all: global row of every local row (host-RNG mode draws for all global rows) */
+  const int64_t* global_rows;   /* n_all, required: row of the whole problem behind every local row (keys the device random
+                                   streams; the host stream draws for all rows of the problem on every rank) */
   st_allreduce_fn allreduce;
   void* ctx;
 } st_partition;

@@ -93,7 +93,12 @@ int st_create(const st_problem* pr, st_handle** out) {
       M.part = true;
       M.rank = pt.rank; M.nranks = pt.nranks; M.n_top_levels = pt.n_top_levels;
       M.rng_row_offset = pt.rng_row_offset; M.n_global_rows = pt.n_global_rows;
-      if (pt.global_rows) M.global_rows.assign(pt.global_rows, pt.global_rows + pr->n_all);
+      // every random stream is keyed by the row's id in the whole problem (device) or drawn for all of its rows (host): without
+      // the map the ranks would draw different numbers for the rows they share
+      if (!pt.global_rows || pt.n_global_rows < pr->n_all) { g_create_error = "partition: global_rows / n_global_rows missing"; delete h; return ST_ERR_INVALID; }
+      for (int64_t i = 0; i < pr->n_all; i++)
+        if (pt.global_rows[i] < 0 || pt.global_rows[i] >= pt.n_global_rows) { g_create_error = "partition: global row out of range"; delete h; return ST_ERR_INVALID; }
+      M.global_rows.assign(pt.global_rows, pt.global_rows + pr->n_all);
       M.allreduce_fn = pt.allreduce; M.allreduce_ctx = pt.ctx;
     }
     {
