@@ -195,9 +195,9 @@ int st_attach_nccl(st_handle* h, const unsigned char* id128);
 
 /* ---- bench / profiling hooks (no reference counterpart) ---- */
 /* One hot-path iteration without host random draws: GIBBS (device normals) + LLW + BUILD(alter, theta_prop)
- * + optional swap + tausq + beta (spamtree_fit.cpp:167-330 minus predict/save).  ms_out[0..4] (when non-NULL) receive the
- * CUDA-event times of {gibbs (+ Gram refresh), llw, build (+ deferred half), tausq + beta, the whole iteration}; the upper
- * levels of the BUILD run on a second stream underneath the sweep, so the first four do not add up to the fifth. */
+ * + optional swap + tausq + beta (spamtree_fit.cpp:167-330 minus predict/save).  ms_out[0..5] (when non-NULL) receive the
+ * CUDA-event times of {gibbs (+ Gram refresh), llw, build on the main stream (+ deferred half), tausq + beta, the whole
+ * iteration, the upper levels of BUILD on the second stream (0 when the iteration is sequential: then [0..3] add up to [4])}. */
 int st_bench_iteration(st_handle* h, const double* theta_prop, int do_swap, uint64_t seed, double* out3, float* ms_out);
 /* row index of the beta step used by st_bench_iteration: 1 = the reference's (the default on a single-GPU
  * handle), 0 = the corrected one (the only one a partitioned handle supports) */

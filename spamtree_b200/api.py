@@ -393,7 +393,7 @@ class SpamTreeMV:
         return o[:cnt.value]
 
     def bench_iteration(self, theta_prop, do_swap=False, seed=0):
-        t, o, ms = _f64(theta_prop), np.zeros(3), np.zeros(5, dtype=np.float32)
+        t, o, ms = _f64(theta_prop), np.zeros(3), np.zeros(6, dtype=np.float32)
         self._chk(lib.st_bench_iteration(self._h, _dp(t), int(bool(do_swap)), int(seed), _dp(o), ms.ctypes.data_as(_lib.c_float_p)))
         return o, ms
 

@@ -555,31 +555,51 @@ cudaError_t launch_llw(const DevTree& T, const DevSlots& D, int rel, int slot0, 
 }
 
 // Sum of the per-block log-density pieces (:987-988 / :815-816), in two parts so that a partitioned run can count the
-// replicated blocks once and all-reduce the rest: block 0 sums [0, n_top) into out[0..2], block 1 sums [n_top, n) into
-// out[4..6]; out[.] = {sum(logdet) + sum(llcomp), sum(logdet), 0 / *fail}.  Fixed summation order: deterministic.
-__global__ void __launch_bounds__(1024) loglik_reduce_kernel(DevSlots D, int rel, int n_top, int n, const int* __restrict__ fail,
-                                                             double* __restrict__ out) {
-  __shared__ double sa[1024], sb[1024];
+// replicated blocks once and all-reduce the rest: part 0 = blocks [0, n_top) -> out[0..2], part 1 = [n_top, n) -> out[4..6];
+// out[.] = {sum(logdet) + sum(llcomp), sum(logdet), 0 / *fail}.  kRedBlocks CTAs per part sum fixed chunks, the last CTA to
+// finish adds the partial sums in chunk order: the summation order is fixed, the result deterministic run to run.
+constexpr int kRedBlocks = 32;
+__global__ void __launch_bounds__(256) loglik_reduce_kernel(DevSlots D, int rel, int n_top, int n, const int* __restrict__ fail,
+                                                            double* __restrict__ out, double* __restrict__ partial,
+                                                            unsigned int* __restrict__ counter) {
+  __shared__ double sa[256], sb[256];
+  __shared__ bool last;
   const DevSlot S = pick_slot(D, D.chain->cur ^ rel);
-  const int first = blockIdx.x ? n_top : 0, last = blockIdx.x ? n : n_top;
+  const int part = blockIdx.y, first = part ? n_top : 0, cnt = (part ? n : n_top) - first;
+  const int chunk = (cnt + kRedBlocks - 1) / kRedBlocks;
+  const int lo = first + blockIdx.x * chunk, hi = min(lo + chunk, first + cnt);
   double a = 0, b = 0;
-  for (int i = first + threadIdx.x; i < last; i += 1024) { a += S.logdet[i]; b += S.llcomp[i]; }
+  for (int i = lo + threadIdx.x; i < hi; i += 256) { a += S.logdet[i]; b += S.llcomp[i]; }
   sa[threadIdx.x] = a;
   sb[threadIdx.x] = b;
   __syncthreads();
-  for (int s = 512; s > 0; s >>= 1) {
+  for (int s = 128; s > 0; s >>= 1) {
     if ((int)threadIdx.x < s) { sa[threadIdx.x] += sa[threadIdx.x + s]; sb[threadIdx.x] += sb[threadIdx.x + s]; }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    double* o = out + 4 * blockIdx.x;
-    o[0] = sa[0] + sb[0];
-    o[1] = sa[0];
-    o[2] = (blockIdx.x && fail) ? (double)*fail : 0.0;
+    partial[(part * kRedBlocks + blockIdx.x) * 2] = sa[0];
+    partial[(part * kRedBlocks + blockIdx.x) * 2 + 1] = sb[0];
+    __threadfence();
+    last = atomicAdd(counter + part, 1u) == kRedBlocks - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double ta = 0, tb = 0;
+    for (int k = 0; k < kRedBlocks; k++) { ta += partial[(part * kRedBlocks + k) * 2]; tb += partial[(part * kRedBlocks + k) * 2 + 1]; }
+    double* o = out + 4 * part;
+    o[0] = ta + tb;
+    o[1] = ta;
+    o[2] = (part && fail) ? (double)*fail : 0.0;
+    counter[part] = 0;  // ready for the next launch
   }
 }
-cudaError_t launch_loglik_reduce(const DevSlots& D, int rel, int n_top, int n, const int* fail, double* out8, cudaStream_t st) {
-  loglik_reduce_kernel<<<2, 1024, 0, st>>>(D, rel, n_top, n, fail, out8);
+cudaError_t launch_loglik_reduce(const DevSlots& D, int rel, int n_top, int n, const int* fail, double* out8, double* scratch,
+                                 cudaStream_t st) {
+  // scratch: 4 * kRedBlocks doubles of partial sums followed by two zero-initialised 32-bit counters
+  loglik_reduce_kernel<<<dim3(kRedBlocks, 2), 256, 0, st>>>(D, rel, n_top, n, fail, out8, scratch,
+                                                            reinterpret_cast<unsigned int*>(scratch + 4 * kRedBlocks));
   return cudaGetLastError();
 }
 
@@ -959,7 +979,10 @@ cudaError_t launch_yhat(const DevTree& T, const double* w, const double* xb, con
 __global__ void chain_set_theta_kernel(ChainDev* C, int rel, const __grid_constant__ ThetaPack P) {
   const int phys = C->cur ^ rel;
   for (int j = threadIdx.x; j < P.n; j += blockDim.x) C->theta[phys][j] = P.theta[j];
-  if (threadIdx.x == 0) C->tab[phys] = P.tab;
+  // (the table word by word, by all threads: CovTab is an int followed by doubles, 8-byte aligned)
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&P.tab);
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(&C->tab[phys]);
+  for (int j = threadIdx.x; j < (int)(sizeof(CovTab) / 8); j += blockDim.x) dst[j] = src[j];
 }
 cudaError_t launch_chain_set_theta(ChainDev* C, int rel, const ThetaPack& pack, cudaStream_t st) {
   chain_set_theta_kernel<<<1, 64, 0, st>>>(C, rel, pack);

@@ -122,7 +122,10 @@ cudaError_t launch_gram(const DevTree& T, const DevSlots& D, int slot0, int nslo
 cudaError_t launch_llw(const DevTree& T, const DevSlots& D, int rel, int slot0, int nslots, const double* w, int maxlen, cudaStream_t st);
 // out8[0..2] = {sum logdet + sum llcomp, sum logdet, 0} over blocks [0, n_top) and out8[4..6] = the same over [n_top, n) with
 // out8[6] = *fail (or 0): the two parts a partitioned run needs (replicated blocks once, the rank's own all-reduced)
-cudaError_t launch_loglik_reduce(const DevSlots& D, int rel, int n_top, int n, const int* fail, double* out8, cudaStream_t st);
+// scratch: kReduceScratch doubles (partial sums + two counters that must start at zero), private to the stream
+constexpr int kReduceScratch = 4 * 32 + 2;
+cudaError_t launch_loglik_reduce(const DevSlots& D, int rel, int n_top, int n, const int* fail, double* out8, double* scratch,
+                                 cudaStream_t st);
 cudaError_t launch_frontier_sum(const DevTree& T, int n, const int* pseudo, const int* c0, const int* c1, const int* vlen,
                                 const int* ulen, double* V, double* U, int do_v, int do_u, cudaStream_t st);
 cudaError_t launch_predict_sample(const DevTree& T, int slot0, int nslots, const double* Hpred, const double* sdpred,

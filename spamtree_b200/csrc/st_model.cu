@@ -524,6 +524,10 @@ int Model::build_layout(std::string& e) {
   n_early_levels_ = 0;
   while (n_early_levels_ + 1 < (int)levels.size() && levels[n_early_levels_].ngrp <= early_thr && !levels[n_early_levels_].deferrable)
     n_early_levels_++;
+  // On one GPU a big tree gains nothing from the overlap (C4: 7.17 vs 7.18 ms, C3: +1 %) — the sweep and the BUILD both fill
+  // the machine — and its per-phase event times stay attributable without it: the overlap is for the latency-dominated
+  // cases, small trees (C1: +30 %, C2: +35 % end to end) and the ranks of a partition (C4 on 8 B200: +11 %)
+  if (!part && n_obs_nodes > 16384) n_early_levels_ = 0;
   if (const char* v = getenv("ST_EARLY_LEVELS")) n_early_levels_ = std::max(0, std::min(atoi(v), (int)levels.size() - 1));
   { int rc = make_groups(pred_level, 2); if (rc) return rc; }
 
@@ -688,6 +692,7 @@ int Model::upload(std::string& e) {
     for (int64_t i = 0; i < n_all; i++) key[i] = pg ? (long long)global_rows[perm[i]] : (long long)perm[i];
     ST_CUDA(dev_upload(key, d_rowkey, owned), "upload rowkey");
   }
+  ST_CUDA(dev_zeros(d_red_scratch, kReduceScratch, owned), "alloc reduce scratch");
   ST_CUDA(dev_zeros(d_xtx, (long long)q * p * p, owned), "alloc xtx");
   ST_CUDA(dev_zeros(d_bscratch, (long long)q * 3 * p * p + 8 * p, owned), "alloc beta scratch");
   if (!part) {  // (partitioned handles: after the sums over the ranks, partition_reduce_constants)
@@ -837,7 +842,7 @@ int Model::allreduce_dev(double* dptr, int64_t n) {
 // replicated blocks (or nothing), [4..6] the rest, all-reduced over the ranks of a partition; [6] = failed factorisations.
 // out3_host (host-driven path) = {loglik_w, logdetCi, failures}: one D2H + synchronisation.
 int Model::reduce_loglik(int rel, const int* fail, double* dev_red8, double* out3_host) {
-  ST_CUDA(launch_loglik_reduce(dslots, rel, part ? n_top_slots : 0, n_obs_nodes, fail, dev_red8, stream), "loglik_reduce");
+  ST_CUDA(launch_loglik_reduce(dslots, rel, part ? n_top_slots : 0, n_obs_nodes, fail, dev_red8, d_red_scratch, stream), "loglik_reduce");
   n_launches++;
   if (part) { int rc = allreduce_dev(dev_red8 + 4, 3); if (rc) return rc; }
   if (!out3_host) return 0;
@@ -1049,7 +1054,7 @@ int Model::deal_with_w(const double* z, uint64_t seed) {
   // failed factorisations, agreed over the ranks of a partition (every rank must take the same exit): the count rides in an
   // 8-double reduction slot, all-reduced on the stream
   double* slot8 = d_scalars + 48;
-  ST_CUDA(launch_loglik_reduce(dslots, 0, 0, 0, d_fail, slot8, stream), "fail count");
+  ST_CUDA(launch_loglik_reduce(dslots, 0, 0, 0, d_fail, slot8, d_red_scratch, stream), "fail count");
   if (part) { rc = allreduce_dev(slot8 + 4, 3); if (rc) return rc; }
   ST_CUDA(cudaMemcpyAsync(h_scalars + 48, slot8, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream), "D2H fail");
   ST_CUDA(cudaStreamSynchronize(stream), "sync");
@@ -1588,11 +1593,12 @@ int Model::bench_iteration(const double* theta_prop, int do_swap, uint64_t seed,
     if (ovl) ST_CUDA(cudaEventElapsedTime(&early, ev[6], ev[7]), "elapsed");
     ms_out[0] = t[0] + t[3];  // GIBBS sweep + the Gram refresh an accepted proposal triggers
     ms_out[1] = t[1];         // LLW
-    // BUILD + accept + the deferred half of an accepted proposal; with the overlap on, the early levels are timed on their own
-    // stream (they run underneath the sweep and LLW, so the phases no longer add up to the step) and added here
-    ms_out[2] = t[2] + early;
+    ms_out[2] = t[2];         // BUILD on the main stream + accept + the deferred half of an accepted proposal
     ms_out[3] = t[4];         // tausq + beta
     ST_CUDA(cudaEventElapsedTime(&ms_out[4], ev[0], ev[5]), "elapsed");  // the whole iteration on the main stream
+    // the upper levels of BUILD when they run on the second stream, underneath the sweep (elapsed there: it includes the time
+    // their thread blocks wait behind the sweep's, so [0..3] + [5] exceeds [4]); 0 when the iteration is sequential
+    ms_out[5] = early;
   }
   return 0;
 }
