@@ -32,7 +32,7 @@ def build_dram_traffic(workload):
     import glob
     import hashlib
     h = hashlib.sha1()
-    for f in ["spamtree_b200/csrc/st_build.cu", "spamtree_b200/csrc/st_device.cuh", "spamtree_b200/csrc/st_kernels.cuh"]:
+    for f in ["spamtree_b200/csrc/st_build.cu", "spamtree_b200/csrc/st_device.cuh", "spamtree_b200/csrc/st_build_plan.cuh"]:
         h.update(open(os.path.join(ROOT, f), "rb").read())
     sha = h.hexdigest()
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_build_dram.json")), reverse=True):

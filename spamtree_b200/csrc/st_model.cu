@@ -87,6 +87,8 @@ Model::~Model() {
   if (stream2) cudaStreamDestroy(stream2);
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
+  if (ev_sweep) cudaEventDestroy(ev_sweep);
+  if (ev_llw) cudaEventDestroy(ev_llw);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -585,6 +587,8 @@ int Model::upload(std::string& e) {
   }
   ST_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming), "cudaEventCreate");
   ST_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming), "cudaEventCreate");
+  ST_CUDA(cudaEventCreateWithFlags(&ev_sweep, cudaEventDisableTiming), "cudaEventCreate");
+  ST_CUDA(cudaEventCreateWithFlags(&ev_llw, cudaEventDisableTiming), "cudaEventCreate");
   for (auto& x : ev) ST_CUDA(cudaEventCreate(&x), "cudaEventCreate");
   // per row
   dvec cx(n_all), cy(n_all), yy(n_all), Xp((size_t)n_all * p), xb(n_all, 0.0);
@@ -692,7 +696,7 @@ int Model::upload(std::string& e) {
     for (int64_t i = 0; i < n_all; i++) key[i] = pg ? (long long)global_rows[perm[i]] : (long long)perm[i];
     ST_CUDA(dev_upload(key, d_rowkey, owned), "upload rowkey");
   }
-  ST_CUDA(dev_zeros(d_red_scratch, kReduceScratch, owned), "alloc reduce scratch");
+  ST_CUDA(dev_zeros(d_red_scratch, 2 * kReduceScratch, owned), "alloc reduce scratch");  // one set per stream
   ST_CUDA(dev_zeros(d_xtx, (long long)q * p * p, owned), "alloc xtx");
   ST_CUDA(dev_zeros(d_bscratch, (long long)q * 3 * p * p + 8 * p, owned), "alloc beta scratch");
   if (!part) {  // (partitioned handles: after the sums over the ranks, partition_reduce_constants)
@@ -767,6 +771,7 @@ int Model::init(std::string& e) {
   if (const char* v = getenv("ST_DEFER")) defer_leaves = atoi(v) != 0;
   if (const char* v = getenv("ST_PDL")) use_pdl = atoi(v) != 0;
   if (const char* v = getenv("ST_OVERLAP")) overlap = atoi(v) != 0;
+  if (const char* v = getenv("ST_LLW_OVERLAP")) llw_overlap = atoi(v) != 0;
   if (const char* v = getenv("ST_MAX_COLS")) max_group_cols = atoi(v);
   if (const char* v = getenv("ST_SMEM_BUDGET")) smem_budget = (size_t)atol(v);
   if (device >= 0) {
@@ -1427,14 +1432,30 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
     if (tev) ST_CUDA(cudaEventRecord(tev[7], stream2), "event");
     ST_CUDA(cudaEventRecord(ev_join, stream2), "event");
   }
+  // LLW of the current slot (HBM-bound: it streams every row block once) is not needed before the accept step: on a
+  // single-GPU handle it runs on the second stream underneath the BUILD of the proposal (tensor-bound, 10 % of the HBM
+  // bandwidth), after the sweep has finished.  (Partitioned handles keep it on the main stream, with their collectives.)
+  const bool llw2 = llw_overlap && !part && o.sample_w && o.sample_theta && stream2 != nullptr;
   if (o.sample_w) {  // :183-187
     rc = enqueue_gibbs(o.seed, true);
     if (rc) return rc;
     if (tev) ST_CUDA(cudaEventRecord(tev[1], stream), "event");
-    ST_CUDA(launch_llw(dt, dslots, 0, 0, n_obs_nodes, d_w, llw_maxlen_, stream), "llw_kernel");
-    n_launches++;
-    rc = reduce_loglik(0, nullptr, d_mc->red_llw, nullptr);
-    if (rc) return rc;
+    if (llw2) {
+      ST_CUDA(cudaEventRecord(ev_sweep, stream), "event");
+      ST_CUDA(cudaStreamWaitEvent(stream2, ev_sweep, 0), "fork");
+      if (tev) ST_CUDA(cudaEventRecord(tev[8], stream2), "event");
+      ST_CUDA(launch_llw(dt, dslots, 0, 0, n_obs_nodes, d_w, llw_maxlen_, stream2), "llw_kernel");
+      n_launches++;
+      ST_CUDA(launch_loglik_reduce(dslots, 0, 0, n_obs_nodes, nullptr, d_mc->red_llw, d_red_scratch + kReduceScratch, stream2), "loglik_reduce");
+      n_launches++;
+      if (tev) ST_CUDA(cudaEventRecord(tev[9], stream2), "event");
+      ST_CUDA(cudaEventRecord(ev_llw, stream2), "event");
+    } else {
+      ST_CUDA(launch_llw(dt, dslots, 0, 0, n_obs_nodes, d_w, llw_maxlen_, stream), "llw_kernel");
+      n_launches++;
+      rc = reduce_loglik(0, nullptr, d_mc->red_llw, nullptr);
+      if (rc) return rc;
+    }
   } else if (tev) {
     ST_CUDA(cudaEventRecord(tev[1], stream), "event");
   }
@@ -1455,6 +1476,7 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
     }
     rc = reduce_loglik(1, d_fail, d_mc->red_build, nullptr);
     if (rc) return rc;
+    if (llw2) ST_CUDA(cudaStreamWaitEvent(stream, ev_llw, 0), "join");
     ST_CUDA(launch_mh_accept(d_mc, accept_mode, o.sample_w ? 1 : 0, stream), "mh_accept_kernel");
     n_launches++;
     // an accepted proposal: the new param_data's childless level gets its backward half, the message Grams are refreshed
@@ -1593,6 +1615,7 @@ int Model::bench_iteration(const double* theta_prop, int do_swap, uint64_t seed,
     if (ovl) ST_CUDA(cudaEventElapsedTime(&early, ev[6], ev[7]), "elapsed");
     ms_out[0] = t[0] + t[3];  // GIBBS sweep + the Gram refresh an accepted proposal triggers
     ms_out[1] = t[1];         // LLW
+    if (llw_overlap && !part && stream2 != nullptr) ST_CUDA(cudaEventElapsedTime(&ms_out[1], ev[8], ev[9]), "elapsed");  // on the second stream, underneath BUILD
     ms_out[2] = t[2];         // BUILD on the main stream + accept + the deferred half of an accepted proposal
     ms_out[3] = t[4];         // tausq + beta
     ST_CUDA(cudaEventElapsedTime(&ms_out[4], ev[0], ev[5]), "elapsed");  // the whole iteration on the main stream

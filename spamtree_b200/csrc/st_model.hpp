@@ -187,7 +187,11 @@ class Model {
   double* h_stage = nullptr;  // pinned n_all staging buffer
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaStream_t stream2 = nullptr;   // the early levels of a proposal's BUILD run here, underneath the Gibbs sweep
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sweep = nullptr, ev_llw = nullptr;
+  // LLW of the current slot on the second stream, underneath BUILD.  Off by default: measured on one B200 it gives 0.8 % at C4
+  // and 2.3 % at C3 (the sweep of the HBM mostly displaces BUILD's own time) and makes LLW's event time meaningless;
+  // ST_LLW_OVERLAP=1 enables it
+  bool llw_overlap = false;
   bool overlap = true;              // ST_OVERLAP=0 disables
   int n_early_levels_ = 0;          // leading tree levels whose BUILD runs underneath the sweep (ST_EARLY_LEVELS overrides)
   cudaEvent_t ev_wready = nullptr, ev_wcopied = nullptr;
@@ -195,7 +199,7 @@ class Model {
   long long* d_iperm = nullptr;     // boundary row -> node-major row
   void* save_registered = nullptr;  // host range page-locked by save_begin
   bool save_pending = false;
-  cudaEvent_t ev[8]{};
+  cudaEvent_t ev[10]{};
   std::vector<void*> owned;  // device allocations to free
   // counters
   double n_launches = 0, f_alg = 0, f_exec = 0, n_cov = 0, f_alg_build = 0, f_exec_build = 0, b_alg_build = 0;

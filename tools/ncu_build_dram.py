@@ -11,7 +11,7 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KERNEL_SOURCES = ["spamtree_b200/csrc/st_build.cu", "spamtree_b200/csrc/st_device.cuh", "spamtree_b200/csrc/st_kernels.cuh"]
+KERNEL_SOURCES = ["spamtree_b200/csrc/st_build.cu", "spamtree_b200/csrc/st_device.cuh", "spamtree_b200/csrc/st_build_plan.cuh"]
 
 
 def sources_sha1():
