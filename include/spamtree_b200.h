@@ -80,7 +80,8 @@ typedef struct {
   const double* beta;          /* p start values */
   double tausq;                /* start value (the ctor receives 1/tausq, spamtree_fit.cpp:104) */
   int32_t device;              /* CUDA device ordinal; < 0: host-only handle (bookkeeping for st_get_index, no compute) */
-  int32_t keep_H;              /* 1: keep H = w_cond_mean_K of observed blocks on device (needed by st_get_node_state "H") */
+  int32_t keep_H;              /* 1: keep H = w_cond_mean_K of observed blocks and the Sigi_tot / Smu_tot probes of the Gibbs
+                                  sweep on the device (needed by st_get_node_state "H", "Sigi_tot", "Smu_tot"); 0: production */
   int64_t smem_panel_bytes;    /* 0 = default; shared-memory budget for one BUILD work group */
   const st_partition* partition; /* NULL: the whole problem on one GPU */
 } st_problem;

@@ -661,8 +661,10 @@ int Model::upload(std::string& e) {
   ST_CUDA(dev_zeros(d_S, s_total, owned), "alloc S");
   ST_CUDA(dev_zeros(d_Hpred, gpred_total, owned), "alloc Hpred");
   ST_CUDA(dev_zeros(d_sdpred, sd_total_, owned), "alloc sdpred");
-  ST_CUDA(dev_zeros(d_probe_sig, ri_total, owned), "alloc probe");
-  ST_CUDA(dev_zeros(d_probe_smu, n_all, owned), "alloc probe");
+  if (probes) {
+    ST_CUDA(dev_zeros(d_probe_sig, ri_total, owned), "alloc probe");
+    ST_CUDA(dev_zeros(d_probe_smu, n_all, owned), "alloc probe");
+  }
   ST_CUDA(dev_zeros(d_scalars, 64 + kMaxStats + 1024, owned), "alloc scalars");
   rowstat_blocks_ = (int)std::min<int64_t>(592, std::max<int64_t>(1, (n_all + 255) / 256));
   ST_CUDA(dev_zeros(d_partial, (long long)rowstat_blocks_ * kMaxStats, owned), "alloc partial");
@@ -774,6 +776,9 @@ int Model::init(std::string& e) {
   if (const char* v = getenv("ST_LLW_OVERLAP")) llw_overlap = atoi(v) != 0;
   if (const char* v = getenv("ST_MAX_COLS")) max_group_cols = atoi(v);
   if (const char* v = getenv("ST_SMEM_BUDGET")) smem_budget = (size_t)atol(v);
+  // the Sigi_tot / Smu_tot probes of the Gibbs sweep (st_get_node_state) exist for the parity tests: like H they are kept only
+  // on handles created with keep_H (the production / bench configuration writes neither)
+  probes = keep_H;
   if (device >= 0) {
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) n_sm = v;
