@@ -74,7 +74,7 @@ typedef struct {
   const int64_t* res_is_ref;   /* n_res flags per tree level */
   int32_t n_res;
   int32_t limited_tree;        /* 1: every block conditions on its direct parent only (make_edges_limited, tree_dep.cpp:133-186;
-                                  spamtree_model.cpp:901-903, 1275-1278); not combined with a partition */
+                                  spamtree_model.cpp:901-903, 1275-1278) */
   const double* theta;         /* n_theta start values (covariance_functions.cpp:34-52 layout) */
   int32_t n_theta;
   const double* beta;          /* p start values */

@@ -89,7 +89,6 @@ int st_create(const st_problem* pr, st_handle** out) {
     if (pr->partition && pr->partition->nranks > 1) {
       const st_partition& pt = *pr->partition;
       if (pt.rank < 0 || pt.rank >= pt.nranks) { g_create_error = "partition: bad rank"; delete h; return ST_ERR_INVALID; }
-      if (M.limited) { g_create_error = "limited_tree = TRUE cannot be combined with a partition"; delete h; return ST_ERR_UNSUPPORTED; }
       M.part = true;
       M.rank = pt.rank; M.nranks = pt.nranks; M.n_top_levels = pt.n_top_levels;
       M.rng_row_offset = pt.rng_row_offset; M.n_global_rows = pt.n_global_rows;

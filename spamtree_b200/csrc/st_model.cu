@@ -333,12 +333,14 @@ int Model::build_layout(std::string& e) {
         while (c < CL.slot0 + CL.nslots && h_lastpar[c] == dd) c++;
         // the pseudo child looks like a child of dd with no rows: chain = chain(dd) + dd
         h_m.push_back(0); h_row0.push_back(0); isref.push_back(0); h_lastpar.push_back(dd);
-        h_k.push_back(h_k[dd] + 1);
+        // (limited trees: a child lists its direct parent only, tree_dep.cpp:133-186 — so does the pseudo child)
+        const int kps = limited ? 0 : h_k[dd];
+        h_k.push_back(kps + 1);
         h_chain_off.push_back((int)h_chain.size());
         int poff = 0;
         long long uo = 0;
-        for (int j = 0; j <= h_k[dd]; j++) {
-          const int a = (j < h_k[dd]) ? h_chain[h_chain_off[dd] + j] : dd;
+        for (int j = 0; j <= kps; j++) {
+          const int a = (j < kps) ? h_chain[h_chain_off[dd] + j] : dd;
           h_chain.push_back(a); h_chain_poff.push_back(poff); h_chain_uoff.push_back((int)uo);
           poff += h_m[a];
           uo += pad2((long long)h_m[a] * h_m[a]);

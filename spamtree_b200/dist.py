@@ -32,12 +32,19 @@ def make_allreduce(device=None):
     return allreduce
 
 
-def partitioned_model(d, tree, theta, beta, tausq, rank, nranks, device, allreduce, keep_H=False, native_nccl=True):
-    """SpamTreeMV of this rank's share of the problem (d: data dict with y/X/coords/mv_id/q; tree: make_tree output)"""
+def partitioned_model(d, tree, theta, beta, tausq, rank, nranks, device, allreduce, keep_H=False, native_nccl=True, limited_tree=False):
+    """SpamTreeMV of this rank's share of the problem (d: data dict with y/X/coords/mv_id/q; tree: make_tree output).
+    limited_tree: every block conditions on its direct parent only (make_edges_limited); the subtrees are still cut along
+    the full ancestor chains."""
     pl = part.plan(tree, d["y"], nranks)
-    sp = part.subproblem(d, tree, pl, rank, nranks)
+    mp = None
+    if limited_tree:
+        from .api import limited_edges_csr
+        lp = limited_edges_csr(tree, d["y"])
+        mp = (lp[0], lp[1])
+    sp = part.subproblem(d, tree, pl, rank, nranks, model_parents=mp)
     sp["allreduce"] = allreduce
-    gm = SpamTreeMV(sp["y"], sp["X"], sp["coords"], sp["mv_id"], sp["res_is_ref"], None, None, False, sp["block_names"],
+    gm = SpamTreeMV(sp["y"], sp["X"], sp["coords"], sp["mv_id"], sp["res_is_ref"], None, None, bool(limited_tree), sp["block_names"],
                     sp["block_groups"], None, beta, theta, tausq, csr=sp["csr"], device=device, keep_H=keep_H,
                     partition=sp if nranks > 1 else None, q=d["q"])
     if nranks > 1 and native_nccl:

@@ -78,15 +78,17 @@ def plan(tree, y, nranks):
     return {"gc": gc, "levels": levels, "owner": owner, "top": top}
 
 
-def subproblem(d, tree, pl, rank, nranks):
-    """Inputs of SpamTreeMV for one rank: the replicated top blocks plus the blocks this rank owns."""
+def subproblem(d, tree, pl, rank, nranks, model_parents=None):
+    """Inputs of SpamTreeMV for one rank: the replicated top blocks plus the blocks this rank owns.
+    model_parents: (ptr, idx) of the parent lists the MODEL uses when they differ from the tree's ancestor chains —
+    limited_tree = TRUE (make_edges_limited: the direct parent only); the plan is always made on the full chains."""
     nb = tree["n_blocks"]
     keep = pl["top"] | (pl["owner"] == rank)
     old = np.flatnonzero(keep)
     new_id = np.full(nb, -1, dtype=np.int64)
     new_id[old] = np.arange(old.size)
     rows = _lists(tree["indexing_ptr"], tree["indexing_idx"])
-    par = _lists(tree["parents_ptr"], tree["parents_idx"])
+    par = _lists(*model_parents) if model_parents is not None else _lists(tree["parents_ptr"], tree["parents_idx"])
     grow = np.sort(np.concatenate([rows[u] for u in old]))           # global boundary rows, boundary order kept
     lrow = np.full(d["y"].size, -1, dtype=np.int64)
     lrow[grow] = np.arange(grow.size)

@@ -47,6 +47,36 @@ def test_plan_is_a_partition_and_balanced():
         part.plan(t, d["y"], 100000)
 
 
+@pytest.mark.parametrize("limited", [False, True])
+def test_partitioned_layout_passes_the_products_validation(limited):
+    """st_create with an st_partition on a host-only handle: the replicated frontier, its pseudo children and the layout are
+    built and validated without a GPU — for full chains and for limited_tree = TRUE (direct parent only, make_edges_limited)"""
+    pb = common.make_problem(3, 12000)
+    d, t = pb["d"], pb["tree"]
+    mp_ = None
+    if limited:
+        lp = sb.limited_edges_csr(t, d["y"])
+        mp_ = (lp[0], lp[1])
+    for nr in (2, 4):
+        pl = part.plan(t, d["y"], nr)
+        for r in range(nr):
+            sp = part.subproblem(d, t, pl, r, nr, model_parents=mp_)
+            sp["allreduce"] = lambda ptr, count: None
+            m = sb.SpamTreeMV(sp["y"], sp["X"], sp["coords"], sp["mv_id"], sp["res_is_ref"], None, None, limited, sp["block_names"],
+                              sp["block_groups"], None, pb["beta"], pb["theta"], pb["tausq"], csr=sp["csr"], device=-1, q=3, partition=sp)
+            if limited:  # every block lists its direct parent only
+                assert max(m.index("parents_indexing", u).size for u in range(m.n_blocks)) <= 60
+            m.close()
+    # a partition without the global row map is refused (the ranks' random streams would differ)
+    sp = part.subproblem(d, t, part.plan(t, d["y"], 2), 0, 2)
+    sp["allreduce"] = lambda ptr, count: None
+    sp["global_rows"] = sp["global_rows"][:10]
+    with pytest.raises((sb.SpamTreeError, ValueError, Exception)):
+        bad = dict(sp, n_global_rows=5)
+        sb.SpamTreeMV(sp["y"], sp["X"], sp["coords"], sp["mv_id"], sp["res_is_ref"], None, None, False, sp["block_names"],
+                      sp["block_groups"], None, pb["beta"], pb["theta"], pb["tausq"], csr=sp["csr"], device=-1, q=3, partition=bad)
+
+
 def _worker(rank, world, port, q, n, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)

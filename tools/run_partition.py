@@ -24,6 +24,7 @@ def relerr(a, b):
 def main():
     q = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
+    limited = len(sys.argv) > 3 and sys.argv[3] == "limited"  # limited_tree = TRUE (make_edges_limited, tree_dep.cpp:133-186)
     rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lrank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
@@ -31,9 +32,11 @@ def main():
     tree = sb.make_tree(d["coords"], d["y"], d["mv_id"])
     theta, beta, tausq = synth.theta_for(q), np.zeros(3), 0.1
     ar = sdist.make_allreduce(torch.device("cuda", lrank))
-    gm, sp, pl = sdist.partitioned_model(d, tree, theta, beta, tausq, rank, world, lrank, ar, keep_H=True)
+    gm, sp, pl = sdist.partitioned_model(d, tree, theta, beta, tausq, rank, world, lrank, ar, keep_H=True, limited_tree=limited)
     csr = (tree["indexing_ptr"], tree["indexing_idx"], tree["parents_ptr"], tree["parents_idx"], tree["children_ptr"], tree["children_idx"])
-    full = sb.SpamTreeMV(d["y"], d["X"], d["coords"], d["mv_id"], tree["res_is_ref"], None, None, False, tree["block_names"],
+    if limited:
+        csr = csr[:2] + sb.limited_edges_csr(tree, d["y"])
+    full = sb.SpamTreeMV(d["y"], d["X"], d["coords"], d["mv_id"], tree["res_is_ref"], None, None, limited, tree["block_names"],
                          tree["block_groups"], None, beta, theta, tausq, csr=csr, device=lrank)
     rng = np.random.default_rng(3)
     w0 = rng.standard_normal(n) * .4
@@ -71,8 +74,8 @@ def main():
     npar = theta.size
     kw = dict(keep=8, burn=40, thin=1, adapting=True, seed=17, rng_mode=0, faithful_beta_index=False)
     sd = np.eye(npar) * (.01 if q == 1 else 1e-5)
-    gm2, sp2, _ = sdist.partitioned_model(d, tree, theta, beta, tausq, rank, world, lrank, ar)
-    full2 = sb.SpamTreeMV(d["y"], d["X"], d["coords"], d["mv_id"], tree["res_is_ref"], None, None, False, tree["block_names"],
+    gm2, sp2, _ = sdist.partitioned_model(d, tree, theta, beta, tausq, rank, world, lrank, ar, limited_tree=limited)
+    full2 = sb.SpamTreeMV(d["y"], d["X"], d["coords"], d["mv_id"], tree["res_is_ref"], None, None, limited, tree["block_names"],
                           tree["block_groups"], None, beta, theta, tausq, csr=csr, device=lrank)
     ra = gm2.mcmc(bounds, sd, **kw)
     rb = full2.mcmc(bounds, sd, **kw)
@@ -84,7 +87,7 @@ def main():
     flag = torch.tensor([1.0 if ok else 0.0], device=f"cuda:{lrank}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("PARTITION PARITY", "OK" if flag.item() == 1.0 else "FAILED", f"(gc={pl['gc']}, ranks={world})", flush=True)
+        print("PARTITION PARITY", "OK" if flag.item() == 1.0 else "FAILED", f"(gc={pl['gc']}, ranks={world}, limited_tree={limited})", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1.0 else 1)
 
