@@ -13,6 +13,7 @@
 
 #include <chrono>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; the ranges cost nothing unless a profiler is attached (ncu --nvtx, nsys)
 
 namespace st {
 
@@ -48,6 +49,13 @@ constexpr int kNcclDouble = 8, kNcclSum = 0;  // ncclFloat64, ncclSum (nccl.h)
 }  // namespace
 
 
+
+// NVTX range over a scope: the phases of an iteration show up by name in a profiler's timeline / can be selected with
+// `ncu --nvtx --nvtx-include "BUILD/"`
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 #define ST_CUDA(call, what)                                   \
   do {                                                        \
@@ -885,6 +893,7 @@ int Model::push_slot_theta(int ps) {
 
 // levels [l0, l1) of a BUILD of the slot `rel` on stream `st`; no_density: their log-density pieces are left to an LLW pass
 int Model::launch_build_levels(int rel, int l0, int l1, bool no_density, cudaStream_t st) {
+  NvtxRange nvtx(no_density ? "BUILD (upper levels, second stream)" : "BUILD");
   // ST_PROFILE_BUILD=1: per-phase clock64() totals of build_level_kernel, printed per level (development aid)
   static const bool profile = getenv("ST_PROFILE_BUILD") != nullptr;
   unsigned long long* d_prof = nullptr;
@@ -935,6 +944,7 @@ int Model::launch_build_levels(int rel, int l0, int l1, bool no_density, cudaStr
 // The deferred half of BUILD: childless non-reference blocks of the slot `rel` get their G (backward sweep over the parked
 // Z).  run_flag (device-resident chain): a device int, the launches are no-ops when it is 0.
 int Model::launch_deferred_half(int rel, const int* run_flag) {
+  NvtxRange nvtx("BUILD deferred half");
   for (auto& L : levels) {
     if (!L.deferrable) continue;
     for (const auto& B : L.build_launches) {
@@ -988,6 +998,7 @@ int Model::draw_normals(uint64_t seed) {
 }
 
 int Model::refresh_grams(const int* run_flag) {
+  NvtxRange nvtx("Gram refresh");
   if (!run_flag) { int rc = complete_slot(cur); if (rc) return rc; }
   for (int g = (int)levels.size() - 1; g >= 0; g--) {
     if (part && n_top_levels >= 1 && g == n_top_levels - 1) {  // children of this level live on several ranks
@@ -1023,6 +1034,7 @@ int Model::refresh_grams(const int* run_flag) {
 
 // the level launches of one Gibbs sweep, leaves to root; fail_ptr: device int that counts failed factorisations
 int Model::gibbs_launch_only(int* fail_ptr) {
+  NvtxRange nvtx("GIBBS");
   for (int g = (int)levels.size() - 1; g >= 0; g--) {
     const LevelInfo& L = levels[g];
     if (part && n_top_levels >= 1 && g == n_top_levels - 1) {
@@ -1121,6 +1133,7 @@ int Model::predict(bool theta_changed) {
 
 // statistics of the beta / tausq steps into d_scalars + 8 (all-reduced over the ranks); no synchronisation
 int Model::enqueue_stats() {
+  NvtxRange nvtx("tausq / beta statistics");
   ST_CUDA(launch_rowstats(dt, d_obs_widx, n_all, p, q, d_w, d_xb, d_partial, rowstat_blocks_, d_scalars + 8, stream), "rowstats_kernel");
   n_launches += 2;
   return allreduce_dev(d_scalars + 8, q * (p + 1));
@@ -1416,6 +1429,7 @@ int Model::enqueue_gibbs(uint64_t seed, bool device_chain) {
 // proposal is already in the alter slot's theta and is taken / rejected (bench hook).  tev != NULL: CUDA events after the
 // phases {start, gibbs, llw, build + accept + deferred half, Gram refresh, tausq + beta}.
 int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_mode) {
+  NvtxRange nvtx("MCMC iteration");
   cudaEvent_t* tev = timing_events_;
   int rc = 0;
   const int nlev = (int)levels.size();
