@@ -96,6 +96,8 @@ Model::~Model() {
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
   if (ev_sweep) cudaEventDestroy(ev_sweep);
+  if (ev_acc) cudaEventDestroy(ev_acc);
+  if (ev_cond) cudaEventDestroy(ev_cond);
   if (ev_llw) cudaEventDestroy(ev_llw);
   if (stream) cudaStreamDestroy(stream);
 }
@@ -597,6 +599,8 @@ int Model::upload(std::string& e) {
   }
   ST_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming), "cudaEventCreate");
   ST_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming), "cudaEventCreate");
+  ST_CUDA(cudaEventCreateWithFlags(&ev_acc, cudaEventDisableTiming), "cudaEventCreate");
+  ST_CUDA(cudaEventCreateWithFlags(&ev_cond, cudaEventDisableTiming), "cudaEventCreate");
   ST_CUDA(cudaEventCreateWithFlags(&ev_sweep, cudaEventDisableTiming), "cudaEventCreate");
   ST_CUDA(cudaEventCreateWithFlags(&ev_llw, cudaEventDisableTiming), "cudaEventCreate");
   for (auto& x : ev) ST_CUDA(cudaEventCreate(&x), "cudaEventCreate");
@@ -943,13 +947,14 @@ int Model::launch_build_levels(int rel, int l0, int l1, bool no_density, cudaStr
 
 // The deferred half of BUILD: childless non-reference blocks of the slot `rel` get their G (backward sweep over the parked
 // Z).  run_flag (device-resident chain): a device int, the launches are no-ops when it is 0.
-int Model::launch_deferred_half(int rel, const int* run_flag) {
+int Model::launch_deferred_half(int rel, const int* run_flag, cudaStream_t st) {
   NvtxRange nvtx("BUILD deferred half");
+  if (!st) st = stream;
   for (auto& L : levels) {
     if (!L.deferrable) continue;
     for (const auto& B : L.build_launches) {
       ST_CUDA(launch_build(1, dt, dslots, rel, nullptr, nullptr, 0, d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w, d_fail, B.ns, 2,
-                           B.smem, stream, B.threads, nullptr, false, run_flag),
+                           B.smem, st, B.threads, nullptr, false, run_flag),
               "build_level_kernel(deferred half)");
       n_launches++;
     }
@@ -958,7 +963,7 @@ int Model::launch_deferred_half(int rel, const int* run_flag) {
 }
 int Model::complete_slot(int pslot) {
   if (!deferred_[pslot]) return 0;
-  const int rc = launch_deferred_half(pslot == cur ? 0 : 1, nullptr);
+  const int rc = launch_deferred_half(pslot == cur ? 0 : 1, nullptr, stream);
   if (rc) return rc;
   deferred_[pslot] = false;
   return 0;
@@ -997,8 +1002,9 @@ int Model::draw_normals(uint64_t seed) {
   return 0;
 }
 
-int Model::refresh_grams(const int* run_flag) {
+int Model::refresh_grams(const int* run_flag, cudaStream_t st) {
   NvtxRange nvtx("Gram refresh");
+  if (!st || part) st = stream;  // (a partitioned handle's collective stays on the main stream)
   if (!run_flag) { int rc = complete_slot(cur); if (rc) return rc; }
   for (int g = (int)levels.size() - 1; g >= 0; g--) {
     if (part && n_top_levels >= 1 && g == n_top_levels - 1) {  // children of this level live on several ranks
@@ -1013,14 +1019,14 @@ int Model::refresh_grams(const int* run_flag) {
     if (levels[g].gram_skip) continue;  // all blocks of the level are fused into their parents
     static const bool profile = getenv("ST_PROFILE_GIBBS") != nullptr;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
-    if (profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, stream); }
+    if (profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, st); }
     ST_CUDA(launch_gram(dt, dslots, levels[g].slot0, levels[g].nslots, d_U, d_S, levels[g].gram_rch, levels[g].gram_ldx, levels[g].gram_tiles,
-                        levels[g].gram_stage_off, levels[g].gram_threads, stream, run_flag),
+                        levels[g].gram_stage_off, levels[g].gram_threads, st, run_flag),
             "gram_level_kernel");
     n_launches++;
     if (profile) {
-      cudaEventRecord(pe1, stream);
-      cudaStreamSynchronize(stream);
+      cudaEventRecord(pe1, st);
+      cudaStreamSynchronize(st);
       float pms = 0;
       cudaEventElapsedTime(&pms, pe0, pe1);
       cudaEventDestroy(pe0); cudaEventDestroy(pe1);
@@ -1441,6 +1447,7 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
   // deepest level is slower than no overlap).  Same arithmetic per block as the sequential order.
   const int n_early = n_early_levels_;
   const bool ovl = overlap && o.sample_w && o.sample_theta && n_early >= 1 && stream2 != nullptr;
+  bool cond2 = false;  // the accepted-proposal work of this iteration runs on the second stream
   if (tev) ST_CUDA(cudaEventRecord(tev[0], stream), "event");
   if (ovl) {
     ST_CUDA(cudaEventRecord(ev_fork, stream), "event");
@@ -1500,12 +1507,26 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
     if (llw2) ST_CUDA(cudaStreamWaitEvent(stream, ev_llw, 0), "join");
     ST_CUDA(launch_mh_accept(d_mc, accept_mode, o.sample_w ? 1 : 0, stream), "mh_accept_kernel");
     n_launches++;
-    // an accepted proposal: the new param_data's childless level gets its backward half, the message Grams are refreshed
-    rc = launch_deferred_half(0, &d_mc->accepted_now);
-    if (rc) return rc;
+    // An accepted proposal: the new param_data's childless level gets its backward half, the message Grams are refreshed.
+    // Neither touches w, XB or the chain's scalars: on a single-GPU handle they run on the second stream while the main
+    // stream goes on with the prediction, the tausq / beta steps and the tick, and are joined at the end of the iteration
+    // (the next sweep needs them).  On the 75 % of the iterations that reject, the ten launches exit at once on their run
+    // flag — underneath the same tail instead of in front of it.
+    cond2 = !part && stream2 != nullptr;
+    cudaStream_t cs = cond2 ? stream2 : stream;
+    if (cond2) {
+      ST_CUDA(cudaEventRecord(ev_acc, stream), "event");
+      ST_CUDA(cudaStreamWaitEvent(stream2, ev_acc, 0), "fork");
+    }
     if (tev) ST_CUDA(cudaEventRecord(tev[3], stream), "event");
-    rc = refresh_grams(&d_mc->accepted_now);
+    if (tev && cond2) ST_CUDA(cudaEventRecord(tev[10], cs), "event");
+    rc = launch_deferred_half(0, &d_mc->accepted_now, cs);
     if (rc) return rc;
+    if (tev) ST_CUDA(cudaEventRecord(cond2 ? tev[11] : tev[3], cs), "event");
+    rc = refresh_grams(&d_mc->accepted_now, cs);
+    if (rc) return rc;
+    if (tev && cond2) ST_CUDA(cudaEventRecord(tev[12], cs), "event");
+    if (cond2) ST_CUDA(cudaEventRecord(ev_cond, stream2), "event");
   } else if (tev) {
     ST_CUDA(cudaEventRecord(tev[3], stream), "event");
   }
@@ -1532,6 +1553,8 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
   ST_CUDA(launch_chain_tick(d_mc, stream), "chain_tick_kernel");
   n_launches++;
   if (tev) ST_CUDA(cudaEventRecord(tev[5], stream), "event");
+  if (cond2) ST_CUDA(cudaStreamWaitEvent(stream, ev_cond, 0), "join");
+  if (tev) ST_CUDA(cudaEventRecord(tev[13], stream), "event");
   return 0;
 }
 
@@ -1636,10 +1659,16 @@ int Model::bench_iteration(const double* theta_prop, int do_swap, uint64_t seed,
     if (ovl) ST_CUDA(cudaEventElapsedTime(&early, ev[6], ev[7]), "elapsed");
     ms_out[0] = t[0] + t[3];  // GIBBS sweep + the Gram refresh an accepted proposal triggers
     ms_out[1] = t[1];         // LLW
+    float dh = 0.f, gr = 0.f;  // single-GPU handles: deferred half and Gram refresh on the second stream, underneath the tail
+    if (!part && stream2 != nullptr) {
+      ST_CUDA(cudaEventElapsedTime(&dh, ev[10], ev[11]), "elapsed");
+      ST_CUDA(cudaEventElapsedTime(&gr, ev[11], ev[12]), "elapsed");
+    }
     if (llw_overlap && !part && stream2 != nullptr) ST_CUDA(cudaEventElapsedTime(&ms_out[1], ev[8], ev[9]), "elapsed");  // on the second stream, underneath BUILD
-    ms_out[2] = t[2];         // BUILD on the main stream + accept + the deferred half of an accepted proposal
+    ms_out[0] += gr;
+    ms_out[2] = t[2] + dh;    // BUILD on the main stream + accept + the deferred half of an accepted proposal
     ms_out[3] = t[4];         // tausq + beta
-    ST_CUDA(cudaEventElapsedTime(&ms_out[4], ev[0], ev[5]), "elapsed");  // the whole iteration on the main stream
+    ST_CUDA(cudaEventElapsedTime(&ms_out[4], ev[0], ev[13]), "elapsed");  // the whole iteration on the main stream
     // the upper levels of BUILD when they run on the second stream, underneath the sweep (elapsed there: it includes the time
     // their thread blocks wait behind the sweep's, so [0..3] + [5] exceeds [4]); 0 when the iteration is sequential
     ms_out[5] = early;

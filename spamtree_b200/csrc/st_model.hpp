@@ -187,7 +187,7 @@ class Model {
   double* h_stage = nullptr;  // pinned n_all staging buffer
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaStream_t stream2 = nullptr;   // the early levels of a proposal's BUILD run here, underneath the Gibbs sweep
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sweep = nullptr, ev_llw = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sweep = nullptr, ev_llw = nullptr, ev_acc = nullptr, ev_cond = nullptr;
   // LLW of the current slot on the second stream, underneath BUILD.  Off by default: measured on one B200 it gives 0.8 % at C4
   // and 2.3 % at C3 (the sweep of the HBM mostly displaces BUILD's own time) and makes LLW's event time meaningless;
   // ST_LLW_OVERLAP=1 enables it
@@ -199,7 +199,7 @@ class Model {
   long long* d_iperm = nullptr;     // boundary row -> node-major row
   void* save_registered = nullptr;  // host range page-locked by save_begin
   bool save_pending = false;
-  cudaEvent_t ev[10]{};
+  cudaEvent_t ev[14]{};
   std::vector<void*> owned;  // device allocations to free
   // counters
   double n_launches = 0, f_alg = 0, f_exec = 0, n_cov = 0, f_alg_build = 0, f_exec_build = 0, b_alg_build = 0;
@@ -241,7 +241,7 @@ class Model {
   int upload(std::string& e);
   int launch_build_levels(int rel, int l0, int l1, bool no_density, cudaStream_t st);
   int complete_slot(int pslot);  // the deferred half of BUILD for the slot's childless levels, if pending
-  int launch_deferred_half(int rel, const int* run_flag);
+  int launch_deferred_half(int rel, const int* run_flag, cudaStream_t st);
   int push_slot_theta(int ps);   // host-driven path: theta[ps] and its covariance table into the device chain state
   int enqueue_gibbs(uint64_t seed, bool device_chain);
   int enqueue_stats();
@@ -260,7 +260,7 @@ class Model {
   AsyncSave save_y_;
   int save_rows_async(AsyncSave& S, double* host_dst);
   bool deferred_[2] = {false, false};
-  int refresh_grams(const int* run_flag = nullptr);
+  int refresh_grams(const int* run_flag = nullptr, cudaStream_t st = nullptr);
   int gibbs_launch_only(int* fail_ptr);
   int rowstats(bool faithful_index);
   std::vector<int> isref_host_;
