@@ -155,12 +155,18 @@ def cpu_baseline_sample(workload, d, t, csr, theta, iters=1, blas=True):
                       f"1 untimed BUILD + 1 untimed iteration, then {iters} timed iteration(s) of {float(np.mean(ts)):.2f} s"}, ts
 
 
-def config_of(workload, d, t, parallelism):
-    """the `config` object both arms print (same keys, same workload)"""
+def config_of(workload, d, t, n_gpus, gc=None):
+    """the `config` object BOTH arms print, value for value: the workload and how the job of N GPUs divides it (the CPU arm
+    times the same workload on the host cores; what it ran on is in its `cpu_baseline`)"""
+    if n_gpus > 1 and gc is None:
+        from spamtree_b200 import partition as part
+        gc = part.plan(t, d["y"], n_gpus)["gc"]
+    par = "single GPU" if n_gpus == 1 else (f"{n_gpus} ranks, subtree partition below tree level {gc} (levels above replicated); NCCL all-reduce of "
+                                            "3 log-density scalars (x2), cut-level messages and beta/tausq statistics per iteration")
     return {"workload": workload, "n": int(d["y"].size), "q": int(d["q"]), "p": 3, "blocks": int(t["n_blocks"]),
             "levels": int(len(t["res_is_ref"])), "theta": "fixed parity point, 0.2% random-walk proposals, every 4th accepted",
             "l2": "working set (G, Ri of both theta slots, >3 GB at C4) is larger than the 126 MB L2; no flush needed",
-            "parallelism": parallelism}
+            "parallelism": par}
 
 
 def run_reference(args, rank, world, emit):
@@ -195,8 +201,9 @@ def run_reference(args, rank, world, emit):
     v = steps / float(np.sum(ts))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_of(args.workload, d, t, "host cores: reference algorithm (CPU oracle port, OpenMP over the blocks of a level); "
-                                "--steps iterations, fewer only if they would not fit ~2.5 minutes"),
+            "config": config_of(args.workload, d, t, args.gpus),
+            "note": "CPU arm: the reference algorithm (oracle port, OpenMP over the blocks of a level) on the host cores; --steps iterations, "
+                    "fewer only if they would not fit ~2.5 minutes",
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": int(cores), "kind": "port", "backend": backend,
                              "sample": f"{steps} timed iteration(s) after {warm} warm-up on the full {args.workload} tree, lean-state oracle"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -351,9 +358,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * elapsed_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": config_of(args.workload, d, t, "single GPU" if world == 1 else
-                                f"{world} ranks, subtree partition below tree level {pl['gc']} (levels above replicated); NCCL all-reduce of "
-                                "3 log-density scalars (x2), cut-level messages and beta/tausq statistics per iteration"),
+            "config": config_of(args.workload, d, t, world, pl["gc"] if pl else None),
             # log-density of the current slot after the warm-up iterations (fixed proposals, fixed accept pattern, random
             # numbers keyed by the row's id in the whole problem): the same number at every N up to summation order
             "parity_probe": {"after_warmup_iterations": args.warmup, "loglik_w": probe_ll, "logdetCi": probe_ld},
