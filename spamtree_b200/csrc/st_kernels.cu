@@ -483,7 +483,8 @@ cudaError_t launch_gram(const DevTree& T, const DevSlots& D, int slot0, int nslo
 // A reference block's rows of the chain factor are [G | -Ri | 0], so its contribution is one streaming product
 // |[G | -Ri] [w_pa ; w_u]|^2 over contiguous rows; the warp stages [w_pa ; w_u] in shared memory once.
 __global__ void __launch_bounds__(kLlwThreads)
-llw_kernel(DevTree T, DevSlots D, int rel, int slot0, int nslots, const double* __restrict__ w, int maxlen) {
+llw_kernel(DevTree T, DevSlots D, int rel, int slot0, int nslots, const double* __restrict__ w, int maxlen,
+           double* __restrict__ vrow, int parked) {
   extern __shared__ __align__(16) double llw_smem[];
   const DevSlot S = pick_slot(D, D.chain->cur ^ rel);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -503,7 +504,8 @@ llw_kernel(DevTree T, DevSlots D, int rel, int slot0, int nslots, const double* 
   }
   for (int j = 0; j < k; j++) {
     const int mj = __shfl_sync(0xffffffffu, a_m, j), po = __shfl_sync(0xffffffffu, a_po, j), ar0 = __shfl_sync(0xffffffffu, a_r0, j);
-    for (int t = lane; t < mj; t += 32) wx[po + t] = w[ar0 + t];
+    // (parked blocks: the vector is v = L^-1 w_pa, read off the rows of the ancestors: their s = -v, see below)
+    for (int t = lane; t < mj; t += 32) wx[po + t] = parked ? -vrow[ar0 + t] : w[ar0 + t];
   }
   const int len = ref ? P + m : P;
   if (ref)
@@ -524,8 +526,16 @@ llw_kernel(DevTree T, DevSlots D, int rel, int slot0, int nslots, const double* 
     s1 = warp_sum(s1);
     if (!ref) {
       const double* Ri = S.Ri + T.rioff[sd];
-      s0 -= Ri[r] * w[row0 + r];
-      s1 -= Ri[r + 1] * w[row0 + r + 1];
+      if (parked) {  // the row holds Z_r (unscaled): H_r w_pa = Z_r'v, e_r = w_r - H_r w_pa, prec_r = Ri_r^2
+        s0 = Ri[r] * (s0 - w[row0 + r]);
+        s1 = Ri[r + 1] * (s1 - w[row0 + r + 1]);
+      } else {
+        s0 -= Ri[r] * w[row0 + r];
+        s1 -= Ri[r + 1] * w[row0 + r + 1];
+      }
+    } else if (vrow != nullptr && lane == 0) {
+      vrow[row0 + r] = s0;  // = -(L^-1 [w_pa ; w_u])_r: what the blocks below read as their v
+      vrow[row0 + r + 1] = s1;
     }
     wc = fma(s0, s0, wc);
     wc = fma(s1, s1, wc);
@@ -535,12 +545,18 @@ llw_kernel(DevTree T, DevSlots D, int rel, int slot0, int nslots, const double* 
     double s0 = 0;
     for (int c = lane; c < len; c += 32) s0 = fma(__ldg(g0 + c), wx[c], s0);
     s0 = warp_sum(s0);
-    if (!ref) s0 -= S.Ri[T.rioff[sd] + r] * w[row0 + r];
+    if (!ref) {
+      const double ri = S.Ri[T.rioff[sd] + r];
+      s0 = parked ? ri * (s0 - w[row0 + r]) : s0 - ri * w[row0 + r];
+    } else if (vrow != nullptr && lane == 0) {
+      vrow[row0 + r] = s0;
+    }
     wc = fma(s0, s0, wc);
   }
   if (lane == 0) S.llcomp[sd] = (double)m * kHl2pi - 0.5 * wc;
 }
-cudaError_t launch_llw(const DevTree& T, const DevSlots& D, int rel, int slot0, int nslots, const double* w, int maxlen, cudaStream_t st) {
+cudaError_t launch_llw(const DevTree& T, const DevSlots& D, int rel, int slot0, int nslots, const double* w, int maxlen, cudaStream_t st,
+                       double* vrow, int parked) {
   if (nslots <= 0) return cudaSuccess;
   const int wpb = kLlwThreads / 32;
   maxlen = (maxlen + 1) & ~1;
@@ -550,7 +566,7 @@ cudaError_t launch_llw(const DevTree& T, const DevSlots& D, int rel, int slot0, 
     cudaError_t e = ensure_dynamic_smem(llw_kernel, smem, optin);
     if (e != cudaSuccess) return e;
   }
-  llw_kernel<<<(nslots + wpb - 1) / wpb, kLlwThreads, smem, st>>>(T, D, rel, slot0, nslots, w, maxlen);
+  llw_kernel<<<(nslots + wpb - 1) / wpb, kLlwThreads, smem, st>>>(T, D, rel, slot0, nslots, w, maxlen, vrow, parked);
   return cudaGetLastError();
 }
 

@@ -52,8 +52,12 @@ cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlots& D, int sl
                          double* probe_sig, double* probe_smu, int* fail, size_t smem, cudaStream_t st, bool pdl = false);
 cudaError_t launch_gram(const DevTree& T, const DevSlots& D, int slot0, int nslots, double* U, double* SigS, int rch,
                         int ldx, int tile_doubles, int stage_off, int threads, cudaStream_t st, const int* run_flag = nullptr);
-// blocks [slot0, slot0 + nslots) of the slot
-cudaError_t launch_llw(const DevTree& T, const DevSlots& D, int rel, int slot0, int nslots, const double* w, int maxlen, cudaStream_t st);
+// blocks [slot0, slot0 + nslots) of the slot.  vrow (or NULL): per row of a reference block, s_r = ([G | -Ri] [w_pa ; w_u])_r =
+// -(L^-1 w)_r is stored as well; parked = 1: the blocks are childless non-reference blocks whose storage still holds the
+// unscaled Z of the forward half of BUILD (st_build.cu) — their log-density pieces are formed from Z and the v = L^-1 w_pa read
+// off vrow (the ancestors must have been through a vrow pass)
+cudaError_t launch_llw(const DevTree& T, const DevSlots& D, int rel, int slot0, int nslots, const double* w, int maxlen, cudaStream_t st,
+                       double* vrow = nullptr, int parked = 0);
 // out8[0..2] = {sum logdet + sum llcomp, sum logdet, 0} over blocks [0, n_top) and out8[4..6] = the same over [n_top, n) with
 // out8[6] = *fail (or 0): the two parts a partitioned run needs (replicated blocks once, the rank's own all-reduced)
 // scratch: kReduceScratch doubles (partial sums + two counters that must start at zero), private to the stream

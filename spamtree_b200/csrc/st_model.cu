@@ -542,7 +542,9 @@ int Model::build_layout(std::string& e) {
   // the machine — and its per-phase event times stay attributable without it: the overlap is for the latency-dominated
   // cases, small trees (C1: +30 %, C2: +35 % end to end) and the ranks of a partition (C4 on 8 B200: +11 %)
   if (!part && n_obs_nodes > 16384) n_early_levels_ = 0;
-  if (const char* v = getenv("ST_EARLY_LEVELS")) n_early_levels_ = std::max(0, std::min(atoi(v), (int)levels.size() - 1));
+  // (ST_EARLY_LEVELS = the number of levels: the whole BUILD underneath the sweep, the childless level's log-density pieces
+  // from its parked Z; not for limited trees, whose children do not stream the rows LLW reads)
+  if (const char* v = getenv("ST_EARLY_LEVELS")) n_early_levels_ = std::max(0, std::min(atoi(v), (int)levels.size() - (limited ? 1 : 0)));
   { int rc = make_groups(pred_level, 2); if (rc) return rc; }
 
   // work counters per iteration (SURVEY §8d formulas on the actual tree)
@@ -713,6 +715,7 @@ int Model::upload(std::string& e) {
     ST_CUDA(dev_upload(key, d_rowkey, owned), "upload rowkey");
   }
   ST_CUDA(dev_zeros(d_red_scratch, 2 * kReduceScratch, owned), "alloc reduce scratch");  // one set per stream
+  ST_CUDA(dev_zeros(d_vrow, n_all, owned), "alloc vrow");
   ST_CUDA(dev_zeros(d_xtx, (long long)q * p * p, owned), "alloc xtx");
   ST_CUDA(dev_zeros(d_bscratch, (long long)q * 3 * p * p + 8 * p, owned), "alloc beta scratch");
   if (!part) {  // (partitioned handles: after the sums over the ranks, partition_reduce_constants)
@@ -1493,9 +1496,19 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
       ST_CUDA(cudaStreamWaitEvent(stream, ev_join, 0), "join");
       rc = launch_build_levels(1, n_early, nlev, false, stream);
       if (rc) return rc;
-      const int nb_early = levels[n_early].slot0;  // blocks of the levels built underneath the sweep
-      ST_CUDA(launch_llw(dt, dslots, 1, 0, nb_early, d_w, llw_maxlen_, stream), "llw_kernel(early levels of the proposal)");
+      // log-density pieces of the levels built underneath the sweep: an LLW pass over their blocks.  A childless level that
+      // was built forward-half only holds Z instead of G: its pieces come from Z and v = L^-1 w_pa, which the pass over the
+      // reference blocks above it leaves in d_vrow row by row.
+      const bool parked_last = n_early == nlev && levels[nlev - 1].deferrable;
+      const int nb_early = (n_early < nlev) ? levels[n_early].slot0 : n_obs_nodes;
+      const int nb_plain = parked_last ? levels[nlev - 1].slot0 : nb_early;
+      ST_CUDA(launch_llw(dt, dslots, 1, 0, nb_plain, d_w, llw_maxlen_, stream, parked_last ? d_vrow : nullptr, 0),
+              "llw_kernel(early levels of the proposal)");
       n_launches++;
+      if (parked_last) {
+        ST_CUDA(launch_llw(dt, dslots, 1, nb_plain, nb_early - nb_plain, d_w, llw_maxlen_, stream, d_vrow, 1), "llw_kernel(parked level)");
+        n_launches++;
+      }
     } else {
       if (accept_mode == 0) { ST_CUDA(launch_mh_propose(d_mc, stream), "mh_propose_kernel"); n_launches++; }
       ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");

@@ -171,6 +171,7 @@ class Model {
   ChainDev *d_mc = nullptr, *h_mc = nullptr;  // the chain state (st_chain.hpp) on the device and its pinned host mirror
   long long* d_rowkey = nullptr;    // node-major row -> row id in the whole problem (key of the device random streams)
   double* d_red_scratch = nullptr;  // partial sums and counters of loglik_reduce_kernel
+  double* d_vrow = nullptr;         // per row of a reference block: -(L^-1 w)_r, written by an LLW pass (see launch_llw)
   double *d_xtx = nullptr, *d_bscratch = nullptr;   // XtX per outcome; scratch of the device beta step
   double *d_theta_mcmc = nullptr, *d_beta_mcmc = nullptr, *d_tausq_mcmc = nullptr, *d_yhat = nullptr;  // sample arrays of a device-resident run
   void* graph_exec_[2] = {nullptr, nullptr};  // cudaGraphExec_t of one device-resident iteration without / with prediction

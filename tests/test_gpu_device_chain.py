@@ -75,9 +75,15 @@ def _replay(pb, bounds, sd0, keep, burn, thin, seed, faithful, adapting=True, pr
     return out
 
 
-@pytest.mark.parametrize("q,n,sd,keep,burn,thin,faithful", [(1, 625, 1e-2, 12, 45, 2, True), (2, 1200, 1e-7, 30, 30, 1, False),
-                                                            (3, 1500, 1e-7, 16, 0, 2, True)])
-def test_device_chain_equals_host_replay(q, n, sd, keep, burn, thin, faithful):
+# early: ST_EARLY_LEVELS, the number of tree levels whose BUILD runs on the second stream underneath the Gibbs sweep (None: the
+# library's choice; 0: sequential; 99: every level, the childless level's log-density pieces then come from its parked Z)
+@pytest.mark.parametrize("q,n,sd,keep,burn,thin,faithful,early", [(1, 625, 1e-2, 12, 45, 2, True, None), (2, 1200, 1e-7, 30, 30, 1, False, None),
+                                                                  (3, 1500, 1e-7, 16, 0, 2, True, None), (3, 1500, 1e-7, 16, 0, 2, True, "0"),
+                                                                  (3, 1500, 1e-7, 16, 0, 2, True, "99"), (1, 625, 1e-2, 12, 45, 2, True, "99"),
+                                                                  (2, 6000, 1e-7, 10, 10, 1, False, "99")])
+def test_device_chain_equals_host_replay(q, n, sd, keep, burn, thin, faithful, early, monkeypatch):
+    if early is not None:
+        monkeypatch.setenv("ST_EARLY_LEVELS", early)
     pb = common.make_problem(q, n)
     bounds = synth.default_bounds(q)
     npar = pb["theta"].size
