@@ -1,7 +1,9 @@
 """ctypes wrapper of the CPU oracle (oracle/spamtree_oracle.cpp).
 
 TEST INFRASTRUCTURE ONLY — imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-arm; never by the product package.  PARITY UNPINNED by the reference's own tests (it has none); see the .cpp header.
+arm; never by the product package.  The reference ships no tests of its own; the oracle is pinned against the
+reference's own sources compiled here (oracle/_ref, tests/test_oracle_vs_reference.py, tests/test_reference_driver.py): see
+the .cpp header.
 """
 import ctypes as C
 import os

@@ -15,6 +15,12 @@
 // bookkeeping bit-exact, H / Ri / Kxx_inv / log-density / Gibbs draws / predict /
 // beta / tausq to <= 1e-10 for q = 1, 2, 3, 5.  (The stand-in's dpotrf/dtrtri/dgemm
 // are plain loops, so the rounding of the reference's real BLAS is not pinned.)
+// Since round 2 the reference's DRIVER (spamtree_fit.cpp: spamtree_mv_mcmc itself), its
+// DAG builders (make_edges, make_edges_limited, part_axis_parallel_lmt) and its
+// Metropolis glue (mh_adapt.h) are part of that build as well, and
+// tests/test_reference_driver.py compares whole chains of or_mcmc with the reference
+// driver's on the shared host random stream (<= 2e-10, typically 1e-14) and the DAG
+// builders bit-exactly.
 // Further pins: analytic known-answer tests derived from the reference source
 // and man pages, and a dense numpy statement of the model's math
 // (tests/test_oracle_pinning.py, tests/dense_twin.py).
@@ -25,7 +31,8 @@
 // dgemm/dsyrk -> loops).  Every function cites the reference file:line it
 // follows (paths relative to /root/reference/).
 //
-// Build: see oracle/Makefile (g++ -O3 -march=native -fopenmp -shared).
+// Build: see oracle/Makefile (g++ -O3 -march=x86-64-v3 -fopenmp -shared; the library travels to the GPU box prebuilt, hence no
+// -march=native).  or_use_blas() optionally routes the dense kernels through the host's OpenBLAS for the timing arms.
 
 #include <algorithm>
 #include <cmath>
