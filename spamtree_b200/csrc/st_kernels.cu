@@ -126,6 +126,43 @@ gibbs_level_kernel(DevTree T, DevSlots D, int slot0, double* __restrict__ w, con
       Sig[e] = s;
       if (probe_sig) probe_sig[T.rioff[sd] + e] = s;
     }
+    // The factorisation depends on theta and tausq only — not on the children's messages — so it runs BEFORE the wait on the
+    // previous (deeper) level: with programmatic dependent launch the 25-pivot latency chains of consecutive levels overlap
+    // instead of queueing behind each other, and only the two triangular solves remain on the level-to-level chain.
+    __syncthreads();
+    bool okc = true;
+    double myinv = 0.0;  // 1 / L(lane, lane)
+    if (warp == 0) {
+      if (m <= 32) {
+        // lane i keeps row i of Sigi_tot in registers, rotated so that the pivot column is a[0]; L overwrites Sig
+        double a[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) a[j] = (lane < m && j <= lane) ? Sig[lane * m + j] : 0.0;
+        cbuf[32 + lane] = 0.0;
+        cbuf[96 + lane] = 0.0;
+        __syncwarp();
+        for (int j = 0; j < m; j++) {
+          double d = __shfl_sync(0xffffffffu, a[0], j);
+          if (!(d > 0.0) || !isfinite(d)) { okc = false; d = 1.0; }
+          const double inv = rsqrt(d), sd = d * inv;
+          const double l = (lane == j) ? sd : ((lane > j) ? a[0] * inv : 0.0);
+          if (lane == j) myinv = inv;
+          if (lane >= j && lane < m) Sig[lane * m + j] = l;
+          // pivot column to every lane through shared memory (tools/microbench/chol_bench.cu: 388 cycles per pivot,
+          // against 1422 with a shuffle per column)
+          double* cc = cbuf + (j & 1) * 64;
+          cc[lane] = l;
+          __syncwarp();
+          const double* cj = cc + j + 1;
+#pragma unroll
+          for (int i = 0; i < 31; i++) a[i] = fma(-l, cj[i], a[i + 1]);
+          a[31] = 0.0;
+        }
+        __syncwarp();
+      } else {
+        okc = warp_chol(Sig, m, m, lane);
+      }
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");  // the children's messages (V) are read from here on
     // Smu_tot = (H'prec)' w_pa + sum_children + tausq_inv (y - XB)  (:1062-1077)
     for (int a = tid; a < m; a += nth) {
@@ -141,45 +178,19 @@ gibbs_level_kernel(DevTree T, DevSlots D, int slot0, double* __restrict__ w, con
     __syncthreads();
     if (warp == 0) {
       // w = Sc'(Sc Smu + z), Sc = chol(Sigi_tot)^-1 (:1054, :1086), done as two triangular solves
-      bool okc = true;
-      if (m <= 32) {
-        // lane i keeps row i of Sigi_tot in registers, rotated so that the pivot column is a[0]; the forward solve
-        // L x = Smu rides along as an extra column; L overwrites Sig for the backward solve L' w = x + z
-        double a[32];
-#pragma unroll
-        for (int j = 0; j < 32; j++) a[j] = (lane < m && j <= lane) ? Sig[lane * m + j] : 0.0;
-        double b = (lane < m) ? smu[lane] : 0.0, myinv = 0.0;
-        cbuf[32 + lane] = 0.0;
-        cbuf[96 + lane] = 0.0;
-        __syncwarp();
-        for (int j = 0; j < m; j++) {
-          double d = __shfl_sync(0xffffffffu, a[0], j);
-          if (!(d > 0.0) || !isfinite(d)) { okc = false; d = 1.0; }
-          const double inv = rsqrt(d), sd = d * inv;
-          const double l = (lane == j) ? sd : ((lane > j) ? a[0] * inv : 0.0);
-          const double xj = __shfl_sync(0xffffffffu, b, j) * inv;
-          if (lane == j) { b = xj; myinv = inv; } else if (lane > j) b = fma(-l, xj, b);
-          if (lane >= j && lane < m) Sig[lane * m + j] = l;
-          // pivot column to every lane through shared memory (tools/microbench/chol_bench.cu: 388 cycles per pivot,
-          // against 1422 with a shuffle per column)
-          double* cc = cbuf + (j & 1) * 64;
-          cc[lane] = l;
-          __syncwarp();
-          const double* cj = cc + j + 1;
-#pragma unroll
-          for (int i = 0; i < 31; i++) a[i] = fma(-l, cj[i], a[i + 1]);
-          a[31] = 0.0;
+      if (okc && m <= 32) {
+        double b = (lane < m) ? smu[lane] : 0.0;
+        for (int j = 0; j < m; j++) {  // forward: L x = Smu
+          const double xj = __shfl_sync(0xffffffffu, b * myinv, j);
+          if (lane == j) b = xj; else if (lane > j && lane < m) b = fma(-Sig[lane * m + j], xj, b);
         }
-        __syncwarp();
-        if (okc) {
-          double y = (lane < m) ? b + rr[lane] : 0.0;  // z, prefetched above
-          for (int j = m - 1; j >= 0; j--) {
-            const double wj = __shfl_sync(0xffffffffu, y * myinv, j);
-            if (lane == j) y = wj; else if (lane < j) y = fma(-Sig[j * m + lane], wj, y);
-          }
-          if (lane < m) { wn[lane] = y; w[row0 + lane] = y; }
+        double y = (lane < m) ? b + rr[lane] : 0.0;  // z, prefetched above
+        for (int j = m - 1; j >= 0; j--) {  // backward: L' w = x + z
+          const double wj = __shfl_sync(0xffffffffu, y * myinv, j);
+          if (lane == j) y = wj; else if (lane < j) y = fma(-Sig[j * m + lane], wj, y);
         }
-      } else if (warp_chol(Sig, m, m, lane)) {
+        if (lane < m) { wn[lane] = y; w[row0 + lane] = y; }
+      } else if (okc) {
         for (int c = 0; c < m; c++) {  // forward: L x = smu
           __syncwarp();
           const double xc = smu[c] / Sig[c * m + c];
@@ -198,8 +209,6 @@ gibbs_level_kernel(DevTree T, DevSlots D, int slot0, double* __restrict__ w, con
         }
         __syncwarp();
         for (int r = lane; r < m; r += 32) { wn[r] = smu[r]; w[row0 + r] = smu[r]; }
-      } else {
-        okc = false;
       }
       if (!okc) {
         if (lane == 0) atomicAdd(fail, 1);
