@@ -311,6 +311,9 @@ __global__ void __launch_bounds__(kGramThreads)
 gram_level_kernel(DevTree T, DevSlots D, int slot0, double* __restrict__ U, double* __restrict__ SigS, int rch, int ldx,
                   int stage_off, const int* __restrict__ run_flag) {
   extern __shared__ __align__(16) double gram_smem[];
+  // programmatic dependent launch: the next (shallower) level stages its rows and forms its own G'G while this one runs;
+  // it waits below, right before it adds the tiles this level stores
+  asm volatile("griddepcontrol.launch_dependents;");
   if (run_flag != nullptr && *run_flag == 0) return;  // device-resident chain: only after an accepted proposal
   const DevSlot S = pick_slot(D, D.chain->cur);       // param_data
   __shared__ int t_po[kMaxChain + 1], t_m[kMaxChain + 1], t_item0[kMaxChain + 2], t_uo[kMaxChain + 1], t_to[kMaxChain + 2];
@@ -454,6 +457,7 @@ gram_level_kernel(DevTree T, DevSlots D, int slot0, double* __restrict__ U, doub
     }
   }
   __syncthreads();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // add the stored tiles of the children that keep theirs, write out (coalesced)
   for (int eg = tid; eg < t_to[ntile]; eg += nth) {
     int j = 0;
@@ -475,7 +479,7 @@ gram_level_kernel(DevTree T, DevSlots D, int slot0, double* __restrict__ U, doub
   }
 }
 cudaError_t launch_gram(const DevTree& T, const DevSlots& D, int slot0, int nslots, double* U, double* SigS, int rch,
-                        int ldx, int tile_doubles, int stage_off, int threads, cudaStream_t st, const int* run_flag) {
+                        int ldx, int tile_doubles, int stage_off, int threads, cudaStream_t st, const int* run_flag, bool pdl) {
   if (nslots <= 0) return cudaSuccess;
   const size_t smem = std::max((size_t)tile_doubles, (size_t)stage_off + (size_t)rch * ldx) * sizeof(double);
   static SmemOptIn optin;
@@ -483,8 +487,17 @@ cudaError_t launch_gram(const DevTree& T, const DevSlots& D, int slot0, int nslo
     cudaError_t e = ensure_dynamic_smem(gram_level_kernel, smem, optin);
     if (e != cudaSuccess) return e;
   }
-  gram_level_kernel<<<nslots, threads, smem, st>>>(T, D, slot0, U, SigS, rch, ldx, stage_off, run_flag);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nslots);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, gram_level_kernel, T, D, slot0, U, SigS, rch, ldx, stage_off, run_flag);
 }
 
 // ------------------------------------------------------------------------------------------------ LLW
@@ -836,8 +849,9 @@ cudaError_t launch_crosscov(const double* x1, const double* y1, const int* q1, l
 
 // U ~ N(0, I), theta' = back(fwd(theta) + paramsd U) clipped (spamtree_fit.cpp:211-215) -> theta and covariance table of the
 // alter slot
-__global__ void mh_propose_kernel(ChainDev* C) {
+__global__ void mh_propose_kernel(ChainDev* C, int* zero) {
   const int npar = C->npar, cur = C->cur, alt = cur ^ 1;
+  if (zero && threadIdx.x == 32) *zero = 0;  // the failure counter of the BUILD that follows (saves a memset node on its chain)
   for (int j = threadIdx.x; j < npar; j += blockDim.x) C->U[j] = philox_normal(C->seed, kStreamU + j, (uint64_t)C->iter);
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -845,8 +859,8 @@ __global__ void mh_propose_kernel(ChainDev* C) {
     make_covtab_hd(C->theta[alt], npar, C->q, C->tab[alt]);
   }
 }
-cudaError_t launch_mh_propose(ChainDev* C, cudaStream_t st) {
-  mh_propose_kernel<<<1, 64, 0, st>>>(C);
+cudaError_t launch_mh_propose(ChainDev* C, cudaStream_t st, int* zero) {
+  mh_propose_kernel<<<1, 64, 0, st>>>(C, zero);
   return cudaGetLastError();
 }
 

@@ -51,7 +51,8 @@ cudaError_t launch_gibbs(int is_ref, const DevTree& T, const DevSlots& D, int sl
                          const double* xb, const double* z, const double* tausq_inv, const double* SigS, double* V,
                          double* probe_sig, double* probe_smu, int* fail, size_t smem, cudaStream_t st, bool pdl = false);
 cudaError_t launch_gram(const DevTree& T, const DevSlots& D, int slot0, int nslots, double* U, double* SigS, int rch,
-                        int ldx, int tile_doubles, int stage_off, int threads, cudaStream_t st, const int* run_flag = nullptr);
+                        int ldx, int tile_doubles, int stage_off, int threads, cudaStream_t st, const int* run_flag = nullptr,
+                        bool pdl = false);  // pdl: only after another gram launch (the kernel waits before it reads the children's tiles only)
 // blocks [slot0, slot0 + nslots) of the slot.  vrow (or NULL): per row of a reference block, s_r = ([G | -Ri] [w_pa ; w_u])_r =
 // -(L^-1 w)_r is stored as well; parked = 1: the blocks are childless non-reference blocks whose storage still holds the
 // unscaled Z of the forward half of BUILD (st_build.cu) — their log-density pieces are formed from Z and the v = L^-1 w_pa read
@@ -81,7 +82,7 @@ cudaError_t launch_crosscov(const double* x1, const double* y1, const int* q1, l
                             cudaStream_t st);
 // ---- the device-resident chain (st_chain.hpp): one tiny kernel per step of spamtree_fit.cpp:203-289 / :376-389
 // proposal: U ~ N(0, I) (Philox), theta' = back(fwd(theta) + paramsd U) into the alter slot's theta, its covariance table
-cudaError_t launch_mh_propose(ChainDev* C, cudaStream_t st);
+cudaError_t launch_mh_propose(ChainDev* C, cudaStream_t st, int* zero = nullptr);  // zero: an int the kernel clears (BUILD failure counter)
 // accept step.  mode 0: Metropolis rule (Jacobian, uniform draw, RAM adaptation); 1: take the proposal if BUILD succeeded;
 // 2: reject (1 / 2: bench hooks).  have_llw: red_llw holds the log-density of the current slot at the new w.
 cudaError_t launch_mh_accept(ChainDev* C, int mode, int have_llw, cudaStream_t st);

@@ -98,6 +98,7 @@ Model::~Model() {
   if (ev_sweep) cudaEventDestroy(ev_sweep);
   if (ev_acc) cudaEventDestroy(ev_acc);
   if (ev_cond) cudaEventDestroy(ev_cond);
+  if (ev_early_llw) cudaEventDestroy(ev_early_llw);
   if (ev_llw) cudaEventDestroy(ev_llw);
   if (stream) cudaStreamDestroy(stream);
 }
@@ -603,6 +604,7 @@ int Model::upload(std::string& e) {
   ST_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming), "cudaEventCreate");
   ST_CUDA(cudaEventCreateWithFlags(&ev_acc, cudaEventDisableTiming), "cudaEventCreate");
   ST_CUDA(cudaEventCreateWithFlags(&ev_cond, cudaEventDisableTiming), "cudaEventCreate");
+  ST_CUDA(cudaEventCreateWithFlags(&ev_early_llw, cudaEventDisableTiming), "cudaEventCreate");
   ST_CUDA(cudaEventCreateWithFlags(&ev_sweep, cudaEventDisableTiming), "cudaEventCreate");
   ST_CUDA(cudaEventCreateWithFlags(&ev_llw, cudaEventDisableTiming), "cudaEventCreate");
   for (auto& x : ev) ST_CUDA(cudaEventCreate(&x), "cudaEventCreate");
@@ -1009,6 +1011,7 @@ int Model::refresh_grams(const int* run_flag, cudaStream_t st) {
   NvtxRange nvtx("Gram refresh");
   if (!st || part) st = stream;  // (a partitioned handle's collective stays on the main stream)
   if (!run_flag) { int rc = complete_slot(cur); if (rc) return rc; }
+  bool chained = false;  // the previous launch on the stream is a gram level: programmatic dependent launch is safe
   for (int g = (int)levels.size() - 1; g >= 0; g--) {
     if (part && n_top_levels >= 1 && g == n_top_levels - 1) {  // children of this level live on several ranks
       // (unconditional also in the device-resident chain: every rank must enter the collective, and summing the unchanged
@@ -1018,14 +1021,16 @@ int Model::refresh_grams(const int* run_flag, cudaStream_t st) {
       n_launches++;
       int rc = allreduce_dev(d_U + u_front0, u_front_len);
       if (rc) return rc;
+      chained = false;
     }
     if (levels[g].gram_skip) continue;  // all blocks of the level are fused into their parents
     static const bool profile = getenv("ST_PROFILE_GIBBS") != nullptr;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (profile) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, st); }
     ST_CUDA(launch_gram(dt, dslots, levels[g].slot0, levels[g].nslots, d_U, d_S, levels[g].gram_rch, levels[g].gram_ldx, levels[g].gram_tiles,
-                        levels[g].gram_stage_off, levels[g].gram_threads, st, run_flag),
+                        levels[g].gram_stage_off, levels[g].gram_threads, st, run_flag, use_pdl && !profile && chained),
             "gram_level_kernel");
+    chained = true;
     n_launches++;
     if (profile) {
       cudaEventRecord(pe1, st);
@@ -1456,8 +1461,8 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
     ST_CUDA(cudaEventRecord(ev_fork, stream), "event");
     ST_CUDA(cudaStreamWaitEvent(stream2, ev_fork, 0), "fork");
     if (tev) ST_CUDA(cudaEventRecord(tev[6], stream2), "event");
-    if (accept_mode == 0) { ST_CUDA(launch_mh_propose(d_mc, stream2), "mh_propose_kernel"); n_launches++; }
-    ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream2), "memset");
+    if (accept_mode == 0) { ST_CUDA(launch_mh_propose(d_mc, stream2, d_fail), "mh_propose_kernel"); n_launches++; }
+    else ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream2), "memset");
     rc = launch_build_levels(1, 0, n_early, true, stream2);
     if (rc) return rc;
     if (tev) ST_CUDA(cudaEventRecord(tev[7], stream2), "event");
@@ -1471,8 +1476,26 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
     rc = enqueue_gibbs(o.seed, true);
     if (rc) return rc;
     if (tev) ST_CUDA(cudaEventRecord(tev[1], stream), "event");
+    if (llw2 || ovl) ST_CUDA(cudaEventRecord(ev_sweep, stream), "event");
+    if (ovl && o.sample_theta) {
+      // log-density pieces of the levels built underneath the sweep: an LLW pass over their blocks with the new w, on the
+      // second stream as well — it runs next to the BUILD of the big levels on the main stream and is joined before the
+      // reduction.  A childless level that was built forward-half only holds Z instead of G: its pieces come from Z and
+      // v = L^-1 w_pa, which the pass over the reference blocks above it leaves in d_vrow row by row.
+      ST_CUDA(cudaStreamWaitEvent(stream2, ev_sweep, 0), "fork");
+      const bool parked_last = n_early == nlev && levels[nlev - 1].deferrable;
+      const int nb_early = (n_early < nlev) ? levels[n_early].slot0 : n_obs_nodes;
+      const int nb_plain = parked_last ? levels[nlev - 1].slot0 : nb_early;
+      ST_CUDA(launch_llw(dt, dslots, 1, 0, nb_plain, d_w, llw_maxlen_, stream2, parked_last ? d_vrow : nullptr, 0),
+              "llw_kernel(early levels of the proposal)");
+      n_launches++;
+      if (parked_last) {
+        ST_CUDA(launch_llw(dt, dslots, 1, nb_plain, nb_early - nb_plain, d_w, llw_maxlen_, stream2, d_vrow, 1), "llw_kernel(parked level)");
+        n_launches++;
+      }
+      ST_CUDA(cudaEventRecord(ev_early_llw, stream2), "event");
+    }
     if (llw2) {
-      ST_CUDA(cudaEventRecord(ev_sweep, stream), "event");
       ST_CUDA(cudaStreamWaitEvent(stream2, ev_sweep, 0), "fork");
       if (tev) ST_CUDA(cudaEventRecord(tev[8], stream2), "event");
       ST_CUDA(launch_llw(dt, dslots, 0, 0, n_obs_nodes, d_w, llw_maxlen_, stream2), "llw_kernel");
@@ -1496,22 +1519,10 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
       ST_CUDA(cudaStreamWaitEvent(stream, ev_join, 0), "join");
       rc = launch_build_levels(1, n_early, nlev, false, stream);
       if (rc) return rc;
-      // log-density pieces of the levels built underneath the sweep: an LLW pass over their blocks.  A childless level that
-      // was built forward-half only holds Z instead of G: its pieces come from Z and v = L^-1 w_pa, which the pass over the
-      // reference blocks above it leaves in d_vrow row by row.
-      const bool parked_last = n_early == nlev && levels[nlev - 1].deferrable;
-      const int nb_early = (n_early < nlev) ? levels[n_early].slot0 : n_obs_nodes;
-      const int nb_plain = parked_last ? levels[nlev - 1].slot0 : nb_early;
-      ST_CUDA(launch_llw(dt, dslots, 1, 0, nb_plain, d_w, llw_maxlen_, stream, parked_last ? d_vrow : nullptr, 0),
-              "llw_kernel(early levels of the proposal)");
-      n_launches++;
-      if (parked_last) {
-        ST_CUDA(launch_llw(dt, dslots, 1, nb_plain, nb_early - nb_plain, d_w, llw_maxlen_, stream, d_vrow, 1), "llw_kernel(parked level)");
-        n_launches++;
-      }
+      ST_CUDA(cudaStreamWaitEvent(stream, ev_early_llw, 0), "join");  // the early levels' log-density pieces (second stream, above)
     } else {
-      if (accept_mode == 0) { ST_CUDA(launch_mh_propose(d_mc, stream), "mh_propose_kernel"); n_launches++; }
-      ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
+      if (accept_mode == 0) { ST_CUDA(launch_mh_propose(d_mc, stream, d_fail), "mh_propose_kernel"); n_launches++; }
+      else ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
       rc = launch_build_levels(1, 0, nlev, false, stream);
       if (rc) return rc;
     }

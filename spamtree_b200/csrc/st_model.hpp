@@ -188,7 +188,8 @@ class Model {
   double* h_stage = nullptr;  // pinned n_all staging buffer
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaStream_t stream2 = nullptr;   // the early levels of a proposal's BUILD run here, underneath the Gibbs sweep
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sweep = nullptr, ev_llw = nullptr, ev_acc = nullptr, ev_cond = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sweep = nullptr, ev_llw = nullptr, ev_acc = nullptr, ev_cond = nullptr,
+              ev_early_llw = nullptr;
   // LLW of the current slot on the second stream, underneath BUILD.  Off by default: measured on one B200 it gives 0.8 % at C4
   // and 2.3 % at C3 (the sweep of the HBM mostly displaces BUILD's own time) and makes LLW's event time meaningless;
   // ST_LLW_OVERLAP=1 enables it
