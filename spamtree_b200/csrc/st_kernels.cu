@@ -597,7 +597,7 @@ cudaError_t launch_llw(const DevTree& T, const DevSlots& D, int rel, int slot0, 
 // out[.] = {sum(logdet) + sum(llcomp), sum(logdet), 0 / *fail}.  kRedBlocks CTAs per part sum fixed chunks, the last CTA to
 // finish adds the partial sums in chunk order: the summation order is fixed, the result deterministic run to run.
 constexpr int kRedBlocks = 32;
-__global__ void __launch_bounds__(256) loglik_reduce_kernel(DevSlots D, int rel, int n_top, int n, const int* __restrict__ fail,
+__global__ void __launch_bounds__(256) loglik_reduce_kernel(DevSlots D, int rel, int n_top, int n, int* __restrict__ fail,
                                                             double* __restrict__ out, double* __restrict__ partial,
                                                             unsigned int* __restrict__ counter) {
   __shared__ double sa[256], sb[256];
@@ -629,11 +629,12 @@ __global__ void __launch_bounds__(256) loglik_reduce_kernel(DevSlots D, int rel,
     double* o = out + 4 * part;
     o[0] = ta + tb;
     o[1] = ta;
-    o[2] = (part && fail) ? (double)*fail : 0.0;
+    o[2] = 0.0;
+    if (part && fail) { o[2] = (double)*fail; *fail = 0; }  // consumed and cleared: the counter is zero between BUILDs
     counter[part] = 0;  // ready for the next launch
   }
 }
-cudaError_t launch_loglik_reduce(const DevSlots& D, int rel, int n_top, int n, const int* fail, double* out8, double* scratch,
+cudaError_t launch_loglik_reduce(const DevSlots& D, int rel, int n_top, int n, int* fail, double* out8, double* scratch,
                                  cudaStream_t st) {
   // scratch: 4 * kRedBlocks doubles of partial sums followed by two zero-initialised 32-bit counters
   loglik_reduce_kernel<<<dim3(kRedBlocks, 2), 256, 0, st>>>(D, rel, n_top, n, fail, out8, scratch,
@@ -849,57 +850,79 @@ cudaError_t launch_crosscov(const double* x1, const double* y1, const int* q1, l
 
 // U ~ N(0, I), theta' = back(fwd(theta) + paramsd U) clipped (spamtree_fit.cpp:211-215) -> theta and covariance table of the
 // alter slot
-__global__ void mh_propose_kernel(ChainDev* C, int* zero) {
+// iter_offset = 1: the proposal of the NEXT iteration, drawn right after this iteration's accept step (before the tick)
+__global__ void mh_propose_kernel(ChainDev* C, int iter_offset) {
   const int npar = C->npar, cur = C->cur, alt = cur ^ 1;
-  if (zero && threadIdx.x == 32) *zero = 0;  // the failure counter of the BUILD that follows (saves a memset node on its chain)
-  for (int j = threadIdx.x; j < npar; j += blockDim.x) C->U[j] = philox_normal(C->seed, kStreamU + j, (uint64_t)C->iter);
+  for (int j = threadIdx.x; j < npar; j += blockDim.x) C->U[j] = philox_normal(C->seed, kStreamU + j, (uint64_t)(C->iter + iter_offset));
   __syncthreads();
   if (threadIdx.x == 0) {
     mh_propose(npar, C->theta[cur], C->bounds, C->paramsd, C->U, C->theta[alt]);
     make_covtab_hd(C->theta[alt], npar, C->q, C->tab[alt]);
   }
 }
-cudaError_t launch_mh_propose(ChainDev* C, cudaStream_t st, int* zero) {
-  mh_propose_kernel<<<1, 64, 0, st>>>(C, zero);
+cudaError_t launch_mh_propose(ChainDev* C, cudaStream_t st, int iter_offset) {
+  mh_propose_kernel<<<1, 64, 0, st>>>(C, iter_offset);
   return cudaGetLastError();
 }
 
 // spamtree_fit.cpp:223-285: log-densities from the two reductions, Jacobian, accept decision, slot swap, RAM adaptation
-__global__ void mh_accept_kernel(ChainDev* C, int mode, int have_llw) {
-  if (threadIdx.x != 0) return;
-  const int npar = C->npar, cur = C->cur, alt = cur ^ 1, m = C->iter;
-  if (have_llw) { C->loglik[cur] = C->red_llw[0] + C->red_llw[4]; C->logdet[cur] = C->red_llw[1] + C->red_llw[5]; }
-  const bool acceptable = C->red_build[6] == 0.0;
-  if (acceptable) {  // on failure the reference leaves the alter slot's log-density untouched (:971-982)
-    C->loglik[alt] = C->red_build[0] + C->red_build[4];
-    C->logdet[alt] = C->red_build[1] + C->red_build[5];
-  } else {
-    C->n_chol_fail++;
+// stage = 1: the adaptation's matrices (paramsd, prodparam, 2 npar^2 of scratch, U) are staged in shared memory — one thread
+// runs a chain of dependent read-modify-writes over them, which in global memory is a chain of L2 round trips
+__global__ void mh_accept_kernel(ChainDev* C, int mode, int have_llw, int stage) {
+  extern __shared__ double acc_smem[];
+  const int npar = C->npar, n2 = npar * npar;
+  const bool adapt = mode == 0 && C->adapting;
+  double *sp = C->paramsd, *pp = C->prodparam, *sc = C->scratch;
+  const double* su = C->U;
+  if (stage && adapt) {
+    sp = acc_smem; pp = sp + n2; sc = pp + n2;
+    double* u = sc + 2 * n2;
+    for (int e = threadIdx.x; e < n2; e += blockDim.x) { sp[e] = C->paramsd[e]; pp[e] = C->prodparam[e]; }
+    for (int e = threadIdx.x; e < npar; e += blockDim.x) u[e] = C->U[e];
+    su = u;
+    __syncthreads();
   }
-  const double new_loglik = C->loglik[alt], current_loglik = C->loglik[cur];
-  if (isnan(current_loglik)) C->nan_loglik = 1;  // spamtree_fit.cpp:234-237
-  bool accepted;
-  double logaccept = 0.0;
-  if (mode == 0) {
-    logaccept = new_loglik - current_loglik + mh_jacobian(npar, C->theta[alt], C->theta[cur], C->bounds);
-    const double u = philox_uniform(C->seed, kStreamAccept, (uint64_t)m);
-    C->last_logaccept = logaccept; C->last_u = u;
-    accepted = (u < mh_accept_prob(logaccept)) && acceptable;
-  } else {
-    accepted = (mode == 1) && acceptable;
+  if (threadIdx.x == 0) {
+    const int cur = C->cur, alt = cur ^ 1, m = C->iter;
+    if (have_llw) { C->loglik[cur] = C->red_llw[0] + C->red_llw[4]; C->logdet[cur] = C->red_llw[1] + C->red_llw[5]; }
+    const bool acceptable = C->red_build[6] == 0.0;
+    if (acceptable) {  // on failure the reference leaves the alter slot's log-density untouched (:971-982)
+      C->loglik[alt] = C->red_build[0] + C->red_build[4];
+      C->logdet[alt] = C->red_build[1] + C->red_build[5];
+    } else {
+      C->n_chol_fail++;
+    }
+    const double new_loglik = C->loglik[alt], current_loglik = C->loglik[cur];
+    if (isnan(current_loglik)) C->nan_loglik = 1;  // spamtree_fit.cpp:234-237
+    bool accepted;
+    double logaccept = 0.0;
+    if (mode == 0) {
+      logaccept = new_loglik - current_loglik + mh_jacobian(npar, C->theta[alt], C->theta[cur], C->bounds);
+      const double u = philox_uniform(C->seed, kStreamAccept, (uint64_t)m);
+      C->last_logaccept = logaccept; C->last_u = u;
+      accepted = (u < mh_accept_prob(logaccept)) && acceptable;
+    } else {
+      accepted = (mode == 1) && acceptable;
+    }
+    if (accepted) {
+      C->n_accepted++;
+      C->cur = alt;  // accept_make_change (:1432-1435): the kernels that follow read the new slot
+      C->pred_valid = 0;
+    }
+    C->accepted_now = accepted ? 1 : 0;
+    if (adapt)  // :285 (a failed chol(S) keeps the previous factor and is counted)
+      if (!ram_adapt(npar, sp, pp, &C->ram_started, su, (acceptable ? 1.0 : 0.0) * exp(logaccept), m, sc))
+        C->n_ram_fail++;
   }
-  if (accepted) {
-    C->n_accepted++;
-    C->cur = alt;  // accept_make_change (:1432-1435): the kernels that follow read the new slot
-    C->pred_valid = 0;
+  if (stage && adapt) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < n2; e += blockDim.x) { C->paramsd[e] = sp[e]; C->prodparam[e] = pp[e]; }
   }
-  C->accepted_now = accepted ? 1 : 0;
-  if (mode == 0 && C->adapting)  // :285 (a failed chol(S) keeps the previous factor and is counted)
-    if (!ram_adapt(npar, C->paramsd, C->prodparam, &C->ram_started, C->U, (acceptable ? 1.0 : 0.0) * exp(logaccept), m, C->scratch))
-      C->n_ram_fail++;
 }
-cudaError_t launch_mh_accept(ChainDev* C, int mode, int have_llw, cudaStream_t st) {
-  mh_accept_kernel<<<1, 32, 0, st>>>(C, mode, have_llw);
+cudaError_t launch_mh_accept(ChainDev* C, int mode, int have_llw, cudaStream_t st, int npar) {
+  const size_t smem = ((size_t)4 * npar * npar + npar) * sizeof(double);
+  const int stage = npar > 0 && smem <= 40 * 1024;
+  mh_accept_kernel<<<1, 64, stage ? smem : 0, st>>>(C, mode, have_llw, stage);
   return cudaGetLastError();
 }
 
@@ -937,7 +960,9 @@ __device__ inline double philox_gamma(uint64_t seed, unsigned long long key, uin
 // stats[j*(p+1) + a] = X_j'(y - w)_a, stats[j*(p+1) + p] = |y - XB - w|^2 over the outcome's observed rows (rowstats_kernel)
 __global__ void tausq_beta_kernel(ChainDev* C, const double* __restrict__ stats, const double* __restrict__ xtx,
                                   double* __restrict__ tausq_inv, double* __restrict__ bcoeff, double* __restrict__ scratch,
-                                  int sample_tausq, int sample_beta) {
+                                  int sample_tausq, int sample_beta, int stage) {
+  extern __shared__ double tb_smem[];  // stage = 1: the p x p work arrays of every outcome (else `scratch` in global memory)
+  if (stage) scratch = tb_smem;
   const int j = threadIdx.x, p = C->p, q = C->q;
   if (j >= q) return;
   const uint64_t it = (uint64_t)C->iter;
@@ -947,9 +972,9 @@ __global__ void tausq_beta_kernel(ChainDev* C, const double* __restrict__ stats,
   }
   if (sample_beta) {
     const double tq = tausq_inv[j];
-    double* Si = scratch + (size_t)j * 3 * p * p;  // precision -> its Cholesky factor (column-major)
-    double* Sc = Si + p * p;                       // inverse of the factor
-    double* v = Sc + p * p;                        // xp | t | bmu | sz
+    double* Si = scratch + (size_t)j * (2 * p * p + 4 * p);  // precision -> its Cholesky factor (column-major)
+    double* Sc = Si + p * p;                                 // inverse of the factor
+    double* v = Sc + p * p;                                  // xp | t | bmu | sz: 4 p doubles of the outcome's own
     for (int a = 0; a < p; a++)
       for (int b = 0; b < p; b++) Si[a + b * p] = tq * xtx[(size_t)j * p * p + (b <= a ? b + a * p : a + b * p)] + (a == b ? .01 : 0.0);  // symmatu; Vi = .01 I (:157)
     if (!mh_chol_lower(Si, p)) { C->gibbs_fail = 1; return; }
@@ -975,8 +1000,10 @@ __global__ void tausq_beta_kernel(ChainDev* C, const double* __restrict__ stats,
   }
 }
 cudaError_t launch_tausq_beta(ChainDev* C, const double* stats, const double* xtx, double* tausq_inv, double* bcoeff,
-                              double* scratch, int sample_tausq, int sample_beta, cudaStream_t st) {
-  tausq_beta_kernel<<<1, 32, 0, st>>>(C, stats, xtx, tausq_inv, bcoeff, scratch, sample_tausq, sample_beta);
+                              double* scratch, int sample_tausq, int sample_beta, cudaStream_t st, int p, int q) {
+  const size_t smem = (size_t)q * (2 * p * p + 4 * p) * sizeof(double);  // the layout of `scratch`
+  const int stage = p > 0 && smem <= 40 * 1024;
+  tausq_beta_kernel<<<1, 32, stage ? smem : 0, st>>>(C, stats, xtx, tausq_inv, bcoeff, scratch, sample_tausq, sample_beta, stage);
   return cudaGetLastError();
 }
 

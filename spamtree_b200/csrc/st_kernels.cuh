@@ -63,7 +63,7 @@ cudaError_t launch_llw(const DevTree& T, const DevSlots& D, int rel, int slot0, 
 // out8[6] = *fail (or 0): the two parts a partitioned run needs (replicated blocks once, the rank's own all-reduced)
 // scratch: kReduceScratch doubles (partial sums + two counters that must start at zero), private to the stream
 constexpr int kReduceScratch = 4 * 32 + 2;
-cudaError_t launch_loglik_reduce(const DevSlots& D, int rel, int n_top, int n, const int* fail, double* out8, double* scratch,
+cudaError_t launch_loglik_reduce(const DevSlots& D, int rel, int n_top, int n, int* fail, double* out8, double* scratch,
                                  cudaStream_t st);
 cudaError_t launch_frontier_sum(const DevTree& T, int n, const int* pseudo, const int* c0, const int* c1, const int* vlen,
                                 const int* ulen, double* V, double* U, int do_v, int do_u, cudaStream_t st);
@@ -82,16 +82,16 @@ cudaError_t launch_crosscov(const double* x1, const double* y1, const int* q1, l
                             cudaStream_t st);
 // ---- the device-resident chain (st_chain.hpp): one tiny kernel per step of spamtree_fit.cpp:203-289 / :376-389
 // proposal: U ~ N(0, I) (Philox), theta' = back(fwd(theta) + paramsd U) into the alter slot's theta, its covariance table
-cudaError_t launch_mh_propose(ChainDev* C, cudaStream_t st, int* zero = nullptr);  // zero: an int the kernel clears (BUILD failure counter)
+cudaError_t launch_mh_propose(ChainDev* C, cudaStream_t st, int iter_offset = 0);  // 1: the next iteration's proposal (after accept, before the tick)
 // accept step.  mode 0: Metropolis rule (Jacobian, uniform draw, RAM adaptation); 1: take the proposal if BUILD succeeded;
 // 2: reject (1 / 2: bench hooks).  have_llw: red_llw holds the log-density of the current slot at the new w.
-cudaError_t launch_mh_accept(ChainDev* C, int mode, int have_llw, cudaStream_t st);
+cudaError_t launch_mh_accept(ChainDev* C, int mode, int have_llw, cudaStream_t st, int npar = 0);  // npar: stages the adaptation in shared memory
 // need_update of spamtree_fit.cpp:300 -> C->predict_build; predict_param <- theta
 cudaError_t launch_predict_gate(ChainDev* C, cudaStream_t st);
 // gibbs_sample_tausq (:1393-1417) then gibbs_sample_beta (:1364-1391) from the statistics of rowstats_kernel, random
 // numbers from Philox; scratch: q * 3 * p * p doubles
 cudaError_t launch_tausq_beta(ChainDev* C, const double* stats, const double* xtx, double* tausq_inv, double* bcoeff,
-                              double* scratch, int sample_tausq, int sample_beta, cudaStream_t st);
+                              double* scratch, int sample_tausq, int sample_beta, cudaStream_t st, int p = 0, int q = 0);
 // the saved iteration's theta / beta / tausq into the device sample arrays (layouts of st_mcmc_out), then C->msaved++
 cudaError_t launch_record(ChainDev* C, const double* tausq_inv, const double* bcoeff, double* theta_mcmc, double* beta_mcmc,
                           double* tausq_mcmc, int keep, cudaStream_t st);

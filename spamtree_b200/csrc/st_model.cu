@@ -93,6 +93,8 @@ Model::~Model() {
   if (ev_wcopied) cudaEventDestroy(ev_wcopied);
   if (copy_stream) cudaStreamDestroy(copy_stream);
   if (stream2) cudaStreamDestroy(stream2);
+  if (stream3) cudaStreamDestroy(stream3);
+  if (ev_prop) cudaEventDestroy(ev_prop);
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
   if (ev_sweep) cudaEventDestroy(ev_sweep);
@@ -599,7 +601,9 @@ int Model::upload(std::string& e) {
     ST_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi), "cudaDeviceGetStreamPriorityRange");
     ST_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, hi), "cudaStreamCreate");
     ST_CUDA(cudaStreamCreateWithPriority(&stream2, cudaStreamNonBlocking, lo), "cudaStreamCreate");
+    ST_CUDA(cudaStreamCreateWithPriority(&stream3, cudaStreamNonBlocking, lo), "cudaStreamCreate");
   }
+  ST_CUDA(cudaEventCreateWithFlags(&ev_prop, cudaEventDisableTiming), "cudaEventCreate");
   ST_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming), "cudaEventCreate");
   ST_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming), "cudaEventCreate");
   ST_CUDA(cudaEventCreateWithFlags(&ev_acc, cudaEventDisableTiming), "cudaEventCreate");
@@ -689,7 +693,7 @@ int Model::upload(std::string& e) {
   ST_CUDA(dev_upload(Bcoeff, d_bcoeff, owned), "upload beta");
   ST_CUDA(dev_upload(tausq_inv, d_tausq_inv, owned), "upload tausq");
   {
-    std::vector<int> z1(1, 0);
+    std::vector<int> z1(4, 0);  // [0] BUILD / Gibbs failures (consumed and cleared by the reduction), [1] prediction BUILD
     ST_CUDA(dev_upload(z1, d_fail, owned), "alloc fail");
   }
   ST_CUDA(cudaMallocHost((void**)&h_scalars, (64 + kMaxStats + 1024) * sizeof(double)), "pinned scalars");
@@ -719,7 +723,7 @@ int Model::upload(std::string& e) {
   ST_CUDA(dev_zeros(d_red_scratch, 2 * kReduceScratch, owned), "alloc reduce scratch");  // one set per stream
   ST_CUDA(dev_zeros(d_vrow, n_all, owned), "alloc vrow");
   ST_CUDA(dev_zeros(d_xtx, (long long)q * p * p, owned), "alloc xtx");
-  ST_CUDA(dev_zeros(d_bscratch, (long long)q * 3 * p * p + 8 * p, owned), "alloc beta scratch");
+  ST_CUDA(dev_zeros(d_bscratch, (long long)q * (3 * p * p + 4 * p) + 8, owned), "alloc beta scratch");  // tausq_beta_kernel's layout
   if (!part) {  // (partitioned handles: after the sums over the ranks, partition_reduce_constants)
     const int rcx = upload_xtx();
     if (rcx) return rcx;
@@ -870,7 +874,7 @@ int Model::allreduce_dev(double* dptr, int64_t n) {
 // sum of the per-block log-density pieces (:987-988 / :815-816) of the slot `rel` into dev_red8 (device): [0..2] the
 // replicated blocks (or nothing), [4..6] the rest, all-reduced over the ranks of a partition; [6] = failed factorisations.
 // out3_host (host-driven path) = {loglik_w, logdetCi, failures}: one D2H + synchronisation.
-int Model::reduce_loglik(int rel, const int* fail, double* dev_red8, double* out3_host) {
+int Model::reduce_loglik(int rel, int* fail, double* dev_red8, double* out3_host) {
   ST_CUDA(launch_loglik_reduce(dslots, rel, part ? n_top_slots : 0, n_obs_nodes, fail, dev_red8, d_red_scratch, stream), "loglik_reduce");
   n_launches++;
   if (part) { int rc = allreduce_dev(dev_red8 + 4, 3); if (rc) return rc; }
@@ -1131,7 +1135,7 @@ int Model::predict(bool theta_changed) {
     int rc = push_slot_theta(cur);
     if (rc) return rc;
     for (const auto& B : pred_level.build_launches) {
-      ST_CUDA(launch_build(2, dt, dslots, 0, d_Hpred, d_sdpred, 0, d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w, d_fail, B.ns, 0,
+      ST_CUDA(launch_build(2, dt, dslots, 0, d_Hpred, d_sdpred, 0, d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w, d_fail + 1, B.ns, 0,
                            B.smem, stream, B.threads, nullptr),
               "build_level_kernel(predict)");
       n_launches++;
@@ -1442,7 +1446,7 @@ int Model::enqueue_gibbs(uint64_t seed, bool device_chain) {
 // taken on the device (st_chain.hpp).  accept_mode: 0 Metropolis rule with a proposal drawn on the device; 1 / 2: the
 // proposal is already in the alter slot's theta and is taken / rejected (bench hook).  tev != NULL: CUDA events after the
 // phases {start, gibbs, llw, build + accept + deferred half, Gram refresh, tausq + beta}.
-int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_mode) {
+int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_mode, bool propose_here, bool propose_next) {
   NvtxRange nvtx("MCMC iteration");
   cudaEvent_t* tev = timing_events_;
   int rc = 0;
@@ -1456,13 +1460,13 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
   const int n_early = n_early_levels_;
   const bool ovl = overlap && o.sample_w && o.sample_theta && n_early >= 1 && stream2 != nullptr;
   bool cond2 = false;  // the accepted-proposal work of this iteration runs on the second stream
+  bool prop3 = false;  // the next iteration's proposal runs on the third stream
   if (tev) ST_CUDA(cudaEventRecord(tev[0], stream), "event");
   if (ovl) {
     ST_CUDA(cudaEventRecord(ev_fork, stream), "event");
     ST_CUDA(cudaStreamWaitEvent(stream2, ev_fork, 0), "fork");
     if (tev) ST_CUDA(cudaEventRecord(tev[6], stream2), "event");
-    if (accept_mode == 0) { ST_CUDA(launch_mh_propose(d_mc, stream2, d_fail), "mh_propose_kernel"); n_launches++; }
-    else ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream2), "memset");
+    if (accept_mode == 0 && propose_here) { ST_CUDA(launch_mh_propose(d_mc, stream2), "mh_propose_kernel"); n_launches++; }
     rc = launch_build_levels(1, 0, n_early, true, stream2);
     if (rc) return rc;
     if (tev) ST_CUDA(cudaEventRecord(tev[7], stream2), "event");
@@ -1521,15 +1525,14 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
       if (rc) return rc;
       ST_CUDA(cudaStreamWaitEvent(stream, ev_early_llw, 0), "join");  // the early levels' log-density pieces (second stream, above)
     } else {
-      if (accept_mode == 0) { ST_CUDA(launch_mh_propose(d_mc, stream, d_fail), "mh_propose_kernel"); n_launches++; }
-      else ST_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream), "memset");
+      if (accept_mode == 0 && propose_here) { ST_CUDA(launch_mh_propose(d_mc, stream), "mh_propose_kernel"); n_launches++; }
       rc = launch_build_levels(1, 0, nlev, false, stream);
       if (rc) return rc;
     }
     rc = reduce_loglik(1, d_fail, d_mc->red_build, nullptr);
     if (rc) return rc;
     if (llw2) ST_CUDA(cudaStreamWaitEvent(stream, ev_llw, 0), "join");
-    ST_CUDA(launch_mh_accept(d_mc, accept_mode, o.sample_w ? 1 : 0, stream), "mh_accept_kernel");
+    ST_CUDA(launch_mh_accept(d_mc, accept_mode, o.sample_w ? 1 : 0, stream, (int)theta[0].size()), "mh_accept_kernel");
     n_launches++;
     // An accepted proposal: the new param_data's childless level gets its backward half, the message Grams are refreshed.
     // Neither touches w, XB or the chain's scalars: on a single-GPU handle they run on the second stream while the main
@@ -1538,9 +1541,19 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
     // flag — underneath the same tail instead of in front of it.
     cond2 = !part && stream2 != nullptr;
     cudaStream_t cs = cond2 ? stream2 : stream;
-    if (cond2) {
-      ST_CUDA(cudaEventRecord(ev_acc, stream), "event");
-      ST_CUDA(cudaStreamWaitEvent(stream2, ev_acc, 0), "fork");
+    prop3 = accept_mode == 0 && propose_next && stream3 != nullptr;
+    if (cond2 || prop3) ST_CUDA(cudaEventRecord(ev_acc, stream), "event");
+    if (cond2) ST_CUDA(cudaStreamWaitEvent(stream2, ev_acc, 0), "fork");
+    if (prop3) {
+      // the NEXT iteration's proposal needs nothing but this accept step (theta, the adapted proposal covariance): it is drawn
+      // now, on a stream of its own underneath the tail, so that the next iteration's BUILD starts without it in front
+      ST_CUDA(cudaStreamWaitEvent(stream3, ev_acc, 0), "fork");
+      ST_CUDA(launch_mh_propose(d_mc, stream3, 1), "mh_propose_kernel(next iteration)");
+      n_launches++;
+      ST_CUDA(cudaEventRecord(ev_prop, stream3), "event");
+    } else if (accept_mode == 0 && propose_next) {
+      ST_CUDA(launch_mh_propose(d_mc, stream, 1), "mh_propose_kernel(next iteration)");
+      n_launches++;
     }
     if (tev) ST_CUDA(cudaEventRecord(tev[3], stream), "event");
     if (tev && cond2) ST_CUDA(cudaEventRecord(tev[10], cs), "event");
@@ -1558,7 +1571,7 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
   if (predicting && o.sample_predicts && o.sample_w && pred_level.nslots > 0) {  // :302-306, predict_std :1234-1358
     ST_CUDA(launch_predict_gate(d_mc, stream), "predict_gate_kernel");
     for (const auto& B : pred_level.build_launches) {
-      ST_CUDA(launch_build(2, dt, dslots, 0, d_Hpred, d_sdpred, 0, d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w, d_fail, B.ns, 0,
+      ST_CUDA(launch_build(2, dt, dslots, 0, d_Hpred, d_sdpred, 0, d_grp_slot0 + B.grp0, d_grp_nn + B.grp0, B.ngrp, d_w, d_fail + 1, B.ns, 0,
                            B.smem, stream, B.threads, nullptr, false, &d_mc->predict_build),
               "build_level_kernel(predict)");
       n_launches++;
@@ -1569,7 +1582,7 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
   if (o.sample_tausq || o.sample_beta) {  // :308-330
     rc = enqueue_stats();
     if (rc) return rc;
-    ST_CUDA(launch_tausq_beta(d_mc, d_scalars + 8, d_xtx, d_tausq_inv, d_bcoeff, d_bscratch, o.sample_tausq, o.sample_beta, stream),
+    ST_CUDA(launch_tausq_beta(d_mc, d_scalars + 8, d_xtx, d_tausq_inv, d_bcoeff, d_bscratch, o.sample_tausq, o.sample_beta, stream, p, q),
             "tausq_beta_kernel");
     n_launches++;
     if (o.sample_beta) { ST_CUDA(launch_xb(dt, n_all, p, d_bcoeff, d_xb, stream), "xb_kernel"); n_launches++; }
@@ -1578,6 +1591,7 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
   n_launches++;
   if (tev) ST_CUDA(cudaEventRecord(tev[5], stream), "event");
   if (cond2) ST_CUDA(cudaStreamWaitEvent(stream, ev_cond, 0), "join");
+  if (prop3) ST_CUDA(cudaStreamWaitEvent(stream, ev_prop, 0), "join");
   if (tev) ST_CUDA(cudaEventRecord(tev[13], stream), "event");
   return 0;
 }
@@ -1631,6 +1645,8 @@ int Model::push_chain_state(const st_mcmc_opts* o, uint64_t seed) {
   }
   // (h_chain is pinned and is not touched again before pull_chain_state's synchronisation: no wait needed here)
   ST_CUDA(cudaMemcpyAsync(d_mc, h_mc, sizeof(ChainDev), cudaMemcpyHostToDevice, stream), "H2D chain");
+  // the BUILD failure counter is zero between BUILDs (the reduction that consumes it clears it); make sure it starts so
+  ST_CUDA(cudaMemsetAsync(d_fail, 0, 4 * sizeof(int), stream), "memset");
   return 0;
 }
 
@@ -1667,7 +1683,7 @@ int Model::bench_iteration(const double* theta_prop, int do_swap, uint64_t seed,
   o.sample_beta = o.sample_tausq = o.sample_theta = o.sample_w = 1;
   o.seed = seed;
   timing_events_ = ev;
-  rc = enqueue_iteration(o, false, do_swap ? 1 : 2);
+  rc = enqueue_iteration(o, false, do_swap ? 1 : 2, false, false);
   timing_events_ = nullptr;
   if (rc) return rc;
   rc = pull_chain_state();
@@ -1774,13 +1790,16 @@ int Model::chain_run(const st_mcmc_opts& o, st_mcmc_out& out) {
     const bool predicting = saved;
     const int which = predicting ? 1 : 0;
     bool launched = false;
-    if (use_graph && m > 0) {  // (iteration 0 runs directly: it also sets the kernels' shared-memory attributes)
+    // The proposal of iteration m + 1 is drawn inside iteration m, right after its accept step; iteration 0 draws its own as
+    // well and the last one draws none (the alter slot's theta then stays the proposal that was built).  Both run directly.
+    const bool first = m == 0, last = m + 1 == mcmc;
+    if (use_graph && !first && !last) {  // (iteration 0 runs directly: it also sets the kernels' shared-memory attributes)
       if (graph_key_[which] != key_base || !graph_exec_[which]) {
         if (graph_exec_[which]) { cudaGraphExecDestroy((cudaGraphExec_t)graph_exec_[which]); graph_exec_[which] = nullptr; }
         cudaGraph_t g = nullptr;
         const double nl0 = n_launches;
         bool ok = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
-        int rcc = ok ? enqueue_iteration(o, predicting, 0) : 0;
+        int rcc = ok ? enqueue_iteration(o, predicting, 0, false, true) : 0;
         if (ok) ok = (cudaStreamEndCapture(stream, &g) == cudaSuccess) && g && rcc == 0;
         cudaGraphExec_t ge = nullptr;
         if (ok) ok = cudaGraphInstantiate(&ge, g, 0) == cudaSuccess;
@@ -1795,7 +1814,7 @@ int Model::chain_run(const st_mcmc_opts& o, st_mcmc_out& out) {
         launched = true;
       }
     }
-    if (!launched) { rc = enqueue_iteration(o, predicting, 0); if (rc) return rc; }
+    if (!launched) { rc = enqueue_iteration(o, predicting, 0, first, !last); if (rc) return rc; }
     if (saved) {  // :376-389
       ST_CUDA(launch_record(d_mc, d_tausq_inv, d_bcoeff, d_theta_mcmc, d_beta_mcmc, d_tausq_mcmc, keep, stream), "record_kernel");
       n_launches++;

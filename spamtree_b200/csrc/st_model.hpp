@@ -153,7 +153,7 @@ class Model {
   int upload_xtx();
   // log-density pieces of the slot `rel` summed into `dev_red8` (+ all-reduce of the rank's own part); out3_host != NULL
   // also brings {loglik_w, logdetCi, failed factorisations} to the host (one synchronisation)
-  int reduce_loglik(int rel, const int* fail, double* dev_red8, double* out3_host);
+  int reduce_loglik(int rel, int* fail, double* dev_red8, double* out3_host);
   // ---- parameters (host copies of the small ones)
   dvec theta[2];
   double loglik_w[2] = {0, 0}, logdetCi[2] = {0, 0};
@@ -189,7 +189,8 @@ class Model {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaStream_t stream2 = nullptr;   // the early levels of a proposal's BUILD run here, underneath the Gibbs sweep
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sweep = nullptr, ev_llw = nullptr, ev_acc = nullptr, ev_cond = nullptr,
-              ev_early_llw = nullptr;
+              ev_early_llw = nullptr, ev_prop = nullptr;
+  cudaStream_t stream3 = nullptr;   // the next iteration's proposal, drawn right after the accept step underneath the tail
   // LLW of the current slot on the second stream, underneath BUILD.  Off by default: measured on one B200 it gives 0.8 % at C4
   // and 2.3 % at C3 (the sweep of the HBM mostly displaces BUILD's own time) and makes LLW's event time meaningless;
   // ST_LLW_OVERLAP=1 enables it
@@ -247,7 +248,7 @@ class Model {
   int push_slot_theta(int ps);   // host-driven path: theta[ps] and its covariance table into the device chain state
   int enqueue_gibbs(uint64_t seed, bool device_chain);
   int enqueue_stats();
-  int enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_mode);
+  int enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_mode, bool propose_here, bool propose_next);
   int push_chain_state(const st_mcmc_opts* o, uint64_t seed);
   int pull_chain_state();
   cudaEvent_t* timing_events_ = nullptr;

@@ -22,7 +22,7 @@ def _replay(pb, bounds, sd0, keep, burn, thin, seed, faithful, adapting=True, pr
     gm.get_loglik_comps_w(0)
     gm.get_loglik_comps_w(1)
     obs = np.isfinite(y)
-    p = 3
+    p = d["X"].shape[1]
     npar = pb["theta"].size
     param = pb["theta"].copy()
     predict_param = param.copy()
@@ -102,6 +102,24 @@ def test_device_chain_equals_host_replay(q, n, sd, keep, burn, thin, faithful, e
     print(f"device-resident chain vs host replay (q={q}, {total} iterations, {h['acc']} accepted):", {k: f"{v:.2e}" for k, v in err.items()})
     # same kernels on both sides; only the scalar glue runs in different places (device vs host libm): agreement far below
     # the 1e-9 contract even after the chain's amplification
+    assert all(v <= 1e-9 for v in err.values()), err
+
+
+@pytest.mark.parametrize("ncol", [1, 2])
+def test_device_chain_with_one_or_two_regressors(ncol):
+    """p < 3 with q > 1: every outcome's work arrays of the beta step must stay its own (the layout once assumed p >= 3)"""
+    pb = common.make_problem(2, 1200)
+    pb["d"] = dict(pb["d"], X=np.ascontiguousarray(pb["d"]["X"][:, :ncol]))
+    pb["beta"] = np.zeros(ncol)
+    bounds, npar = synth.default_bounds(2), pb["theta"].size
+    sd0 = np.eye(npar) * 1e-7
+    gm = common.product_model(pb, keep_H=False)
+    r = gm.mcmc(bounds, sd0, 12, 6, 1, adapting=True, faithful_beta_index=False, rng_mode=1, seed=21)
+    gm.close()
+    h = _replay(pb, bounds, sd0, 12, 6, 1, 21, False)
+    assert r["n_accepted"] == h["acc"]
+    err = {"beta": relerr(r["beta_mcmc"], np.array(h["beta"]).transpose(1, 0, 2)), "tausq": relerr(r["tausq_mcmc"], np.array(h["tausq"]).T),
+           "w": relerr(r["w_mcmc"], np.array(h["w"]).T), "yhat": relerr(r["yhat_mcmc"], np.array(h["yhat"]).T)}
     assert all(v <= 1e-9 for v in err.values()), err
 
 
