@@ -600,11 +600,12 @@ constexpr int kRedBlocks = 32;
 __global__ void __launch_bounds__(256) loglik_reduce_kernel(DevSlots D, int rel, int n_top, int n, int* __restrict__ fail,
                                                             double* __restrict__ out, double* __restrict__ partial,
                                                             unsigned int* __restrict__ counter) {
+  const int nblk = gridDim.x;  // CTAs per part: kRedBlocks, or 1 for a small tree (one CTA sums a part: no second stage to wait for)
   __shared__ double sa[256], sb[256];
   __shared__ bool last;
   const DevSlot S = pick_slot(D, D.chain->cur ^ rel);
   const int part = blockIdx.y, first = part ? n_top : 0, cnt = (part ? n : n_top) - first;
-  const int chunk = (cnt + kRedBlocks - 1) / kRedBlocks;
+  const int chunk = (cnt + nblk - 1) / nblk;
   const int lo = first + blockIdx.x * chunk, hi = min(lo + chunk, first + cnt);
   double a = 0, b = 0;
   for (int i = lo + threadIdx.x; i < hi; i += 256) { a += S.logdet[i]; b += S.llcomp[i]; }
@@ -618,14 +619,18 @@ __global__ void __launch_bounds__(256) loglik_reduce_kernel(DevSlots D, int rel,
   if (threadIdx.x == 0) {
     partial[(part * kRedBlocks + blockIdx.x) * 2] = sa[0];
     partial[(part * kRedBlocks + blockIdx.x) * 2 + 1] = sb[0];
-    __threadfence();
-    last = atomicAdd(counter + part, 1u) == kRedBlocks - 1;
+    if (nblk > 1) {
+      __threadfence();
+      last = atomicAdd(counter + part, 1u) == (unsigned)nblk - 1;
+    } else {
+      last = true;
+    }
   }
   __syncthreads();
   if (last && threadIdx.x == 0) {
     __threadfence();
     double ta = 0, tb = 0;
-    for (int k = 0; k < kRedBlocks; k++) { ta += partial[(part * kRedBlocks + k) * 2]; tb += partial[(part * kRedBlocks + k) * 2 + 1]; }
+    for (int k = 0; k < nblk; k++) { ta += partial[(part * kRedBlocks + k) * 2]; tb += partial[(part * kRedBlocks + k) * 2 + 1]; }
     double* o = out + 4 * part;
     o[0] = ta + tb;
     o[1] = ta;
@@ -637,7 +642,8 @@ __global__ void __launch_bounds__(256) loglik_reduce_kernel(DevSlots D, int rel,
 cudaError_t launch_loglik_reduce(const DevSlots& D, int rel, int n_top, int n, int* fail, double* out8, double* scratch,
                                  cudaStream_t st) {
   // scratch: 4 * kRedBlocks doubles of partial sums followed by two zero-initialised 32-bit counters
-  loglik_reduce_kernel<<<dim3(kRedBlocks, 2), 256, 0, st>>>(D, rel, n_top, n, fail, out8, scratch,
+  // (the choice depends on the tree only: a handle always sums in the same order)
+  loglik_reduce_kernel<<<dim3(n <= 8192 ? 1 : kRedBlocks, 2), 256, 0, st>>>(D, rel, n_top, n, fail, out8, scratch,
                                                             reinterpret_cast<unsigned int*>(scratch + 4 * kRedBlocks));
   return cudaGetLastError();
 }
@@ -882,6 +888,19 @@ __global__ void mh_accept_kernel(ChainDev* C, int mode, int have_llw, int stage)
     su = u;
     __syncthreads();
   }
+  // the Jacobian's terms (four logarithms each) and the uniform draw by separate threads; thread 0 adds the terms in
+  // mh_jacobian's order (st_mh.hpp), so the sum is the same
+  __shared__ double s_term[kMaxPar];
+  __shared__ double s_u;
+  if (mode == 0) {
+    const int cur0 = C->cur, alt0 = cur0 ^ 1;
+    for (int j = threadIdx.x; j < npar; j += blockDim.x) {
+      const double lo = C->bounds[j], hi = C->bounds[j + npar], pj = C->theta[cur0][j], nj = C->theta[alt0][j];
+      s_term[j] = (-log(hi - pj) - log(pj - lo)) - (-log(hi - nj) - log(nj - lo));
+    }
+    if (threadIdx.x == blockDim.x - 1) s_u = philox_uniform(C->seed, kStreamAccept, (uint64_t)C->iter);
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
     const int cur = C->cur, alt = cur ^ 1, m = C->iter;
     if (have_llw) { C->loglik[cur] = C->red_llw[0] + C->red_llw[4]; C->logdet[cur] = C->red_llw[1] + C->red_llw[5]; }
@@ -897,8 +916,10 @@ __global__ void mh_accept_kernel(ChainDev* C, int mode, int have_llw, int stage)
     bool accepted;
     double logaccept = 0.0;
     if (mode == 0) {
-      logaccept = new_loglik - current_loglik + mh_jacobian(npar, C->theta[alt], C->theta[cur], C->bounds);
-      const double u = philox_uniform(C->seed, kStreamAccept, (uint64_t)m);
+      double jac = 0;
+      for (int j = 0; j < npar; j++) jac += s_term[j];
+      logaccept = new_loglik - current_loglik + jac;
+      const double u = s_u;
       C->last_logaccept = logaccept; C->last_u = u;
       accepted = (u < mh_accept_prob(logaccept)) && acceptable;
     } else {
@@ -944,14 +965,15 @@ cudaError_t launch_predict_gate(ChainDev* C, cudaStream_t st) {
 }
 
 // Marsaglia-Tsang gamma(shape >= 1, scale) on a Philox stream (the host path's HostRng::gamma, st_common.hpp)
-__device__ inline double philox_gamma(uint64_t seed, unsigned long long key, uint64_t counter, double shape, double scale) {
+// x0, u0: the first attempt's normal and uniform, drawn by other threads (same streams: same value)
+__device__ inline double philox_gamma(uint64_t seed, unsigned long long key, uint64_t counter, double shape, double scale, double x0, double u0) {
   const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
   for (unsigned long long att = 0;; att++) {
-    const double x = philox_normal(seed, key + (att << 8), counter);
+    const double x = att ? philox_normal(seed, key + (att << 8), counter) : x0;
     double v = 1.0 + c * x;
     if (v <= 0) continue;
     v = v * v * v;
-    const double u = philox_uniform(seed, key + (att << 8) + 128, counter);
+    const double u = att ? philox_uniform(seed, key + (att << 8) + 128, counter) : u0;
     if (u < 1.0 - 0.0331 * x * x * x * x) return d * v * scale;
     if (log(u) < 0.5 * x * x + d * (1.0 - v + log(v))) return d * v * scale;
   }
@@ -964,11 +986,26 @@ __global__ void tausq_beta_kernel(ChainDev* C, const double* __restrict__ stats,
   extern __shared__ double tb_smem[];  // stage = 1: the p x p work arrays of every outcome (else `scratch` in global memory)
   if (stage) scratch = tb_smem;
   const int j = threadIdx.x, p = C->p, q = C->q;
-  if (j >= q) return;
   const uint64_t it = (uint64_t)C->iter;
+  // every draw by a thread of its own (a normal is a Philox block, a logarithm, a square root and a sincospi: the one thread
+  // per outcome that used to draw p + 2 of them in sequence spent most of its time there)
+  __shared__ double s_zb[kMaxStats], s_gx[kMaxQ], s_gu[kMaxQ];
+  const bool par_draws = q * p <= kMaxStats;
+  if (par_draws) {
+    const int nz = sample_beta ? q * p : 0, ng = sample_tausq ? q : 0;
+    for (int t = threadIdx.x; t < nz + 2 * ng; t += blockDim.x) {
+      if (t < nz) s_zb[t] = philox_normal(C->seed, kStreamBeta + ((unsigned long long)(t / p) << 32) + (t % p), it);
+      else if (t < nz + ng) s_gx[t - nz] = philox_normal(C->seed, kStreamGamma + ((unsigned long long)(t - nz) << 32), it);
+      else s_gu[t - nz - ng] = philox_uniform(C->seed, kStreamGamma + ((unsigned long long)(t - nz - ng) << 32) + 128, it);
+    }
+    __syncthreads();
+  }
+  if (j >= q) return;
   if (sample_tausq) {
     const double bcore = stats[j * (p + 1) + p];
-    tausq_inv[j] = philox_gamma(C->seed, kStreamGamma + ((unsigned long long)j << 32), it, 2.01 + C->nobs[j] / 2.0, 1.0 / (1.0 + .5 * bcore));
+    const unsigned long long gk = kStreamGamma + ((unsigned long long)j << 32);
+    const double x0 = par_draws ? s_gx[j] : philox_normal(C->seed, gk, it), u0 = par_draws ? s_gu[j] : philox_uniform(C->seed, gk + 128, it);
+    tausq_inv[j] = philox_gamma(C->seed, gk, it, 2.01 + C->nobs[j] / 2.0, 1.0 / (1.0 + .5 * bcore), x0, u0);
   }
   if (sample_beta) {
     const double tq = tausq_inv[j];
@@ -991,7 +1028,7 @@ __global__ void tausq_beta_kernel(ChainDev* C, const double* __restrict__ stats,
     for (int a = 0; a < p; a++) xp[a] = tq * stats[j * (p + 1) + a];  // Vim = 0 (:158-159)
     for (int a = 0; a < p; a++) { double s = 0; for (int b = 0; b <= a; b++) s += Sc[a + b * p] * xp[b]; t[a] = s; }
     for (int a = 0; a < p; a++) { double s = 0; for (int b = a; b < p; b++) s += Sc[b + a * p] * t[b]; bmu[a] = s; }
-    for (int a = 0; a < p; a++) xp[a] = philox_normal(C->seed, kStreamBeta + ((unsigned long long)j << 32) + a, it);
+    for (int a = 0; a < p; a++) xp[a] = par_draws ? s_zb[j * p + a] : philox_normal(C->seed, kStreamBeta + ((unsigned long long)j << 32) + a, it);
     for (int a = 0; a < p; a++) {
       double s = 0;
       for (int b = a; b < p; b++) s += Sc[b + a * p] * xp[b];
@@ -1003,7 +1040,7 @@ cudaError_t launch_tausq_beta(ChainDev* C, const double* stats, const double* xt
                               double* scratch, int sample_tausq, int sample_beta, cudaStream_t st, int p, int q) {
   const size_t smem = (size_t)q * (2 * p * p + 4 * p) * sizeof(double);  // the layout of `scratch`
   const int stage = p > 0 && smem <= 40 * 1024;
-  tausq_beta_kernel<<<1, 32, stage ? smem : 0, st>>>(C, stats, xtx, tausq_inv, bcoeff, scratch, sample_tausq, sample_beta, stage);
+  tausq_beta_kernel<<<1, 64, stage ? smem : 0, st>>>(C, stats, xtx, tausq_inv, bcoeff, scratch, sample_tausq, sample_beta, stage);
   return cudaGetLastError();
 }
 

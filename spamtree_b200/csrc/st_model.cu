@@ -1587,11 +1587,12 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
     n_launches++;
     if (o.sample_beta) { ST_CUDA(launch_xb(dt, n_all, p, d_bcoeff, d_xb, stream), "xb_kernel"); n_launches++; }
   }
+  // (the next iteration's proposal reads the iteration counter: it must be through before the tick)
+  if (prop3) ST_CUDA(cudaStreamWaitEvent(stream, ev_prop, 0), "join");
   ST_CUDA(launch_chain_tick(d_mc, stream), "chain_tick_kernel");
   n_launches++;
   if (tev) ST_CUDA(cudaEventRecord(tev[5], stream), "event");
   if (cond2) ST_CUDA(cudaStreamWaitEvent(stream, ev_cond, 0), "join");
-  if (prop3) ST_CUDA(cudaStreamWaitEvent(stream, ev_prop, 0), "join");
   if (tev) ST_CUDA(cudaEventRecord(tev[13], stream), "event");
   return 0;
 }
