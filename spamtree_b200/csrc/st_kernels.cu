@@ -1046,7 +1046,8 @@ cudaError_t launch_tausq_beta(ChainDev* C, const double* stats, const double* xt
 
 // save (spamtree_fit.cpp:376-382): column msaved of theta_mcmc (npar x keep), tausq_mcmc (q x keep), beta_mcmc (p x keep x q)
 __global__ void record_kernel(ChainDev* C, const double* __restrict__ tausq_inv, const double* __restrict__ bcoeff,
-                              double* __restrict__ theta_mcmc, double* __restrict__ beta_mcmc, double* __restrict__ tausq_mcmc, int keep) {
+                              double* __restrict__ theta_mcmc, double* __restrict__ beta_mcmc, double* __restrict__ tausq_mcmc, int keep,
+                              int tick) {
   const int ms = C->msaved, npar = C->npar, p = C->p, q = C->q;
   if (ms < keep) {
     for (int j = threadIdx.x; j < npar; j += blockDim.x) theta_mcmc[j + (size_t)ms * npar] = C->theta[C->cur][j];
@@ -1054,11 +1055,14 @@ __global__ void record_kernel(ChainDev* C, const double* __restrict__ tausq_inv,
     for (int e = threadIdx.x; e < p * q; e += blockDim.x) { const int a = e % p, j = e / p; beta_mcmc[a + (size_t)ms * p + (size_t)j * p * keep] = bcoeff[e]; }
   }
   __syncthreads();
-  if (threadIdx.x == 0) C->msaved = ms + 1;
+  if (threadIdx.x == 0) {
+    C->msaved = ms + 1;
+    if (tick) C->iter++;  // (the end of a saved iteration: chain_tick_kernel's work rides along)
+  }
 }
 cudaError_t launch_record(ChainDev* C, const double* tausq_inv, const double* bcoeff, double* theta_mcmc, double* beta_mcmc,
-                          double* tausq_mcmc, int keep, cudaStream_t st) {
-  record_kernel<<<1, 64, 0, st>>>(C, tausq_inv, bcoeff, theta_mcmc, beta_mcmc, tausq_mcmc, keep);
+                          double* tausq_mcmc, int keep, cudaStream_t st, int tick) {
+  record_kernel<<<1, 64, 0, st>>>(C, tausq_inv, bcoeff, theta_mcmc, beta_mcmc, tausq_mcmc, keep, tick);
   return cudaGetLastError();
 }
 

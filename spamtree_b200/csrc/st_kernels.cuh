@@ -94,7 +94,7 @@ cudaError_t launch_tausq_beta(ChainDev* C, const double* stats, const double* xt
                               double* scratch, int sample_tausq, int sample_beta, cudaStream_t st, int p = 0, int q = 0);
 // the saved iteration's theta / beta / tausq into the device sample arrays (layouts of st_mcmc_out), then C->msaved++
 cudaError_t launch_record(ChainDev* C, const double* tausq_inv, const double* bcoeff, double* theta_mcmc, double* beta_mcmc,
-                          double* tausq_mcmc, int keep, cudaStream_t st);
+                          double* tausq_mcmc, int keep, cudaStream_t st, int tick = 0);  // tick: also advances the iteration counter
 // yhat = XB + w + tausq^(1/2) N(0,1) in boundary order (spamtree_fit.cpp:384)
 cudaError_t launch_yhat(const DevTree& T, const double* w, const double* xb, const double* tausq_inv, const long long* iperm,
                         const long long* rowkey, long long n, const ChainDev* C, double* out, cudaStream_t st);

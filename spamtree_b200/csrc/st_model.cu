@@ -95,6 +95,8 @@ Model::~Model() {
   if (stream2) cudaStreamDestroy(stream2);
   if (stream3) cudaStreamDestroy(stream3);
   if (ev_prop) cudaEventDestroy(ev_prop);
+  if (ev_zfree) cudaEventDestroy(ev_zfree);
+  if (d_samp_) cudaFree(d_samp_);
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
   if (ev_sweep) cudaEventDestroy(ev_sweep);
@@ -604,6 +606,7 @@ int Model::upload(std::string& e) {
     ST_CUDA(cudaStreamCreateWithPriority(&stream3, cudaStreamNonBlocking, lo), "cudaStreamCreate");
   }
   ST_CUDA(cudaEventCreateWithFlags(&ev_prop, cudaEventDisableTiming), "cudaEventCreate");
+  ST_CUDA(cudaEventCreateWithFlags(&ev_zfree, cudaEventDisableTiming), "cudaEventCreate");
   ST_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming), "cudaEventCreate");
   ST_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming), "cudaEventCreate");
   ST_CUDA(cudaEventCreateWithFlags(&ev_acc, cudaEventDisableTiming), "cudaEventCreate");
@@ -1435,10 +1438,12 @@ int Model::get_index(const std::string& which, int u, int c, int64_t* out, int64
 
 // ------------------------------------------------------------------------------------------------ device-resident iteration
 // One Gibbs sweep, enqueued only: normals keyed by (seed, row, iteration), Gram refresh and deferred half are the callers'
-int Model::enqueue_gibbs(uint64_t seed, bool device_chain) {
-  ST_CUDA(launch_normals(d_z, n_all, seed, device_chain ? 0 : sweep_counter++, d_rowkey, device_chain ? &d_mc->iter : nullptr, stream),
-          "normals_kernel");
-  n_launches++;
+int Model::enqueue_gibbs(uint64_t seed, bool device_chain, bool draw) {
+  if (draw) {  // (draw = false: the previous iteration of the device-resident chain already drew this sweep's normals)
+    ST_CUDA(launch_normals(d_z, n_all, seed, device_chain ? 0 : sweep_counter++, d_rowkey, device_chain ? &d_mc->iter : nullptr, stream),
+            "normals_kernel");
+    n_launches++;
+  }
   return gibbs_launch_only(device_chain ? &d_mc->gibbs_fail : d_fail);
 }
 
@@ -1446,7 +1451,7 @@ int Model::enqueue_gibbs(uint64_t seed, bool device_chain) {
 // taken on the device (st_chain.hpp).  accept_mode: 0 Metropolis rule with a proposal drawn on the device; 1 / 2: the
 // proposal is already in the alter slot's theta and is taken / rejected (bench hook).  tev != NULL: CUDA events after the
 // phases {start, gibbs, llw, build + accept + deferred half, Gram refresh, tausq + beta}.
-int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_mode, bool propose_here, bool propose_next) {
+int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_mode, bool draws_here, bool draws_next, int record_keep) {
   NvtxRange nvtx("MCMC iteration");
   cudaEvent_t* tev = timing_events_;
   int rc = 0;
@@ -1466,7 +1471,7 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
     ST_CUDA(cudaEventRecord(ev_fork, stream), "event");
     ST_CUDA(cudaStreamWaitEvent(stream2, ev_fork, 0), "fork");
     if (tev) ST_CUDA(cudaEventRecord(tev[6], stream2), "event");
-    if (accept_mode == 0 && propose_here) { ST_CUDA(launch_mh_propose(d_mc, stream2), "mh_propose_kernel"); n_launches++; }
+    if (accept_mode == 0 && draws_here) { ST_CUDA(launch_mh_propose(d_mc, stream2), "mh_propose_kernel"); n_launches++; }
     rc = launch_build_levels(1, 0, n_early, true, stream2);
     if (rc) return rc;
     if (tev) ST_CUDA(cudaEventRecord(tev[7], stream2), "event");
@@ -1477,7 +1482,7 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
   // bandwidth), after the sweep has finished.  (Partitioned handles keep it on the main stream, with their collectives.)
   const bool llw2 = llw_overlap && !part && o.sample_w && o.sample_theta && stream2 != nullptr;
   if (o.sample_w) {  // :183-187
-    rc = enqueue_gibbs(o.seed, true);
+    rc = enqueue_gibbs(o.seed, true, draws_here);
     if (rc) return rc;
     if (tev) ST_CUDA(cudaEventRecord(tev[1], stream), "event");
     if (llw2 || ovl) ST_CUDA(cudaEventRecord(ev_sweep, stream), "event");
@@ -1525,7 +1530,7 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
       if (rc) return rc;
       ST_CUDA(cudaStreamWaitEvent(stream, ev_early_llw, 0), "join");  // the early levels' log-density pieces (second stream, above)
     } else {
-      if (accept_mode == 0 && propose_here) { ST_CUDA(launch_mh_propose(d_mc, stream), "mh_propose_kernel"); n_launches++; }
+      if (accept_mode == 0 && draws_here) { ST_CUDA(launch_mh_propose(d_mc, stream), "mh_propose_kernel"); n_launches++; }
       rc = launch_build_levels(1, 0, nlev, false, stream);
       if (rc) return rc;
     }
@@ -1541,7 +1546,7 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
     // flag — underneath the same tail instead of in front of it.
     cond2 = !part && stream2 != nullptr;
     cudaStream_t cs = cond2 ? stream2 : stream;
-    prop3 = accept_mode == 0 && propose_next && stream3 != nullptr;
+    prop3 = accept_mode == 0 && draws_next && stream3 != nullptr;
     if (cond2 || prop3) ST_CUDA(cudaEventRecord(ev_acc, stream), "event");
     if (cond2) ST_CUDA(cudaStreamWaitEvent(stream2, ev_acc, 0), "fork");
     if (prop3) {
@@ -1551,7 +1556,7 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
       ST_CUDA(launch_mh_propose(d_mc, stream3, 1), "mh_propose_kernel(next iteration)");
       n_launches++;
       ST_CUDA(cudaEventRecord(ev_prop, stream3), "event");
-    } else if (accept_mode == 0 && propose_next) {
+    } else if (accept_mode == 0 && draws_next) {
       ST_CUDA(launch_mh_propose(d_mc, stream, 1), "mh_propose_kernel(next iteration)");
       n_launches++;
     }
@@ -1579,6 +1584,20 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
     ST_CUDA(launch_predict_sample(dt, pred_level.slot0, pred_level.nslots, d_Hpred, d_sdpred, d_w, d_z, stream), "predict_sample_kernel");
     n_launches += 2;
   }
+  if (draws_next && o.sample_w) {
+    // the NEXT sweep's normals (Philox counter = iteration + 1), once this iteration's last reader of d_z — the prediction
+    // draw — is through: on the third stream, underneath the tail, so that the next sweep starts with its first level
+    if (stream3) {
+      ST_CUDA(cudaEventRecord(ev_zfree, stream), "event");
+      ST_CUDA(cudaStreamWaitEvent(stream3, ev_zfree, 0), "fork");
+      ST_CUDA(launch_normals(d_z, n_all, o.seed, 1, d_rowkey, &d_mc->iter, stream3), "normals_kernel(next iteration)");
+      ST_CUDA(cudaEventRecord(ev_prop, stream3), "event");
+      prop3 = true;
+    } else {
+      ST_CUDA(launch_normals(d_z, n_all, o.seed, 1, d_rowkey, &d_mc->iter, stream), "normals_kernel(next iteration)");
+    }
+    n_launches++;
+  }
   if (o.sample_tausq || o.sample_beta) {  // :308-330
     rc = enqueue_stats();
     if (rc) return rc;
@@ -1589,7 +1608,10 @@ int Model::enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_
   }
   // (the next iteration's proposal reads the iteration counter: it must be through before the tick)
   if (prop3) ST_CUDA(cudaStreamWaitEvent(stream, ev_prop, 0), "join");
-  ST_CUDA(launch_chain_tick(d_mc, stream), "chain_tick_kernel");
+  if (record_keep > 0)  // a saved iteration (:376-382): theta, tausq, beta into the device sample arrays, and the tick
+    ST_CUDA(launch_record(d_mc, d_tausq_inv, d_bcoeff, d_theta_mcmc, d_beta_mcmc, d_tausq_mcmc, record_keep, stream, 1), "record_kernel");
+  else
+    ST_CUDA(launch_chain_tick(d_mc, stream), "chain_tick_kernel");
   n_launches++;
   if (tev) ST_CUDA(cudaEventRecord(tev[5], stream), "event");
   if (cond2) ST_CUDA(cudaStreamWaitEvent(stream, ev_cond, 0), "join");
@@ -1684,7 +1706,7 @@ int Model::bench_iteration(const double* theta_prop, int do_swap, uint64_t seed,
   o.sample_beta = o.sample_tausq = o.sample_theta = o.sample_w = 1;
   o.seed = seed;
   timing_events_ = ev;
-  rc = enqueue_iteration(o, false, do_swap ? 1 : 2, false, false);
+  rc = enqueue_iteration(o, false, do_swap ? 1 : 2, true, false);
   timing_events_ = nullptr;
   if (rc) return rc;
   rc = pull_chain_state();
@@ -1750,10 +1772,13 @@ int Model::chain_run(const st_mcmc_opts& o, st_mcmc_out& out) {
   if (rc) return rc;
   const int npar = (int)theta[0].size(), keep = o.keep, mcmc = o.thin * o.keep + o.burn;
   // sample arrays on the device, copied out once at the end
-  double* dsamp = nullptr;
   const size_t n_th = (size_t)npar * keep, n_be = (size_t)p * keep * q, n_ta = (size_t)q * keep;
-  ST_CUDA(cudaMalloc((void**)&dsamp, std::max<size_t>(n_th + n_be + n_ta, 1) * sizeof(double)), "alloc samples");
-  struct Free { double* p; ~Free() { if (p) cudaFree(p); } } free_samp{dsamp};
+  if (n_th + n_be + n_ta > samp_cap_ || !d_samp_) {
+    if (d_samp_) { cudaFree(d_samp_); d_samp_ = nullptr; }
+    samp_cap_ = std::max<size_t>(n_th + n_be + n_ta, 1);
+    ST_CUDA(cudaMalloc((void**)&d_samp_, samp_cap_ * sizeof(double)), "alloc samples");
+  }
+  double* dsamp = d_samp_;
   d_theta_mcmc = dsamp; d_beta_mcmc = dsamp + n_th; d_tausq_mcmc = dsamp + n_th + n_be;
   rc = push_chain_state(&o, o.seed);
   if (rc) return rc;
@@ -1781,8 +1806,14 @@ int Model::chain_run(const st_mcmc_opts& o, st_mcmc_out& out) {
   // one CUDA graph per kind of iteration (with / without prediction); partitioned handles enqueue directly (their
   // collectives are library calls on the stream)
   static const bool no_graph = getenv("ST_GRAPH") && atoi(getenv("ST_GRAPH")) == 0;
-  bool use_graph = !part && !no_graph;
-  const int key_base = (o.sample_beta ? 1 : 0) | (o.sample_tausq ? 2 : 0) | (o.sample_theta ? 4 : 0) | (o.sample_w ? 8 : 0) | (o.sample_predicts ? 16 : 0);
+  // partitioned handles enqueue every iteration directly.  Capturing the library's NCCL collectives into the graph is
+  // possible (ST_PART_GRAPH=1, experimental) and measured: C3 on 2 GPUs 894 against 885 it/s end to end — but one 2-rank run
+  // of tools/run_partition.py hung with it, so it is not the default
+  static const bool part_graph = getenv("ST_PART_GRAPH") && atoi(getenv("ST_PART_GRAPH")) == 1;
+  bool use_graph = !no_graph && (!part || (nccl_comm != nullptr && part_graph));
+  // (a graph holds the addresses and the layout of the sample arrays: keep and their base are part of its key)
+  const long long key_base = ((o.sample_beta ? 1 : 0) | (o.sample_tausq ? 2 : 0) | (o.sample_theta ? 4 : 0) | (o.sample_w ? 8 : 0) | (o.sample_predicts ? 16 : 0)) +
+                             32LL * keep + (long long)(reinterpret_cast<uintptr_t>(d_samp_) >> 4) * 1000003LL;
   int msaved = 0;
   const auto t0 = std::chrono::steady_clock::now();
   for (int m = 0; m < mcmc; m++) {
@@ -1800,7 +1831,7 @@ int Model::chain_run(const st_mcmc_opts& o, st_mcmc_out& out) {
         cudaGraph_t g = nullptr;
         const double nl0 = n_launches;
         bool ok = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
-        int rcc = ok ? enqueue_iteration(o, predicting, 0, false, true) : 0;
+        int rcc = ok ? enqueue_iteration(o, predicting, 0, false, true, saved ? keep : 0) : 0;
         if (ok) ok = (cudaStreamEndCapture(stream, &g) == cudaSuccess) && g && rcc == 0;
         cudaGraphExec_t ge = nullptr;
         if (ok) ok = cudaGraphInstantiate(&ge, g, 0) == cudaSuccess;
@@ -1815,10 +1846,8 @@ int Model::chain_run(const st_mcmc_opts& o, st_mcmc_out& out) {
         launched = true;
       }
     }
-    if (!launched) { rc = enqueue_iteration(o, predicting, 0, first, !last); if (rc) return rc; }
+    if (!launched) { rc = enqueue_iteration(o, predicting, 0, first, !last, saved ? keep : 0); if (rc) return rc; }
     if (saved) {  // :376-389
-      ST_CUDA(launch_record(d_mc, d_tausq_inv, d_bcoeff, d_theta_mcmc, d_beta_mcmc, d_tausq_mcmc, keep, stream), "record_kernel");
-      n_launches++;
       if (save_w) { rc = save_w_async(out.w_mcmc + (size_t)msaved * n_all); if (rc) return rc; }
       if (save_y) {
         if (save_y_.pending) ST_CUDA(cudaStreamWaitEvent(stream, save_y_.copied, 0), "wait for the previous save");

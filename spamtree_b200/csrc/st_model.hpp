@@ -175,7 +175,9 @@ class Model {
   double *d_xtx = nullptr, *d_bscratch = nullptr;   // XtX per outcome; scratch of the device beta step
   double *d_theta_mcmc = nullptr, *d_beta_mcmc = nullptr, *d_tausq_mcmc = nullptr, *d_yhat = nullptr;  // sample arrays of a device-resident run
   void* graph_exec_[2] = {nullptr, nullptr};  // cudaGraphExec_t of one device-resident iteration without / with prediction
-  int graph_key_[2] = {-1, -1};
+  long long graph_key_[2] = {-1, -1};
+  double* d_samp_ = nullptr;        // theta / beta / tausq samples of a device-resident run (kept between runs: the graphs hold its address)
+  size_t samp_cap_ = 0;
   double graph_launches_[2] = {0, 0};
   double *d_w = nullptr, *d_xb = nullptr, *d_z = nullptr, *d_V = nullptr, *d_U = nullptr, *d_S = nullptr;
   double *d_Hpred = nullptr, *d_sdpred = nullptr;
@@ -189,7 +191,7 @@ class Model {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaStream_t stream2 = nullptr;   // the early levels of a proposal's BUILD run here, underneath the Gibbs sweep
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sweep = nullptr, ev_llw = nullptr, ev_acc = nullptr, ev_cond = nullptr,
-              ev_early_llw = nullptr, ev_prop = nullptr;
+              ev_early_llw = nullptr, ev_prop = nullptr, ev_zfree = nullptr;
   cudaStream_t stream3 = nullptr;   // the next iteration's proposal, drawn right after the accept step underneath the tail
   // LLW of the current slot on the second stream, underneath BUILD.  Off by default: measured on one B200 it gives 0.8 % at C4
   // and 2.3 % at C3 (the sweep of the HBM mostly displaces BUILD's own time) and makes LLW's event time meaningless;
@@ -246,9 +248,9 @@ class Model {
   int complete_slot(int pslot);  // the deferred half of BUILD for the slot's childless levels, if pending
   int launch_deferred_half(int rel, const int* run_flag, cudaStream_t st);
   int push_slot_theta(int ps);   // host-driven path: theta[ps] and its covariance table into the device chain state
-  int enqueue_gibbs(uint64_t seed, bool device_chain);
+  int enqueue_gibbs(uint64_t seed, bool device_chain, bool draw = true);
   int enqueue_stats();
-  int enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_mode, bool propose_here, bool propose_next);
+  int enqueue_iteration(const st_mcmc_opts& o, bool predicting, int accept_mode, bool draws_here, bool draws_next, int record_keep = 0);
   int push_chain_state(const st_mcmc_opts* o, uint64_t seed);
   int pull_chain_state();
   cudaEvent_t* timing_events_ = nullptr;

@@ -1,5 +1,5 @@
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-for w in C1 C2 C3; do
-  python bench.py --workload $w --steps 200 --warmup 5 --no-cpu-baseline --no-predict-leg 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('$w value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'acc',d['e2e']['accepted'],'gibbs',round(d['device_ms_per_step']['gibbs'],4))"; done
-python tools/timeline.py C1 24 1e-4 2>&1 | grep -v Warn | grep -A40 "rejected"
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
+timeout 600 $TR tools/run_partition.py 3 20000 2>&1 | grep -v "^W\|warn" | tail -12
+ST_PART_GRAPH=0 timeout 600 $TR tools/run_partition.py 2 12000 2>&1 | grep -v "^W\|warn" | tail -4
+for g in 1 0; do ST_PART_GRAPH=$g timeout 600 $TR bench.py --gpus 2 --workload C3 --steps 60 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('C3 n2 graph=$g value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'acc',d['e2e']['accepted'],d['parity_probe']['loglik_w'])"; done

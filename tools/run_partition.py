@@ -84,6 +84,18 @@ def main():
     ok &= ra["n_accepted"] == rb["n_accepted"] and et < 1e-8 and ebt < 1e-7 and ew < 1e-6
     print(f"[rank {rank}] CHAIN 48 it: accepted {ra['n_accepted']}/{rb['n_accepted']} theta {et:.2e} beta {ebt:.2e} w {ew:.2e} "
           f"time partitioned {ra['mcmc_time']:.3f}s single {rb['mcmc_time']:.3f}s", flush=True)
+    # device-resident chains (rng_mode 1): Philox streams keyed by the row's id in the whole problem, so the partitioned run
+    # draws what the single-GPU run draws; saves included (thin 2: saved and unsaved iterations)
+    kd = dict(keep=10, burn=11, thin=2, adapting=True, seed=23, rng_mode=1, faithful_beta_index=False)
+    gm3, sp3, _ = sdist.partitioned_model(d, tree, theta, beta, tausq, rank, world, lrank, ar, limited_tree=limited)
+    full3 = sb.SpamTreeMV(d["y"], d["X"], d["coords"], d["mv_id"], tree["res_is_ref"], None, None, limited, tree["block_names"],
+                          tree["block_groups"], None, beta, theta, tausq, csr=csr, device=lrank)
+    rc, rd = gm3.mcmc(bounds, sd, **kd), full3.mcmc(bounds, sd, **kd)
+    et, ebt = relerr(rc["theta_mcmc"], rd["theta_mcmc"]), relerr(rc["beta_mcmc"], rd["beta_mcmc"])
+    ew, ey = relerr(rc["w_mcmc"], rd["w_mcmc"][sp3["global_rows"]]), relerr(rc["yhat_mcmc"], rd["yhat_mcmc"][sp3["global_rows"]])
+    ok &= rc["n_accepted"] == rd["n_accepted"] and et < 1e-8 and ebt < 1e-7 and ew < 1e-6 and ey < 1e-6
+    print(f"[rank {rank}] DEVICE CHAIN 31 it: accepted {rc['n_accepted']}/{rd['n_accepted']} theta {et:.2e} beta {ebt:.2e} w {ew:.2e} yhat {ey:.2e} "
+          f"time partitioned {rc['mcmc_time']:.3f}s single {rd['mcmc_time']:.3f}s", flush=True)
     flag = torch.tensor([1.0 if ok else 0.0], device=f"cuda:{lrank}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -42,8 +42,8 @@ def main():
     ev.sort(key=lambda e: e["ts"])
     print(f"{name}: {iters} iterations, accepted {r['n_accepted']}, mcmc_time {r['mcmc_time'] * 1e3:.3f} ms -> "
           f"{r['mcmc_time'] * 1e6 / iters:.1f} us / iteration; {len(ev)} device activities")
-    # iteration boundaries: the normals kernel opens every sweep
-    starts = [i for i, e in enumerate(ev) if "normals_kernel" in e["name"]]
+    # iteration boundaries: the childless level opens every sweep (the normals are drawn underneath the previous iteration's tail)
+    starts = [i for i, e in enumerate(ev) if "gibbs_level_kernel<0>" in e["name"] or "gibbs_level_kernel<(int)0>" in e["name"]]
     if len(starts) < 4:
         print("no iteration markers found")
         return
