@@ -17,31 +17,11 @@ import spamtree_b200 as sb  # noqa: E402
 from spamtree_b200 import synth  # noqa: E402
 
 
-def main():
-    name = sys.argv[1] if len(sys.argv) > 1 else "C1"
-    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 12
-    sd = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-8
-    torch.cuda.init()
-    d = synth.make_config(name)
-    q = d["q"]
-    tree = sb.make_tree(d["coords"], d["y"], d["mv_id"])
-    csr = (tree["indexing_ptr"], tree["indexing_idx"], tree["parents_ptr"], tree["parents_idx"], tree["children_ptr"], tree["children_idx"])
-    theta = synth.theta_for(q)
-    gm = sb.SpamTreeMV(d["y"], d["X"], d["coords"], d["mv_id"], tree["res_is_ref"], None, None, False, tree["block_names"],
-                       tree["block_groups"], None, np.zeros(3), theta, 0.1, csr=csr, keep_H=False)
-    bounds, npar = synth.default_bounds(q), theta.size
-    kw = dict(burn=0, thin=1, adapting=True, rng_mode=1, sample_predicts=False, save_w=True, save_yhat=False)
-    gm.mcmc(bounds, np.eye(npar) * sd, keep=5, seed=4, **kw)
-    with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        r = gm.mcmc(bounds, np.eye(npar) * sd, keep=iters, seed=5, **kw)
-        torch.cuda.synchronize()
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    path = os.path.join(ROOT, "gpurun_out", f"timeline_{name}.json")
-    prof.export_chrome_trace(path)
+def report(path, name, head=""):
+    """one accepted and one rejected iteration of a saved trace (also offline: timeline.py --json trace.json)"""
     ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
     ev.sort(key=lambda e: e["ts"])
-    print(f"{name}: {iters} iterations, accepted {r['n_accepted']}, mcmc_time {r['mcmc_time'] * 1e3:.3f} ms -> "
-          f"{r['mcmc_time'] * 1e6 / iters:.1f} us / iteration; {len(ev)} device activities")
+    print(f"{name}: {head}; {len(ev)} device activities")
     # iteration boundaries: the childless level opens every sweep (the normals are drawn underneath the previous iteration's tail)
     starts = [i for i, e in enumerate(ev) if "gibbs_level_kernel<0>" in e["name"] or "gibbs_level_kernel<(int)0>" in e["name"]]
     if len(starts) < 4:
@@ -66,6 +46,33 @@ def main():
             nm = e["name"].replace("st::", "").replace("void ", "").split("(")[0][:34]
             grid = e.get("args", {}).get("grid", "")
             print(f"  +{e['ts'] - t0:7.1f}  dur {e['dur']:6.1f}  end {e['ts'] + e['dur'] - t0:7.1f}  gap {gap:6.1f}  s{st:<3} {nm:34s} {grid}")
+
+
+def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--json":
+        report(sys.argv[2], os.path.basename(sys.argv[2]))
+        return
+    name = sys.argv[1] if len(sys.argv) > 1 else "C1"
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+    sd = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-8
+    torch.cuda.init()
+    d = synth.make_config(name)
+    q = d["q"]
+    tree = sb.make_tree(d["coords"], d["y"], d["mv_id"])
+    csr = (tree["indexing_ptr"], tree["indexing_idx"], tree["parents_ptr"], tree["parents_idx"], tree["children_ptr"], tree["children_idx"])
+    theta = synth.theta_for(q)
+    gm = sb.SpamTreeMV(d["y"], d["X"], d["coords"], d["mv_id"], tree["res_is_ref"], None, None, False, tree["block_names"],
+                       tree["block_groups"], None, np.zeros(3), theta, 0.1, csr=csr, keep_H=False)
+    bounds, npar = synth.default_bounds(q), theta.size
+    kw = dict(burn=0, thin=1, adapting=True, rng_mode=1, sample_predicts=False, save_w=True, save_yhat=False)
+    gm.mcmc(bounds, np.eye(npar) * sd, keep=5, seed=4, **kw)
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        r = gm.mcmc(bounds, np.eye(npar) * sd, keep=iters, seed=5, **kw)
+        torch.cuda.synchronize()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    path = os.path.join(ROOT, "gpurun_out", f"timeline_{name}.json")
+    prof.export_chrome_trace(path)
+    report(path, name, f"{iters} iterations, accepted {r['n_accepted']}, mcmc_time {r['mcmc_time'] * 1e3:.3f} ms -> {r['mcmc_time'] * 1e6 / iters:.1f} us / iteration")
     gm.close()
 
 
