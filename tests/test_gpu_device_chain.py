@@ -123,6 +123,26 @@ def test_device_chain_with_one_or_two_regressors(ncol):
     assert all(v <= 1e-9 for v in err.values()), err
 
 
+@pytest.mark.parametrize("keep,burn,thin", [(1, 0, 1), (2, 0, 1), (1, 2, 1), (2, 1, 3)])
+def test_very_short_device_chains(keep, burn, thin):
+    """one, two, three ... iterations: the first iteration draws its own proposal and normals, every other one finds them drawn
+    by its predecessor, the last one draws none — the alter slot must still hold the proposal that was built"""
+    pb = common.make_problem(1, 625)
+    bounds, npar = synth.default_bounds(1), pb["theta"].size
+    sd0 = np.eye(npar) * 1e-2
+    gm = common.product_model(pb, keep_H=False)
+    r = gm.mcmc(bounds, sd0, keep, burn, thin, adapting=True, faithful_beta_index=True, rng_mode=1, seed=9)
+    # after the run the host-driven operations continue from the chain's state: the alter slot is the last proposal's BUILD
+    ll_alt = gm.get_loglik_comps_w(1)
+    gm.close()
+    h = _replay(pb, bounds, sd0, keep, burn, thin, 9, True)
+    assert r["n_accepted"] == h["acc"]
+    err = {"theta": relerr(r["theta_mcmc"], np.array(h["theta"]).T), "beta": relerr(r["beta_mcmc"], np.array(h["beta"]).transpose(1, 0, 2)),
+           "w": relerr(r["w_mcmc"], np.array(h["w"]).T), "yhat": relerr(r["yhat_mcmc"], np.array(h["yhat"]).T)}
+    assert all(v <= 1e-9 for v in err.values()), err
+    assert ll_alt[0] and np.isfinite(ll_alt[1])
+
+
 def test_device_chain_is_reproducible_and_seed_dependent():
     pb = common.make_problem(2, 900)
     bounds, npar = synth.default_bounds(2), pb["theta"].size
