@@ -177,6 +177,26 @@ def test_lockstep_chain_matches_oracle_chain():
         om.close()
 
 
+@pytest.mark.parametrize("ncol", [1, 2])
+def test_lockstep_chain_with_one_or_two_regressors(ncol):
+    """p = 1 (intercept-only design) and p = 2 with q = 2 against the oracle, which tests/test_reference_driver.py pins to the
+    reference's own driver at these sizes"""
+    from spamtree_b200 import synth
+    pb = common.make_problem(2, 900)
+    pb["d"] = dict(pb["d"], X=np.ascontiguousarray(pb["d"]["X"][:, :ncol]))
+    pb["beta"] = np.zeros(ncol)
+    gm, om = common.product_model(pb), common.oracle_model(pb)
+    bounds, npar = synth.default_bounds(2), pb["theta"].size
+    kw = dict(keep=20, burn=0, thin=1, adapting=True, seed=4)
+    rg = gm.mcmc(bounds, np.eye(npar) * 1e-7, rng_mode=0, **kw)
+    ro = om.mcmc(bounds, np.eye(npar) * 1e-7, **kw)
+    assert rg["n_accepted"] == ro["n_accepted"] and rg["beta_mcmc"].shape[0] == ncol
+    for k in ("theta_mcmc", "beta_mcmc", "tausq_mcmc", "w_mcmc", "yhat_mcmc"):
+        assert relerr(rg[k], ro[k]) <= TOL, (k, relerr(rg[k], ro[k]))
+    gm.close()
+    om.close()
+
+
 def _batch_means_se(x, nb=20):
     x = np.asarray(x, dtype=np.float64)
     L = x.size // nb

@@ -157,3 +157,24 @@ def test_oracle_chain_equals_the_references_own_driver(q, n, missing, limited, s
     for k in ("theta_mcmc", "tausq_mcmc", "beta_mcmc", "paramsd", "w_mcmc", "yhat_mcmc"):
         assert relerr(o[k], r[k]) <= tol, (k, relerr(o[k], r[k]))
     om.close()
+
+
+@pytest.mark.parametrize("ncol", [1, 2])
+def test_oracle_chain_with_one_or_two_regressors_vs_the_reference(ncol):
+    """p = 1 (an intercept-only design, the commonest call of spamtree()) and p = 2 with q = 2: the beta step's p x p algebra
+    (spamtree_model.cpp:1364-1391) at sizes where any layout that assumes p >= 3 goes wrong"""
+    pb = common.make_problem(2, 900)
+    d, t = pb["d"], pb["tree"]
+    X = np.ascontiguousarray(d["X"][:, :ncol])
+    pb["d"] = dict(d, X=X)
+    pb["beta"] = np.zeros(ncol)
+    bounds, npar = synth.default_bounds(2), pb["theta"].size
+    msd = np.eye(npar) * 1e-7
+    r = ref.spamtree_mv_mcmc(d["y"], X, d["coords"], d["mv_id"], t["res_is_ref"], pb["csr"], False, t["block_names"], t["block_groups"],
+                             pb["beta"], pb["theta"], pb["tausq"], bounds, msd, 20, 0, 1, adapting=True, sample_predicts=True, seed=4)
+    om = common.oracle_model(pb, flags=0)
+    o = om.mcmc(bounds, msd, 20, 0, 1, adapting=True, sample_predicts=True, seed=4)
+    assert r["beta_mcmc"].shape[0] == ncol
+    for k in ("theta_mcmc", "tausq_mcmc", "beta_mcmc", "w_mcmc", "yhat_mcmc"):
+        assert relerr(o[k], r[k]) <= 5e-9, (k, relerr(o[k], r[k]))
+    om.close()
