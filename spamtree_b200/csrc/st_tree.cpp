@@ -7,11 +7,15 @@
 #include "st_tree.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <limits>
 #include <numeric>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 
 namespace st {
 
@@ -22,6 +26,15 @@ void kthresholds(const double* x, int64_t n, int k, double* res) {
   if (k <= 1) return;
   dvec xs(x, x + n);
   std::sort(xs.begin(), xs.end());
+  for (unsigned int i = 1; i < (unsigned int)k; i++) {
+    unsigned int Q1 = (unsigned int)(i * (unsigned int)n / (unsigned int)k);
+    res[i - 1] = xs[Q1];
+  }
+}
+
+// the same order statistics from an array that is already sorted (make_tree asks for them at every level of both grids)
+static void kthresholds_sorted(const dvec& xs, int k, double* res) {
+  const int64_t n = (int64_t)xs.size();
   for (unsigned int i = 1; i < (unsigned int)k; i++) {
     unsigned int Q1 = (unsigned int)(i * (unsigned int)n / (unsigned int)k);
     res[i - 1] = xs[Q1];
@@ -268,6 +281,15 @@ bool make_tree(const double* coords, const double* y, const int64_t* mv_id, int6
   const double* X0 = coords;
   const double* X1 = coords + n_all;
   const int K[2] = {K0, K1};
+  // ST_PROFILE_TREE=1: wall-clock per section on stderr (development aid)
+  static const bool prof = getenv("ST_PROFILE_TREE") != nullptr;
+  auto tlast = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!prof) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[tree profile] %-28s %.3f s\n", what, std::chrono::duration<double>(now - tlast).count());
+    tlast = now;
+  };
   const int axis_size = (int)std::lround(std::pow((double)cell_size, 0.5));  // R/spamtree_fit.R:229-233
   const double max_res = (tree_depth <= 0) ? std::numeric_limits<double>::infinity() : (double)(start_level + tree_depth);
 
@@ -277,6 +299,9 @@ bool make_tree(const double* coords, const double* y, const int64_t* mv_id, int6
   if (na == 0) { err = "no observed rows"; return false; }
   dvec a0(na), a1(na);
   for (int64_t i = 0; i < na; i++) { a0[i] = X0[avail[i]]; a1[i] = X1[avail[i]]; }
+  dvec s0(a0), s1(a1);  // sorted once: every grid of every level takes its quantiles from them
+  std::sort(s0.begin(), s0.end());
+  std::sort(s1.begin(), s1.end());
 
   T.n_all = n_all;
   T.blocking.assign(n_all, 0);
@@ -286,7 +311,7 @@ bool make_tree(const double* coords, const double* y, const int64_t* mv_id, int6
   ivec cx = avail;  // observed rows not yet placed
   // block-grid cell (per axis) of every observed row at every loop level, and the block name living in each cell
   std::vector<std::vector<int>> lvl_c0, lvl_c1;              // per level, per avail position
-  std::vector<std::unordered_map<int64_t, int64_t>> lvl_cell2block;  // per level: cell key -> block name
+  std::vector<std::vector<int64_t>> lvl_cell2block;  // per level: cell key -> block name (0: no row placed there), dense
   std::vector<int> lvl_res;
   int64_t max_block_number = 0;
   int res = start_level + 1, res_ix = 1;
@@ -308,50 +333,62 @@ bool make_tree(const double* coords, const double* y, const int64_t* mv_id, int6
     const double grid_size = kk0 * kk1;
     if (grid_size < (double)cx.size()) {  // :84
       dvec t0((size_t)kk0 - 1), t1((size_t)kk1 - 1);
-      kthresholds(a0.data(), na, (int)kk0, t0.data());
-      kthresholds(a1.data(), na, (int)kk1, t1.data());
+      kthresholds_sorted(s0, (int)kk0, t0.data());
+      kthresholds_sorted(s1, (int)kk1, t1.data());
       std::vector<int> c0, c1;
       cells_of(cx, t0, t1, c0, c1);
-      // one row per non-empty knot cell: smallest mix64(ix ^ seed)  (stand-in for sample(), :92)
-      std::vector<int64_t> ord(cx.size());
-      std::iota(ord.begin(), ord.end(), 0);
-      auto key = [&](int64_t i) { return (int64_t)c0[i] * (int64_t)(kk1 + 1) + c1[i]; };
-      std::sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) {
-        const int64_t ka = key(a), kb = key(b);
-        if (ka != kb) return ka < kb;
-        return mix64((uint64_t)cx[a] ^ seed) < mix64((uint64_t)cx[b] ^ seed);
-      });
-      for (size_t s = 0; s < ord.size();) {
-        size_t e = s;
-        while (e < ord.size() && key(ord[e]) == key(ord[s])) e++;
-        const int64_t r = cx[ord[s]];
-        picked.push_back(r);
-        if (cherrypick_group_locations)  // :94-99: every unplaced row at the same location comes along
-          for (size_t k = s + 1; k < e; k++) {
-            const int64_t r2 = cx[ord[k]];
-            if (X0[r2] == X0[r] && X1[r2] == X1[r]) picked.push_back(r2);
-          }
-        s = e;
+      // one row per non-empty knot cell: smallest mix64(ix ^ seed)  (stand-in for sample(), :92).  mix64 is a bijection, so
+      // the winner of a cell is unique: one pass finds it (no sort of the unplaced rows by cell)
+      const int64_t kstride = (int64_t)(kk1 + 1);
+      auto key = [&](size_t i) { return (int64_t)c0[i] * kstride + c1[i]; };
+      const int64_t nkeys = ((int64_t)kk0 + 1) * kstride;
+      const bool dense = nkeys <= 8 * (int64_t)cx.size() + 4096;
+      std::vector<int64_t> win_dense;                 // cell -> position in cx of its winner (-1: empty)
+      std::unordered_map<int64_t, int64_t> win_map;
+      if (dense) win_dense.assign((size_t)nkeys, -1);
+      std::vector<uint64_t> mixv(cx.size());
+      for (size_t i = 0; i < cx.size(); i++) {
+        mixv[i] = mix64((uint64_t)cx[i] ^ seed);
+        const int64_t k = key(i);
+        if (dense) {
+          int64_t& wv = win_dense[(size_t)k];
+          if (wv < 0 || mixv[i] < mixv[(size_t)wv]) wv = (int64_t)i;
+        } else {
+          auto it = win_map.find(k);
+          if (it == win_map.end()) win_map.emplace(k, (int64_t)i);
+          else if (mixv[i] < mixv[(size_t)it->second]) it->second = (int64_t)i;
+        }
+      }
+      auto winner_of = [&](int64_t k) { return dense ? win_dense[(size_t)k] : win_map.find(k)->second; };
+      for (size_t i = 0; i < cx.size(); i++) {
+        const int64_t wv = winner_of(key(i));
+        if ((int64_t)i == wv) { picked.push_back(cx[i]); continue; }
+        if (cherrypick_group_locations) {  // :94-99: every unplaced row at the winner's location comes along
+          const int64_t r = cx[(size_t)wv], r2 = cx[i];
+          if (X0[r2] == X0[r] && X1[r2] == X1[r]) picked.push_back(r2);
+        }
       }
       std::sort(picked.begin(), picked.end());
+      lap("  knots: pick one row per cell");
     } else {
       picked = cx;  // :106-108
     }
     // block grid (:118) and block names of the picked rows (:121-130)
     const int kb0 = (int)std::pow((double)K[0], res - 1), kb1 = (int)std::pow((double)K[1], res - 1);
     dvec tb0(std::max(0, kb0 - 1)), tb1(std::max(0, kb1 - 1));
-    kthresholds(a0.data(), na, kb0, tb0.data());
-    kthresholds(a1.data(), na, kb1, tb1.data());
+    kthresholds_sorted(s0, kb0, tb0.data());
+    kthresholds_sorted(s1, kb1, tb1.data());
     std::vector<int> pc0, pc1;
     cells_of(picked, tb0, tb1, pc0, pc1);
     ivec pb = axis_parallel_block(pc0, pc1);
-    std::unordered_map<int64_t, int64_t> cell2block;
+    lap("  block grid + names");
+    std::vector<int64_t> cell2block((size_t)(kb0 + 1) * (size_t)(kb1 + 1), 0);
     int64_t new_max = max_block_number;
     for (size_t i = 0; i < picked.size(); i++) {
       const int64_t b = max_block_number + pb[i];
       T.blocking[picked[i]] = b;
       T.res[picked[i]] = res;
-      cell2block[(int64_t)pc0[i] * (int64_t)(kb1 + 1) + pc1[i]] = b;
+      cell2block[(size_t)pc0[i] * (size_t)(kb1 + 1) + pc1[i]] = b;
       new_max = std::max(new_max, b);
     }
     max_block_number = new_max;
@@ -367,9 +404,10 @@ bool make_tree(const double* coords, const double* y, const int64_t* mv_id, int6
     cells_of(avail, tb0, tb1, ac0, ac1);
     lvl_c0.push_back(ac0);
     lvl_c1.push_back(ac1);
-    lvl_cell2block.push_back(cell2block);
+    lvl_cell2block.push_back(std::move(cell2block));
     lvl_res.push_back(kb1 + 1);
     last_level_rows = picked;
+    lap("  cells of all rows");
     T.res_is_ref.push_back(1);
     res++;
     res_ix++;
@@ -383,15 +421,22 @@ bool make_tree(const double* coords, const double* y, const int64_t* mv_id, int6
   for (int64_t i = 0; i < n_all; i++) placed[i] = T.blocking[i] > 0;
   std::vector<ivec> chains;
   {
+    // (most rows share their chain with the other rows of their leaf cell: distinct chains are collected by hashing first,
+    // only those are sorted)
     std::vector<std::vector<int64_t>> rows;
+    struct VecHash {
+      size_t operator()(const ivec& v) const {
+        uint64_t h = 0x9E3779B97F4A7C15ULL;
+        for (int64_t x : v) h = mix64(h ^ (uint64_t)x);
+        return (size_t)h;
+      }
+    };
+    std::unordered_set<ivec, VecHash> seen_chains;
+    ivec ch(nlev);
     for (int64_t ai = 0; ai < na; ai++) {
       if (!placed[avail[ai]]) continue;
-      ivec ch(nlev);
-      for (int l = 0; l < nlev; l++) {
-        auto it = lvl_cell2block[l].find((int64_t)lvl_c0[l][ai] * lvl_res[l] + lvl_c1[l][ai]);
-        ch[l] = (it == lvl_cell2block[l].end()) ? 0 : it->second;
-      }
-      rows.push_back(ch);
+      for (int l = 0; l < nlev; l++) ch[l] = lvl_cell2block[l][(size_t)lvl_c0[l][ai] * (size_t)lvl_res[l] + lvl_c1[l][ai]];
+      if (seen_chains.insert(ch).second) rows.push_back(ch);
     }
     // arrange(): ascending by columns, NA (0) last; then unique
     auto na_last = [](int64_t v) { return v == 0 ? std::numeric_limits<int64_t>::max() : v; };
@@ -403,6 +448,7 @@ bool make_tree(const double* coords, const double* y, const int64_t* mv_id, int6
     rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
     chains.swap(rows);
   }
+  lap("chains (parchi_map)");
   int ncols = nlev;
   max_block_number = 0;
   for (int64_t i = 0; i < n_all; i++) max_block_number = std::max(max_block_number, T.blocking[i]);
@@ -467,6 +513,7 @@ bool make_tree(const double* coords, const double* y, const int64_t* mv_id, int6
     for (int64_t b : nblock) max_block_number = std::max(max_block_number, b);
     cur_max_res = res_left;
   }
+  lap("leftovers: 1-NN + join");
   if (T.res_is_ref.size() == 1) T.res_is_ref[0] = 1;  // :307-309
   if (!missing.empty()) {  // rows to predict (:317-413)
     ivec pblock, nblock;
@@ -478,6 +525,7 @@ bool make_tree(const double* coords, const double* y, const int64_t* mv_id, int6
     T.res_is_ref.push_back(0);
     for (int64_t b : nblock) max_block_number = std::max(max_block_number, b);
   }
+  lap("missing rows: 1-NN + join");
   // parchi_map %>% unique()
   std::sort(chains.begin(), chains.end());
   chains.erase(std::unique(chains.begin(), chains.end()), chains.end());
@@ -501,6 +549,7 @@ bool make_tree(const double* coords, const double* y, const int64_t* mv_id, int6
   int64_t nb2 = 0;
   make_edges(T.parchimat.data(), T.parchi_rows, ncols, non_empty.data(), (int64_t)non_empty.size(), T.res_is_ref.data(),
              false, T.parents, T.children, nb2);
+  lap("parchimat + make_edges");
   if (nb2 != n_blocks) {
     // make_edges sizes by max(last column) (tree_dep.cpp:80); pad so that every block name has an entry
     T.parents.ptr.resize(n_blocks + 1, T.parents.ptr.back());
@@ -522,6 +571,7 @@ bool make_tree(const double* coords, const double* y, const int64_t* mv_id, int6
   T.indexing.idx.resize(n_all);
   ivec fill(T.indexing.ptr.begin(), T.indexing.ptr.end() - 1);
   for (int64_t i = 0; i < n_all; i++) T.indexing.idx[fill[T.blocking[i] - 1]++] = i;
+  lap("names, groups, indexing");
   return true;
 }
 
